@@ -1,0 +1,119 @@
+"""Build recipes for the in-tree native libraries.
+
+  ezrt_b200/libezrt_b200.so   the product: C ABI (include/ezrt.h) + host scene pipeline + sm_100a kernels
+  oracle/libezrt_oracle.so    the CPU oracle (test infrastructure, see oracle/README.md)
+  oracle/_ref/libhdrloader_ref.so   the one reference translation unit that compiles stand-alone
+                                     (P5/lib/hdrloader.cpp), built only where /root/reference exists
+
+Parity needs bit-identical fp32 arithmetic on host and device, hence
+  host  : -ffp-contract=off -mfma      (FMA only where ezrt_math.h spells it)
+  device: -fmad=false, IEEE div/sqrt, no FTZ (nvcc defaults), never -use_fast_math
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "ezrt_b200", "csrc")
+INCLUDE = os.path.join(ROOT, "include")
+PRODUCT_SO = os.path.join(ROOT, "ezrt_b200", "libezrt_b200.so")
+ORACLE_SO = os.path.join(ROOT, "oracle", "libezrt_oracle.so")
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+REF_HDR_SO = os.path.join(REF_DIR, "libhdrloader_ref.so")
+REFERENCE_P5 = "/root/reference/part 5 -- Importance Sampling & Low Discrepancy Sequence/source code"
+
+HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-mfma", "-Wall"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-mfma", "-Xptxas", "-v",
+]
+
+
+def _nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd, log=None):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if log:
+        with open(log, "w") as f:
+            f.write(" ".join(cmd) + "\n" + r.stdout)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+    return r.stdout
+
+
+def _headers():
+    hs = [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
+    hs += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".inc"))]
+    return hs
+
+
+def build_product(force=False, verbose=False):
+    """nvcc + g++ -> ezrt_b200/libezrt_b200.so (cross-compiles for sm_100a without a GPU)."""
+    nvcc = _nvcc()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found: cannot build libezrt_b200.so")
+    cu = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    cpp = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cpp"))
+    if not force and not _newer(PRODUCT_SO, cu + cpp + _headers()):
+        return PRODUCT_SO
+    objdir = os.path.join(ROOT, "build", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    for src in cu:
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        out = _run([nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj],
+                   log=os.path.join(objdir, os.path.basename(src) + ".ptxas.log"))
+        if verbose:
+            print(out)
+        objs.append(obj)
+    for src in cpp:
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        _run(["g++"] + HOST_FLAGS + ["-pthread", "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj])
+        objs.append(obj)
+    _run([nvcc, "-shared", "-o", PRODUCT_SO] + objs + ["-Xcompiler", "-pthread", "-cudart", "static"])
+    return PRODUCT_SO
+
+
+def build_oracle(force=False):
+    src = os.path.join(ROOT, "oracle", "ezrt_oracle.cpp")
+    deps = [src] + [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
+    if force or _newer(ORACLE_SO, deps):
+        _run(["g++"] + HOST_FLAGS + ["-fopenmp", "-Wno-misleading-indentation", "-shared", "-I", INCLUDE, src, "-o", ORACLE_SO])
+    return ORACLE_SO
+
+
+def build_reference_hdrloader(force=False):
+    """oracle/_ref: compile the reference's own hdrloader.cpp where it lies (never copied)."""
+    src = os.path.join(REFERENCE_P5, "lib", "hdrloader.cpp")
+    shim = os.path.join(ROOT, "oracle", "ref_hdrloader_shim.cpp")
+    if not os.path.exists(src):
+        return REF_HDR_SO if os.path.exists(REF_HDR_SO) else None
+    os.makedirs(REF_DIR, exist_ok=True)
+    if force or _newer(REF_HDR_SO, [src, shim]):
+        _run(["g++", "-O2", "-fPIC", "-shared", "-w", "-I", os.path.join(REFERENCE_P5, "lib"), src, shim, "-o", REF_HDR_SO])
+    return REF_HDR_SO
+
+
+def build_all(force=False, verbose=False):
+    build_product(force=force, verbose=verbose)
+    build_oracle(force=force)
+    build_reference_hdrloader(force=force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("built", PRODUCT_SO, ORACLE_SO)

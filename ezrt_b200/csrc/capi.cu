@@ -1,0 +1,577 @@
+// capi.cu -- device half of the C ABI (include/ezrt.h): scene upload/repack, render
+// orchestration (wavefront + megakernel), image partition helpers and the single-function
+// test entry points.  Host-side scene building lives in host_scene.cpp.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "device_scene.h"
+#include "ezrt.h"
+#include "ezrt_internal.h"
+#include "ezrt_math.h"
+#include "kernels.h"
+
+#define CU_CHECK(call)                                                                                  \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return ezrt_set_error(EZRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                                  __FILE__, __LINE__);                                                  \
+    } while (0)
+
+namespace {
+
+struct DeviceBuffer {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return EZRT_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e != cudaSuccess) return ezrt_set_error(EZRT_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+        bytes = need;
+        return EZRT_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+// tiles of part `rank` of `count` (ezrt_internal.h): row-major tile order, (tx+ty)%count == rank
+std::vector<TileDev> partition_tiles(int width, int height, int rank, int count) {
+    std::vector<TileDev> tiles;
+    int tx_n = (width + EZRT_TILE - 1) / EZRT_TILE, ty_n = (height + EZRT_TILE - 1) / EZRT_TILE;
+    int offset = 0;
+    for (int ty = 0; ty < ty_n; ty++)
+        for (int tx = 0; tx < tx_n; tx++) {
+            if ((tx + ty) % count != rank) continue;
+            TileDev t;
+            t.x0 = tx * EZRT_TILE;
+            t.y0 = ty * EZRT_TILE;
+            t.w = std::min(EZRT_TILE, width - t.x0);
+            t.h = std::min(EZRT_TILE, height - t.y0);
+            t.pixel_offset = offset;
+            offset += t.w * t.h;
+            tiles.push_back(t);
+        }
+    return tiles;
+}
+
+}  // namespace
+
+struct ezrt_scene {
+    int device = 0;
+    int n_sms = 148;
+    SceneDev dev{};
+    DeviceBuffer nodes, tri_geo, tri_shade, materials, hdr, hdr_cache;
+    int n_materials = 0;
+    int tree_depth = 0;
+    // render state (lazily sized)
+    DeviceBuffer tiles_buf, queue_buf[2], shadow_buf, lo_buf, le_buf, counters_buf, totals_buf, fb_buf;
+    int tiles_key[4] = {-1, -1, -1, -1};
+    std::vector<TileDev> tiles;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    bool have_timing = false;
+    unsigned long long launches = 0;
+};
+
+namespace {
+
+int carve_queue(DeviceBuffer& buf, size_t capacity, PathQueue& q) {
+    size_t per = sizeof(float4) * 4 + sizeof(uint2);
+    int rc = buf.ensure(per * capacity + 256);
+    if (rc) return rc;
+    char* p = (char*)buf.p;
+    q.ray_o = (float4*)p; p += sizeof(float4) * capacity;
+    q.ray_d = (float4*)p; p += sizeof(float4) * capacity;
+    q.hist = (float4*)p;  p += sizeof(float4) * capacity;
+    q.fr = (float4*)p;    p += sizeof(float4) * capacity;
+    q.meta = (uint2*)p;
+    return EZRT_OK;
+}
+int carve_shadow(DeviceBuffer& buf, size_t capacity, ShadowQueue& q) {
+    int rc = buf.ensure(sizeof(float4) * 3 * capacity + 256);
+    if (rc) return rc;
+    char* p = (char*)buf.p;
+    q.ray_o = (float4*)p; p += sizeof(float4) * capacity;
+    q.ray_d = (float4*)p; p += sizeof(float4) * capacity;
+    q.contrib = (float4*)p;
+    return EZRT_OK;
+}
+
+int validate_params(const ezrt_scene* scene, const ezrt_render_params* p) {
+    if (!scene || !p) return ezrt_set_error(EZRT_ERR_INVALID, "render: null argument");
+    if (p->width <= 0 || p->height <= 0 || p->spp < 0) return ezrt_set_error(EZRT_ERR_INVALID, "render: bad image size/spp");
+    if (p->mode < 0 || p->mode > 3) return ezrt_set_error(EZRT_ERR_INVALID, "render: unknown mode %d", p->mode);
+    if (p->max_bounce < 0 || p->max_bounce > 64) return ezrt_set_error(EZRT_ERR_INVALID, "render: max_bounce out of range");
+    if (p->out_channels != 3 && p->out_channels != 4) return ezrt_set_error(EZRT_ERR_INVALID, "render: out_channels must be 3 or 4");
+    if (p->part_count < 1 || p->part_rank < 0 || p->part_rank >= p->part_count)
+        return ezrt_set_error(EZRT_ERR_INVALID, "render: bad partition %d/%d", p->part_rank, p->part_count);
+    if (p->mode == EZRT_MODE_DISNEY_IS_MIS_P5 && (!scene->dev.hdr || !scene->dev.hdr_cache))
+        return ezrt_set_error(EZRT_ERR_INVALID, "render: IS/MIS mode needs an HDR map and its cache");
+    return EZRT_OK;
+}
+
+int prepare_tiles(ezrt_scene* s, const ezrt_render_params* p, cudaStream_t st) {
+    int key[4] = {p->width, p->height, p->part_rank, p->part_count};
+    if (memcmp(key, s->tiles_key, sizeof(key)) == 0) return EZRT_OK;
+    s->tiles = partition_tiles(p->width, p->height, p->part_rank, p->part_count);
+    size_t bytes = sizeof(TileDev) * std::max<size_t>(1, s->tiles.size());
+    int rc = s->tiles_buf.ensure(bytes);
+    if (rc) return rc;
+    if (!s->tiles.empty()) CU_CHECK(cudaMemcpyAsync(s->tiles_buf.p, s->tiles.data(), sizeof(TileDev) * s->tiles.size(), cudaMemcpyHostToDevice, st));
+    CU_CHECK(cudaStreamSynchronize(st));  // s->tiles is pageable host memory
+    memcpy(s->tiles_key, key, sizeof(key));
+    return EZRT_OK;
+}
+
+RenderDev make_render_dev(const ezrt_scene* s, const ezrt_render_params* p) {
+    RenderDev rd;
+    rd.width = p->width; rd.height = p->height;
+    rd.mode = p->mode; rd.max_bounce = p->max_bounce; rd.traverse = p->traverse;
+    memcpy(rd.eye, p->eye, sizeof(rd.eye));
+    memcpy(rd.cam, p->camera_rotate, sizeof(rd.cam));
+    memcpy(rd.env, p->env_color, sizeof(rd.env));
+    rd.first_frame = p->first_frame;
+    rd.out_channels = p->out_channels;
+    rd.compact_out = (p->part_count > 1) ? 1 : 0;
+    rd.n_tiles = (int)s->tiles.size();
+    return rd;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------
+// scene upload + repack (replaces the TBO / texture uploads P5/main.cpp:878-906)
+// ------------------------------------------------------------------------------------------
+int ezrt_scene_create(int device, const float* tris, int n_triangles, const float* nodes, int n_nodes, const float* hdr,
+                      const float* hdr_cache, int hdr_w, int hdr_h, int hdr_filter_linear, ezrt_scene** out_scene) {
+    if (!tris || !nodes || !out_scene || n_triangles <= 0 || n_nodes < 2)
+        return ezrt_set_error(EZRT_ERR_INVALID, "scene_create: need triangles and at least the dummy + root node");
+    if ((hdr || hdr_cache) && (hdr_w <= 0 || hdr_h <= 0)) return ezrt_set_error(EZRT_ERR_INVALID, "scene_create: bad HDR size");
+    if (n_triangles >= (1 << 24)) return ezrt_set_error(EZRT_ERR_INVALID, "scene_create: more than 2^24 triangles (ints-as-floats limit)");
+    int n_dev = 0;
+    CU_CHECK(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return ezrt_set_error(EZRT_ERR_CUDA, "scene_create: no CUDA device %d (have %d)", device, n_dev);
+    CU_CHECK(cudaSetDevice(device));
+
+    // ---- decode + validate the tree (getBVHNode, P5/fsh:138-155) ----
+    struct HNode { int left, right, n, index; };
+    std::vector<HNode> hn(n_nodes);
+    for (int i = 0; i < n_nodes; i++) {
+        const float* s = nodes + (size_t)i * EZRT_BVHNODE_FLOATS;
+        hn[i].left = (int)s[0]; hn[i].right = (int)s[1]; hn[i].n = (int)s[3]; hn[i].index = (int)s[4];
+    }
+    std::vector<int> inner_id(n_nodes, -1);
+    std::vector<char> seen(n_nodes, 0);
+    int n_inner = 0, max_depth = 0;
+    {
+        std::vector<std::pair<int, int>> stk;
+        stk.push_back({1, 1});
+        while (!stk.empty()) {
+            auto [i, depth] = stk.back();
+            stk.pop_back();
+            if (i < 1 || i >= n_nodes) return ezrt_set_error(EZRT_ERR_BAD_TREE, "scene_create: child index %d out of range", i);
+            if (seen[i]) return ezrt_set_error(EZRT_ERR_BAD_TREE, "scene_create: node %d reachable twice", i);
+            seen[i] = 1;
+            max_depth = std::max(max_depth, depth);
+            const HNode& nd = hn[i];
+            if (nd.n > 0) {
+                if (nd.n > EZRT_LEAF_MAX_N) return ezrt_set_error(EZRT_ERR_BAD_TREE, "scene_create: leaf %d holds %d > %d triangles", i, nd.n, EZRT_LEAF_MAX_N);
+                if (nd.index < 0 || nd.index + nd.n > n_triangles) return ezrt_set_error(EZRT_ERR_BAD_TREE, "scene_create: leaf %d range out of bounds", i);
+            } else {
+                // the shader would read the dummy node 0 for a missing child (P5/fsh:278-302); not supported
+                if (nd.left <= 0 || nd.right <= 0) return ezrt_set_error(EZRT_ERR_BAD_TREE, "scene_create: inner node %d lacks a child", i);
+                stk.push_back({nd.right, depth + 1});
+                stk.push_back({nd.left, depth + 1});
+            }
+        }
+    }
+    if (max_depth + 1 > EZRT_MAX_STACK) return ezrt_set_error(EZRT_ERR_BAD_TREE, "scene_create: tree depth %d exceeds %d", max_depth, EZRT_MAX_STACK - 1);
+    for (int i = 1; i < n_nodes; i++)
+        if (seen[i] && hn[i].n <= 0) inner_id[i] = n_inner++;
+
+    auto child_ref = [&](int c) -> int {
+        if (hn[c].n > 0) return (int)(EZRT_LEAF_FLAG | ((uint32_t)hn[c].index << 7) | (uint32_t)hn[c].n);
+        return inner_id[c];
+    };
+    std::vector<float4> gnodes((size_t)std::max(1, n_inner) * 4);
+    for (int i = 1; i < n_nodes; i++) {
+        if (inner_id[i] < 0) continue;
+        const float* L = nodes + (size_t)hn[i].left * EZRT_BVHNODE_FLOATS;
+        const float* R = nodes + (size_t)hn[i].right * EZRT_BVHNODE_FLOATS;
+        float4* g = &gnodes[(size_t)inner_id[i] * 4];
+        int rl = child_ref(hn[i].left), rr = child_ref(hn[i].right);
+        float fl, fr;
+        memcpy(&fl, &rl, 4);
+        memcpy(&fr, &rr, 4);
+        g[0] = make_float4(L[6], L[7], L[8], fl);
+        g[1] = make_float4(L[9], L[10], L[11], fr);
+        g[2] = make_float4(R[6], R[7], R[8], 0.0f);
+        g[3] = make_float4(R[9], R[10], R[11], 0.0f);
+    }
+
+    // ---- triangles: geometry records, shading records, de-duplicated material table ----
+    std::vector<float4> geo((size_t)n_triangles * 4), shade((size_t)n_triangles * 3);
+    std::map<std::string, int> mat_ids;
+    std::vector<float4> mats;
+    float max_abs = 0.0f;
+    for (int i = 0; i < n_triangles; i++) {
+        const float* s = tris + (size_t)i * EZRT_TRIANGLE_FLOATS;
+        ez_vec3 p1 = ez_v3(s[0], s[1], s[2]), p2 = ez_v3(s[3], s[4], s[5]), p3 = ez_v3(s[6], s[7], s[8]);
+        for (int k = 0; k < 9; k++) max_abs = ez_max(max_abs, ez_abs(s[k]));
+        ez_vec3 N = ez_normalize(ez_cross(ez_sub(p2, p1), ez_sub(p3, p1)));  // hitTriangle, P5/fsh:172
+        float d0 = ez_dot(N, p1);                                            // P5/fsh:184
+        geo[(size_t)i * 4 + 0] = make_float4(p1.x, p1.y, p1.z, N.x);
+        geo[(size_t)i * 4 + 1] = make_float4(p2.x, p2.y, p2.z, N.y);
+        geo[(size_t)i * 4 + 2] = make_float4(p3.x, p3.y, p3.z, N.z);
+        geo[(size_t)i * 4 + 3] = make_float4(d0, 0.0f, 0.0f, 0.0f);
+        std::string key((const char*)(s + 18), sizeof(float) * EZRT_MATERIAL_FLOATS);
+        auto it = mat_ids.find(key);
+        int id;
+        if (it == mat_ids.end()) {
+            id = (int)mat_ids.size();
+            mat_ids.emplace(key, id);
+            const float* m = s + 18;
+            mats.push_back(make_float4(m[0], m[1], m[2], m[3]));
+            mats.push_back(make_float4(m[4], m[5], m[6], m[7]));
+            mats.push_back(make_float4(m[8], m[9], m[10], m[11]));
+            mats.push_back(make_float4(m[12], m[13], m[14], m[15]));
+            mats.push_back(make_float4(m[16], m[17], 0.0f, 0.0f));
+        } else {
+            id = it->second;
+        }
+        float fid;
+        memcpy(&fid, &id, 4);
+        shade[(size_t)i * 3 + 0] = make_float4(s[9], s[10], s[11], fid);
+        shade[(size_t)i * 3 + 1] = make_float4(s[12], s[13], s[14], 0.0f);
+        shade[(size_t)i * 3 + 2] = make_float4(s[15], s[16], s[17], 0.0f);
+    }
+
+    ezrt_scene* sc = new (std::nothrow) ezrt_scene();
+    if (!sc) return ezrt_set_error(EZRT_ERR_NOMEM, "scene_create: out of host memory");
+    sc->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) sc->n_sms = prop.multiProcessorCount;
+    int rc = EZRT_OK;
+    auto upload = [&](DeviceBuffer& b, const void* src, size_t bytes) -> int {
+        int r = b.ensure(std::max<size_t>(bytes, 16));
+        if (r) return r;
+        if (bytes && cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+            return ezrt_set_error(EZRT_ERR_CUDA, "scene_create: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return EZRT_OK;
+    };
+    if (!rc) rc = upload(sc->nodes, gnodes.data(), gnodes.size() * sizeof(float4));
+    if (!rc) rc = upload(sc->tri_geo, geo.data(), geo.size() * sizeof(float4));
+    if (!rc) rc = upload(sc->tri_shade, shade.data(), shade.size() * sizeof(float4));
+    if (!rc) rc = upload(sc->materials, mats.data(), mats.size() * sizeof(float4));
+    if (!rc && hdr) rc = upload(sc->hdr, hdr, sizeof(float) * 3 * (size_t)hdr_w * hdr_h);
+    if (!rc && hdr_cache) rc = upload(sc->hdr_cache, hdr_cache, sizeof(float) * 3 * (size_t)hdr_w * hdr_h);
+    if (!rc && cudaStreamCreateWithFlags(&sc->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = ezrt_set_error(EZRT_ERR_CUDA, "scene_create: stream");
+    if (!rc && (cudaEventCreate(&sc->ev_start) != cudaSuccess || cudaEventCreate(&sc->ev_stop) != cudaSuccess)) rc = ezrt_set_error(EZRT_ERR_CUDA, "scene_create: events");
+    if (rc) {
+        ezrt_scene_destroy(sc);
+        return rc;
+    }
+    sc->n_materials = (int)mat_ids.size();
+    sc->tree_depth = max_depth;
+    SceneDev& d = sc->dev;
+    d.nodes = (const float4*)sc->nodes.p;
+    d.tri_geo = (const float4*)sc->tri_geo.p;
+    d.tri_shade = (const float4*)sc->tri_shade.p;
+    d.materials = (const float4*)sc->materials.p;
+    d.hdr = hdr ? (const float*)sc->hdr.p : nullptr;
+    d.hdr_cache = hdr_cache ? (const float*)sc->hdr_cache.p : nullptr;
+    d.hdr_w = hdr_w; d.hdr_h = hdr_h; d.hdr_linear = hdr_filter_linear ? 1 : 0;
+    d.root_ref = child_ref(1);
+    d.n_triangles = n_triangles;
+    d.n_inner = n_inner;
+    d.prune_delta = max_abs * 1.52587890625e-05f;  // 2^-16 * scene extent (DESIGN.md "pruning")
+    *out_scene = sc;
+    return EZRT_OK;
+}
+
+int ezrt_scene_destroy(ezrt_scene* s) {
+    if (!s) return EZRT_OK;
+    cudaSetDevice(s->device);
+    s->nodes.release(); s->tri_geo.release(); s->tri_shade.release(); s->materials.release();
+    s->hdr.release(); s->hdr_cache.release(); s->tiles_buf.release();
+    s->queue_buf[0].release(); s->queue_buf[1].release(); s->shadow_buf.release();
+    s->lo_buf.release(); s->le_buf.release(); s->counters_buf.release(); s->totals_buf.release(); s->fb_buf.release();
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    if (s->ev_start) cudaEventDestroy(s->ev_start);
+    if (s->ev_stop) cudaEventDestroy(s->ev_stop);
+    delete s;
+    return EZRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// render
+// ------------------------------------------------------------------------------------------
+int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, void* cuda_stream) {
+    int rc = validate_params(s, p);
+    if (rc) return rc;
+    if (!d_fb) return ezrt_set_error(EZRT_ERR_INVALID, "render: null framebuffer");
+    CU_CHECK(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    rc = prepare_tiles(s, p, st);
+    if (rc) return rc;
+    rc = s->totals_buf.ensure(sizeof(unsigned long long) * 4);
+    if (rc) return rc;
+    unsigned long long* totals = (unsigned long long*)s->totals_buf.p;
+    CU_CHECK(cudaEventRecord(s->ev_start, st));
+    CU_CHECK(cudaMemsetAsync(totals, 0, sizeof(unsigned long long) * 4, st));
+    s->launches = 0;
+    s->have_timing = true;
+    RenderDev rd = make_render_dev(s, p);
+    const TileDev* d_tiles = (const TileDev*)s->tiles_buf.p;
+    const bool prune = (p->traverse == EZRT_TRAVERSE_PRUNED);
+    if (rd.n_tiles == 0 || p->spp == 0) {
+        CU_CHECK(cudaEventRecord(s->ev_stop, st));
+        return EZRT_OK;
+    }
+
+    if (p->pipeline == EZRT_PIPELINE_MEGAKERNEL) {
+        launch_megakernel(s->dev, rd, d_tiles, prune, p->spp, d_fb, totals, st);
+        s->launches++;
+        CU_CHECK(cudaGetLastError());
+        CU_CHECK(cudaEventRecord(s->ev_stop, st));
+        return EZRT_OK;
+    }
+
+    const size_t per_frame = (size_t)rd.n_tiles * EZRT_TILE_PIXELS;
+    int F = p->frames_per_batch;
+    if (F <= 0) F = (int)std::max<size_t>(1, ((size_t)4 << 20) / per_frame);
+    F = std::min(F, p->spp);
+    const size_t capacity = per_frame * (size_t)F;
+    if (capacity >= ((size_t)1 << 31)) return ezrt_set_error(EZRT_ERR_INVALID, "render: batch too large");
+    PathQueue q[2];
+    ShadowQueue sq{};
+    if ((rc = carve_queue(s->queue_buf[0], capacity, q[0]))) return rc;
+    if ((rc = carve_queue(s->queue_buf[1], capacity, q[1]))) return rc;
+    const bool is_mode = (p->mode == EZRT_MODE_DISNEY_IS_MIS_P5);
+    if ((rc = carve_shadow(s->shadow_buf, is_mode ? capacity : 1, sq))) return rc;
+    if ((rc = s->lo_buf.ensure(sizeof(float4) * capacity))) return rc;
+    if ((rc = s->le_buf.ensure(sizeof(float4) * capacity))) return rc;
+    const int n_stages = p->max_bounce + 2;
+    // counters: [0,n) queue sizes, [n,2n) shadow sizes, [2n,3n) extend work, [3n,4n) shadow work
+    if ((rc = s->counters_buf.ensure(sizeof(uint32_t) * 4 * n_stages))) return rc;
+    uint32_t* cnt = (uint32_t*)s->counters_buf.p;
+    uint32_t *q_count = cnt, *s_count = cnt + n_stages, *w_ext = cnt + 2 * n_stages, *w_sh = cnt + 3 * n_stages;
+    float4* Lo = (float4*)s->lo_buf.p;
+    float4* Le = (float4*)s->le_buf.p;
+
+    for (int done = 0; done < p->spp; done += F) {
+        const int nf = std::min(F, p->spp - done);
+        const uint32_t n_slots = (uint32_t)(per_frame * (size_t)nf);
+        const uint32_t batch_first = p->first_frame + (uint32_t)done;
+        CU_CHECK(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * 4 * n_stages, st));
+        launch_generate(rd, d_tiles, n_slots, batch_first, q[0], &q_count[0], s->n_sms, st);
+        s->launches++;
+        for (int b = 0; b <= p->max_bounce; b++) {
+            PathQueue& qin = q[b & 1];
+            PathQueue& qout = q[(b + 1) & 1];
+            launch_extend(s->dev, prune, qin, &q_count[b], &w_ext[b], n_slots, s->n_sms, st);
+            launch_shade(s->dev, rd, d_tiles, b, batch_first, qin, &q_count[b], qout, &q_count[b + 1], sq, &s_count[b], Lo, Le,
+                         n_slots, s->n_sms, st);
+            s->launches += 2;
+            if (is_mode && b < p->max_bounce) {
+                launch_shadow(s->dev, prune, sq, &s_count[b], &w_sh[b], Lo, n_slots, s->n_sms, st);
+                s->launches++;
+            }
+        }
+        launch_blend(rd, d_tiles, nf, batch_first, Lo, Le, d_fb, st);
+        launch_tally(q_count, s_count, p->max_bounce + 1, totals, st);
+        s->launches += 2;
+    }
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaEventRecord(s->ev_stop, st));
+    return EZRT_OK;
+}
+
+int ezrt_render(ezrt_scene* s, const ezrt_render_params* p, float* framebuffer) {
+    int rc = validate_params(s, p);
+    if (rc) return rc;
+    if (!framebuffer) return ezrt_set_error(EZRT_ERR_INVALID, "render: null framebuffer");
+    CU_CHECK(cudaSetDevice(s->device));
+    int64_t npix = ezrt_partition_pixels(p->width, p->height, p->part_rank, p->part_count);
+    size_t bytes = sizeof(float) * (size_t)npix * p->out_channels;
+    rc = s->fb_buf.ensure(std::max<size_t>(bytes, 16));
+    if (rc) return rc;
+    cudaStream_t st = s->own_stream;
+    if (p->first_frame > 0) CU_CHECK(cudaMemcpyAsync(s->fb_buf.p, framebuffer, bytes, cudaMemcpyHostToDevice, st));
+    rc = ezrt_render_device(s, p, (float*)s->fb_buf.p, st);
+    if (rc) return rc;
+    CU_CHECK(cudaMemcpyAsync(framebuffer, s->fb_buf.p, bytes, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    return EZRT_OK;
+}
+
+int ezrt_get_counters(ezrt_scene* s, ezrt_counters* out) {
+    if (!s || !out) return ezrt_set_error(EZRT_ERR_INVALID, "get_counters: null argument");
+    memset(out, 0, sizeof(*out));
+    if (!s->have_timing) return EZRT_OK;
+    CU_CHECK(cudaSetDevice(s->device));
+    CU_CHECK(cudaEventSynchronize(s->ev_stop));
+    unsigned long long t[4] = {0, 0, 0, 0};
+    CU_CHECK(cudaMemcpy(t, s->totals_buf.p, sizeof(t), cudaMemcpyDeviceToHost));
+    float ms = 0.0f;
+    CU_CHECK(cudaEventElapsedTime(&ms, s->ev_start, s->ev_stop));
+    out->primary_rays = t[0]; out->bounce_rays = t[1]; out->shadow_rays = t[2];
+    out->rays = t[0] + t[1] + t[2];
+    out->samples = t[3];
+    out->kernel_launches = s->launches;
+    out->device_ms = ms;
+    return EZRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// image partition
+// ------------------------------------------------------------------------------------------
+int64_t ezrt_partition_pixels(int width, int height, int rank, int count) {
+    if (width <= 0 || height <= 0 || count < 1 || rank < 0 || rank >= count) return EZRT_ERR_INVALID;
+    int64_t n = 0;
+    for (const TileDev& t : partition_tiles(width, height, rank, count)) n += (int64_t)t.w * t.h;
+    return n;
+}
+
+int ezrt_partition_scatter(const float* d_compact, float* d_full, int width, int height, int channels, int rank, int count,
+                           void* cuda_stream) {
+    if (!d_compact || !d_full || channels < 1) return ezrt_set_error(EZRT_ERR_INVALID, "partition_scatter: bad argument");
+    std::vector<TileDev> tiles = partition_tiles(width, height, rank, count);
+    if (tiles.empty()) return EZRT_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    TileDev* d_tiles = nullptr;
+    CU_CHECK(cudaMalloc(&d_tiles, sizeof(TileDev) * tiles.size()));
+    cudaError_t e = cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(TileDev) * tiles.size(), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        launch_partition_scatter(d_compact, d_full, d_tiles, (int)tiles.size(), width, channels, st);
+        e = cudaStreamSynchronize(st);
+    }
+    cudaFree(d_tiles);
+    if (e != cudaSuccess) return ezrt_set_error(EZRT_ERR_CUDA, "partition_scatter: %s", cudaGetErrorString(e));
+    return EZRT_OK;
+}
+
+int ezrt_partition_scatter_host(const float* compact, float* full, int width, int height, int channels, int rank, int count) {
+    if (!compact || !full || channels < 1) return ezrt_set_error(EZRT_ERR_INVALID, "partition_scatter_host: bad argument");
+    for (const TileDev& t : partition_tiles(width, height, rank, count))
+        for (int iy = 0; iy < t.h; iy++)
+            for (int ix = 0; ix < t.w; ix++) {
+                size_t src = ((size_t)t.pixel_offset + (size_t)iy * t.w + ix) * channels;
+                size_t dst = ((size_t)(t.y0 + iy) * width + (t.x0 + ix)) * channels;
+                for (int c = 0; c < channels; c++) full[dst + c] = compact[src + c];
+            }
+    return EZRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// single-function entry points (parity tests)
+// ------------------------------------------------------------------------------------------
+int ezrt_trace_rays(ezrt_scene* s, int n, const float* origins, const float* dirs, int traverse, int any_hit, int p3_normal_fudge,
+                    int32_t* out_hit, float* out_distance, int32_t* out_triangle, int32_t* out_inside, float* out_point,
+                    float* out_normal) {
+    if (!s || n < 0 || !origins || !dirs || !out_hit || !out_distance || !out_triangle || !out_inside || !out_point || !out_normal)
+        return ezrt_set_error(EZRT_ERR_INVALID, "trace_rays: null argument");
+    if (n == 0) return EZRT_OK;
+    CU_CHECK(cudaSetDevice(s->device));
+    DeviceBuffer buf;
+    size_t fN = sizeof(float) * (size_t)n;
+    int rc = buf.ensure(fN * 3 * 4 + fN * 4 + 256);
+    if (rc) return rc;
+    float* d_o = (float*)buf.p;
+    float* d_d = d_o + 3 * (size_t)n;
+    float* d_point = d_d + 3 * (size_t)n;
+    float* d_normal = d_point + 3 * (size_t)n;
+    float* d_dist = d_normal + 3 * (size_t)n;
+    int* d_hit = (int*)(d_dist + n);
+    int* d_tri = d_hit + n;
+    int* d_inside = d_tri + n;
+    cudaStream_t st = s->own_stream;
+    cudaError_t e = cudaMemcpyAsync(d_o, origins, fN * 3, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dirs, fN * 3, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        launch_trace_rays(s->dev, traverse == EZRT_TRAVERSE_PRUNED, any_hit != 0, n, d_o, d_d, p3_normal_fudge, d_hit, d_dist, d_tri,
+                          d_inside, d_point, d_normal, st);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_hit, d_hit, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_distance, d_dist, fN, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_triangle, d_tri, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_inside, d_inside, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_point, d_point, fN * 3, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_normal, d_normal, fN * 3, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    buf.release();
+    if (e != cudaSuccess) return ezrt_set_error(EZRT_ERR_CUDA, "trace_rays: %s", cudaGetErrorString(e));
+    return EZRT_OK;
+}
+
+int ezrt_eval_brdf(int device, int which, int n, const float* V, const float* N, const float* L, const float* xi,
+                   const float* materials, float* out) {
+    if (n < 0 || !V || !N || !materials || !out || which < 0 || which > 3) return ezrt_set_error(EZRT_ERR_INVALID, "eval_brdf: bad argument");
+    if (which != 3 && !L) return ezrt_set_error(EZRT_ERR_INVALID, "eval_brdf: L required");
+    if (which == 3 && !xi) return ezrt_set_error(EZRT_ERR_INVALID, "eval_brdf: xi required");
+    if (n == 0) return EZRT_OK;
+    CU_CHECK(cudaSetDevice(device));
+    DeviceBuffer buf;
+    size_t f3 = sizeof(float) * 3 * (size_t)n;
+    int rc = buf.ensure(f3 * 5 + sizeof(float) * 18 * (size_t)n + 256);
+    if (rc) return rc;
+    float* dV = (float*)buf.p;
+    float* dN = dV + 3 * (size_t)n;
+    float* dL = dN + 3 * (size_t)n;
+    float* dXi = dL + 3 * (size_t)n;
+    float* dOut = dXi + 3 * (size_t)n;
+    float* dM = dOut + 3 * (size_t)n;
+    cudaError_t e = cudaMemcpy(dV, V, f3, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dN, N, f3, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && L) e = cudaMemcpy(dL, L, f3, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && xi) e = cudaMemcpy(dXi, xi, f3, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dM, materials, sizeof(float) * 18 * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        launch_eval_brdf(which, n, dV, dN, L ? dL : nullptr, xi ? dXi : nullptr, dM, dOut, 0);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dOut, f3, cudaMemcpyDeviceToHost);
+    buf.release();
+    if (e != cudaSuccess) return ezrt_set_error(EZRT_ERR_CUDA, "eval_brdf: %s", cudaGetErrorString(e));
+    return EZRT_OK;
+}
+
+int ezrt_eval_math(int device, int which, int n, const float* a, const float* b, float* out) {
+    if (n < 0 || !a || !out || which < 0 || which > 6) return ezrt_set_error(EZRT_ERR_INVALID, "eval_math: bad argument");
+    if (n == 0) return EZRT_OK;
+    CU_CHECK(cudaSetDevice(device));
+    DeviceBuffer buf;
+    size_t fN = sizeof(float) * (size_t)n;
+    int rc = buf.ensure(fN * 3 + 256);
+    if (rc) return rc;
+    float* dA = (float*)buf.p;
+    float* dB = dA + n;
+    float* dO = dB + n;
+    cudaError_t e = cudaMemcpy(dA, a, fN, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && b) e = cudaMemcpy(dB, b, fN, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        launch_eval_math(which, n, dA, b ? dB : nullptr, dO, 0);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dO, fN, cudaMemcpyDeviceToHost);
+    buf.release();
+    if (e != cudaSuccess) return ezrt_set_error(EZRT_ERR_CUDA, "eval_math: %s", cudaGetErrorString(e));
+    return EZRT_OK;
+}
+
+}  // extern "C"

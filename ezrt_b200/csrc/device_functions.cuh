@@ -1,0 +1,652 @@
+// device_functions.cuh -- sm_100a device code of the hot path: BVH traversal, ray/triangle and
+// ray/box tests, Disney BRDF evaluate/sample/pdf, wang-hash + Sobol samplers, HDR lookups.
+// Replaces the GLSL of P5/shaders/fshader.fsh (and its P3/P4 variants) and the C++ twins
+// hitTriangle/hitAABB/hitBVH of P2/main.cpp:212-238,:449-485.  Every function cites the
+// reference lines it must agree with; arithmetic is the normative fp32 of ezrt_math.h
+// (compile with -fmad=false: FMA only where EZ_FMA spells it).
+#ifndef EZRT_DEVICE_FUNCTIONS_CUH
+#define EZRT_DEVICE_FUNCTIONS_CUH
+
+#include "device_scene.h"
+#include "ezrt.h"
+#include "ezrt_math.h"
+
+__constant__ uint32_t c_sobolV[8 * 32] = {
+#include "ezrt_sobol_table.inc"
+};
+
+typedef ez_vec3 vec3;
+
+__device__ __forceinline__ vec3 f4xyz(float4 q) { return ez_v3(q.x, q.y, q.z); }
+__device__ __forceinline__ vec3 splat3(float s) { return ez_v3(s, s, s); }
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// ------------------------------------------------------------------------------------------
+// RNG + low-discrepancy samplers
+// ------------------------------------------------------------------------------------------
+// wang_hash / rand, P5/fsh:320-331
+__device__ __forceinline__ uint32_t wang_hash(uint32_t& seed) {
+    seed = (seed ^ 61u) ^ (seed >> 16);
+    seed *= 9u;
+    seed = seed ^ (seed >> 4);
+    seed *= 0x27d4eb2du;
+    seed = seed ^ (seed >> 15);
+    return seed;
+}
+__device__ __forceinline__ float rand01(uint32_t& seed) {
+    return __uint2float_rn(wang_hash(seed)) * 2.3283064365386963e-10f;  // float(h) / 4294967296.0
+}
+// seed initialiser, P5/fsh:315-318
+__device__ __forceinline__ uint32_t pixel_seed(uint32_t px, uint32_t py, uint32_t frame) {
+    return (px * 1973u + py * 9277u + frame * 26699u) | 1u;
+}
+// sobol(d, grayCode(i)), P5/fsh:356-369
+__device__ __forceinline__ float sobol_gray(uint32_t d, uint32_t i) {
+    uint32_t g = i ^ (i >> 1);
+    uint32_t result = 0;
+    uint32_t offset = (d * 32u) & 255u;
+    for (uint32_t j = 0; g != 0; g >>= 1, j++)
+        if (g & 1u) result ^= c_sobolV[(j + offset) & 255u];
+    return __uint2float_rn(result) * 2.3283064365386963e-10f;  // * (1.0f/float(0xFFFFFFFFU))
+}
+// CranleyPattersonRotation, P5/fsh:378-396
+__device__ __forceinline__ void cp_rotate(float& x, float& y, uint32_t px, uint32_t py) {
+    uint32_t pseed = (px * 1973u + py * 9277u + 59u * 26699u) | 1u;  // uint(114514/1919) = 59
+    float u = rand01(pseed);
+    float v = rand01(pseed);
+    x += u;
+    if (x > 1.0f) x -= 1.0f;
+    if (x < 0.0f) x += 1.0f;
+    y += v;
+    if (y > 1.0f) y -= 1.0f;
+    if (y < 0.0f) y += 1.0f;
+}
+
+// ------------------------------------------------------------------------------------------
+// BVH traversal (hitBVH P5/fsh:254-306, hitArray :238-251, hitTriangle :160-217, hitAABB :220-233)
+// ------------------------------------------------------------------------------------------
+struct HitRec {
+    float t;    // EZ_INF on miss
+    int tri;    // -1 on miss
+};
+
+// Slab test of one child box.  Returns whether the reference would push the child (d > 0) and
+// the distance d it sorts by; t0 is the entry distance (pruning only).  FAST: all 1/d finite,
+// no NaN can arise, so FMNMX (fminf/fmaxf) equals the GLSL ternary min/max; otherwise the
+// ternaries are used literally (NaN propagation as in the oracle).
+template <bool FAST>
+__device__ __forceinline__ bool box_test(vec3 o, vec3 inv, float4 qa, float4 qb, float& dist, float& t0out) {
+    float fx = (qb.x - o.x) * inv.x, fy = (qb.y - o.y) * inv.y, fz = (qb.z - o.z) * inv.z;
+    float nx = (qa.x - o.x) * inv.x, ny = (qa.y - o.y) * inv.y, nz = (qa.z - o.z) * inv.z;
+    float t1, t0;
+    if (FAST) {
+        t1 = fminf(fmaxf(fx, nx), fminf(fmaxf(fy, ny), fmaxf(fz, nz)));
+        t0 = fmaxf(fminf(fx, nx), fmaxf(fminf(fy, ny), fminf(fz, nz)));
+    } else {
+        t1 = ez_min(ez_max(fx, nx), ez_min(ez_max(fy, ny), ez_max(fz, nz)));
+        t0 = ez_max(ez_min(fx, nx), ez_max(ez_min(fy, ny), ez_min(fz, nz)));
+    }
+    t0out = t0;
+    float d = (t1 >= t0) ? ((t0 > 0.0f) ? t0 : t1) : -1.0f;
+    dist = d;
+    return d > 0.0f;
+}
+
+// Ray/triangle test against the repacked record.  Accepts exactly the hits hitTriangle accepts
+// that are also strictly closer than `best` (the only ones hitArray/hitBVH can keep).
+__device__ __forceinline__ bool tri_test(const float4* __restrict__ rec, vec3 o, vec3 d, float best, float& tout) {
+    float4 q0 = ldg4(rec + 0), q1 = ldg4(rec + 1), q2 = ldg4(rec + 2), q3 = ldg4(rec + 3);
+    vec3 N = ez_v3(q0.w, q1.w, q2.w);
+    float nd = ez_dot(N, d);
+    if (ez_abs(nd) < 0.00001f) return false;                    // :181 (|dot(+-N,d)| is sign-free)
+    float t = EZ_DIV(q3.x - ez_dot(o, N), nd);                  // :184 (sign of N cancels exactly)
+    if (t < 0.0005f) return false;                              // :185
+    if (!(t < best)) return false;                              // :245, :273 strict <, first wins
+    vec3 p1 = f4xyz(q0), p2 = f4xyz(q1), p3 = f4xyz(q2);
+    vec3 P = ez_add(o, ez_scale(d, t));                         // :188
+    float s1 = ez_dot(ez_cross(ez_sub(p2, p1), ez_sub(P, p1)), N);  // :191-195 (N unflipped: r1/r2 swap)
+    float s2 = ez_dot(ez_cross(ez_sub(p3, p2), ez_sub(P, p2)), N);
+    float s3 = ez_dot(ez_cross(ez_sub(p1, p3), ez_sub(P, p3)), N);
+    bool r1 = (s1 > 0.0f && s2 > 0.0f && s3 > 0.0f);
+    bool r2 = (s1 < 0.0f && s2 < 0.0f && s3 < 0.0f);
+    if (!(r1 || r2)) return false;
+    tout = t;
+    return true;
+}
+
+__device__ __forceinline__ bool prune_test(float t0, float best, float slack) {
+    return t0 > (best + (best * 0.000244140625f + slack));
+}
+
+// hitBVH.  PRUNE: skip sub-trees whose box entry lies beyond the best hit (+ conservative slack);
+// ANYHIT: return on the first accepted triangle (shadow rays only need isHit, P5/fsh:826-829).
+template <bool PRUNE, bool ANYHIT, bool FAST>
+__device__ __forceinline__ HitRec trace_impl(const SceneDev& sc, vec3 o, vec3 d, vec3 inv, float slack) {
+    HitRec res;
+    res.t = EZ_INF;
+    res.tri = -1;
+    int stack[EZRT_MAX_STACK];
+    float stack_t0[PRUNE ? EZRT_MAX_STACK : 1];
+    int sp = 0;
+    int ref = sc.root_ref;
+    float ref_t0 = -1.0f;
+    while (true) {
+        if (ref < 0) {  // leaf: hitArray(index, index+n-1)
+            uint32_t bits = (uint32_t)ref & 0x7fffffffu;
+            int n = (int)(bits & 127u);
+            int first = (int)(bits >> 7);
+            const float4* rec = sc.tri_geo + (size_t)first * 4;
+            for (int i = 0; i < n; i++, rec += 4) {
+                float t;
+                if (tri_test(rec, o, d, res.t, t)) {
+                    res.t = t;
+                    res.tri = first + i;
+                    if (ANYHIT) return res;
+                }
+            }
+        } else {
+            const float4* nd = sc.nodes + (size_t)ref * 4;
+            float4 q0 = ldg4(nd + 0), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
+            float d1, d2, e1, e2;
+            bool h1 = box_test<FAST>(o, inv, q0, q1, d1, e1);
+            bool h2 = box_test<FAST>(o, inv, q2, q3, d2, e2);
+            int rl = __float_as_int(q0.w), rr = __float_as_int(q1.w);
+            if (PRUNE) {
+                if (h1 && prune_test(e1, res.t, slack)) h1 = false;
+                if (h2 && prune_test(e2, res.t, slack)) h2 = false;
+            }
+            if (h1 && h2) {  // near child first, far child pushed (P5/fsh:290-297)
+                bool leftFirst = d1 < d2;
+                int nearRef = leftFirst ? rl : rr, farRef = leftFirst ? rr : rl;
+                if (PRUNE) stack_t0[sp] = leftFirst ? e2 : e1;
+                stack[sp++] = farRef;
+                ref = nearRef;
+                if (PRUNE) ref_t0 = leftFirst ? e1 : e2;
+                continue;
+            } else if (h1) {
+                ref = rl;
+                if (PRUNE) ref_t0 = e1;
+                continue;
+            } else if (h2) {
+                ref = rr;
+                if (PRUNE) ref_t0 = e2;
+                continue;
+            }
+        }
+        // pop
+        while (true) {
+            if (sp == 0) return res;
+            --sp;
+            ref = stack[sp];
+            if (PRUNE) {
+                ref_t0 = stack_t0[sp];
+                if (prune_test(ref_t0, res.t, slack)) continue;
+            }
+            break;
+        }
+    }
+}
+
+template <bool PRUNE, bool ANYHIT>
+__device__ __forceinline__ HitRec trace_ray(const SceneDev& sc, vec3 o, vec3 d) {
+    vec3 inv = ez_v3(EZ_DIV(1.0f, d.x), EZ_DIV(1.0f, d.y), EZ_DIV(1.0f, d.z));  // hitAABB :221
+    float ax = ez_abs(inv.x), ay = ez_abs(inv.y), az = ez_abs(inv.z);
+    float m = ez_max(ax, ez_max(ay, az));
+    bool finite = (ax < 3.0e38f) && (ay < 3.0e38f) && (az < 3.0e38f);  // false for inf and NaN
+    float slack = sc.prune_delta * m;
+    if (finite) return trace_impl<PRUNE, ANYHIT, true>(sc, o, d, inv, slack);
+    return trace_impl<PRUNE, ANYHIT, false>(sc, o, d, inv, slack);
+}
+
+// ------------------------------------------------------------------------------------------
+// hit geometry + material for the final closest hit (tail of hitTriangle :198-214, getMaterial :110-135)
+// ------------------------------------------------------------------------------------------
+struct MaterialDev {
+    vec3 emissive, baseColor;
+    float subsurface, metallic, specular, specularTint, roughness, anisotropic, sheen, sheenTint, clearcoat,
+        clearcoatGloss;
+};
+
+__device__ __forceinline__ MaterialDev load_material(const SceneDev& sc, int matId) {
+    const float4* m = sc.materials + (size_t)matId * 5;
+    float4 a = ldg4(m), b = ldg4(m + 1), c = ldg4(m + 2), d = ldg4(m + 3);
+    MaterialDev r;
+    r.emissive = ez_v3(a.x, a.y, a.z);
+    r.baseColor = ez_v3(a.w, b.x, b.y);
+    r.subsurface = b.z; r.metallic = b.w; r.specular = c.x; r.specularTint = c.y;
+    r.roughness = c.z; r.anisotropic = c.w; r.sheen = d.x; r.sheenTint = d.y;
+    r.clearcoat = d.z; r.clearcoatGloss = d.w;
+    return r;
+}
+__device__ __forceinline__ vec3 load_emissive(const SceneDev& sc, int matId) {
+    float4 a = ldg4(sc.materials + (size_t)matId * 5);
+    return ez_v3(a.x, a.y, a.z);
+}
+
+struct SurfaceHit {
+    vec3 P, N;   // hitPoint, shading normal (flipped when hit from inside)
+    int matId;
+};
+
+// Recomputes P and the interpolated normal for (ray, t, tri).  p3fudge selects the P3/P4
+// barycentric denominators (P3/fsh:273-274) instead of P5's "+1e-7" (P5/fsh:206-207).
+__device__ __forceinline__ SurfaceHit surface_hit(const SceneDev& sc, vec3 o, vec3 d, float t, int tri, bool p3fudge) {
+    const float4* g = sc.tri_geo + (size_t)tri * 4;
+    float4 q0 = ldg4(g), q1 = ldg4(g + 1), q2 = ldg4(g + 2);
+    const float4* s = sc.tri_shade + (size_t)tri * 3;
+    float4 m0 = ldg4(s), m1 = ldg4(s + 1), m2 = ldg4(s + 2);
+    vec3 p1 = f4xyz(q0), p2 = f4xyz(q1), p3 = f4xyz(q2);
+    vec3 Ng = ez_v3(q0.w, q1.w, q2.w);
+    bool inside = ez_dot(Ng, d) > 0.0f;  // :175
+    vec3 P = ez_add(o, ez_scale(d, t));
+    float alpha, beta;
+    float an = (-(P.x - p2.x)) * (p3.y - p2.y) + (P.y - p2.y) * (p3.x - p2.x);
+    float bn = (-(P.x - p3.x)) * (p1.y - p3.y) + (P.y - p3.y) * (p1.x - p3.x);
+    if (!p3fudge) {
+        alpha = EZ_DIV(an, ((-(p1.x - p2.x)) * (p3.y - p2.y) + (p1.y - p2.y) * (p3.x - p2.x)) + 1e-7f);
+        beta = EZ_DIV(bn, ((-(p2.x - p3.x)) * (p1.y - p3.y) + (p2.y - p3.y) * (p1.x - p3.x)) + 1e-7f);
+    } else {
+        alpha = EZ_DIV(an, (-((p1.x - p2.x) - 0.00005f)) * ((p3.y - p2.y) + 0.00005f) +
+                               ((p1.y - p2.y) + 0.00005f) * ((p3.x - p2.x) + 0.00005f));
+        beta = EZ_DIV(bn, (-((p2.x - p3.x) - 0.00005f)) * ((p1.y - p3.y) + 0.00005f) +
+                              ((p2.y - p3.y) + 0.00005f) * ((p1.x - p3.x) + 0.00005f));
+    }
+    float gama = (1.0f - alpha) - beta;
+    vec3 Ns = ez_add(ez_add(ez_scale(f4xyz(m0), alpha), ez_scale(f4xyz(m1), beta)), ez_scale(f4xyz(m2), gama));
+    Ns = ez_normalize(Ns);
+    SurfaceHit r;
+    r.P = P;
+    r.N = inside ? ez_neg(Ns) : Ns;
+    r.matId = __float_as_int(m0.w);
+    return r;
+}
+__device__ __forceinline__ int tri_material(const SceneDev& sc, int tri) {
+    return __float_as_int(ldg4(sc.tri_shade + (size_t)tri * 3).w);
+}
+
+// ------------------------------------------------------------------------------------------
+// Disney principled BRDF, P5/fsh:400-549 (isotropic) and P4/fsh:375-473 (anisotropic)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float SchlickFresnel(float u) {
+    float m = ez_clamp(1.0f - u, 0.0f, 1.0f);
+    float m2 = m * m;
+    return m2 * m2 * m;
+}
+__device__ __forceinline__ float GTR1(float NdotH, float a) {
+    if (a >= 1.0f) return EZ_DIV(1.0f, EZ_PI);
+    float a2 = a * a;
+    float t = 1.0f + (a2 - 1.0f) * NdotH * NdotH;
+    return EZ_DIV(a2 - 1.0f, EZ_PI * ez_log(a2) * t);
+}
+__device__ __forceinline__ float GTR2(float NdotH, float a) {
+    float a2 = a * a;
+    float t = 1.0f + (a2 - 1.0f) * NdotH * NdotH;
+    return EZ_DIV(a2, EZ_PI * t * t);
+}
+__device__ __forceinline__ float GTR2_aniso(float NdotH, float HdotX, float HdotY, float ax, float ay) {
+    float s = ez_sqr(EZ_DIV(HdotX, ax)) + ez_sqr(EZ_DIV(HdotY, ay)) + NdotH * NdotH;
+    return EZ_DIV(1.0f, EZ_PI * ax * ay * ez_sqr(s));
+}
+__device__ __forceinline__ float smithG_GGX(float NdotV, float alphaG) {
+    float a = alphaG * alphaG;
+    float b = NdotV * NdotV;
+    return EZ_DIV(1.0f, NdotV + EZ_SQRT(a + b - a * b));
+}
+__device__ __forceinline__ float smithG_GGX_aniso(float NdotV, float VdotX, float VdotY, float ax, float ay) {
+    return EZ_DIV(1.0f, NdotV + EZ_SQRT(ez_sqr(VdotX * ax) + ez_sqr(VdotY * ay) + ez_sqr(NdotV)));
+}
+// getTangent, P5/fsh:553-558
+__device__ __forceinline__ void get_tangent(vec3 N, vec3& tangent, vec3& bitangent) {
+    vec3 helper = ez_v3(1.0f, 0.0f, 0.0f);
+    if (ez_abs(N.x) > 0.999f) helper = ez_v3(0.0f, 0.0f, 1.0f);
+    bitangent = ez_normalize(ez_cross(N, helper));
+    tangent = ez_normalize(ez_cross(N, bitangent));
+}
+
+template <bool ANISO>
+__device__ __forceinline__ vec3 brdf_evaluate(vec3 V, vec3 N, vec3 L, const MaterialDev& mat) {
+    float NdotL = ez_dot(N, L);
+    float NdotV = ez_dot(N, V);
+    if (NdotL < 0.0f || NdotV < 0.0f) return splat3(0.0f);
+
+    vec3 H = ez_normalize(ez_add(L, V));
+    float NdotH = ez_dot(N, H);
+    float LdotH = ez_dot(L, H);
+
+    vec3 Cdlin = mat.baseColor;
+    float Cdlum = 0.3f * Cdlin.x + 0.6f * Cdlin.y + 0.1f * Cdlin.z;
+    vec3 Ctint = (Cdlum > 0.0f) ? ez_divs(Cdlin, Cdlum) : splat3(1.0f);
+    vec3 Cspec = ez_scale(ez_vmix(splat3(1.0f), Ctint, mat.specularTint), mat.specular);
+    vec3 Cspec0 = ez_vmix(ez_scale(Cspec, 0.08f), Cdlin, mat.metallic);
+    vec3 Csheen = ez_vmix(splat3(1.0f), Ctint, mat.sheenTint);
+
+    float Fd90 = 0.5f + 2.0f * LdotH * LdotH * mat.roughness;
+    float FL = SchlickFresnel(NdotL);
+    float FV = SchlickFresnel(NdotV);
+    float Fd = ez_mix(1.0f, Fd90, FL) * ez_mix(1.0f, Fd90, FV);
+
+    float Fss90 = LdotH * LdotH * mat.roughness;
+    float Fss = ez_mix(1.0f, Fss90, FL) * ez_mix(1.0f, Fss90, FV);
+    float ss = 1.25f * (Fss * (EZ_DIV(1.0f, NdotL + NdotV) - 0.5f) + 0.5f);
+
+    float Ds, Gs;
+    float FH = SchlickFresnel(LdotH);
+    vec3 Fs = ez_vmix(Cspec0, splat3(1.0f), FH);
+    if (!ANISO) {
+        float alpha = ez_max(0.001f, ez_sqr(mat.roughness));
+        Ds = GTR2(NdotH, alpha);
+        Gs = smithG_GGX(NdotL, mat.roughness);
+        Gs *= smithG_GGX(NdotV, mat.roughness);
+    } else {
+        vec3 X, Y;
+        get_tangent(N, X, Y);
+        float aspect = EZ_SQRT(1.0f - mat.anisotropic * 0.9f);
+        float ax = ez_max(0.001f, EZ_DIV(ez_sqr(mat.roughness), aspect));
+        float ay = ez_max(0.001f, ez_sqr(mat.roughness) * aspect);
+        Ds = GTR2_aniso(NdotH, ez_dot(H, X), ez_dot(H, Y), ax, ay);
+        Gs = smithG_GGX_aniso(NdotL, ez_dot(L, X), ez_dot(L, Y), ax, ay);
+        Gs *= smithG_GGX_aniso(NdotV, ez_dot(V, X), ez_dot(V, Y), ax, ay);
+    }
+
+    float Dr = GTR1(NdotH, ez_mix(0.1f, 0.001f, mat.clearcoatGloss));
+    float Fr = ez_mix(0.04f, 1.0f, FH);
+    float Gr = smithG_GGX(NdotL, 0.25f) * smithG_GGX(NdotV, 0.25f);
+
+    vec3 Fsheen = ez_scale(Csheen, FH * mat.sheen);
+    vec3 diffuse = ez_add(ez_scale(Cdlin, EZ_DIV(1.0f, EZ_PI) * ez_mix(Fd, ss, mat.subsurface)), Fsheen);
+    vec3 specular = ez_scale(ez_scale(Fs, Gs), Ds);
+    vec3 clearcoat = splat3(0.25f * Gr * Fr * Dr * mat.clearcoat);
+    return ez_add(ez_add(ez_scale(diffuse, 1.0f - mat.metallic), specular), clearcoat);
+}
+
+// BRDF_Pdf, P5/fsh:715-752
+__device__ __forceinline__ float brdf_pdf(vec3 V, vec3 N, vec3 L, const MaterialDev& mat) {
+    float NdotL = ez_dot(N, L);
+    float NdotV = ez_dot(N, V);
+    if (NdotL < 0.0f || NdotV < 0.0f) return 0.0f;
+    vec3 H = ez_normalize(ez_add(L, V));
+    float NdotH = ez_dot(N, H);
+    float alpha = ez_max(0.001f, ez_sqr(mat.roughness));
+    float Ds = GTR2(NdotH, alpha);
+    float Dr = GTR1(NdotH, ez_mix(0.1f, 0.001f, mat.clearcoatGloss));
+    float LH4 = 4.0f * ez_dot(L, H);
+    float pdf_diffuse = EZ_DIV(NdotL, EZ_PI);
+    float pdf_specular = EZ_DIV(Ds * NdotH, LH4);
+    float pdf_clearcoat = EZ_DIV(Dr * NdotH, LH4);
+    float r_diffuse = 1.0f - mat.metallic;
+    float r_specular = 1.0f;
+    float r_clearcoat = 0.25f * mat.clearcoat;
+    float r_sum = r_diffuse + r_specular + r_clearcoat;
+    float p_diffuse = EZ_DIV(r_diffuse, r_sum);
+    float p_specular = EZ_DIV(r_specular, r_sum);
+    float p_clearcoat = EZ_DIV(r_clearcoat, r_sum);
+    float pdf = p_diffuse * pdf_diffuse + p_specular * pdf_specular + p_clearcoat * pdf_clearcoat;
+    return ez_max(1e-10f, pdf);
+}
+__device__ __forceinline__ float mis_mix_weight(float a, float b) {  // P5/fsh:754-757
+    float t = a * a;
+    return EZ_DIV(t, b * b + t);
+}
+
+// ------------------------------------------------------------------------------------------
+// direction samplers, P5/fsh:561-664
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ vec3 to_normal_hemisphere(vec3 v, vec3 N) {
+    vec3 helper = ez_v3(1.0f, 0.0f, 0.0f);
+    if (ez_abs(N.x) > 0.999f) helper = ez_v3(0.0f, 0.0f, 1.0f);
+    vec3 tangent = ez_normalize(ez_cross(N, helper));
+    vec3 bitangent = ez_normalize(ez_cross(N, tangent));
+    return ez_add(ez_add(ez_scale(tangent, v.x), ez_scale(bitangent, v.y)), ez_scale(N, v.z));
+}
+__device__ __forceinline__ vec3 sample_hemisphere(float xi_1, float xi_2) {
+    float z = xi_1;
+    float r = ez_max(0.0f, EZ_SQRT(1.0f - z * z));
+    float phi = 2.0f * EZ_PI * xi_2;
+    return ez_v3(r * ez_cos(phi), r * ez_sin(phi), z);
+}
+__device__ __forceinline__ vec3 half_vector_to_L(float sin_theta_h, float cos_theta_h, float phi_h, vec3 V, vec3 N) {
+    float sin_phi_h = ez_sin(phi_h);
+    float cos_phi_h = ez_cos(phi_h);
+    vec3 H = ez_v3(sin_theta_h * cos_phi_h, sin_theta_h * sin_phi_h, cos_theta_h);
+    H = to_normal_hemisphere(H, N);
+    return ez_reflect(ez_neg(V), H);
+}
+// SampleBRDF, P5/fsh:633-664
+__device__ __forceinline__ vec3 sample_brdf(float xi_1, float xi_2, float xi_3, vec3 V, vec3 N, const MaterialDev& mat) {
+    float alpha_GTR1 = ez_mix(0.1f, 0.001f, mat.clearcoatGloss);
+    float alpha_GTR2 = ez_max(0.001f, ez_sqr(mat.roughness));
+    float r_diffuse = 1.0f - mat.metallic;
+    float r_specular = 1.0f;
+    float r_clearcoat = 0.25f * mat.clearcoat;
+    float r_sum = r_diffuse + r_specular + r_clearcoat;
+    float p_diffuse = EZ_DIV(r_diffuse, r_sum);
+    float p_specular = EZ_DIV(r_specular, r_sum);
+    float rd = xi_3;
+    if (rd <= p_diffuse) {  // SampleCosineHemisphere :579-590
+        float r = EZ_SQRT(xi_1);
+        float theta = xi_2 * 2.0f * EZ_PI;
+        float x = r * ez_cos(theta);
+        float y = r * ez_sin(theta);
+        float z = EZ_SQRT(1.0f - x * x - y * y);
+        return to_normal_hemisphere(ez_v3(x, y, z), N);
+    } else if (p_diffuse < rd && rd <= p_diffuse + p_specular) {  // SampleGTR2 :593-610
+        float phi_h = 2.0f * EZ_PI * xi_1;
+        float cos_theta_h = EZ_SQRT(EZ_DIV(1.0f - xi_2, 1.0f + (alpha_GTR2 * alpha_GTR2 - 1.0f) * xi_2));
+        float sin_theta_h = EZ_SQRT(ez_max(0.0f, 1.0f - cos_theta_h * cos_theta_h));
+        return half_vector_to_L(sin_theta_h, cos_theta_h, phi_h, V, N);
+    } else if (p_diffuse + p_specular < rd) {  // SampleGTR1 :613-630
+        float phi_h = 2.0f * EZ_PI * xi_1;
+        float a2 = alpha_GTR1 * alpha_GTR1;
+        float cos_theta_h = EZ_SQRT(EZ_DIV(1.0f - ez_pow(a2, 1.0f - xi_2), 1.0f - a2));
+        float sin_theta_h = EZ_SQRT(ez_max(0.0f, 1.0f - cos_theta_h * cos_theta_h));
+        return half_vector_to_L(sin_theta_h, cos_theta_h, phi_h, V, N);
+    }
+    return ez_v3(0.0f, 1.0f, 0.0f);
+}
+
+// ------------------------------------------------------------------------------------------
+// HDR environment: texture2D restated as plain loads (fp32 bilinear / nearest, CLAMP_TO_EDGE)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ vec3 texel3(const float* img, int idx) {
+    const float* p = img + (size_t)idx * 3;
+    return ez_v3(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+__device__ __forceinline__ int clampi(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
+__device__ __forceinline__ vec3 tex2d(const float* img, int W, int H, float u, float v, int linear) {
+    if (!linear) {
+        int ix = clampi((int)ez_floor(u * (float)W), W - 1), iy = clampi((int)ez_floor(v * (float)H), H - 1);
+        return texel3(img, iy * W + ix);
+    }
+    float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
+    float fx0 = ez_floor(x), fy0 = ez_floor(y);
+    float ax = x - fx0, ay = y - fy0;
+    int x0 = (int)fx0, y0 = (int)fy0;
+    int x1 = clampi(x0 + 1, W - 1), y1 = clampi(y0 + 1, H - 1);
+    x0 = clampi(x0, W - 1);
+    y0 = clampi(y0, H - 1);
+    vec3 t00 = texel3(img, y0 * W + x0), t10 = texel3(img, y0 * W + x1);
+    vec3 t01 = texel3(img, y1 * W + x0), t11 = texel3(img, y1 * W + x1);
+    return ez_vmix(ez_vmix(t00, t10, ax), ez_vmix(t01, t11, ax), ay);
+}
+// toSphericalCoord, P5/fsh:684-690
+__device__ __forceinline__ void to_spherical(vec3 v, float& ou, float& ov) {
+    float u = ez_atan2(v.z, v.x), w = ez_asin(v.y);
+    u = EZ_DIV(u, 2.0f * EZ_PI);
+    w = EZ_DIV(w, EZ_PI);
+    u += 0.5f;
+    w += 0.5f;
+    ou = u;
+    ov = 1.0f - w;
+}
+// hdrColor P5/fsh:693-697; sampleHdr P3/fsh:151-156 (clamped to 10) / P4/fsh:366-371
+__device__ __forceinline__ vec3 hdr_color(const SceneDev& sc, const RenderDev& rd, vec3 L) {
+    vec3 color;
+    if (!sc.hdr) {
+        color = ez_v3(rd.env[0], rd.env[1], rd.env[2]);
+    } else {
+        float u, v;
+        to_spherical(ez_normalize(L), u, v);
+        color = tex2d(sc.hdr, sc.hdr_w, sc.hdr_h, u, v, sc.hdr_linear);
+    }
+    if (rd.mode == EZRT_MODE_DIFFUSE_P3) color = ez_vmin(color, splat3(10.0f));
+    return color;
+}
+// SampleHdr, P5/fsh:667-679
+__device__ __forceinline__ vec3 sample_hdr(const SceneDev& sc, float xi_1, float xi_2) {
+    vec3 c = tex2d(sc.hdr_cache, sc.hdr_w, sc.hdr_h, xi_1, xi_2, sc.hdr_linear);
+    float x = c.x, y = 1.0f - c.y;
+    float phi = 2.0f * EZ_PI * (x - 0.5f);
+    float theta = EZ_PI * (y - 0.5f);
+    float ct = ez_cos(theta);
+    return ez_v3(ct * ez_cos(phi), ez_sin(theta), ct * ez_sin(phi));
+}
+// hdrPdf, P5/fsh:701-712
+__device__ __forceinline__ float hdr_pdf(const SceneDev& sc, vec3 L) {
+    float u, v;
+    to_spherical(ez_normalize(L), u, v);
+    float pdf = tex2d(sc.hdr_cache, sc.hdr_w, sc.hdr_h, u, v, sc.hdr_linear).z;
+    float theta = EZ_PI * (0.5f - v);
+    float sin_theta = ez_max(ez_sin(theta), 1e-10f);
+    int res = sc.hdr_w;
+    float p_convert = EZ_DIV((float)(res * res / 2), 2.0f * EZ_PI * EZ_PI * sin_theta);
+    return pdf * p_convert;
+}
+
+// ------------------------------------------------------------------------------------------
+// camera ray, main() P5/fsh:920-925
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void primary_ray(const RenderDev& rd, uint32_t px, uint32_t py, uint32_t frame, uint32_t& seed,
+                                            vec3& o, vec3& d) {
+    seed = pixel_seed(px, py, frame);
+    float pixx = EZ_DIV((float)px + 0.5f, (float)rd.width) * 2.0f - 1.0f;
+    float pixy = EZ_DIV((float)py + 0.5f, (float)rd.height) * 2.0f - 1.0f;
+    float aax = EZ_DIV(rand01(seed) - 0.5f, (float)rd.width);
+    float aay = EZ_DIV(rand01(seed) - 0.5f, (float)rd.height);
+    float vx = pixx + aax, vy = pixy + aay, vz = -1.5f, vw = 0.0f;
+    const float* m = rd.cam;
+    vec3 dir = ez_v3(((m[0] * vx + m[4] * vy) + m[8] * vz) + m[12] * vw,
+                     ((m[1] * vx + m[5] * vy) + m[9] * vz) + m[13] * vw,
+                     ((m[2] * vx + m[6] * vy) + m[10] * vz) + m[14] * vw);
+    o = ez_v3(rd.eye[0], rd.eye[1], rd.eye[2]);
+    d = ez_normalize(dir);
+}
+
+// ------------------------------------------------------------------------------------------
+// one bounce of the integrators (P3/fsh:381-410, P4/fsh:483-514, P5/fsh:767-804, P5/fsh:815-887)
+// ------------------------------------------------------------------------------------------
+struct PathRegs {
+    vec3 o, d;          // current ray
+    uint32_t seed;
+    vec3 history, f_r;  // throughput before this bounce, BRDF value of this bounce
+    float cosine_i, pdf;
+};
+struct ShadowRay {
+    bool valid;
+    vec3 o, d, contrib;
+};
+
+// Lo += a*b*c*s/p evaluated left to right as GLSL does
+__device__ __forceinline__ vec3 contrib3(vec3 a, vec3 b, vec3 c, float s, float p) {
+    return ez_divs(ez_scale(ez_mul(ez_mul(a, b), c), s), p);
+}
+
+// Account for the result (t,tri) of tracing p's ray, which was generated at bounce-1 (bounce==0:
+// the primary ray), then -- if the path continues -- sample the next direction and fill p with the
+// next ray.  Returns false when the path ends.  Lo/Le/primary_miss are the sample's accumulators.
+__device__ __forceinline__ bool shade_step(const SceneDev& sc, const RenderDev& rd, int bounce, PathRegs& p, float hit_t,
+                                           int hit_tri, uint32_t px, uint32_t py, uint32_t frame, vec3& Lo, vec3& Le,
+                                           bool& primary_miss, ShadowRay& sh) {
+    sh.valid = false;
+    const int mode = rd.mode;
+    const bool is_mode = (mode == EZRT_MODE_DISNEY_IS_MIS_P5);
+    if (bounce == 0) {
+        Lo = splat3(0.0f);
+        Le = splat3(0.0f);
+        primary_miss = false;
+        if (hit_tri < 0) {  // P5/fsh:931-933
+            Lo = hdr_color(sc, rd, p.d);
+            primary_miss = true;
+            return false;
+        }
+    } else {
+        if (is_mode && p.pdf <= 0.0f) return false;  // P5/fsh:865
+        if (hit_tri < 0) {  // miss: sky contribution, then break
+            vec3 sky = hdr_color(sc, rd, p.d);
+            if (is_mode) {  // P5/fsh:868-878
+                float pdf_light = hdr_pdf(sc, p.d);
+                float mis_weight = mis_mix_weight(p.pdf, pdf_light);
+                vec3 c = ez_divs(ez_scale(ez_mul(ez_mul(ez_scale(p.history, mis_weight), sky), p.f_r), p.cosine_i), p.pdf);
+                Lo = ez_add(Lo, c);
+            } else {
+                Lo = ez_add(Lo, contrib3(p.history, sky, p.f_r, p.cosine_i, p.pdf));
+            }
+            return false;
+        }
+    }
+    const bool fudge = (mode == EZRT_MODE_DIFFUSE_P3 || mode == EZRT_MODE_DISNEY_ANISO_P4);
+    SurfaceHit hit = surface_hit(sc, p.o, p.d, hit_t, hit_tri, fudge);
+    MaterialDev mat = load_material(sc, hit.matId);
+    if (bounce == 0) {
+        Le = mat.emissive;  // P5/fsh:936
+    } else {
+        Lo = ez_add(Lo, contrib3(p.history, mat.emissive, p.f_r, p.cosine_i, p.pdf));
+        p.history = ez_mul(p.history, ez_divs(ez_scale(p.f_r, p.cosine_i), p.pdf));
+    }
+    if (bounce >= rd.max_bounce) return false;
+
+    vec3 V = ez_neg(p.d);
+    vec3 N = hit.N;
+    vec3 L;
+    if (is_mode) {
+        // environment importance sample + shadow ray, P5/fsh:820-842
+        float r1 = rand01(p.seed);
+        float r2 = rand01(p.seed);
+        vec3 Lh = sample_hdr(sc, r1, r2);
+        float NdotLh = ez_dot(N, Lh);
+        if (NdotLh > 0.0f) {
+            vec3 color = hdr_color(sc, rd, Lh);
+            float pdf_light = hdr_pdf(sc, Lh);
+            vec3 f_r = brdf_evaluate<false>(V, N, Lh, mat);
+            float pdf_brdf = brdf_pdf(V, N, Lh, mat);
+            float mis_weight = mis_mix_weight(pdf_light, pdf_brdf);
+            sh.valid = true;
+            sh.o = hit.P;
+            sh.d = Lh;
+            sh.contrib = ez_divs(ez_scale(ez_mul(ez_mul(ez_scale(p.history, mis_weight), color), f_r), NdotLh), pdf_light);
+        }
+        float xi_1 = sobol_gray((uint32_t)bounce * 2u, frame + 1u);
+        float xi_2 = sobol_gray((uint32_t)bounce * 2u + 1u, frame + 1u);
+        cp_rotate(xi_1, xi_2, px, py);
+        float xi_3 = rand01(p.seed);
+        L = sample_brdf(xi_1, xi_2, xi_3, V, N, mat);
+        float NdotL = ez_dot(N, L);
+        if (NdotL <= 0.0f) return false;  // :854
+        p.f_r = brdf_evaluate<false>(V, N, L, mat);
+        p.pdf = brdf_pdf(V, N, L, mat);   // <= 0: traced, then break (:860-865)
+        p.cosine_i = NdotL;
+    } else {
+        vec3 Lh;
+        if (mode == EZRT_MODE_DISNEY_SOBOL_P5) {  // P5/fsh:771-776
+            float u = sobol_gray((uint32_t)bounce * 2u, frame + 1u);
+            float v = sobol_gray((uint32_t)bounce * 2u + 1u, frame + 1u);
+            cp_rotate(u, v, px, py);
+            Lh = sample_hemisphere(u, v);
+        } else {  // P3/fsh:110-115: z = rand(), then phi
+            float z = rand01(p.seed);
+            float r = ez_max(0.0f, EZ_SQRT(1.0f - z * z));
+            float phi = 2.0f * EZ_PI * rand01(p.seed);
+            Lh = ez_v3(r * ez_cos(phi), r * ez_sin(phi), z);
+        }
+        L = to_normal_hemisphere(Lh, N);
+        p.pdf = EZ_DIV(1.0f, 2.0f * EZ_PI);
+        p.cosine_i = ez_max(0.0f, ez_dot(L, N));
+        if (mode == EZRT_MODE_DIFFUSE_P3) p.f_r = ez_divs(mat.baseColor, EZ_PI);
+        else if (mode == EZRT_MODE_DISNEY_ANISO_P4) p.f_r = brdf_evaluate<true>(V, N, L, mat);
+        else p.f_r = brdf_evaluate<false>(V, N, L, mat);
+    }
+    p.o = hit.P;
+    p.d = L;
+    return true;
+}
+
+#endif

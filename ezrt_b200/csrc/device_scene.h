@@ -1,0 +1,78 @@
+// device_scene.h -- HBM layouts of the repacked scene and per-render constants.
+//
+// The C ABI accepts the reference's layouts (Triangle_encoded 144 B, BVHNode_encoded 48 B,
+// P5/main.cpp:60-76); ezrt_scene_create() repacks them once into 128-bit-aligned records:
+//
+//   inner node (64 B, "children in parent"): one 4 x float4 record per INNER node holding both
+//       child boxes and both child references, so a traversal step is one 64-byte fetch instead
+//       of the shader's three dependent 48-byte getBVHNode()s (P5/fsh:266,281,285):
+//         q0 = (AA_left.xyz , ref_left )   q1 = (BB_left.xyz , ref_right)
+//         q2 = (AA_right.xyz, 0)           q3 = (BB_right.xyz, 0)
+//       ref >= 0 : index of an inner-node record;  ref < 0 : leaf, bits = 1|index(24)|n(7)
+//   triangle geometry (64 B): q0 = (p1, N.x) q1 = (p2, N.y) q2 = (p3, N.z) q3 = (d0,0,0,0)
+//       N = normalize(cross(p2-p1, p3-p1)) and d0 = dot(N,p1) are the ray-independent part of
+//       hitTriangle (P5/fsh:172,184), evaluated once with the same fp32 operations.
+//   triangle shading (48 B): (n1, matId) (n2, 0) (n3, 0)  -- fetched only for the final hit
+//   material table (80 B each): the 18-float material block de-duplicated (materials
+//       are stored per triangle in the reference), padded to 5 x float4.
+#ifndef EZRT_DEVICE_SCENE_H
+#define EZRT_DEVICE_SCENE_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define EZRT_MAX_STACK 64        // >= validated tree depth + 1 (the shader's bound is 256, P5/fsh:260)
+#define EZRT_LEAF_FLAG 0x80000000u
+#define EZRT_LEAF_MAX_N 127
+#define EZRT_TILE 16             // == EZRT_PART_TILE
+#define EZRT_TILE_PIXELS 256
+
+struct SceneDev {
+    const float4* nodes;      // 4 float4 per inner node
+    const float4* tri_geo;    // 4 float4 per triangle
+    const float4* tri_shade;  // 3 float4 per triangle
+    const float4* materials;  // 5 float4 per material
+    const float* hdr;         // W*H*3 or null
+    const float* hdr_cache;   // W*H*3 or null
+    int hdr_w, hdr_h, hdr_linear;
+    int root_ref;
+    int n_triangles;
+    int n_inner;
+    float prune_delta;        // 2^-16 * max |vertex coordinate|
+};
+
+struct RenderDev {
+    int width, height;
+    int mode, max_bounce;
+    int traverse;             // ezrt_traverse
+    float eye[3];
+    float cam[16];            // column-major cameraRotate
+    float env[3];
+    uint32_t first_frame;
+    int out_channels;
+    int compact_out;          // 1: write tile-major compact buffer (part_count > 1)
+    int n_tiles;              // tiles owned by this part
+};
+
+// One owned 16x16 tile (clipped at the image border)
+struct TileDev {
+    int x0, y0, w, h;
+    int pixel_offset;         // offset of the tile's first pixel in the compact buffer
+};
+
+// SoA path state of the wavefront pipeline (one set per queue; two queues ping-pong).
+struct PathQueue {
+    float4* ray_o;    // (origin.xyz, hit distance written by extend)
+    float4* ray_d;    // (direction.xyz, hit triangle as int bits written by extend)
+    float4* hist;     // (history.xyz, cosine_i)
+    float4* fr;       // (f_r.xyz, pdf)   pdf <= 0 marks "break after trace" (P5/fsh:865)
+    uint2* meta;      // (rng seed, sample slot)
+};
+
+struct ShadowQueue {
+    float4* ray_o;    // (origin.xyz, sample slot as bits)
+    float4* ray_d;    // (direction.xyz, -)
+    float4* contrib;  // (contribution.xyz, -)
+};
+
+#endif

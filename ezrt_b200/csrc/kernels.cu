@@ -1,0 +1,420 @@
+// kernels.cu -- sm_100a kernels of the wavefront path tracer and their launchers.
+//
+// Pipeline per batch of `nf` frames (= display() calls, P5/main.cpp:697-748) x owned pixels:
+//   k_generate : camera rays (main(), P5/fsh:920-925)                     -> queue 0
+//   per bounce b = 0..maxBounce:
+//     k_extend : hitBVH for every queued ray (persistent warps, dynamic fetch)
+//     k_shade  : account the hit/miss, NEE + BRDF sampling, warp-ballot compaction -> queue b+1
+//     k_shadow : any-hit trace of the environment shadow rays (IS mode only)
+//   k_blend    : running mean into the framebuffer in frame order (P5/fsh:942-947)
+// No host synchronisation inside a render: queue sizes live in device counters.
+#include "kernels.h"
+
+#include "device_functions.cuh"
+
+// ------------------------------------------------------------------------------------------
+// slot <-> pixel mapping.  A sample slot is (frame_in_batch, tile, in_tile); in_tile enumerates
+// the 16x16 tile as eight 8x4 sub-blocks so that a warp covers a compact 8x4 pixel block.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void in_tile_xy(int in_tile, int& ix, int& iy) {
+    int sub = in_tile >> 5, lane = in_tile & 31;
+    ix = (sub & 1) * 8 + (lane & 7);
+    iy = (sub >> 1) * 4 + (lane >> 3);
+}
+__device__ __forceinline__ bool slot_pixel(const RenderDev& rd, const TileDev* __restrict__ tiles, uint32_t slot,
+                                           uint32_t& px, uint32_t& py, uint32_t& frame_in_batch) {
+    uint32_t per_frame = (uint32_t)rd.n_tiles * EZRT_TILE_PIXELS;
+    frame_in_batch = slot / per_frame;
+    uint32_t r = slot - frame_in_batch * per_frame;
+    TileDev t = tiles[r >> 8];
+    int ix, iy;
+    in_tile_xy((int)(r & 255u), ix, iy);
+    px = (uint32_t)(t.x0 + ix);
+    py = (uint32_t)(t.y0 + iy);
+    return ix < t.w && iy < t.h;
+}
+
+// warp-aggregated append: returns this lane's position in the output queue (valid lanes only)
+__device__ __forceinline__ uint32_t warp_append(bool valid, uint32_t* counter) {
+    unsigned mask = __ballot_sync(0xffffffffu, valid);
+    if (mask == 0u) return 0u;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_generate(RenderDev rd, const TileDev* __restrict__ tiles, uint32_t n_slots,
+                                                  uint32_t batch_first_frame, PathQueue q, uint32_t* q_count) {
+    uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t n_round = (n_slots + 31u) & ~31u;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_round; slot += stride) {
+        uint32_t px = 0, py = 0, fib = 0;
+        bool valid = (slot < n_slots) && slot_pixel(rd, tiles, slot, px, py, fib);
+        uint32_t pos = warp_append(valid, q_count);
+        if (!valid) continue;
+        uint32_t seed;
+        vec3 o, d;
+        primary_ray(rd, px, py, batch_first_frame + fib, seed, o, d);
+        q.ray_o[pos] = make_float4(o.x, o.y, o.z, 0.0f);
+        q.ray_d[pos] = make_float4(d.x, d.y, d.z, 0.0f);
+        q.meta[pos] = make_uint2(seed, slot);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// extend: closest hit for every ray of the queue.  Persistent warps fetch 32 rays at a time from
+// a global work counter so long traversals do not stall a statically assigned tail.
+// ------------------------------------------------------------------------------------------
+template <bool PRUNE>
+__global__ void __launch_bounds__(EZRT_EXTEND_THREADS) k_extend(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
+                                                                uint32_t* work) {
+    const uint32_t n = *q_count;
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t i = base + (uint32_t)lane;
+        if (i < n) {
+            float4 o4 = q.ray_o[i], d4 = q.ray_d[i];
+            HitRec h = trace_ray<PRUNE, false>(sc, ez_v3(o4.x, o4.y, o4.z), ez_v3(d4.x, d4.y, d4.z));
+            q.ray_o[i].w = h.t;
+            q.ray_d[i].w = __int_as_float(h.tri);
+        }
+    }
+}
+
+template <bool PRUNE>
+__global__ void __launch_bounds__(EZRT_EXTEND_THREADS) k_shadow(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count,
+                                                                uint32_t* work, float4* __restrict__ Lo) {
+    const uint32_t n = *s_count;
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        uint32_t i = base + (uint32_t)lane;
+        if (i < n) {
+            float4 o4 = sq.ray_o[i], d4 = sq.ray_d[i];
+            HitRec h = trace_ray<PRUNE, true>(sc, ez_v3(o4.x, o4.y, o4.z), ez_v3(d4.x, d4.y, d4.z));
+            if (h.tri < 0) {  // unoccluded: Lo += contribution (P5/fsh:829-841); one path per slot -> no race
+                uint32_t slot = __float_as_uint(o4.w);
+                float4 c = sq.contrib[i];
+                float4 lo = Lo[slot];
+                lo.x += c.x; lo.y += c.y; lo.z += c.z;
+                Lo[slot] = lo;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_shade(SceneDev sc, RenderDev rd, const TileDev* __restrict__ tiles, int bounce,
+                                               uint32_t batch_first_frame, PathQueue qin, const uint32_t* __restrict__ in_count,
+                                               PathQueue qout, uint32_t* out_count, ShadowQueue sq, uint32_t* s_count,
+                                               float4* __restrict__ Lo, float4* __restrict__ Le) {
+    const uint32_t n = *in_count;
+    const uint32_t n_round = (n + 31u) & ~31u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool alive = false;
+        PathRegs p;
+        ShadowRay sh;
+        sh.valid = false;
+        uint32_t slot = 0;
+        if (i < n) {
+            float4 o4 = qin.ray_o[i], d4 = qin.ray_d[i];
+            uint2 meta = qin.meta[i];
+            slot = meta.y;
+            p.o = ez_v3(o4.x, o4.y, o4.z);
+            p.d = ez_v3(d4.x, d4.y, d4.z);
+            p.seed = meta.x;
+            vec3 lo = splat3(0.0f), le = splat3(0.0f);
+            bool pmiss = false;
+            if (bounce > 0) {
+                float4 h4 = qin.hist[i], f4 = qin.fr[i];
+                p.history = ez_v3(h4.x, h4.y, h4.z);
+                p.cosine_i = h4.w;
+                p.f_r = ez_v3(f4.x, f4.y, f4.z);
+                p.pdf = f4.w;
+                float4 l4 = Lo[slot];
+                lo = ez_v3(l4.x, l4.y, l4.z);
+            } else {
+                p.history = splat3(1.0f);
+                p.f_r = splat3(0.0f);
+                p.cosine_i = 0.0f;
+                p.pdf = 1.0f;
+            }
+            uint32_t px, py, fib;
+            slot_pixel(rd, tiles, slot, px, py, fib);
+            alive = shade_step(sc, rd, bounce, p, o4.w, __float_as_int(d4.w), px, py, batch_first_frame + fib, lo, le, pmiss, sh);
+            Lo[slot] = make_float4(lo.x, lo.y, lo.z, pmiss ? 1.0f : 0.0f);
+            if (bounce == 0) Le[slot] = make_float4(le.x, le.y, le.z, 0.0f);
+        }
+        uint32_t pos = warp_append(alive, out_count);
+        if (alive) {
+            qout.ray_o[pos] = make_float4(p.o.x, p.o.y, p.o.z, 0.0f);
+            qout.ray_d[pos] = make_float4(p.d.x, p.d.y, p.d.z, 0.0f);
+            qout.hist[pos] = make_float4(p.history.x, p.history.y, p.history.z, p.cosine_i);
+            qout.fr[pos] = make_float4(p.f_r.x, p.f_r.y, p.f_r.z, p.pdf);
+            qout.meta[pos] = make_uint2(p.seed, slot);
+        }
+        if (rd.mode == EZRT_MODE_DISNEY_IS_MIS_P5) {
+            uint32_t spos = warp_append(sh.valid, s_count);
+            if (sh.valid) {
+                sq.ray_o[spos] = make_float4(sh.o.x, sh.o.y, sh.o.z, __uint_as_float(slot));
+                sq.ray_d[spos] = make_float4(sh.d.x, sh.d.y, sh.d.z, 0.0f);
+                sq.contrib[spos] = make_float4(sh.contrib.x, sh.contrib.y, sh.contrib.z, 0.0f);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// blend: color = Le + Li (or the sky for a primary miss), running mean in frame order
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t fb_index(const RenderDev& rd, const TileDev& t, int ix, int iy) {
+    if (rd.compact_out) return (size_t)t.pixel_offset + (size_t)iy * t.w + ix;
+    return (size_t)(t.y0 + iy) * rd.width + (t.x0 + ix);
+}
+
+__global__ void __launch_bounds__(256) k_blend(RenderDev rd, const TileDev* __restrict__ tiles, int nf, uint32_t batch_first_frame,
+                                               const float4* __restrict__ Lo, const float4* __restrict__ Le, float* __restrict__ fb) {
+    uint32_t per_frame = (uint32_t)rd.n_tiles * EZRT_TILE_PIXELS;
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= per_frame) return;
+    TileDev t = tiles[r >> 8];
+    int ix, iy;
+    in_tile_xy((int)(r & 255u), ix, iy);
+    if (ix >= t.w || iy >= t.h) return;
+    size_t idx = fb_index(rd, t, ix, iy) * (size_t)rd.out_channels;
+    vec3 acc = (batch_first_frame == 0u) ? splat3(0.0f) : ez_v3(fb[idx], fb[idx + 1], fb[idx + 2]);
+    for (int f = 0; f < nf; f++) {
+        float4 lo = Lo[(size_t)f * per_frame + r];
+        float4 le = Le[(size_t)f * per_frame + r];
+        vec3 color = (lo.w != 0.0f) ? ez_v3(lo.x, lo.y, lo.z) : ez_add(ez_v3(le.x, le.y, le.z), ez_v3(lo.x, lo.y, lo.z));
+        float a = EZ_DIV(1.0f, __uint2float_rn(batch_first_frame + (uint32_t)f + 1u));
+        acc = ez_vmix(acc, color, a);
+    }
+    fb[idx] = acc.x; fb[idx + 1] = acc.y; fb[idx + 2] = acc.z;
+    if (rd.out_channels == 4) fb[idx + 3] = 1.0f;
+}
+
+// totals[0..2] += primary, bounce, shadow rays of this batch; totals[3] += samples
+__global__ void k_tally(const uint32_t* __restrict__ q_counts, const uint32_t* __restrict__ s_counts, int n_stages,
+                        unsigned long long* totals) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long bounce = 0, shadow = 0;
+    for (int b = 1; b < n_stages; b++) bounce += q_counts[b];
+    for (int b = 0; b < n_stages; b++) shadow += s_counts[b];
+    totals[0] += q_counts[0];
+    totals[1] += bounce;
+    totals[2] += shadow;
+    totals[3] += q_counts[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// megakernel: one thread = one pixel, all frames and bounces in registers (cross-check pipeline)
+// ------------------------------------------------------------------------------------------
+template <bool PRUNE>
+__global__ void __launch_bounds__(128) k_megakernel(SceneDev sc, RenderDev rd, const TileDev* __restrict__ tiles, int spp,
+                                                    float* __restrict__ fb, unsigned long long* totals) {
+    uint32_t per_frame = (uint32_t)rd.n_tiles * EZRT_TILE_PIXELS;
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= per_frame) return;
+    TileDev t = tiles[r >> 8];
+    int ix, iy;
+    in_tile_xy((int)(r & 255u), ix, iy);
+    if (ix >= t.w || iy >= t.h) return;
+    uint32_t px = (uint32_t)(t.x0 + ix), py = (uint32_t)(t.y0 + iy);
+    size_t idx = fb_index(rd, t, ix, iy) * (size_t)rd.out_channels;
+    vec3 acc = (rd.first_frame == 0u) ? splat3(0.0f) : ez_v3(fb[idx], fb[idx + 1], fb[idx + 2]);
+    unsigned long long n_primary = 0, n_bounce = 0, n_shadow = 0;
+    for (int s = 0; s < spp; s++) {
+        uint32_t frame = rd.first_frame + (uint32_t)s;
+        PathRegs p;
+        primary_ray(rd, px, py, frame, p.seed, p.o, p.d);
+        p.history = splat3(1.0f);
+        p.f_r = splat3(0.0f);
+        p.cosine_i = 0.0f;
+        p.pdf = 1.0f;
+        vec3 lo = splat3(0.0f), le = splat3(0.0f);
+        bool pmiss = false;
+        for (int bounce = 0;; bounce++) {
+            HitRec h = trace_ray<PRUNE, false>(sc, p.o, p.d);
+            if (bounce == 0) n_primary++; else n_bounce++;
+            ShadowRay sh;
+            bool alive = shade_step(sc, rd, bounce, p, h.t, h.tri, px, py, frame, lo, le, pmiss, sh);
+            if (sh.valid) {
+                HitRec hs = trace_ray<PRUNE, true>(sc, sh.o, sh.d);
+                n_shadow++;
+                if (hs.tri < 0) lo = ez_add(lo, sh.contrib);
+            }
+            if (!alive) break;
+        }
+        vec3 color = pmiss ? lo : ez_add(le, lo);
+        float a = EZ_DIV(1.0f, __uint2float_rn(frame + 1u));
+        acc = ez_vmix(acc, color, a);
+    }
+    fb[idx] = acc.x; fb[idx + 1] = acc.y; fb[idx + 2] = acc.z;
+    if (rd.out_channels == 4) fb[idx + 3] = 1.0f;
+    atomicAdd(&totals[0], n_primary);
+    atomicAdd(&totals[1], n_bounce);
+    atomicAdd(&totals[2], n_shadow);
+    atomicAdd(&totals[3], n_primary);
+}
+
+// ------------------------------------------------------------------------------------------
+// single-function entry points (parity tests)
+// ------------------------------------------------------------------------------------------
+template <bool PRUNE, bool ANYHIT>
+__global__ void k_trace_rays(SceneDev sc, int n, const float* __restrict__ o, const float* __restrict__ d, int p3fudge,
+                             int* hit, float* dist, int* tri, int* inside, float* point, float* normal) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vec3 ro = ez_v3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), rdv = ez_v3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+    HitRec h = trace_ray<PRUNE, ANYHIT>(sc, ro, rdv);
+    hit[i] = h.tri >= 0;
+    dist[i] = h.t;
+    tri[i] = h.tri;
+    vec3 P = splat3(0.0f), N = splat3(0.0f);
+    int ins = 0;
+    if (h.tri >= 0) {
+        SurfaceHit s = surface_hit(sc, ro, rdv, h.t, h.tri, p3fudge != 0);
+        P = s.P;
+        N = s.N;
+        const float4* g = sc.tri_geo + (size_t)h.tri * 4;
+        vec3 Ng = ez_v3(ldg4(g).w, ldg4(g + 1).w, ldg4(g + 2).w);
+        ins = ez_dot(Ng, rdv) > 0.0f;
+    }
+    inside[i] = ins;
+    point[3 * i] = P.x; point[3 * i + 1] = P.y; point[3 * i + 2] = P.z;
+    normal[3 * i] = N.x; normal[3 * i + 1] = N.y; normal[3 * i + 2] = N.z;
+}
+
+__device__ __forceinline__ MaterialDev material_from18(const float* m) {
+    MaterialDev r;
+    r.emissive = ez_v3(m[0], m[1], m[2]);
+    r.baseColor = ez_v3(m[3], m[4], m[5]);
+    r.subsurface = m[6]; r.metallic = m[7]; r.specular = m[8]; r.specularTint = m[9];
+    r.roughness = m[10]; r.anisotropic = m[11]; r.sheen = m[12]; r.sheenTint = m[13];
+    r.clearcoat = m[14]; r.clearcoatGloss = m[15];
+    return r;
+}
+
+__global__ void k_eval_brdf(int which, int n, const float* V, const float* N, const float* L, const float* xi,
+                            const float* materials, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vec3 v = ez_v3(V[3 * i], V[3 * i + 1], V[3 * i + 2]);
+    vec3 nn = ez_v3(N[3 * i], N[3 * i + 1], N[3 * i + 2]);
+    vec3 l = L ? ez_v3(L[3 * i], L[3 * i + 1], L[3 * i + 2]) : splat3(0.0f);
+    MaterialDev m = material_from18(materials + (size_t)i * 18);
+    vec3 r = splat3(0.0f);
+    if (which == 0) r = brdf_evaluate<false>(v, nn, l, m);
+    else if (which == 1) r = brdf_evaluate<true>(v, nn, l, m);
+    else if (which == 2) r.x = brdf_pdf(v, nn, l, m);
+    else if (which == 3) r = sample_brdf(xi[3 * i], xi[3 * i + 1], xi[3 * i + 2], v, nn, m);
+    out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
+}
+
+__global__ void k_eval_math(int which, int n, const float* a, const float* b, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = a[i], y = b ? b[i] : 0.0f, r = 0.0f;
+    switch (which) {
+        case 0: r = ez_sin(x); break;
+        case 1: r = ez_cos(x); break;
+        case 2: r = ez_log(x); break;
+        case 3: r = ez_exp(x); break;
+        case 4: r = ez_pow(x, y); break;
+        case 5: r = ez_atan2(x, y); break;
+        case 6: r = ez_asin(x); break;
+    }
+    out[i] = r;
+}
+
+// compact tile-major part buffer -> full row-major framebuffer
+__global__ void k_partition_scatter(const float* __restrict__ compact, float* __restrict__ full, const TileDev* __restrict__ tiles,
+                                    int n_tiles, int width, int channels) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (uint32_t)n_tiles * EZRT_TILE_PIXELS) return;
+    TileDev t = tiles[r >> 8];
+    int ix = (int)(r & 15u), iy = (int)((r & 255u) >> 4);
+    if (ix >= t.w || iy >= t.h) return;
+    size_t src = ((size_t)t.pixel_offset + (size_t)iy * t.w + ix) * channels;
+    size_t dst = ((size_t)(t.y0 + iy) * width + (t.x0 + ix)) * channels;
+    for (int c = 0; c < channels; c++) full[dst + c] = compact[src + c];
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots, uint32_t batch_first_frame, PathQueue q,
+                     uint32_t* q_count, int n_sms, cudaStream_t st) {
+    int blocks = std::min(div_up(n_slots, 256), n_sms * 8);
+    k_generate<<<blocks, 256, 0, st>>>(rd, tiles, n_slots, batch_first_frame, q, q_count);
+}
+void launch_extend(const SceneDev& sc, bool prune, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t n_max,
+                   int n_sms, cudaStream_t st) {
+    int blocks = std::min(div_up(n_max, EZRT_EXTEND_THREADS), n_sms * EZRT_EXTEND_BLOCKS_PER_SM);
+    if (blocks < 1) blocks = 1;
+    if (prune) k_extend<true><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, q, q_count, work);
+    else k_extend<false><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, q, q_count, work);
+}
+void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo,
+                   uint32_t n_max, int n_sms, cudaStream_t st) {
+    int blocks = std::min(div_up(n_max, EZRT_EXTEND_THREADS), n_sms * EZRT_EXTEND_BLOCKS_PER_SM);
+    if (blocks < 1) blocks = 1;
+    if (prune) k_shadow<true><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, sq, s_count, work, Lo);
+    else k_shadow<false><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, sq, s_count, work, Lo);
+}
+void launch_shade(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, int bounce, uint32_t batch_first_frame,
+                  PathQueue qin, const uint32_t* in_count, PathQueue qout, uint32_t* out_count, ShadowQueue sq,
+                  uint32_t* s_count, float4* Lo, float4* Le, uint32_t n_max, int n_sms, cudaStream_t st) {
+    int blocks = std::min(div_up(n_max, 128), n_sms * 16);
+    if (blocks < 1) blocks = 1;
+    k_shade<<<blocks, 128, 0, st>>>(sc, rd, tiles, bounce, batch_first_frame, qin, in_count, qout, out_count, sq, s_count, Lo, Le);
+}
+void launch_blend(const RenderDev& rd, const TileDev* tiles, int nf, uint32_t batch_first_frame, const float4* Lo,
+                  const float4* Le, float* fb, cudaStream_t st) {
+    uint32_t per_frame = (uint32_t)rd.n_tiles * EZRT_TILE_PIXELS;
+    k_blend<<<div_up(per_frame, 256), 256, 0, st>>>(rd, tiles, nf, batch_first_frame, Lo, Le, fb);
+}
+void launch_tally(const uint32_t* q_counts, const uint32_t* s_counts, int n_stages, unsigned long long* totals, cudaStream_t st) {
+    k_tally<<<1, 32, 0, st>>>(q_counts, s_counts, n_stages, totals);
+}
+void launch_megakernel(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, bool prune, int spp, float* fb,
+                       unsigned long long* totals, cudaStream_t st) {
+    uint32_t per_frame = (uint32_t)rd.n_tiles * EZRT_TILE_PIXELS;
+    if (prune) k_megakernel<true><<<div_up(per_frame, 128), 128, 0, st>>>(sc, rd, tiles, spp, fb, totals);
+    else k_megakernel<false><<<div_up(per_frame, 128), 128, 0, st>>>(sc, rd, tiles, spp, fb, totals);
+}
+void launch_trace_rays(const SceneDev& sc, bool prune, bool anyhit, int n, const float* o, const float* d, int p3fudge, int* hit,
+                       float* dist, int* tri, int* inside, float* point, float* normal, cudaStream_t st) {
+    int blocks = div_up(n, 128);
+    if (prune && anyhit) k_trace_rays<true, true><<<blocks, 128, 0, st>>>(sc, n, o, d, p3fudge, hit, dist, tri, inside, point, normal);
+    else if (prune) k_trace_rays<true, false><<<blocks, 128, 0, st>>>(sc, n, o, d, p3fudge, hit, dist, tri, inside, point, normal);
+    else if (anyhit) k_trace_rays<false, true><<<blocks, 128, 0, st>>>(sc, n, o, d, p3fudge, hit, dist, tri, inside, point, normal);
+    else k_trace_rays<false, false><<<blocks, 128, 0, st>>>(sc, n, o, d, p3fudge, hit, dist, tri, inside, point, normal);
+}
+void launch_eval_brdf(int which, int n, const float* V, const float* N, const float* L, const float* xi, const float* materials,
+                      float* out, cudaStream_t st) {
+    k_eval_brdf<<<div_up(n, 128), 128, 0, st>>>(which, n, V, N, L, xi, materials, out);
+}
+void launch_eval_math(int which, int n, const float* a, const float* b, float* out, cudaStream_t st) {
+    k_eval_math<<<div_up(n, 256), 256, 0, st>>>(which, n, a, b, out);
+}
+void launch_partition_scatter(const float* compact, float* full, const TileDev* tiles, int n_tiles, int width, int channels,
+                              cudaStream_t st) {
+    if (n_tiles <= 0) return;
+    k_partition_scatter<<<div_up((long long)n_tiles * EZRT_TILE_PIXELS, 256), 256, 0, st>>>(compact, full, tiles, n_tiles, width, channels);
+}

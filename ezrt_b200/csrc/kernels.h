@@ -1,0 +1,35 @@
+// kernels.h -- launchers of kernels.cu (internal to libezrt_b200.so)
+#ifndef EZRT_KERNELS_H
+#define EZRT_KERNELS_H
+
+#include <algorithm>
+
+#include "device_scene.h"
+
+// extend/shadow kernels: persistent blocks, EZRT_EXTEND_BLOCKS_PER_SM resident per SM
+#define EZRT_EXTEND_THREADS 128
+#define EZRT_EXTEND_BLOCKS_PER_SM 6
+
+void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots, uint32_t batch_first_frame, PathQueue q,
+                     uint32_t* q_count, int n_sms, cudaStream_t st);
+void launch_extend(const SceneDev& sc, bool prune, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t n_max,
+                   int n_sms, cudaStream_t st);
+void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo,
+                   uint32_t n_max, int n_sms, cudaStream_t st);
+void launch_shade(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, int bounce, uint32_t batch_first_frame,
+                  PathQueue qin, const uint32_t* in_count, PathQueue qout, uint32_t* out_count, ShadowQueue sq,
+                  uint32_t* s_count, float4* Lo, float4* Le, uint32_t n_max, int n_sms, cudaStream_t st);
+void launch_blend(const RenderDev& rd, const TileDev* tiles, int nf, uint32_t batch_first_frame, const float4* Lo,
+                  const float4* Le, float* fb, cudaStream_t st);
+void launch_tally(const uint32_t* q_counts, const uint32_t* s_counts, int n_stages, unsigned long long* totals, cudaStream_t st);
+void launch_megakernel(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, bool prune, int spp, float* fb,
+                       unsigned long long* totals, cudaStream_t st);
+void launch_trace_rays(const SceneDev& sc, bool prune, bool anyhit, int n, const float* o, const float* d, int p3fudge, int* hit,
+                       float* dist, int* tri, int* inside, float* point, float* normal, cudaStream_t st);
+void launch_eval_brdf(int which, int n, const float* V, const float* N, const float* L, const float* xi, const float* materials,
+                      float* out, cudaStream_t st);
+void launch_eval_math(int which, int n, const float* a, const float* b, float* out, cudaStream_t st);
+void launch_partition_scatter(const float* compact, float* full, const TileDev* tiles, int n_tiles, int width, int channels,
+                              cudaStream_t st);
+
+#endif

@@ -1,0 +1,218 @@
+/*
+ * ezrt.h -- C ABI of ezrt_b200: the B200-native drop-in for EzRT's path-tracing hot path.
+ *
+ * The reference (AKGWSB/EzRT) has no plugin/FFI interface; its de-facto boundary is "what
+ * main() hands to pass1 and what pass1 leaves in lastFrame" (SURVEY.md 8b).  Every entry
+ * point below cites the reference code it replaces.  Path aliases: P2/ P3/ P4/ P5/ = the
+ * "source code" directory of tutorial part 2..5; fsh = shaders/fshader.fsh.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types; all functions return 0 on success or
+ *     a negative ezrt_status; ezrt_last_error() gives a thread-local message.  The
+ *     reference prints and exit(-1)s (P5/main.cpp:178-182, :283-286); this ABI never exits.
+ *   - the caller owns every input array and every output buffer; a scene handle owns its
+ *     device allocations.  One handle = one CUDA device; calls on one handle are
+ *     serialised by the caller; different handles may be driven from different threads.
+ *   - "tris" is an array of Triangle_encoded (P5/main.cpp:60-69): 36 packed floats
+ *     (p1 p2 p3 n1 n2 n3 emissive baseColor param1..param4), stride 144 B.
+ *   - "nodes" is an array of BVHNode_encoded (P5/main.cpp:71-76): 12 packed floats
+ *     (left,right,0)(n,index,0) AA BB, ints stored as floats; element 0 is the dummy
+ *     testNode, the root is element 1 (P5/main.cpp:830-838, P5/fsh:263).
+ *   - framebuffers are linear-radiance fp32, row 0 = bottom row (GL convention), the
+ *     content of pass1's colour attachment 0 / lastFrame (P5/fsh:942-947) before any
+ *     tone mapping.
+ */
+#ifndef EZRT_H
+#define EZRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EZRT_TRIANGLE_FLOATS 36 /* Triangle_encoded, P5/main.cpp:60-69 */
+#define EZRT_BVHNODE_FLOATS 12  /* BVHNode_encoded,  P5/main.cpp:71-76 */
+#define EZRT_MATERIAL_FLOATS 18 /* emissive, baseColor, 12 scalars: P5/main.cpp:27-42 */
+
+typedef enum ezrt_status {
+    EZRT_OK = 0,
+    EZRT_ERR_INVALID = -1,   /* bad argument */
+    EZRT_ERR_IO = -2,        /* file could not be opened / parsed */
+    EZRT_ERR_CUDA = -3,      /* CUDA runtime error or no device */
+    EZRT_ERR_BAD_TREE = -4,  /* node array is not a tree the traversal can walk */
+    EZRT_ERR_NOMEM = -5
+} ezrt_status;
+
+/* Integrator modes = the four per-pixel loops the reference ships. */
+typedef enum ezrt_mode {
+    EZRT_MODE_DIFFUSE_P3 = 0,      /* P3/fsh:376-446  diffuse, uniform hemisphere, wang-hash   */
+    EZRT_MODE_DISNEY_ANISO_P4 = 1, /* P4/fsh:478-550  anisotropic Disney, uniform hemisphere   */
+    EZRT_MODE_DISNEY_SOBOL_P5 = 2, /* P5/fsh:762-807  Disney + Sobol/CP rotation               */
+    EZRT_MODE_DISNEY_IS_MIS_P5 = 3 /* P5/fsh:810-890  BRDF + HDR importance sampling, MIS      */
+} ezrt_mode;
+
+/* BVH traversal policy.  REFERENCE walks every box the ray overlaps (P5/fsh:254-306, no
+ * best-distance pruning).  PRUNED additionally skips a subtree when its box entry distance
+ * exceeds the current best hit by a conservative margin; it returns bit-identical hits
+ * (DESIGN.md "pruning") and is the default. */
+typedef enum ezrt_traverse {
+    EZRT_TRAVERSE_PRUNED = 0,
+    EZRT_TRAVERSE_REFERENCE = 1
+} ezrt_traverse;
+
+typedef enum ezrt_pipeline {
+    EZRT_PIPELINE_WAVEFRONT = 0, /* generate / extend / shade / shadow / blend kernels */
+    EZRT_PIPELINE_MEGAKERNEL = 1 /* one thread per pixel, literal loop (cross-check)   */
+} ezrt_pipeline;
+
+/* Everything display() passes to pass1 per frame (P5/main.cpp:709-745, :919-923) plus
+ * the constants that are literals in the shaders. */
+typedef struct ezrt_render_params {
+    int32_t width, height;   /* uniform width,height  (P5/main.cpp:922-923)                  */
+    int32_t spp;             /* number of consecutive display() calls to perform             */
+    uint32_t first_frame;    /* frameCounter of the first call (P5/main.cpp:719); 0 = fresh  */
+    int32_t max_bounce;      /* literal in main(): P5/fsh:935 (2), P4/fsh:540 (4), P3 (2)    */
+    int32_t mode;            /* ezrt_mode                                                    */
+    float eye[3];            /* uniform eye           (P5/main.cpp:710-711, :717)            */
+    float camera_rotate[16]; /* uniform cameraRotate, column-major inverse(lookAt) (:712-718) */
+    float env_color[3];      /* colour of a miss when the scene has no HDR map               */
+    int32_t traverse;        /* ezrt_traverse                                                */
+    int32_t pipeline;        /* ezrt_pipeline                                                */
+    int32_t out_channels;    /* 3 (RGB) or 4 (RGBA, alpha = 1 as in P5/fsh:947)              */
+    /* image partition for multi-GPU rendering: the image is cut into 16x16 tiles, tile
+     * (tx,ty) belongs to part (tx+ty) % part_count; a part renders only its tiles and
+     * writes them compactly (tile-major) unless part_count == 1. */
+    int32_t part_rank, part_count;
+    int32_t frames_per_batch; /* wavefront: display() calls traced concurrently (0 = auto)   */
+    int32_t reserved[4];
+} ezrt_render_params;
+
+typedef struct ezrt_counters {
+    uint64_t rays;          /* hitBVH invocations: primary + bounce + shadow     */
+    uint64_t primary_rays, bounce_rays, shadow_rays;
+    uint64_t samples;       /* pixel-samples = fragment shader invocations                   */
+    uint64_t kernel_launches;
+    double device_ms;       /* CUDA-event time of the last render on its stream              */
+} ezrt_counters;
+
+typedef struct ezrt_scene ezrt_scene; /* device-resident scene (replaces the two TBOs + 2 textures) */
+
+const char* ezrt_last_error(void);
+int ezrt_version(void);
+
+/* ----------------------------------------------------------------------------------------
+ * Device side: the hot path.
+ * -------------------------------------------------------------------------------------- */
+
+/* Replaces the texture-buffer uploads P5/main.cpp:878-906: copies the reference-layout
+ * arrays to the GPU `device` and repacks them for the kernels.  hdr / hdr_cache may be
+ * NULL (then hdr_w = hdr_h = 0).  hdr rows are stored top-to-bottom as HDRLoader returns
+ * them (P5/lib/hdrloader.cpp:76-91); hdr_cache is calculateHdrCache()'s output
+ * (P5/main.cpp:592-689).  hdr_filter_linear: 1 = GL_LINEAR (P5/main.cpp:196-199),
+ * 0 = GL_NEAREST (P3/main.cpp:195-196). */
+int ezrt_scene_create(int device, const float* tris, int n_triangles, const float* nodes, int n_nodes,
+                      const float* hdr, const float* hdr_cache, int hdr_w, int hdr_h,
+                      int hdr_filter_linear, ezrt_scene** out_scene);
+int ezrt_scene_destroy(ezrt_scene* scene);
+
+/* render(width,height,spp) -> framebuffer: equals `spp` consecutive display() calls
+ * (P5/main.cpp:697-748) each drawing pass1 (P5/fsh:894-949) and copying to lastFrame.
+ * `framebuffer` is a HOST buffer, in/out: when first_frame > 0 it must hold lastFrame.
+ * Size: n_pixels(part) * out_channels floats, see ezrt_partition_pixels(). */
+int ezrt_render(ezrt_scene* scene, const ezrt_render_params* params, float* framebuffer);
+
+/* Same, but `d_framebuffer` is DEVICE memory on the scene's GPU and the work is enqueued on
+ * `cuda_stream` (a cudaStream_t, NULL = default stream) without host synchronisation. */
+int ezrt_render_device(ezrt_scene* scene, const ezrt_render_params* params, float* d_framebuffer,
+                       void* cuda_stream);
+
+/* Counters of the most recent render on this scene (synchronises the stream). */
+int ezrt_get_counters(ezrt_scene* scene, ezrt_counters* out);
+
+/* Number of pixels part `rank` of `count` owns for a width x height image. */
+int64_t ezrt_partition_pixels(int width, int height, int rank, int count);
+/* Device kernel: scatter the compact tile-major buffer of part `rank` into a full
+ * width x height framebuffer (both device pointers, same channel count). */
+int ezrt_partition_scatter(const float* d_compact, float* d_full, int width, int height, int channels,
+                           int rank, int count, void* cuda_stream);
+/* Host version of the same scatter (used by the CPU/gloo path and by tests). */
+int ezrt_partition_scatter_host(const float* compact, float* full, int width, int height, int channels,
+                                int rank, int count);
+
+/* Single-function entry points of the hot path (device), for parity tests: trace `n` rays
+ * (origins/dirs: n x 3 floats, host) through hitBVH (P5/fsh:254-306; C++ twin
+ * P2/main.cpp:466-485) and return per ray: hit flag, distance, triangle index, isInside,
+ * hit point, shading normal. any_hit=1 stops at the first hit (shadow rays, P5/fsh:826-829). */
+int ezrt_trace_rays(ezrt_scene* scene, int n, const float* origins, const float* dirs, int traverse,
+                    int any_hit, int p3_normal_fudge, int32_t* out_hit, float* out_distance,
+                    int32_t* out_triangle, int32_t* out_inside, float* out_point, float* out_normal);
+
+/* Evaluate the BRDF functions on the device for n (V,N,L,material) tuples: which = 0
+ * BRDF_Evaluate (P5/fsh:500-549), 1 BRDF_Evaluate aniso (P4/fsh:412-473), 2 BRDF_Pdf
+ * (P5/fsh:715-752; result in out[3*i]), 3 SampleBRDF (P5/fsh:633-664; xi = n x 3). */
+int ezrt_eval_brdf(int device, int which, int n, const float* V, const float* N, const float* L,
+                   const float* xi, const float* materials, float* out);
+
+/* Evaluate a ezrt_math.h function on the device for n inputs (parity of the arithmetic
+ * definition): which = 0 sin, 1 cos, 2 log, 3 exp, 4 pow(a,b), 5 atan2(a,b), 6 asin. */
+int ezrt_eval_math(int device, int which, int n, const float* a, const float* b, float* out);
+
+/* ----------------------------------------------------------------------------------------
+ * Host side: the scene pipeline that feeds the path (stays on the CPU, north_star).
+ * -------------------------------------------------------------------------------------- */
+
+typedef struct ezrt_trilist ezrt_trilist; /* std::vector<Triangle> of P5/main.cpp:801 */
+
+ezrt_trilist* ezrt_trilist_create(void);
+void ezrt_trilist_destroy(ezrt_trilist* list);
+int ezrt_trilist_size(const ezrt_trilist* list);
+
+/* getTransformMatrix (P5/main.cpp:255-271): translate * rotate(x,y,z degrees) * scale,
+ * column-major out[16]. */
+void ezrt_transform_matrix(const float rotate_deg[3], const float translate[3], const float scale[3],
+                           float out[16]);
+/* readObj (P5/main.cpp:274-392) incl. its unit-box normalisation quirk (:317-318),
+ * transform, smooth-normal generation and per-mesh material (18 floats: emissive,
+ * baseColor, subsurface, metallic, specular, specularTint, roughness, anisotropic, sheen,
+ * sheenTint, clearcoat, clearcoatGloss, IOR, transmission). */
+int ezrt_trilist_read_obj(ezrt_trilist* list, const char* path, const float material[EZRT_MATERIAL_FLOATS],
+                          const float trans[16], int smooth_normal);
+/* Same parser on an in-memory OBJ text (synthetic meshes). */
+int ezrt_trilist_read_obj_text(ezrt_trilist* list, const char* text, size_t len,
+                               const float material[EZRT_MATERIAL_FLOATS], const float trans[16],
+                               int smooth_normal);
+/* Append already-built triangles in Triangle_encoded layout. */
+int ezrt_trilist_append_encoded(ezrt_trilist* list, const float* tris, int n);
+
+typedef enum ezrt_bvh_builder {
+    EZRT_BVH_SAH_FAST = 0,    /* same tree as SAH_LITERAL, keys pre-computed, subtrees in parallel */
+    EZRT_BVH_SAH_LITERAL = 1, /* buildBVHwithSAH exactly as written (P5/main.cpp:458-589)   */
+    EZRT_BVH_MEDIAN = 2       /* buildBVH (P5/main.cpp:395-455)                              */
+} ezrt_bvh_builder;
+
+/* Sorts the list's triangles in place and builds the node array: nodes{testNode};
+ * buildBVHwithSAH(triangles, nodes, 0, N-1, leaf_n) (P5/main.cpp:830-838).  Returns the
+ * node count (incl. dummy node 0) or a negative status. */
+int ezrt_trilist_build_bvh(ezrt_trilist* list, int leaf_n, int builder);
+int ezrt_trilist_node_count(const ezrt_trilist* list);
+/* Encode as P5/main.cpp:843-871 into caller buffers (36 floats/triangle, 12 floats/node). */
+int ezrt_trilist_encode_triangles(const ezrt_trilist* list, float* tris_out);
+int ezrt_trilist_encode_nodes(const ezrt_trilist* list, float* nodes_out);
+
+/* HDRLoader::load (P5/lib/hdrloader.cpp:29-97): Radiance .hdr -> float RGB rows.  Call with
+ * cols = NULL to query width/height. */
+int ezrt_hdr_load(const char* path, int* width, int* height, float* cols);
+/* calculateHdrCache (P5/main.cpp:592-689): (sample_x, sample_y, pdf) lookup texture. */
+int ezrt_hdr_cache(const float* hdr, int width, int height, float* cache_out);
+
+/* Camera of display() (P5/main.cpp:710-713): orbit angles in degrees + radius ->
+ * eye, cameraRotate = inverse(lookAt(eye, 0, +y)), column-major. */
+void ezrt_camera_orbit(float rotate_angle_deg, float up_angle_deg, float r, float eye[3],
+                       float camera_rotate[16]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EZRT_H */
