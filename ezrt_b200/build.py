@@ -104,7 +104,12 @@ def build_reference_hdrloader(force=False):
         return REF_HDR_SO if os.path.exists(REF_HDR_SO) else None
     os.makedirs(REF_DIR, exist_ok=True)
     if force or _newer(REF_HDR_SO, [src, shim]):
-        _run(["g++", "-O2", "-fPIC", "-shared", "-w", "-I", os.path.join(REFERENCE_P5, "lib"), src, shim, "-o", REF_HDR_SO])
+        # the prefix header reroutes the source's sscanf("%ld" into int) call, which is UB on LP64
+        prefix = os.path.join(ROOT, "oracle", "ref_hdrloader_prefix.h")
+        obj = os.path.join(REF_DIR, "hdrloader.o")
+        _run(["g++", "-O2", "-fPIC", "-w", "-include", prefix, "-I", os.path.join(REFERENCE_P5, "lib"), "-c", src, "-o", obj])
+        _run(["g++", "-O2", "-fPIC", "-shared", "-w", "-I", os.path.join(REFERENCE_P5, "lib"), obj, shim, "-o", REF_HDR_SO])
+        os.remove(obj)
     return REF_HDR_SO
 
 

@@ -1,0 +1,294 @@
+"""GPU parity tests: the sm_100a path (through the C ABI) against the CPU oracle, bit for bit.
+
+The north_star tolerance is 1e-4 per-channel L-infinity on the same Sobol seed; because host
+and device evaluate the same fp32 operation sequence (include/ezrt_math.h) the tests assert
+the stronger property: identical bits (NaNs in identical places)."""
+import numpy as np
+import pytest
+
+from ezrt_b200 import api, scenes
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # north_star: per-channel L-inf vs the reference CPU render
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_same_bits(a, b, what=""):
+    a = np.asarray(a, dtype=np.float32); b = np.asarray(b, dtype=np.float32)
+    assert a.shape == b.shape, what
+    same = (_bits(a) == _bits(b)) | (np.isnan(a) & np.isnan(b))
+    if not same.all():
+        bad = np.argwhere(~same)
+        linf = np.nanmax(np.abs(a.astype(np.float64) - b.astype(np.float64)))
+        raise AssertionError("%s: %d of %d values differ (first at %s: %r vs %r), L-inf %.3g" %
+                             (what, len(bad), a.size, bad[0], a[tuple(bad[0])], b[tuple(bad[0])], linf))
+
+
+@pytest.fixture(scope="module")
+def gpu_bunny(bunny_scene):
+    tris, nodes, eye, cam = bunny_scene
+    sc = api.Scene(tris, nodes)
+    yield sc
+    sc.close()
+
+
+@pytest.fixture(scope="module")
+def gpu_grid(grid_scene):
+    tris, nodes, eye, cam = grid_scene
+    sc = api.Scene(tris, nodes)
+    yield sc
+    sc.close()
+
+
+# ------------------------------------------------------------------ arithmetic definition
+@pytest.mark.parametrize("which,name", [(0, "sin"), (1, "cos"), (2, "log"), (3, "exp"), (4, "pow"), (5, "atan2"), (6, "asin")])
+def test_math_bit_exact(oracle, which, name):
+    rng = np.random.default_rng(100 + which)
+    n = 200000
+    if name in ("sin", "cos"):
+        a = np.concatenate([rng.uniform(-14, 14, n), rng.uniform(-1e-3, 1e-3, 1000), [0.0, 6.2831852, 3.1415926, 1e4, -1e4]])
+        b = None
+    elif name == "log":
+        a = np.concatenate([rng.uniform(1e-7, 4, n), np.exp(rng.uniform(-80, 80, 5000)), [1.0, 1e-6, 0.01, 0.0, -1.0, 1e-42]])
+        b = None
+    elif name == "exp":
+        a = np.concatenate([rng.uniform(-20, 20, n), rng.uniform(-110, 95, 5000), [0.0]])
+        b = None
+    elif name == "pow":
+        a = rng.uniform(1e-6, 1.0, n); b = rng.uniform(0, 1, n)
+    elif name == "atan2":
+        a = np.concatenate([rng.uniform(-2, 2, n), [0, 0, 1, -1, 0.0]]); b = np.concatenate([rng.uniform(-2, 2, n), [0, 1, 0, 0, -1.0]])
+    else:
+        a = np.concatenate([rng.uniform(-1, 1, n), [1.0, -1.0, 1.0000001, 0.5, 1e-5, 0.0]]); b = None
+    a = a.astype(np.float32); b = None if b is None else b.astype(np.float32)
+    assert_same_bits(api.eval_math(which, a, b), oracle.eval_math(which, a, b), name)
+
+
+def _random_brdf_inputs(n, seed):
+    rng = np.random.default_rng(seed)
+
+    def unit(v):
+        return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+
+    N = unit(rng.normal(size=(n, 3)))
+    V = unit(N + 0.9 * rng.normal(size=(n, 3)))
+    L = unit(N + 0.9 * rng.normal(size=(n, 3)))
+    mats = np.zeros((n, 18), np.float32)
+    mats[:, 0:3] = rng.uniform(0, 5, (n, 3)) * (rng.uniform(size=(n, 1)) < 0.1)
+    mats[:, 3:6] = rng.uniform(0, 1, (n, 3))
+    mats[:, 6:16] = rng.uniform(0, 1, (n, 10))
+    mats[::7, 10] = 0.0  # roughness 0
+    mats[::11, 15] = 1.0  # clearcoatGloss 1
+    mats[::13, 3:6] = 0.0  # black base colour -> Cdlum == 0 branch
+    mats[:, 16] = 1.0
+    xi = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    return V, N, L, xi, mats
+
+
+@pytest.mark.parametrize("which,name", [(0, "BRDF_Evaluate"), (1, "BRDF_Evaluate_aniso_P4"), (2, "BRDF_Pdf"), (3, "SampleBRDF")])
+def test_brdf_bit_exact(oracle, which, name):
+    V, N, L, xi, mats = _random_brdf_inputs(100000, 7 + which)
+    assert_same_bits(api.eval_brdf(which, V, N, L, xi, mats), oracle.eval_brdf(which, V, N, L, xi, mats), name)
+
+
+# ------------------------------------------------------------------ hitBVH / hitTriangle / hitAABB
+def _random_rays(n, seed, extent=3.0):
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(-extent, extent, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    # axis-aligned and zero-component directions exercise the inf/NaN slab arithmetic (P5/fsh:221-230)
+    d[:64] = 0.0
+    d[:64, 0] = 1.0
+    d[64:128] = np.array([0.0, -1.0, 0.0], np.float32)
+    d[128:160, 2] = 0.0
+    d[128:160] /= np.linalg.norm(d[128:160], axis=1, keepdims=True)
+    return o, d
+
+
+@pytest.mark.parametrize("traverse", [api.TRAVERSE_PRUNED, api.TRAVERSE_REFERENCE])
+@pytest.mark.parametrize("fudge", [False, True])
+def test_trace_rays_match_oracle(oracle, bunny_scene, gpu_bunny, traverse, fudge):
+    tris, nodes, eye, cam = bunny_scene
+    o, d = _random_rays(20000, 11)
+    got = gpu_bunny.trace_rays(o, d, traverse=traverse, p3_normal_fudge=fudge)
+    ref = oracle.trace_rays(tris, nodes, o, d, traverse=api.TRAVERSE_REFERENCE, p3_fudge=fudge)
+    assert ref["hit"].sum() > 1000
+    np.testing.assert_array_equal(got["hit"], ref["hit"])
+    np.testing.assert_array_equal(got["triangle"], ref["triangle"])
+    np.testing.assert_array_equal(got["inside"], ref["inside"])
+    assert_same_bits(got["distance"], ref["distance"], "distance")
+    assert_same_bits(got["point"], ref["point"], "hitPoint")
+    assert_same_bits(got["normal"], ref["normal"], "normal")
+
+
+def test_any_hit_equals_closest_hit_flag(gpu_grid):
+    o, d = _random_rays(20000, 13, extent=2.5)
+    closest = gpu_grid.trace_rays(o, d)
+    anyhit = gpu_grid.trace_rays(o, d, any_hit=True)
+    np.testing.assert_array_equal(anyhit["hit"], closest["hit"])
+
+
+def test_p2_demo_ray_bvh_equals_brute_force(oracle, bunny_scene, gpu_bunny):
+    """The reference's only intersection fixture: P2/main.cpp:581-586, ray (0,0,1) -> normalize(0.1,-0.1,-0.7),
+    hitBVH must equal the brute-force scan (commented cross-check at :585)."""
+    tris, nodes, eye, cam = bunny_scene
+    d = np.array([[0.1, -0.1, -0.7]], np.float64)
+    d = (d / np.linalg.norm(d)).astype(np.float32)
+    o = np.array([[0, 0, 1]], np.float32)
+    brute = oracle.trace_rays(tris, nodes, o, d, brute=True)
+    got = gpu_bunny.trace_rays(o, d)
+    assert brute["hit"][0] == 1
+    assert got["triangle"][0] == brute["triangle"][0]
+    assert_same_bits(got["distance"], brute["distance"], "P2 demo ray")
+
+
+# ------------------------------------------------------------------ whole-image parity
+def _cfg(eye, cam, **kw):
+    base = dict(width=96, height=64, spp=3, max_bounce=2, eye=tuple(eye), camera_rotate=tuple(cam), env_color=(0.35, 0.45, 0.6))
+    base.update(kw)
+    return api.RenderConfig(**base)
+
+
+@pytest.mark.parametrize("pipeline", [api.PIPELINE_WAVEFRONT, api.PIPELINE_MEGAKERNEL])
+@pytest.mark.parametrize("mode,bounces", [(api.MODE_DIFFUSE_P3, 3), (api.MODE_DISNEY_ANISO_P4, 4), (api.MODE_DISNEY_SOBOL_P5, 2)])
+def test_render_matches_oracle_bunny(oracle, bunny_scene, gpu_bunny, mode, bounces, pipeline):
+    tris, nodes, eye, cam = bunny_scene
+    cfg = _cfg(eye, cam, mode=mode, max_bounce=bounces, pipeline=pipeline)
+    ref, rc = oracle.render(tris, nodes, cfg)
+    got = gpu_bunny.render(cfg)
+    c = gpu_bunny.counters()
+    assert np.abs(np.nan_to_num(got) - np.nan_to_num(ref)).max() <= TOL
+    assert_same_bits(got, ref, "image mode %d" % mode)
+    assert (c.primary_rays, c.bounce_rays, c.shadow_rays) == (rc["rays_primary"], rc["rays_bounce"], rc["rays_shadow"])
+
+
+@pytest.mark.parametrize("pipeline", [api.PIPELINE_WAVEFRONT, api.PIPELINE_MEGAKERNEL])
+@pytest.mark.parametrize("mode", [api.MODE_DISNEY_ANISO_P4, api.MODE_DISNEY_SOBOL_P5])
+def test_render_matches_oracle_grid_materials(oracle, grid_scene, gpu_grid, mode, pipeline):
+    tris, nodes, eye, cam = grid_scene
+    cfg = _cfg(eye, cam, mode=mode, max_bounce=3, pipeline=pipeline, width=80, height=48, spp=2)
+    ref, rc = oracle.render(tris, nodes, cfg)
+    got = gpu_grid.render(cfg)
+    assert_same_bits(got, ref, "grid image mode %d" % mode)
+    assert gpu_grid.counters().rays == rc["rays"]
+
+
+@pytest.mark.parametrize("pipeline", [api.PIPELINE_WAVEFRONT, api.PIPELINE_MEGAKERNEL])
+@pytest.mark.parametrize("linear", [True, False])
+def test_render_is_mis_matches_oracle(oracle, grid_scene, small_hdr, pipeline, linear):
+    tris, nodes, eye, cam = grid_scene
+    hdr, cache = small_hdr
+    sc = api.Scene(tris, nodes, hdr, cache, hdr_filter_linear=linear)
+    try:
+        cfg = _cfg(eye, cam, mode=api.MODE_DISNEY_IS_MIS_P5, max_bounce=2, pipeline=pipeline, width=80, height=48, spp=3)
+        ref, rc = oracle.render(tris, nodes, cfg, hdr=hdr, hdr_cache=cache, hdr_linear=linear)
+        got = sc.render(cfg)
+        c = sc.counters()
+        assert rc["rays_shadow"] > 0
+        assert_same_bits(got, ref, "IS/MIS image")
+        assert (c.primary_rays, c.bounce_rays, c.shadow_rays) == (rc["rays_primary"], rc["rays_bounce"], rc["rays_shadow"])
+    finally:
+        sc.close()
+
+
+def test_hdr_environment_diffuse_clamp(oracle, bunny_scene, small_hdr):
+    """P3's sampleHdr clamps the environment to 10 (P3/fsh:151-156); nearest filtering as P3/main.cpp:195-196."""
+    tris, nodes, eye, cam = bunny_scene
+    hdr, cache = small_hdr
+    sc = api.Scene(tris, nodes, hdr, cache, hdr_filter_linear=False)
+    try:
+        cfg = _cfg(eye, cam, mode=api.MODE_DIFFUSE_P3, max_bounce=2)
+        ref, _ = oracle.render(tris, nodes, cfg, hdr=hdr, hdr_cache=cache, hdr_linear=False)
+        assert_same_bits(sc.render(cfg), ref, "P3 + HDR")
+    finally:
+        sc.close()
+
+
+def test_c1_config_matches_oracle(oracle, bunny_scene, gpu_bunny):
+    """BASELINE.json configs[0]: bunny-class scene, 256x256, 4 spp, 3 bounces (diffuse)."""
+    tris, nodes, eye, cam = bunny_scene
+    cfg = _cfg(eye, cam, width=256, height=256, spp=4, max_bounce=3, mode=api.MODE_DIFFUSE_P3)
+    ref, rc = oracle.render(tris, nodes, cfg)
+    got = gpu_bunny.render(cfg)
+    assert np.abs(got - ref).max() <= TOL
+    assert_same_bits(got, ref, "C1")
+    assert gpu_bunny.counters().rays == rc["rays"]
+
+
+def test_accumulation_continues_from_lastframe(oracle, bunny_scene, gpu_bunny):
+    """spp frames in one call == the same frames in two calls with first_frame advanced (P5/fsh:942-944)."""
+    tris, nodes, eye, cam = bunny_scene
+    whole = gpu_bunny.render(_cfg(eye, cam, spp=5, mode=api.MODE_DISNEY_SOBOL_P5, frames_per_batch=2))
+    part = gpu_bunny.render(_cfg(eye, cam, spp=2, mode=api.MODE_DISNEY_SOBOL_P5))
+    part = gpu_bunny.render(_cfg(eye, cam, spp=3, first_frame=2, mode=api.MODE_DISNEY_SOBOL_P5), framebuffer=part.reshape(-1, 3).copy())
+    assert_same_bits(whole, part, "split accumulation")
+    ref, _ = oracle.render(tris, nodes, _cfg(eye, cam, spp=5, mode=api.MODE_DISNEY_SOBOL_P5))
+    assert_same_bits(whole, ref, "5 spp vs oracle")
+
+
+def test_rgba_output(bunny_scene, gpu_bunny):
+    tris, nodes, eye, cam = bunny_scene
+    rgb = gpu_bunny.render(_cfg(eye, cam))
+    rgba = gpu_bunny.render(_cfg(eye, cam, out_channels=4))
+    assert_same_bits(rgba[..., :3], rgb, "rgba")
+    assert (rgba[..., 3] == 1.0).all()
+
+
+# ------------------------------------------------------------------ size-independent properties at larger sizes
+def test_pruned_equals_reference_traversal_large(gpu_grid, grid_scene):
+    """Pruning must not change a single bit: full-size property test (no oracle needed)."""
+    tris, nodes, eye, cam = grid_scene
+    cfg = _cfg(eye, cam, width=640, height=360, spp=4, max_bounce=3, mode=api.MODE_DISNEY_SOBOL_P5)
+    a = gpu_grid.render(cfg)
+    ca = gpu_grid.counters()
+    cfg.traverse = api.TRAVERSE_REFERENCE
+    b = gpu_grid.render(cfg)
+    cb = gpu_grid.counters()
+    assert_same_bits(a, b, "pruned vs reference traversal")
+    assert ca.rays == cb.rays and ca.rays > 640 * 360 * 4
+
+
+def test_wavefront_equals_megakernel_large(gpu_grid, grid_scene):
+    tris, nodes, eye, cam = grid_scene
+    cfg = _cfg(eye, cam, width=512, height=288, spp=3, max_bounce=4, mode=api.MODE_DISNEY_ANISO_P4)
+    a = gpu_grid.render(cfg)
+    cfg.pipeline = api.PIPELINE_MEGAKERNEL
+    b = gpu_grid.render(cfg)
+    assert_same_bits(a, b, "wavefront vs megakernel")
+
+
+@pytest.mark.parametrize("count", [2, 3, 8])
+def test_partitioned_render_equals_whole(gpu_bunny, bunny_scene, count):
+    """Any image partition gives bit-identical pixels: render each part, scatter, compare."""
+    tris, nodes, eye, cam = bunny_scene
+    W, H = 200, 120  # not a multiple of the 16-pixel tile
+    whole = gpu_bunny.render(_cfg(eye, cam, width=W, height=H, spp=2))
+    full = np.zeros((H, W, 3), np.float32)
+    total = 0
+    for rank in range(count):
+        part = gpu_bunny.render(_cfg(eye, cam, width=W, height=H, spp=2, part_rank=rank, part_count=count))
+        assert part.shape[0] == api.partition_pixels(W, H, rank, count)
+        total += part.shape[0]
+        api.partition_scatter_host(part, full, W, H, 3, rank, count)
+    assert total == W * H
+    assert_same_bits(full, whole, "partitioned image")
+
+
+def test_errors_are_reported_not_fatal(bunny_scene):
+    tris, nodes, eye, cam = bunny_scene
+    bad = nodes.copy()
+    bad[1, 0] = 0  # root loses its left child -> the shader would read the dummy node
+    with pytest.raises(api.EzrtError) as e:
+        api.Scene(tris, bad)
+    assert e.value.code == -4
+    sc = api.Scene(tris, nodes)
+    try:
+        with pytest.raises(api.EzrtError):
+            sc.render(_cfg(eye, cam, mode=api.MODE_DISNEY_IS_MIS_P5))  # no HDR map
+    finally:
+        sc.close()
