@@ -21,7 +21,7 @@ class RenderParams(C.Structure):
         ("eye", C.c_float * 3), ("camera_rotate", C.c_float * 16), ("env_color", C.c_float * 3),
         ("traverse", C.c_int32), ("pipeline", C.c_int32), ("out_channels", C.c_int32),
         ("part_rank", C.c_int32), ("part_count", C.c_int32), ("frames_per_batch", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("profile", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -43,6 +43,7 @@ SIGNATURES = {
     "ezrt_render": (C.c_int, [C.c_void_p, C.POINTER(RenderParams), c_float_p]),
     "ezrt_render_device": (C.c_int, [C.c_void_p, C.POINTER(RenderParams), C.c_void_p, C.c_void_p]),
     "ezrt_get_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
+    "ezrt_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "ezrt_partition_pixels": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ezrt_partition_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ezrt_partition_scatter_host": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -75,8 +76,9 @@ class EzrtError(RuntimeError):
 
 def _load():
     path = _build.PRODUCT_SO
-    if not os.path.exists(path):
-        # in-tree build; raises if nvcc is missing -- there is no CPU fallback for the product
+    # in-tree incremental build (no-op when the .so is newer than its sources); without nvcc a
+    # prebuilt .so is used as is, and a missing one raises -- there is no CPU fallback
+    if not os.path.exists(path) or _build._nvcc() is not None:
         _build.build_product()
     lib = C.CDLL(path)
     for name, (restype, argtypes) in SIGNATURES.items():

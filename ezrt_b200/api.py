@@ -180,6 +180,7 @@ class RenderConfig:
     part_rank: int = 0
     part_count: int = 1
     frames_per_batch: int = 0
+    profile: int = 0
 
     def to_struct(self):
         p = RenderParams()
@@ -190,6 +191,7 @@ class RenderConfig:
         p.env_color[:] = [float(x) for x in self.env_color]
         p.traverse, p.pipeline, p.out_channels = int(self.traverse), int(self.pipeline), int(self.out_channels)
         p.part_rank, p.part_count, p.frames_per_batch = int(self.part_rank), int(self.part_count), int(self.frames_per_batch)
+        p.profile = int(self.profile)
         return p
 
 
@@ -245,6 +247,13 @@ class Scene:
         c = Counters()
         check(lib.ezrt_get_counters(self._h, C.byref(c)))
         return c
+
+    def kernel_times(self):
+        """{class: (ms, launches)} of the last render with cfg.profile = 1."""
+        ms = (C.c_double * 4)()
+        n = (C.c_uint64 * 4)()
+        check(lib.ezrt_get_kernel_times(self._h, ms, n))
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(("extend", "shade", "shadow", "other"))}
 
     def trace_rays(self, origins, dirs, traverse=TRAVERSE_PRUNED, any_hit=False, p3_normal_fudge=False):
         """hitBVH for n rays on the device (P5/fsh:254-306)."""

@@ -83,6 +83,28 @@ struct ezrt_scene {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool have_timing = false;
     unsigned long long launches = 0;
+    // params.profile: one event pair per launch, summed per kernel class by ezrt_get_kernel_times
+    std::vector<cudaEvent_t> ev_pool;
+    struct Span { int cls; int e0, e1; };
+    std::vector<Span> spans;
+    size_t ev_used = 0;
+    bool profiling = false;
+    int span_begin(int cls, cudaStream_t st) {
+        if (!profiling) return -1;
+        while (ev_pool.size() < ev_used + 2) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return -1;
+            ev_pool.push_back(e);
+        }
+        Span sp{cls, (int)ev_used, (int)ev_used + 1};
+        ev_used += 2;
+        cudaEventRecord(ev_pool[sp.e0], st);
+        spans.push_back(sp);
+        return (int)spans.size() - 1;
+    }
+    void span_end(int id, cudaStream_t st) {
+        if (id >= 0) cudaEventRecord(ev_pool[spans[id].e1], st);
+    }
 };
 
 namespace {
@@ -313,6 +335,7 @@ int ezrt_scene_destroy(ezrt_scene* s) {
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
     if (s->ev_stop) cudaEventDestroy(s->ev_stop);
+    for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
     delete s;
     return EZRT_OK;
 }
@@ -335,6 +358,9 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     CU_CHECK(cudaMemsetAsync(totals, 0, sizeof(unsigned long long) * 4, st));
     s->launches = 0;
     s->have_timing = true;
+    s->profiling = (p->profile != 0);
+    s->spans.clear();
+    s->ev_used = 0;
     RenderDev rd = make_render_dev(s, p);
     const TileDev* d_tiles = (const TileDev*)s->tiles_buf.p;
     const bool prune = (p->traverse == EZRT_TRAVERSE_PRUNED);
@@ -344,7 +370,9 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     }
 
     if (p->pipeline == EZRT_PIPELINE_MEGAKERNEL) {
+        int sp = s->span_begin(0, st);
         launch_megakernel(s->dev, rd, d_tiles, prune, p->spp, d_fb, totals, st);
+        s->span_end(sp, st);
         s->launches++;
         CU_CHECK(cudaGetLastError());
         CU_CHECK(cudaEventRecord(s->ev_stop, st));
@@ -378,22 +406,32 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
         const uint32_t n_slots = (uint32_t)(per_frame * (size_t)nf);
         const uint32_t batch_first = p->first_frame + (uint32_t)done;
         CU_CHECK(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * 4 * n_stages, st));
+        int sp = s->span_begin(3, st);
         launch_generate(rd, d_tiles, n_slots, batch_first, q[0], &q_count[0], s->n_sms, st);
+        s->span_end(sp, st);
         s->launches++;
         for (int b = 0; b <= p->max_bounce; b++) {
             PathQueue& qin = q[b & 1];
             PathQueue& qout = q[(b + 1) & 1];
+            sp = s->span_begin(0, st);
             launch_extend(s->dev, prune, qin, &q_count[b], &w_ext[b], n_slots, s->n_sms, st);
+            s->span_end(sp, st);
+            sp = s->span_begin(1, st);
             launch_shade(s->dev, rd, d_tiles, b, batch_first, qin, &q_count[b], qout, &q_count[b + 1], sq, &s_count[b], Lo, Le,
                          n_slots, s->n_sms, st);
+            s->span_end(sp, st);
             s->launches += 2;
             if (is_mode && b < p->max_bounce) {
+                sp = s->span_begin(2, st);
                 launch_shadow(s->dev, prune, sq, &s_count[b], &w_sh[b], Lo, n_slots, s->n_sms, st);
+                s->span_end(sp, st);
                 s->launches++;
             }
         }
+        sp = s->span_begin(3, st);
         launch_blend(rd, d_tiles, nf, batch_first, Lo, Le, d_fb, st);
         launch_tally(q_count, s_count, p->max_bounce + 1, totals, st);
+        s->span_end(sp, st);
         s->launches += 2;
     }
     CU_CHECK(cudaGetLastError());
@@ -434,6 +472,21 @@ int ezrt_get_counters(ezrt_scene* s, ezrt_counters* out) {
     out->samples = t[3];
     out->kernel_launches = s->launches;
     out->device_ms = ms;
+    return EZRT_OK;
+}
+
+int ezrt_get_kernel_times(ezrt_scene* s, double* ms, uint64_t* launches) {
+    if (!s || !ms || !launches) return ezrt_set_error(EZRT_ERR_INVALID, "get_kernel_times: null argument");
+    for (int k = 0; k < 4; k++) { ms[k] = 0.0; launches[k] = 0; }
+    if (!s->have_timing || s->spans.empty()) return EZRT_OK;
+    CU_CHECK(cudaSetDevice(s->device));
+    CU_CHECK(cudaEventSynchronize(s->ev_stop));
+    for (const auto& sp : s->spans) {
+        float t = 0.0f;
+        CU_CHECK(cudaEventElapsedTime(&t, s->ev_pool[sp.e0], s->ev_pool[sp.e1]));
+        ms[sp.cls] += t;
+        launches[sp.cls] += 1;
+    }
     return EZRT_OK;
 }
 

@@ -86,7 +86,8 @@ typedef struct ezrt_render_params {
      * writes them compactly (tile-major) unless part_count == 1. */
     int32_t part_rank, part_count;
     int32_t frames_per_batch; /* wavefront: display() calls traced concurrently (0 = auto)   */
-    int32_t reserved[4];
+    int32_t profile;          /* 1: bracket every kernel with CUDA events (ezrt_get_kernel_times) */
+    int32_t reserved[3];
 } ezrt_render_params;
 
 typedef struct ezrt_counters {
@@ -130,6 +131,11 @@ int ezrt_render_device(ezrt_scene* scene, const ezrt_render_params* params, floa
 
 /* Counters of the most recent render on this scene (synchronises the stream). */
 int ezrt_get_counters(ezrt_scene* scene, ezrt_counters* out);
+
+/* Per-kernel-class device time of the most recent render with params.profile = 1 (CUDA events on
+ * the render's stream; synchronises).  Classes: 0 extend (hitBVH, closest hit), 1 shade,
+ * 2 shadow (hitBVH, any hit), 3 other (generate, blend, tally).  ms[4], launches[4]. */
+int ezrt_get_kernel_times(ezrt_scene* scene, double* ms, uint64_t* launches);
 
 /* Number of pixels part `rank` of `count` owns for a width x height image. */
 int64_t ezrt_partition_pixels(int width, int height, int rank, int count);
