@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -321,6 +322,10 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.n_triangles = n_triangles;
     d.n_inner = n_inner;
     d.prune_delta = max_abs * 1.52587890625e-05f;  // 2^-16 * scene extent (DESIGN.md "pruning")
+    d.refill_thresh = 24;
+    d.inner_thresh = 16;
+    if (const char* e = getenv("EZRT_REFILL_T")) d.refill_thresh = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("EZRT_INNER_T")) d.inner_thresh = std::max(1, std::min(32, atoi(e)));
     *out_scene = sc;
     return EZRT_OK;
 }

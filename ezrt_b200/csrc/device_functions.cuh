@@ -199,6 +199,155 @@ __device__ __forceinline__ HitRec trace_ray(const SceneDev& sc, vec3 o, vec3 d) 
 }
 
 // ------------------------------------------------------------------------------------------
+// Persistent-warp traversal ("while-while" with per-lane refill).  Incoherent bounce rays have
+// very different traversal lengths; a warp that waits for its longest ray runs at ~4 of 32
+// lanes (ncu, profiles/r1a).  Here a lane that finishes its ray takes the next one from the
+// global work counter (warp-aggregated atomicAdd) while its neighbours keep traversing, and the
+// inner-node loop is separated from the leaf loop so lanes at inner nodes do not wait for lanes
+// testing triangles.  Per ray the visit order -- and therefore the result -- is exactly that
+// of trace_impl / the shader's hitBVH.
+//   io.load(i, o, d) fetches ray i; io.store(i, hit) receives its result.
+// ------------------------------------------------------------------------------------------
+#define EZRT_REF_DONE ((int)0x80000000)   // leaf flag with n == 0: no real leaf has this encoding
+
+template <bool PRUNE, bool ANYHIT, class RayIO>
+__device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n, uint32_t* work, RayIO io) {
+    const int refill_thresh = sc.refill_thresh;  // go back to refill when fewer lanes than this are busy
+    const int inner_thresh = sc.inner_thresh;    // leave the inner-node phase when fewer lanes than this walk
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int stack[EZRT_MAX_STACK];
+    float stack_t0[PRUNE ? EZRT_MAX_STACK : 1];
+    int sp = 0;
+    int ray = -1;              // index of the ray this lane is tracing, -1 = idle
+    int ref = EZRT_REF_DONE;
+    vec3 o = splat3(0.0f), d = splat3(0.0f), inv = splat3(0.0f);
+    float slack = 0.0f, best = EZ_INF;
+    int best_tri = -1;
+    bool exhausted = false;    // warp-uniform: the work counter has run past n
+
+    while (true) {
+        // ---------------- refill idle lanes ----------------
+        unsigned need = __ballot_sync(FULL, ray < 0);
+        if (need != 0u && !exhausted) {
+            int cnt = __popc(need);
+            int leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(work, (uint32_t)cnt);
+            base = __shfl_sync(FULL, base, leader);
+            if (base + (uint32_t)cnt >= n) exhausted = true;
+            if (ray < 0) {
+                uint32_t idx = base + (uint32_t)__popc(need & lt_mask);
+                if (idx < n) {
+                    io.load(idx, o, d);
+                    inv = ez_v3(EZ_DIV(1.0f, d.x), EZ_DIV(1.0f, d.y), EZ_DIV(1.0f, d.z));
+                    float ax = ez_abs(inv.x), ay = ez_abs(inv.y), az = ez_abs(inv.z);
+                    slack = sc.prune_delta * ez_max(ax, ez_max(ay, az));
+                    if ((ax < 3.0e38f) && (ay < 3.0e38f) && (az < 3.0e38f)) {
+                        ray = (int)idx;
+                        ref = sc.root_ref;
+                        sp = 0;
+                        best = EZ_INF;
+                        best_tri = -1;
+                    } else {  // a zero / NaN direction component: literal ternary min/max path (rare)
+                        io.store(idx, trace_impl<PRUNE, ANYHIT, false>(sc, o, d, inv, slack));
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(FULL, ray >= 0) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---------------- traverse ----------------
+        // Two warp-synchronous phases per macro-step ("while-while" with votes):
+        //   inner phase: lanes standing at an inner node visit it, one node per iteration, for as
+        //                long as at least `inner_thresh` lanes want to (lanes that reached a leaf or
+        //                finished wait) -- or until nobody waits at a leaf;
+        //   leaf phase : every lane standing at a leaf tests its triangles and pops.
+        // Measured before this split (profiles/r1b): 70% of all issued instructions were inner-node
+        // visits running at 5.8 of 32 lanes, because the warp waited for its longest walk per leaf.
+        unsigned busy;
+        do {
+            while (true) {
+                const bool at_inner = (ray >= 0) && (ref >= 0);
+                const unsigned m_inner = __ballot_sync(FULL, at_inner);
+                if (m_inner == 0u) break;
+                if (__popc(m_inner) < inner_thresh) {
+                    const unsigned m_leaf = __ballot_sync(FULL, (ray >= 0) && (ref < 0));
+                    if (m_leaf != 0u) break;
+                }
+                if (at_inner) {
+                    const float4* nd = sc.nodes + (size_t)ref * 4;
+                    float4 q0 = ldg4(nd + 0), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
+                    float d1, d2, e1, e2;
+                    bool h1 = box_test<true>(o, inv, q0, q1, d1, e1);
+                    bool h2 = box_test<true>(o, inv, q2, q3, d2, e2);
+                    int rl = __float_as_int(q0.w), rr = __float_as_int(q1.w);
+                    if (PRUNE) {
+                        if (h1 && prune_test(e1, best, slack)) h1 = false;
+                        if (h2 && prune_test(e2, best, slack)) h2 = false;
+                    }
+                    if (h1 && h2) {
+                        bool leftFirst = d1 < d2;
+                        if (PRUNE) stack_t0[sp] = leftFirst ? e2 : e1;
+                        stack[sp++] = leftFirst ? rr : rl;
+                        ref = leftFirst ? rl : rr;
+                    } else if (h1) {
+                        ref = rl;
+                    } else if (h2) {
+                        ref = rr;
+                    } else {  // pop
+                        ref = EZRT_REF_DONE;
+                        while (sp > 0) {
+                            --sp;
+                            if (PRUNE && prune_test(stack_t0[sp], best, slack)) continue;
+                            ref = stack[sp];
+                            break;
+                        }
+                    }
+                }
+            }
+            if (ray >= 0 && ref < 0) {  // lanes still at an inner node (vote cut the phase short) skip this
+                if (ref != EZRT_REF_DONE) {  // leaf: hitArray(index, index+n-1)
+                    uint32_t bits = (uint32_t)ref & 0x7fffffffu;
+                    int cnt = (int)(bits & 127u);
+                    int first = (int)(bits >> 7);
+                    const float4* rec = sc.tri_geo + (size_t)first * 4;
+                    bool stop = false;
+                    for (int i = 0; i < cnt; i++, rec += 4) {
+                        float t;
+                        if (tri_test(rec, o, d, best, t)) {
+                            best = t;
+                            best_tri = first + i;
+                            if (ANYHIT) { stop = true; break; }
+                        }
+                    }
+                    ref = EZRT_REF_DONE;
+                    if (!stop) {
+                        while (sp > 0) {
+                            --sp;
+                            if (PRUNE && prune_test(stack_t0[sp], best, slack)) continue;
+                            ref = stack[sp];
+                            break;
+                        }
+                    }
+                }
+                if (ref == EZRT_REF_DONE) {  // ray finished
+                    HitRec h;
+                    h.t = best;
+                    h.tri = best_tri;
+                    io.store((uint32_t)ray, h);
+                    ray = -1;
+                }
+            }
+            busy = __ballot_sync(FULL, ray >= 0);
+        } while (busy != 0u && (exhausted || __popc(busy) >= refill_thresh));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // hit geometry + material for the final closest hit (tail of hitTriangle :198-214, getMaterial :110-135)
 // ------------------------------------------------------------------------------------------
 struct MaterialDev {

@@ -39,6 +39,8 @@ struct SceneDev {
     int n_triangles;
     int n_inner;
     float prune_delta;        // 2^-16 * max |vertex coordinate|
+    int refill_thresh;        // persistent traversal tunables (env EZRT_REFILL_T / EZRT_INNER_T)
+    int inner_thresh;
 };
 
 struct RenderDev {

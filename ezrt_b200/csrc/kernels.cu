@@ -69,49 +69,54 @@ __global__ void __launch_bounds__(256) k_generate(RenderDev rd, const TileDev* _
 // extend: closest hit for every ray of the queue.  Persistent warps fetch 32 rays at a time from
 // a global work counter so long traversals do not stall a statically assigned tail.
 // ------------------------------------------------------------------------------------------
+struct ExtendIO {
+    PathQueue q;
+    __device__ __forceinline__ void load(uint32_t i, vec3& o, vec3& d) const {
+        float4 o4 = q.ray_o[i], d4 = q.ray_d[i];
+        o = ez_v3(o4.x, o4.y, o4.z);
+        d = ez_v3(d4.x, d4.y, d4.z);
+    }
+    __device__ __forceinline__ void store(uint32_t i, HitRec h) const {
+        q.ray_o[i].w = h.t;
+        q.ray_d[i].w = __int_as_float(h.tri);
+    }
+};
+
 template <bool PRUNE>
 __global__ void __launch_bounds__(EZRT_EXTEND_THREADS) k_extend(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
                                                                 uint32_t* work) {
-    const uint32_t n = *q_count;
-    const int lane = threadIdx.x & 31;
-    while (true) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t i = base + (uint32_t)lane;
-        if (i < n) {
-            float4 o4 = q.ray_o[i], d4 = q.ray_d[i];
-            HitRec h = trace_ray<PRUNE, false>(sc, ez_v3(o4.x, o4.y, o4.z), ez_v3(d4.x, d4.y, d4.z));
-            q.ray_o[i].w = h.t;
-            q.ray_d[i].w = __int_as_float(h.tri);
-        }
-    }
+    ExtendIO io;
+    io.q = q;
+    extend_persistent<PRUNE, false>(sc, *q_count, work, io);
 }
+
+// shadow rays: any hit; an unoccluded ray adds its precomputed contribution (P5/fsh:829-841).
+// One path per sample slot -> no two lanes touch the same Lo entry.
+struct ShadowIO {
+    ShadowQueue sq;
+    float4* Lo;
+    __device__ __forceinline__ void load(uint32_t i, vec3& o, vec3& d) const {
+        float4 o4 = sq.ray_o[i], d4 = sq.ray_d[i];
+        o = ez_v3(o4.x, o4.y, o4.z);
+        d = ez_v3(d4.x, d4.y, d4.z);
+    }
+    __device__ __forceinline__ void store(uint32_t i, HitRec h) const {
+        if (h.tri >= 0) return;
+        uint32_t slot = __float_as_uint(sq.ray_o[i].w);
+        float4 c = sq.contrib[i];
+        float4 lo = Lo[slot];
+        lo.x += c.x; lo.y += c.y; lo.z += c.z;
+        Lo[slot] = lo;
+    }
+};
 
 template <bool PRUNE>
 __global__ void __launch_bounds__(EZRT_EXTEND_THREADS) k_shadow(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count,
                                                                 uint32_t* work, float4* __restrict__ Lo) {
-    const uint32_t n = *s_count;
-    const int lane = threadIdx.x & 31;
-    while (true) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        uint32_t i = base + (uint32_t)lane;
-        if (i < n) {
-            float4 o4 = sq.ray_o[i], d4 = sq.ray_d[i];
-            HitRec h = trace_ray<PRUNE, true>(sc, ez_v3(o4.x, o4.y, o4.z), ez_v3(d4.x, d4.y, d4.z));
-            if (h.tri < 0) {  // unoccluded: Lo += contribution (P5/fsh:829-841); one path per slot -> no race
-                uint32_t slot = __float_as_uint(o4.w);
-                float4 c = sq.contrib[i];
-                float4 lo = Lo[slot];
-                lo.x += c.x; lo.y += c.y; lo.z += c.z;
-                Lo[slot] = lo;
-            }
-        }
-    }
+    ShadowIO io;
+    io.sq = sq;
+    io.Lo = Lo;
+    extend_persistent<PRUNE, true>(sc, *s_count, work, io);
 }
 
 // ------------------------------------------------------------------------------------------
