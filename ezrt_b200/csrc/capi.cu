@@ -240,10 +240,10 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         float fl, fr;
         memcpy(&fl, &rl, 4);
         memcpy(&fr, &rr, 4);
-        g[0] = make_float4(L[6], L[7], L[8], fl);
-        g[1] = make_float4(L[9], L[10], L[11], fr);
-        g[2] = make_float4(R[6], R[7], R[8], 0.0f);
-        g[3] = make_float4(R[9], R[10], R[11], 0.0f);
+        g[0] = make_float4(L[6], L[7], L[9], L[10]);   // left : AA.x AA.y | BB.x BB.y
+        g[1] = make_float4(R[6], R[7], R[9], R[10]);   // right: AA.x AA.y | BB.x BB.y
+        g[2] = make_float4(L[8], L[11], R[8], R[11]);  // left AA.z BB.z  | right AA.z BB.z
+        g[3] = make_float4(fl, fr, 0.0f, 0.0f);        // child references
     }
 
     // ---- triangles: geometry records, shading records, de-duplicated material table ----
@@ -324,6 +324,8 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.prune_delta = max_abs * 1.52587890625e-05f;  // 2^-16 * scene extent (DESIGN.md "pruning")
     d.refill_thresh = 24;
     d.inner_thresh = 16;
+    d.leaf_thresh = 8;
+    if (const char* e = getenv("EZRT_LEAF_T")) d.leaf_thresh = std::max(1, std::min(33, atoi(e)));
     if (const char* e = getenv("EZRT_REFILL_T")) d.refill_thresh = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("EZRT_INNER_T")) d.inner_thresh = std::max(1, std::min(32, atoi(e)));
     *out_scene = sc;

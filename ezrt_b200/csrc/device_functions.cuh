@@ -70,26 +70,86 @@ struct HitRec {
     int tri;    // -1 on miss
 };
 
-// Slab test of one child box.  Returns whether the reference would push the child (d > 0) and
-// the distance d it sorts by; t0 is the entry distance (pruning only).  FAST: all 1/d finite,
-// no NaN can arise, so FMNMX (fminf/fmaxf) equals the GLSL ternary min/max; otherwise the
-// ternaries are used literally (NaN propagation as in the oracle).
+// ---- packed fp32x2 arithmetic (sm_100a FADD2 / FMUL2): two independent IEEE-rn operations per
+// instruction on an aligned register pair -- same bits as two scalar ops, half the issue slots.
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pk2_make(float lo, float hi) {
+    pk2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void pk2_split(pk2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ pk2 pk2_add(pk2 a, pk2 b) {
+    pk2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ pk2 pk2_mul(pk2 a, pk2 b) {
+    pk2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// Per-ray constants of the slab test: -origin and 1/direction as register pairs.
+struct RaySlab {
+    pk2 no_xy, no_zz, inv_xy, inv_zz;
+};
+__device__ __forceinline__ RaySlab make_ray_slab(vec3 o, vec3 inv) {
+    RaySlab r;
+    r.no_xy = pk2_make(-o.x, -o.y);
+    r.no_zz = pk2_make(-o.z, -o.z);
+    r.inv_xy = pk2_make(inv.x, inv.y);
+    r.inv_zz = pk2_make(inv.z, inv.z);
+    return r;
+}
+
+struct NodeVisit {
+    bool h1, h2;        // would the shader push the left / right child (hitAABB > 0, P5/fsh:290-302)
+    float d1, d2;       // hitAABB distances the children are ordered by
+    float e1, e2;       // slab entry distances (pruning only)
+    int rl, rr;         // child references
+};
+
+// hitAABB (P5/fsh:220-233) for both children of one inner node: (BB - S) * invdir and
+// (AA - S) * invdir as 6 FADD2 + 6 FMUL2 ((x - s) == (x + (-s)) exactly), then min/max.
+// FAST: all 1/d finite, no NaN can arise, FMNMX equals the GLSL ternaries; otherwise the
+// ternaries are evaluated literally (NaN behaviour of the oracle).
 template <bool FAST>
-__device__ __forceinline__ bool box_test(vec3 o, vec3 inv, float4 qa, float4 qb, float& dist, float& t0out) {
-    float fx = (qb.x - o.x) * inv.x, fy = (qb.y - o.y) * inv.y, fz = (qb.z - o.z) * inv.z;
-    float nx = (qa.x - o.x) * inv.x, ny = (qa.y - o.y) * inv.y, nz = (qa.z - o.z) * inv.z;
-    float t1, t0;
+__device__ __forceinline__ NodeVisit node_visit(const float4* __restrict__ nd, const RaySlab& rs) {
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(nd);
+    ulonglong2 q0 = __ldg(p + 0), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
+    int2 refs = __ldg(reinterpret_cast<const int2*>(nd + 3));
+    float lnx, lny, lfx, lfy, rnx, rny, rfx, rfy, lnz, lfz, rnz, rfz;
+    pk2_split(pk2_mul(pk2_add(q0.x, rs.no_xy), rs.inv_xy), lnx, lny);  // left  (AA - S) * inv, x y
+    pk2_split(pk2_mul(pk2_add(q0.y, rs.no_xy), rs.inv_xy), lfx, lfy);  // left  (BB - S) * inv, x y
+    pk2_split(pk2_mul(pk2_add(q1.x, rs.no_xy), rs.inv_xy), rnx, rny);  // right (AA - S) * inv, x y
+    pk2_split(pk2_mul(pk2_add(q1.y, rs.no_xy), rs.inv_xy), rfx, rfy);  // right (BB - S) * inv, x y
+    pk2_split(pk2_mul(pk2_add(q2.x, rs.no_zz), rs.inv_zz), lnz, lfz);  // left  z: (AA.z, BB.z)
+    pk2_split(pk2_mul(pk2_add(q2.y, rs.no_zz), rs.inv_zz), rnz, rfz);  // right z
+    float lt1, lt0, rt1, rt0;
     if (FAST) {
-        t1 = fminf(fmaxf(fx, nx), fminf(fmaxf(fy, ny), fmaxf(fz, nz)));
-        t0 = fmaxf(fminf(fx, nx), fmaxf(fminf(fy, ny), fminf(fz, nz)));
+        lt1 = fminf(fmaxf(lfx, lnx), fminf(fmaxf(lfy, lny), fmaxf(lfz, lnz)));
+        lt0 = fmaxf(fminf(lfx, lnx), fmaxf(fminf(lfy, lny), fminf(lfz, lnz)));
+        rt1 = fminf(fmaxf(rfx, rnx), fminf(fmaxf(rfy, rny), fmaxf(rfz, rnz)));
+        rt0 = fmaxf(fminf(rfx, rnx), fmaxf(fminf(rfy, rny), fminf(rfz, rnz)));
     } else {
-        t1 = ez_min(ez_max(fx, nx), ez_min(ez_max(fy, ny), ez_max(fz, nz)));
-        t0 = ez_max(ez_min(fx, nx), ez_max(ez_min(fy, ny), ez_min(fz, nz)));
+        lt1 = ez_min(ez_max(lfx, lnx), ez_min(ez_max(lfy, lny), ez_max(lfz, lnz)));
+        lt0 = ez_max(ez_min(lfx, lnx), ez_max(ez_min(lfy, lny), ez_min(lfz, lnz)));
+        rt1 = ez_min(ez_max(rfx, rnx), ez_min(ez_max(rfy, rny), ez_max(rfz, rnz)));
+        rt0 = ez_max(ez_min(rfx, rnx), ez_max(ez_min(rfy, rny), ez_min(rfz, rnz)));
     }
-    t0out = t0;
-    float d = (t1 >= t0) ? ((t0 > 0.0f) ? t0 : t1) : -1.0f;
-    dist = d;
-    return d > 0.0f;
+    NodeVisit v;
+    v.e1 = lt0;
+    v.e2 = rt0;
+    v.d1 = (lt1 >= lt0) ? ((lt0 > 0.0f) ? lt0 : lt1) : -1.0f;
+    v.d2 = (rt1 >= rt0) ? ((rt0 > 0.0f) ? rt0 : rt1) : -1.0f;
+    v.h1 = v.d1 > 0.0f;
+    v.h2 = v.d2 > 0.0f;
+    v.rl = refs.x;
+    v.rr = refs.y;
+    return v;
 }
 
 // Ray/triangle test against the repacked record.  Accepts exactly the hits hitTriangle accepts
@@ -130,6 +190,7 @@ __device__ __forceinline__ HitRec trace_impl(const SceneDev& sc, vec3 o, vec3 d,
     int sp = 0;
     int ref = sc.root_ref;
     float ref_t0 = -1.0f;
+    const RaySlab rs = make_ray_slab(o, inv);
     while (true) {
         if (ref < 0) {  // leaf: hitArray(index, index+n-1)
             uint32_t bits = (uint32_t)ref & 0x7fffffffu;
@@ -145,12 +206,10 @@ __device__ __forceinline__ HitRec trace_impl(const SceneDev& sc, vec3 o, vec3 d,
                 }
             }
         } else {
-            const float4* nd = sc.nodes + (size_t)ref * 4;
-            float4 q0 = ldg4(nd + 0), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
-            float d1, d2, e1, e2;
-            bool h1 = box_test<FAST>(o, inv, q0, q1, d1, e1);
-            bool h2 = box_test<FAST>(o, inv, q2, q3, d2, e2);
-            int rl = __float_as_int(q0.w), rr = __float_as_int(q1.w);
+            NodeVisit nv = node_visit<FAST>(sc.nodes + (size_t)ref * 4, rs);
+            bool h1 = nv.h1, h2 = nv.h2;
+            const float d1 = nv.d1, d2 = nv.d2, e1 = nv.e1, e2 = nv.e2;
+            const int rl = nv.rl, rr = nv.rr;
             if (PRUNE) {
                 if (h1 && prune_test(e1, res.t, slack)) h1 = false;
                 if (h2 && prune_test(e2, res.t, slack)) h2 = false;
@@ -214,6 +273,7 @@ template <bool PRUNE, bool ANYHIT, class RayIO>
 __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n, uint32_t* work, RayIO io) {
     const int refill_thresh = sc.refill_thresh;  // go back to refill when fewer lanes than this are busy
     const int inner_thresh = sc.inner_thresh;    // leave the inner-node phase when fewer lanes than this walk
+    const int leaf_thresh = sc.leaf_thresh;      // ... or when at least this many lanes wait at a leaf
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -223,6 +283,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
     int ray = -1;              // index of the ray this lane is tracing, -1 = idle
     int ref = EZRT_REF_DONE;
     vec3 o = splat3(0.0f), d = splat3(0.0f), inv = splat3(0.0f);
+    RaySlab rs = make_ray_slab(o, inv);
     float slack = 0.0f, best = EZ_INF;
     int best_tri = -1;
     bool exhausted = false;    // warp-uniform: the work counter has run past n
@@ -245,6 +306,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
                     float ax = ez_abs(inv.x), ay = ez_abs(inv.y), az = ez_abs(inv.z);
                     slack = sc.prune_delta * ez_max(ax, ez_max(ay, az));
                     if ((ax < 3.0e38f) && (ay < 3.0e38f) && (az < 3.0e38f)) {
+                        rs = make_ray_slab(o, inv);
                         ray = (int)idx;
                         ref = sc.root_ref;
                         sp = 0;
@@ -274,17 +336,13 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
                 const bool at_inner = (ray >= 0) && (ref >= 0);
                 const unsigned m_inner = __ballot_sync(FULL, at_inner);
                 if (m_inner == 0u) break;
-                if (__popc(m_inner) < inner_thresh) {
-                    const unsigned m_leaf = __ballot_sync(FULL, (ray >= 0) && (ref < 0));
-                    if (m_leaf != 0u) break;
-                }
+                const unsigned m_wait = __ballot_sync(FULL, (ray >= 0) && (ref < 0));
+                if (m_wait != 0u && (__popc(m_inner) < inner_thresh || __popc(m_wait) >= leaf_thresh)) break;
                 if (at_inner) {
-                    const float4* nd = sc.nodes + (size_t)ref * 4;
-                    float4 q0 = ldg4(nd + 0), q1 = ldg4(nd + 1), q2 = ldg4(nd + 2), q3 = ldg4(nd + 3);
-                    float d1, d2, e1, e2;
-                    bool h1 = box_test<true>(o, inv, q0, q1, d1, e1);
-                    bool h2 = box_test<true>(o, inv, q2, q3, d2, e2);
-                    int rl = __float_as_int(q0.w), rr = __float_as_int(q1.w);
+                    NodeVisit nv = node_visit<true>(sc.nodes + (size_t)ref * 4, rs);
+                    bool h1 = nv.h1, h2 = nv.h2;
+                    const float d1 = nv.d1, d2 = nv.d2, e1 = nv.e1, e2 = nv.e2;
+                    const int rl = nv.rl, rr = nv.rr;
                     if (PRUNE) {
                         if (h1 && prune_test(e1, best, slack)) h1 = false;
                         if (h2 && prune_test(e2, best, slack)) h2 = false;
@@ -309,38 +367,75 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
                     }
                 }
             }
-            if (ray >= 0 && ref < 0) {  // lanes still at an inner node (vote cut the phase short) skip this
-                if (ref != EZRT_REF_DONE) {  // leaf: hitArray(index, index+n-1)
-                    uint32_t bits = (uint32_t)ref & 0x7fffffffu;
-                    int cnt = (int)(bits & 127u);
-                    int first = (int)(bits >> 7);
-                    const float4* rec = sc.tri_geo + (size_t)first * 4;
-                    bool stop = false;
-                    for (int i = 0; i < cnt; i++, rec += 4) {
+            // ---- leaf phase, warp-cooperative: the warp takes up to four waiting leaves at a time
+            // and gives each an octet of lanes, one triangle per lane (leaves hold <= 8 triangles in
+            // reference-built trees; longer leaves take several passes).  The owner's ray travels by
+            // shuffle; the octet's hits are min-reduced on the key (t bits, triangle index), which is
+            // hitArray's "strictly closer, first index wins" rule (P5/fsh:242-249).
+            const bool at_leaf = (ray >= 0) && (ref < 0) && (ref != EZRT_REF_DONE);
+            unsigned m_leaf = __ballot_sync(FULL, at_leaf);
+            const uint32_t my_bits = (uint32_t)ref & 0x7fffffffu;
+            const int my_cnt = at_leaf ? (int)(my_bits & 127u) : 0;
+            const int my_first = (int)(my_bits >> 7);
+            bool stop = false;
+            while (m_leaf != 0u) {
+                int j0 = __ffs(m_leaf) - 1; m_leaf &= m_leaf - 1u;
+                int j1 = -1, j2 = -1, j3 = -1;
+                if (m_leaf) { j1 = __ffs(m_leaf) - 1; m_leaf &= m_leaf - 1u; }
+                if (m_leaf) { j2 = __ffs(m_leaf) - 1; m_leaf &= m_leaf - 1u; }
+                if (m_leaf) { j3 = __ffs(m_leaf) - 1; m_leaf &= m_leaf - 1u; }
+                const int q = lane >> 3, k = lane & 7;
+                const int owner = (q == 0) ? j0 : (q == 1) ? j1 : (q == 2) ? j2 : j3;
+                const int src = (owner < 0) ? lane : owner;
+                vec3 ro, rdir;
+                ro.x = __shfl_sync(FULL, o.x, src); ro.y = __shfl_sync(FULL, o.y, src); ro.z = __shfl_sync(FULL, o.z, src);
+                rdir.x = __shfl_sync(FULL, d.x, src); rdir.y = __shfl_sync(FULL, d.y, src); rdir.z = __shfl_sync(FULL, d.z, src);
+                const float rbest = __shfl_sync(FULL, best, src);
+                const int rfirst = __shfl_sync(FULL, my_first, src);
+                const int rcnt_all = __shfl_sync(FULL, my_cnt, src);  // every lane must take part in the shuffle
+                const int rcnt = (owner < 0) ? 0 : rcnt_all;
+                unsigned long long key = 0xffffffffffffffffull;
+                for (int kb = 0; __ballot_sync(FULL, kb < rcnt) != 0u; kb += 8) {
+                    const int ti = kb + k;
+                    if (ti < rcnt) {
                         float t;
-                        if (tri_test(rec, o, d, best, t)) {
-                            best = t;
-                            best_tri = first + i;
-                            if (ANYHIT) { stop = true; break; }
-                        }
-                    }
-                    ref = EZRT_REF_DONE;
-                    if (!stop) {
-                        while (sp > 0) {
-                            --sp;
-                            if (PRUNE && prune_test(stack_t0[sp], best, slack)) continue;
-                            ref = stack[sp];
-                            break;
+                        if (tri_test(sc.tri_geo + (size_t)(rfirst + ti) * 4, ro, rdir, rbest, t)) {
+                            unsigned long long kk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)(rfirst + ti);
+                            key = (kk < key) ? kk : key;
                         }
                     }
                 }
-                if (ref == EZRT_REF_DONE) {  // ray finished
-                    HitRec h;
-                    h.t = best;
-                    h.tri = best_tri;
-                    io.store((uint32_t)ray, h);
-                    ray = -1;
+                // min over the octet
+                for (int off = 1; off < 8; off <<= 1) {
+                    unsigned long long other = __shfl_xor_sync(FULL, key, off);
+                    key = (other < key) ? other : key;
                 }
+                // owners read the result of their octet
+                const int back = (lane == j0) ? 0 : (lane == j1) ? 8 : (lane == j2) ? 16 : (lane == j3) ? 24 : lane;
+                const unsigned long long res = __shfl_sync(FULL, key, back);
+                if (at_leaf && (lane == j0 || lane == j1 || lane == j2 || lane == j3) && res != 0xffffffffffffffffull) {
+                    best = __uint_as_float((unsigned)(res >> 32));
+                    best_tri = (int)(unsigned)(res & 0xffffffffull);
+                    if (ANYHIT) stop = true;
+                }
+            }
+            if (at_leaf) {  // pop (hitBVH continues with the next stack entry)
+                ref = EZRT_REF_DONE;
+                if (!stop) {
+                    while (sp > 0) {
+                        --sp;
+                        if (PRUNE && prune_test(stack_t0[sp], best, slack)) continue;
+                        ref = stack[sp];
+                        break;
+                    }
+                }
+            }
+            if (ray >= 0 && ref == EZRT_REF_DONE) {  // ray finished
+                HitRec h;
+                h.t = best;
+                h.tri = best_tri;
+                io.store((uint32_t)ray, h);
+                ray = -1;
             }
             busy = __ballot_sync(FULL, ray >= 0);
         } while (busy != 0u && (exhausted || __popc(busy) >= refill_thresh));

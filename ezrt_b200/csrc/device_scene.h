@@ -5,9 +5,10 @@
 //
 //   inner node (64 B, "children in parent"): one 4 x float4 record per INNER node holding both
 //       child boxes and both child references, so a traversal step is one 64-byte fetch instead
-//       of the shader's three dependent 48-byte getBVHNode()s (P5/fsh:266,281,285):
-//         q0 = (AA_left.xyz , ref_left )   q1 = (BB_left.xyz , ref_right)
-//         q2 = (AA_right.xyz, 0)           q3 = (BB_right.xyz, 0)
+//       of the shader's three dependent 48-byte getBVHNode()s (P5/fsh:266,281,285).  Components
+//       are paired for the packed FADD2/FMUL2 slab arithmetic:
+//         q0 = (AA_l.x, AA_l.y, BB_l.x, BB_l.y)   q1 = (AA_r.x, AA_r.y, BB_r.x, BB_r.y)
+//         q2 = (AA_l.z, BB_l.z, AA_r.z, BB_r.z)   q3 = (ref_left, ref_right, 0, 0)
 //       ref >= 0 : index of an inner-node record;  ref < 0 : leaf, bits = 1|index(24)|n(7)
 //   triangle geometry (64 B): q0 = (p1, N.x) q1 = (p2, N.y) q2 = (p3, N.z) q3 = (d0,0,0,0)
 //       N = normalize(cross(p2-p1, p3-p1)) and d0 = dot(N,p1) are the ray-independent part of
@@ -41,6 +42,7 @@ struct SceneDev {
     float prune_delta;        // 2^-16 * max |vertex coordinate|
     int refill_thresh;        // persistent traversal tunables (env EZRT_REFILL_T / EZRT_INNER_T)
     int inner_thresh;
+    int leaf_thresh;
 };
 
 struct RenderDev {

@@ -10,6 +10,8 @@
 // No host synchronisation inside a render: queue sizes live in device counters.
 #include "kernels.h"
 
+#include <cstdlib>
+
 #include "device_functions.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -363,6 +365,16 @@ __global__ void k_partition_scatter(const float* __restrict__ compact, float* __
 // ------------------------------------------------------------------------------------------
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// resident persistent blocks per SM for the extend/shadow kernels (env EZRT_EXTEND_BPS overrides)
+static int extend_blocks_per_sm() {
+    static int v = 0;
+    if (v == 0) {
+        v = EZRT_EXTEND_BLOCKS_PER_SM;
+        if (const char* e = getenv("EZRT_EXTEND_BPS")) v = std::max(1, std::min(16, atoi(e)));
+    }
+    return v;
+}
+
 void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots, uint32_t batch_first_frame, PathQueue q,
                      uint32_t* q_count, int n_sms, cudaStream_t st) {
     int blocks = std::min(div_up(n_slots, 256), n_sms * 8);
@@ -370,14 +382,14 @@ void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots
 }
 void launch_extend(const SceneDev& sc, bool prune, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t n_max,
                    int n_sms, cudaStream_t st) {
-    int blocks = std::min(div_up(n_max, EZRT_EXTEND_THREADS), n_sms * EZRT_EXTEND_BLOCKS_PER_SM);
+    int blocks = std::min(div_up(n_max, EZRT_EXTEND_THREADS), n_sms * extend_blocks_per_sm());
     if (blocks < 1) blocks = 1;
     if (prune) k_extend<true><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, q, q_count, work);
     else k_extend<false><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, q, q_count, work);
 }
 void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo,
                    uint32_t n_max, int n_sms, cudaStream_t st) {
-    int blocks = std::min(div_up(n_max, EZRT_EXTEND_THREADS), n_sms * EZRT_EXTEND_BLOCKS_PER_SM);
+    int blocks = std::min(div_up(n_max, EZRT_EXTEND_THREADS), n_sms * extend_blocks_per_sm());
     if (blocks < 1) blocks = 1;
     if (prune) k_shadow<true><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, sq, s_count, work, Lo);
     else k_shadow<false><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, sq, s_count, work, Lo);
