@@ -77,7 +77,8 @@ struct ezrt_scene {
     int n_materials = 0;
     int tree_depth = 0;
     // render state (lazily sized)
-    DeviceBuffer tiles_buf, queue_buf[2], shadow_buf, lo_buf, le_buf, counters_buf, totals_buf, fb_buf;
+    DeviceBuffer tiles_buf, queue_buf[2], shadow_buf, lo_buf, le_buf, counters_buf, totals_buf, fb_buf, sort_buf;
+    int sort_rays = 1;  // env EZRT_SORT_RAYS=0 disables the bounce-ray sort
     int tiles_key[4] = {-1, -1, -1, -1};
     std::vector<TileDev> tiles;
     cudaStream_t own_stream = nullptr;
@@ -251,10 +252,15 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     std::map<std::string, int> mat_ids;
     std::vector<float4> mats;
     float max_abs = 0.0f;
+    float bmin[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bmax[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
     for (int i = 0; i < n_triangles; i++) {
         const float* s = tris + (size_t)i * EZRT_TRIANGLE_FLOATS;
         ez_vec3 p1 = ez_v3(s[0], s[1], s[2]), p2 = ez_v3(s[3], s[4], s[5]), p3 = ez_v3(s[6], s[7], s[8]);
-        for (int k = 0; k < 9; k++) max_abs = ez_max(max_abs, ez_abs(s[k]));
+        for (int k = 0; k < 9; k++) {
+            max_abs = ez_max(max_abs, ez_abs(s[k]));
+            if (s[k] < bmin[k % 3]) bmin[k % 3] = s[k];
+            if (s[k] > bmax[k % 3]) bmax[k % 3] = s[k];
+        }
         ez_vec3 N = ez_normalize(ez_cross(ez_sub(p2, p1), ez_sub(p3, p1)));  // hitTriangle, P5/fsh:172
         float d0 = ez_dot(N, p1);                                            // P5/fsh:184
         geo[(size_t)i * 4 + 0] = make_float4(p1.x, p1.y, p1.z, N.x);
@@ -322,9 +328,17 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.n_triangles = n_triangles;
     d.n_inner = n_inner;
     d.prune_delta = max_abs * 1.52587890625e-05f;  // 2^-16 * scene extent (DESIGN.md "pruning")
+    for (int k = 0; k < 3; k++) {
+        d.bmin[k] = bmin[k];
+        float ext = bmax[k] - bmin[k];
+        d.cell_scale[k] = (ext > 0.0f) ? 32.0f / ext : 0.0f;
+    }
+    if (const char* e = getenv("EZRT_SORT_RAYS")) sc->sort_rays = atoi(e);
     d.refill_thresh = 24;
     d.inner_thresh = 16;
     d.leaf_thresh = 8;
+    d.work_chunk = 128;
+    if (const char* e = getenv("EZRT_CHUNK")) d.work_chunk = std::max(32, std::min(65536, atoi(e)));
     if (const char* e = getenv("EZRT_LEAF_T")) d.leaf_thresh = std::max(1, std::min(33, atoi(e)));
     if (const char* e = getenv("EZRT_REFILL_T")) d.refill_thresh = std::max(1, std::min(32, atoi(e)));
     if (const char* e = getenv("EZRT_INNER_T")) d.inner_thresh = std::max(1, std::min(32, atoi(e)));
@@ -338,7 +352,7 @@ int ezrt_scene_destroy(ezrt_scene* s) {
     s->nodes.release(); s->tri_geo.release(); s->tri_shade.release(); s->materials.release();
     s->hdr.release(); s->hdr_cache.release(); s->tiles_buf.release();
     s->queue_buf[0].release(); s->queue_buf[1].release(); s->shadow_buf.release();
-    s->lo_buf.release(); s->le_buf.release(); s->counters_buf.release(); s->totals_buf.release(); s->fb_buf.release();
+    s->lo_buf.release(); s->le_buf.release(); s->counters_buf.release(); s->totals_buf.release(); s->fb_buf.release(); s->sort_buf.release();
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
     if (s->ev_stop) cudaEventDestroy(s->ev_stop);
@@ -407,6 +421,10 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     uint32_t *q_count = cnt, *s_count = cnt + n_stages, *w_ext = cnt + 2 * n_stages, *w_sh = cnt + 3 * n_stages;
     float4* Lo = (float4*)s->lo_buf.p;
     float4* Le = (float4*)s->le_buf.p;
+    if ((rc = s->sort_buf.ensure(sizeof(uint32_t) * (2 * capacity + EZRT_SORT_BINS + 64)))) return rc;
+    uint32_t* sort_keys = (uint32_t*)s->sort_buf.p;
+    uint32_t* sort_perm = sort_keys + capacity;
+    uint32_t* sort_bins = sort_perm + capacity;
 
     for (int done = 0; done < p->spp; done += F) {
         const int nf = std::min(F, p->spp - done);
@@ -420,8 +438,16 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
         for (int b = 0; b <= p->max_bounce; b++) {
             PathQueue& qin = q[b & 1];
             PathQueue& qout = q[(b + 1) & 1];
+            const uint32_t* perm = nullptr;
+            if (b > 0 && s->sort_rays) {  // camera rays are coherent as generated; bounce rays are sorted
+                sp = s->span_begin(3, st);
+                launch_ray_sort(s->dev, qin, &q_count[b], sort_keys, sort_bins, sort_perm, n_slots, s->n_sms, st);
+                s->span_end(sp, st);
+                s->launches += 3;
+                perm = sort_perm;
+            }
             sp = s->span_begin(0, st);
-            launch_extend(s->dev, prune, qin, &q_count[b], &w_ext[b], n_slots, s->n_sms, st);
+            launch_extend(s->dev, prune, qin, &q_count[b], &w_ext[b], perm, n_slots, s->n_sms, st);
             s->span_end(sp, st);
             sp = s->span_begin(1, st);
             launch_shade(s->dev, rd, d_tiles, b, batch_first, qin, &q_count[b], qout, &q_count[b + 1], sq, &s_count[b], Lo, Le,

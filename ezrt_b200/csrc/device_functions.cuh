@@ -92,6 +92,15 @@ __device__ __forceinline__ pk2 pk2_mul(pk2 a, pk2 b) {
     return r;
 }
 
+// 256-bit read-only global loads (32-byte aligned)
+__device__ __forceinline__ void ldg256_b64(const void* p, ulonglong2& a, ulonglong2& b) {
+    asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a.x), "=l"(a.y), "=l"(b.x), "=l"(b.y) : "l"(p));
+}
+__device__ __forceinline__ void ldg256_f32(const void* p, float4& a, float4& b) {
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
 // Per-ray constants of the slab test: -origin and 1/direction as register pairs.
 struct RaySlab {
     pk2 no_xy, no_zz, inv_xy, inv_zz;
@@ -118,9 +127,12 @@ struct NodeVisit {
 // ternaries are evaluated literally (NaN behaviour of the oracle).
 template <bool FAST>
 __device__ __forceinline__ NodeVisit node_visit(const float4* __restrict__ nd, const RaySlab& rs) {
-    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(nd);
-    ulonglong2 q0 = __ldg(p + 0), q1 = __ldg(p + 1), q2 = __ldg(p + 2);
-    int2 refs = __ldg(reinterpret_cast<const int2*>(nd + 3));
+    // the 64-byte record as two 256-bit loads (sm_100a LDG.E.256): the traversal is bound by L1
+    // wavefronts -- every lane reads a different line -- so half the load instructions is half the cost
+    ulonglong2 q0, q1, q2, q3;
+    ldg256_b64(nd, q0, q1);
+    ldg256_b64(nd + 2, q2, q3);
+    int2 refs = make_int2((int)(unsigned)(q3.x & 0xffffffffull), (int)(unsigned)(q3.x >> 32));
     float lnx, lny, lfx, lfy, rnx, rny, rfx, rfy, lnz, lfz, rnz, rfz;
     pk2_split(pk2_mul(pk2_add(q0.x, rs.no_xy), rs.inv_xy), lnx, lny);  // left  (AA - S) * inv, x y
     pk2_split(pk2_mul(pk2_add(q0.y, rs.no_xy), rs.inv_xy), lfx, lfy);  // left  (BB - S) * inv, x y
@@ -155,7 +167,9 @@ __device__ __forceinline__ NodeVisit node_visit(const float4* __restrict__ nd, c
 // Ray/triangle test against the repacked record.  Accepts exactly the hits hitTriangle accepts
 // that are also strictly closer than `best` (the only ones hitArray/hitBVH can keep).
 __device__ __forceinline__ bool tri_test(const float4* __restrict__ rec, vec3 o, vec3 d, float best, float& tout) {
-    float4 q0 = ldg4(rec + 0), q1 = ldg4(rec + 1), q2 = ldg4(rec + 2), q3 = ldg4(rec + 3);
+    float4 q0, q1, q2, q3;
+    ldg256_f32(rec, q0, q1);
+    ldg256_f32(rec + 2, q2, q3);
     vec3 N = ez_v3(q0.w, q1.w, q2.w);
     float nd = ez_dot(N, d);
     if (ez_abs(nd) < 0.00001f) return false;                    // :181 (|dot(+-N,d)| is sign-free)
@@ -277,8 +291,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    int stack[EZRT_MAX_STACK];
-    float stack_t0[PRUNE ? EZRT_MAX_STACK : 1];
+    int2 stack[EZRT_MAX_STACK];  // (child reference, slab entry distance bits): one 8-byte local store / load
     int sp = 0;
     int ray = -1;              // index of the ray this lane is tracing, -1 = idle
     int ref = EZRT_REF_DONE;
@@ -287,20 +300,26 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
     float slack = 0.0f, best = EZ_INF;
     int best_tri = -1;
     bool exhausted = false;    // warp-uniform: the work counter has run past n
+    uint32_t chunk_pos = 0, chunk_end = 0;  // warp-uniform: this warp's current range of ray indices
+    const uint32_t chunk = (uint32_t)sc.work_chunk;
 
     while (true) {
         // ---------------- refill idle lanes ----------------
+        // Work is taken in per-warp chunks of `chunk` consecutive rays (one atomicAdd per chunk): the
+        // lanes of a warp keep tracing neighbours of the (sorted) ray order even as they refill.
         unsigned need = __ballot_sync(FULL, ray < 0);
         if (need != 0u && !exhausted) {
-            int cnt = __popc(need);
-            int leader = __ffs(need) - 1;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(work, (uint32_t)cnt);
-            base = __shfl_sync(FULL, base, leader);
-            if (base + (uint32_t)cnt >= n) exhausted = true;
-            if (ray < 0) {
-                uint32_t idx = base + (uint32_t)__popc(need & lt_mask);
-                if (idx < n) {
+            if (chunk_pos >= chunk_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(work, chunk);
+                base = __shfl_sync(FULL, base, 0);
+                chunk_pos = base;
+                chunk_end = (base + chunk < n) ? base + chunk : n;
+                if (base >= n) exhausted = true;
+            }
+            if (!exhausted && ray < 0) {
+                uint32_t idx = chunk_pos + (uint32_t)__popc(need & lt_mask);
+                if (idx < chunk_end) {
                     io.load(idx, o, d);
                     inv = ez_v3(EZ_DIV(1.0f, d.x), EZ_DIV(1.0f, d.y), EZ_DIV(1.0f, d.z));
                     float ax = ez_abs(inv.x), ay = ez_abs(inv.y), az = ez_abs(inv.z);
@@ -316,6 +335,10 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
                         io.store(idx, trace_impl<PRUNE, ANYHIT, false>(sc, o, d, inv, slack));
                     }
                 }
+            }
+            if (!exhausted) {
+                uint32_t take = (uint32_t)__popc(need);
+                chunk_pos = (chunk_pos + take < chunk_end) ? chunk_pos + take : chunk_end;
             }
         }
         if (__ballot_sync(FULL, ray >= 0) == 0u) {
@@ -349,8 +372,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
                     }
                     if (h1 && h2) {
                         bool leftFirst = d1 < d2;
-                        if (PRUNE) stack_t0[sp] = leftFirst ? e2 : e1;
-                        stack[sp++] = leftFirst ? rr : rl;
+                        stack[sp++] = make_int2(leftFirst ? rr : rl, __float_as_int(leftFirst ? e2 : e1));
                         ref = leftFirst ? rl : rr;
                     } else if (h1) {
                         ref = rl;
@@ -359,9 +381,9 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
                     } else {  // pop
                         ref = EZRT_REF_DONE;
                         while (sp > 0) {
-                            --sp;
-                            if (PRUNE && prune_test(stack_t0[sp], best, slack)) continue;
-                            ref = stack[sp];
+                            const int2 e = stack[--sp];
+                            if (PRUNE && prune_test(__int_as_float(e.y), best, slack)) continue;
+                            ref = e.x;
                             break;
                         }
                     }
@@ -423,9 +445,9 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
                 ref = EZRT_REF_DONE;
                 if (!stop) {
                     while (sp > 0) {
-                        --sp;
-                        if (PRUNE && prune_test(stack_t0[sp], best, slack)) continue;
-                        ref = stack[sp];
+                        const int2 e = stack[--sp];
+                        if (PRUNE && prune_test(__int_as_float(e.y), best, slack)) continue;
+                        ref = e.x;
                         break;
                     }
                 }

@@ -27,6 +27,8 @@
 #define EZRT_LEAF_MAX_N 127
 #define EZRT_TILE 16             // == EZRT_PART_TILE
 #define EZRT_TILE_PIXELS 256
+#define EZRT_SORT_BITS 18         // ray sort key: direction octant (3) | 5-5-5 Morton cell of the origin
+#define EZRT_SORT_BINS (1 << EZRT_SORT_BITS)
 
 struct SceneDev {
     const float4* nodes;      // 4 float4 per inner node
@@ -43,6 +45,9 @@ struct SceneDev {
     int refill_thresh;        // persistent traversal tunables (env EZRT_REFILL_T / EZRT_INNER_T)
     int inner_thresh;
     int leaf_thresh;
+    int work_chunk;           // rays a warp takes from the work counter at a time (env EZRT_CHUNK)
+    float bmin[3];            // scene bounding box (ray-sort cells)
+    float cell_scale[3];      // 32 / extent per axis
 };
 
 struct RenderDev {

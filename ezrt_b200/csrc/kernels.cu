@@ -71,24 +71,118 @@ __global__ void __launch_bounds__(256) k_generate(RenderDev rd, const TileDev* _
 // extend: closest hit for every ray of the queue.  Persistent warps fetch 32 rays at a time from
 // a global work counter so long traversals do not stall a statically assigned tail.
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// Ray sort (bounce rays): counting sort of ray indices by key = direction octant | Morton cell of
+// the origin.  Diffuse bounce rays leave the shade kernel in path order with unrelated directions;
+// after the sort the 32 rays a warp fetches start close together and head the same way, so their
+// traversals touch the same nodes (L1 hits, lanes finishing together).  Only the index permutation
+// is sorted: rays and results stay where they are, and every ray's result is independent of the
+// order in which rays are traced.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread5(uint32_t v) {  // 5 bits -> every third bit
+    v &= 31u;
+    v = (v | (v << 8)) & 0x100fu;
+    v = (v | (v << 4)) & 0x10c3u;
+    v = (v | (v << 2)) & 0x1249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t ray_sort_key(const SceneDev& sc, float4 o4, float4 d4) {
+    int cx = min(31, max(0, (int)((o4.x - sc.bmin[0]) * sc.cell_scale[0])));
+    int cy = min(31, max(0, (int)((o4.y - sc.bmin[1]) * sc.cell_scale[1])));
+    int cz = min(31, max(0, (int)((o4.z - sc.bmin[2]) * sc.cell_scale[2])));
+    uint32_t oct = (d4.x < 0.0f ? 1u : 0u) | (d4.y < 0.0f ? 2u : 0u) | (d4.z < 0.0f ? 4u : 0u);
+    return (oct << 15) | spread5((uint32_t)cx) | (spread5((uint32_t)cy) << 1) | (spread5((uint32_t)cz) << 2);
+}
+
+__global__ void __launch_bounds__(256) k_sort_hist(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count, uint32_t* __restrict__ keys,
+                                                   uint32_t* __restrict__ bins) {
+    const uint32_t n = *q_count;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t key = ray_sort_key(sc, q.ray_o[i], q.ray_d[i]);
+        keys[i] = key;
+        atomicAdd(&bins[key], 1u);
+    }
+}
+
+// exclusive scan of the EZRT_SORT_BINS counters, one block of 1024 threads
+__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* __restrict__ bins) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    constexpr int PER = 8;  // elements per thread per round
+    for (uint32_t base = 0; base < EZRT_SORT_BINS; base += 1024 * PER) {
+        uint32_t v[PER];
+        uint32_t sum = 0;
+        const uint32_t idx = base + (uint32_t)tid * PER;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            v[k] = bins[idx + k];
+            sum += v[k];
+        }
+        uint32_t incl = sum;
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = warp_sums[lane];
+            uint32_t wi = w;
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, wi, off);
+                if (lane >= off) wi += t;
+            }
+            warp_sums[lane] = wi - w;  // exclusive prefix of warp totals
+        }
+        __syncthreads();
+        uint32_t excl = carry + warp_sums[wid] + (incl - sum);
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            bins[idx + k] = excl;
+            excl += v[k];
+        }
+        __syncthreads();
+        if (tid == 1023) carry = excl;  // total so far
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict__ q_count, const uint32_t* __restrict__ keys,
+                                                      uint32_t* __restrict__ bins, uint32_t* __restrict__ perm) {
+    const uint32_t n = *q_count;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t pos = atomicAdd(&bins[keys[i]], 1u);
+        perm[pos] = i;
+    }
+}
+
 struct ExtendIO {
     PathQueue q;
+    const uint32_t* perm;  // null: trace in queue order
     __device__ __forceinline__ void load(uint32_t i, vec3& o, vec3& d) const {
-        float4 o4 = q.ray_o[i], d4 = q.ray_d[i];
+        const uint32_t j = perm ? perm[i] : i;
+        float4 o4 = q.ray_o[j], d4 = q.ray_d[j];
         o = ez_v3(o4.x, o4.y, o4.z);
         d = ez_v3(d4.x, d4.y, d4.z);
     }
     __device__ __forceinline__ void store(uint32_t i, HitRec h) const {
-        q.ray_o[i].w = h.t;
-        q.ray_d[i].w = __int_as_float(h.tri);
+        const uint32_t j = perm ? perm[i] : i;
+        q.ray_o[j].w = h.t;
+        q.ray_d[j].w = __int_as_float(h.tri);
     }
 };
 
 template <bool PRUNE>
-__global__ void __launch_bounds__(EZRT_EXTEND_THREADS) k_extend(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
-                                                                uint32_t* work) {
+__global__ void __launch_bounds__(EZRT_EXTEND_THREADS, EZRT_EXTEND_MIN_BLOCKS) k_extend(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
+                                                                uint32_t* work, const uint32_t* __restrict__ perm) {
     ExtendIO io;
     io.q = q;
+    io.perm = perm;
     extend_persistent<PRUNE, false>(sc, *q_count, work, io);
 }
 
@@ -113,7 +207,7 @@ struct ShadowIO {
 };
 
 template <bool PRUNE>
-__global__ void __launch_bounds__(EZRT_EXTEND_THREADS) k_shadow(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count,
+__global__ void __launch_bounds__(EZRT_EXTEND_THREADS, EZRT_EXTEND_MIN_BLOCKS) k_shadow(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count,
                                                                 uint32_t* work, float4* __restrict__ Lo) {
     ShadowIO io;
     io.sq = sq;
@@ -380,12 +474,21 @@ void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots
     int blocks = std::min(div_up(n_slots, 256), n_sms * 8);
     k_generate<<<blocks, 256, 0, st>>>(rd, tiles, n_slots, batch_first_frame, q, q_count);
 }
-void launch_extend(const SceneDev& sc, bool prune, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t n_max,
-                   int n_sms, cudaStream_t st) {
+void launch_extend(const SceneDev& sc, bool prune, PathQueue q, const uint32_t* q_count, uint32_t* work, const uint32_t* perm,
+                   uint32_t n_max, int n_sms, cudaStream_t st) {
     int blocks = std::min(div_up(n_max, EZRT_EXTEND_THREADS), n_sms * extend_blocks_per_sm());
     if (blocks < 1) blocks = 1;
-    if (prune) k_extend<true><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, q, q_count, work);
-    else k_extend<false><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, q, q_count, work);
+    if (prune) k_extend<true><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, q, q_count, work, perm);
+    else k_extend<false><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, q, q_count, work, perm);
+}
+// counting sort of the queue's ray indices into `perm` (3 kernels; bins must hold EZRT_SORT_BINS counters)
+void launch_ray_sort(const SceneDev& sc, PathQueue q, const uint32_t* q_count, uint32_t* keys, uint32_t* bins, uint32_t* perm,
+                     uint32_t n_max, int n_sms, cudaStream_t st) {
+    cudaMemsetAsync(bins, 0, sizeof(uint32_t) * EZRT_SORT_BINS, st);
+    int blocks = std::max(1, std::min(div_up(n_max, 256), n_sms * 8));
+    k_sort_hist<<<blocks, 256, 0, st>>>(sc, q, q_count, keys, bins);
+    k_sort_scan<<<1, 1024, 0, st>>>(bins);
+    k_sort_scatter<<<blocks, 256, 0, st>>>(q_count, keys, bins, perm);
 }
 void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo,
                    uint32_t n_max, int n_sms, cudaStream_t st) {

@@ -8,12 +8,17 @@
 
 // extend/shadow kernels: persistent blocks, EZRT_EXTEND_BLOCKS_PER_SM resident per SM
 #define EZRT_EXTEND_THREADS 128
-#define EZRT_EXTEND_BLOCKS_PER_SM 6
+#define EZRT_EXTEND_BLOCKS_PER_SM 8
+#ifndef EZRT_EXTEND_MIN_BLOCKS
+#define EZRT_EXTEND_MIN_BLOCKS 8   // register cap 64: 8 x 128 threads resident per SM
+#endif
 
 void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots, uint32_t batch_first_frame, PathQueue q,
                      uint32_t* q_count, int n_sms, cudaStream_t st);
-void launch_extend(const SceneDev& sc, bool prune, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t n_max,
-                   int n_sms, cudaStream_t st);
+void launch_extend(const SceneDev& sc, bool prune, PathQueue q, const uint32_t* q_count, uint32_t* work, const uint32_t* perm,
+                   uint32_t n_max, int n_sms, cudaStream_t st);
+void launch_ray_sort(const SceneDev& sc, PathQueue q, const uint32_t* q_count, uint32_t* keys, uint32_t* bins, uint32_t* perm,
+                     uint32_t n_max, int n_sms, cudaStream_t st);
 void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo,
                    uint32_t n_max, int n_sms, cudaStream_t st);
 void launch_shade(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, int bounce, uint32_t batch_first_frame,
