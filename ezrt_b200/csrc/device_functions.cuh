@@ -126,12 +126,35 @@ struct NodeVisit {
 // FAST: all 1/d finite, no NaN can arise, FMNMX equals the GLSL ternaries; otherwise the
 // ternaries are evaluated literally (NaN behaviour of the oracle).
 template <bool FAST>
+__device__ __forceinline__ NodeVisit node_visit_q(ulonglong2 q0, ulonglong2 q1, ulonglong2 q2, ulonglong2 q3, const RaySlab& rs);
+
+// record from global memory: two 256-bit loads (sm_100a LDG.E.256).  The traversal is bound by L1
+// wavefronts -- every lane reads a different line -- so half the load instructions is half the cost.
+template <bool FAST>
 __device__ __forceinline__ NodeVisit node_visit(const float4* __restrict__ nd, const RaySlab& rs) {
-    // the 64-byte record as two 256-bit loads (sm_100a LDG.E.256): the traversal is bound by L1
-    // wavefronts -- every lane reads a different line -- so half the load instructions is half the cost
     ulonglong2 q0, q1, q2, q3;
     ldg256_b64(nd, q0, q1);
     ldg256_b64(nd + 2, q2, q3);
+    return node_visit_q<FAST>(q0, q1, q2, q3, rs);
+}
+// record of the top tree levels from shared memory (stride EZRT_TOP_STRIDE float4 = 80 B, so the
+// 16-byte pieces of different records spread over the banks), else from global memory
+template <bool FAST>
+__device__ __forceinline__ NodeVisit node_visit_top(const SceneDev& sc, const float4* smem_top, int top_nodes, int ref, const RaySlab& rs) {
+    ulonglong2 q0, q1, q2, q3;
+    if (ref < top_nodes) {
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(smem_top + ref * EZRT_TOP_STRIDE);
+        q0 = p[0]; q1 = p[1]; q2 = p[2]; q3 = p[3];
+    } else {
+        const float4* nd = sc.nodes + (size_t)ref * 4;
+        ldg256_b64(nd, q0, q1);
+        ldg256_b64(nd + 2, q2, q3);
+    }
+    return node_visit_q<FAST>(q0, q1, q2, q3, rs);
+}
+
+template <bool FAST>
+__device__ __forceinline__ NodeVisit node_visit_q(ulonglong2 q0, ulonglong2 q1, ulonglong2 q2, ulonglong2 q3, const RaySlab& rs) {
     int2 refs = make_int2((int)(unsigned)(q3.x & 0xffffffffull), (int)(unsigned)(q3.x >> 32));
     float lnx, lny, lfx, lfy, rnx, rny, rfx, rfy, lnz, lfz, rnz, rfz;
     pk2_split(pk2_mul(pk2_add(q0.x, rs.no_xy), rs.inv_xy), lnx, lny);  // left  (AA - S) * inv, x y
@@ -284,7 +307,8 @@ __device__ __forceinline__ HitRec trace_ray(const SceneDev& sc, vec3 o, vec3 d) 
 #define EZRT_REF_DONE ((int)0x80000000)   // leaf flag with n == 0: no real leaf has this encoding
 
 template <bool PRUNE, bool ANYHIT, class RayIO>
-__device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n, uint32_t* work, RayIO io) {
+__device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n, uint32_t* work, RayIO io, const float4* smem_top) {
+    const int top_nodes = sc.top_nodes;
     const int refill_thresh = sc.refill_thresh;  // go back to refill when fewer lanes than this are busy
     const int inner_thresh = sc.inner_thresh;    // leave the inner-node phase when fewer lanes than this walk
     const int leaf_thresh = sc.leaf_thresh;      // ... or when at least this many lanes wait at a leaf
@@ -362,7 +386,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
                 const unsigned m_wait = __ballot_sync(FULL, (ray >= 0) && (ref < 0));
                 if (m_wait != 0u && (__popc(m_inner) < inner_thresh || __popc(m_wait) >= leaf_thresh)) break;
                 if (at_inner) {
-                    NodeVisit nv = node_visit<true>(sc.nodes + (size_t)ref * 4, rs);
+                    NodeVisit nv = node_visit_top<true>(sc, smem_top, top_nodes, ref, rs);
                     bool h1 = nv.h1, h2 = nv.h2;
                     const float d1 = nv.d1, d2 = nv.d2, e1 = nv.e1, e2 = nv.e2;
                     const int rl = nv.rl, rr = nv.rr;

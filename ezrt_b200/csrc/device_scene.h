@@ -25,6 +25,8 @@
 #define EZRT_MAX_STACK 64        // >= validated tree depth + 1 (the shader's bound is 256, P5/fsh:260)
 #define EZRT_LEAF_FLAG 0x80000000u
 #define EZRT_LEAF_MAX_N 127
+#define EZRT_TOP_NODES_MAX 1023   // 10 full levels; 80 B each in shared memory (bank-conflict padding)
+#define EZRT_TOP_STRIDE 5         // float4 per shared-memory record
 #define EZRT_TILE 16             // == EZRT_PART_TILE
 #define EZRT_TILE_PIXELS 256
 #define EZRT_SORT_BITS 18         // ray sort key: direction octant (3) | 5-5-5 Morton cell of the origin
@@ -41,6 +43,7 @@ struct SceneDev {
     int root_ref;
     int n_triangles;
     int n_inner;
+    int top_nodes;            // records [0, top_nodes) = the top tree levels, staged in shared memory
     float prune_delta;        // 2^-16 * max |vertex coordinate|
     int refill_thresh;        // persistent traversal tunables (env EZRT_REFILL_T / EZRT_INNER_T)
     int inner_thresh;

@@ -161,6 +161,14 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict
     }
 }
 
+// the top tree levels, copied from global memory by every persistent block at kernel start
+extern __shared__ float4 g_smem_top[];
+__device__ __forceinline__ void stage_top_nodes(const SceneDev& sc) {
+    const int n4 = sc.top_nodes * 4;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) g_smem_top[(i >> 2) * EZRT_TOP_STRIDE + (i & 3)] = sc.nodes[i];
+    __syncthreads();
+}
+
 struct ExtendIO {
     PathQueue q;
     const uint32_t* perm;  // null: trace in queue order
@@ -178,12 +186,13 @@ struct ExtendIO {
 };
 
 template <bool PRUNE>
-__global__ void __launch_bounds__(EZRT_EXTEND_THREADS, EZRT_EXTEND_MIN_BLOCKS) k_extend(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
+__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_extend(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
                                                                 uint32_t* work, const uint32_t* __restrict__ perm) {
     ExtendIO io;
     io.q = q;
     io.perm = perm;
-    extend_persistent<PRUNE, false>(sc, *q_count, work, io);
+    stage_top_nodes(sc);
+    extend_persistent<PRUNE, false>(sc, *q_count, work, io, g_smem_top);
 }
 
 // shadow rays: any hit; an unoccluded ray adds its precomputed contribution (P5/fsh:829-841).
@@ -207,12 +216,13 @@ struct ShadowIO {
 };
 
 template <bool PRUNE>
-__global__ void __launch_bounds__(EZRT_EXTEND_THREADS, EZRT_EXTEND_MIN_BLOCKS) k_shadow(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count,
+__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_shadow(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count,
                                                                 uint32_t* work, float4* __restrict__ Lo) {
     ShadowIO io;
     io.sq = sq;
     io.Lo = Lo;
-    extend_persistent<PRUNE, true>(sc, *s_count, work, io);
+    stage_top_nodes(sc);
+    extend_persistent<PRUNE, true>(sc, *s_count, work, io, g_smem_top);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -459,7 +469,16 @@ __global__ void k_partition_scatter(const float* __restrict__ compact, float* __
 // ------------------------------------------------------------------------------------------
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-// resident persistent blocks per SM for the extend/shadow kernels (env EZRT_EXTEND_BPS overrides)
+// persistent extend/shadow kernels: block size and resident blocks per SM (each block stages its own
+// copy of the top tree levels in shared memory); env EZRT_EXTEND_THREADS / EZRT_EXTEND_BPS override
+static int extend_threads() {
+    static int v = 0;
+    if (v == 0) {
+        v = EZRT_EXTEND_THREADS;
+        if (const char* e = getenv("EZRT_EXTEND_THREADS")) v = std::max(32, std::min(EZRT_EXTEND_MAX_THREADS, (atoi(e) / 32) * 32));
+    }
+    return v;
+}
 static int extend_blocks_per_sm() {
     static int v = 0;
     if (v == 0) {
@@ -468,7 +487,14 @@ static int extend_blocks_per_sm() {
     }
     return v;
 }
-
+template <class K>
+static size_t extend_smem(K kernel, const SceneDev& sc) {
+    size_t bytes = (size_t)sc.top_nodes * EZRT_TOP_STRIDE * sizeof(float4);
+    static size_t configured = 0;
+    (void)configured;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bytes, 1024));
+    return bytes;
+}
 void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots, uint32_t batch_first_frame, PathQueue q,
                      uint32_t* q_count, int n_sms, cudaStream_t st) {
     int blocks = std::min(div_up(n_slots, 256), n_sms * 8);
@@ -476,10 +502,11 @@ void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots
 }
 void launch_extend(const SceneDev& sc, bool prune, PathQueue q, const uint32_t* q_count, uint32_t* work, const uint32_t* perm,
                    uint32_t n_max, int n_sms, cudaStream_t st) {
-    int blocks = std::min(div_up(n_max, EZRT_EXTEND_THREADS), n_sms * extend_blocks_per_sm());
+    const int threads = extend_threads();
+    int blocks = std::min(div_up(n_max, threads), n_sms * extend_blocks_per_sm());
     if (blocks < 1) blocks = 1;
-    if (prune) k_extend<true><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, q, q_count, work, perm);
-    else k_extend<false><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, q, q_count, work, perm);
+    if (prune) k_extend<true><<<blocks, threads, extend_smem(k_extend<true>, sc), st>>>(sc, q, q_count, work, perm);
+    else k_extend<false><<<blocks, threads, extend_smem(k_extend<false>, sc), st>>>(sc, q, q_count, work, perm);
 }
 // counting sort of the queue's ray indices into `perm` (3 kernels; bins must hold EZRT_SORT_BINS counters)
 void launch_ray_sort(const SceneDev& sc, PathQueue q, const uint32_t* q_count, uint32_t* keys, uint32_t* bins, uint32_t* perm,
@@ -492,10 +519,11 @@ void launch_ray_sort(const SceneDev& sc, PathQueue q, const uint32_t* q_count, u
 }
 void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo,
                    uint32_t n_max, int n_sms, cudaStream_t st) {
-    int blocks = std::min(div_up(n_max, EZRT_EXTEND_THREADS), n_sms * extend_blocks_per_sm());
+    const int threads = extend_threads();
+    int blocks = std::min(div_up(n_max, threads), n_sms * extend_blocks_per_sm());
     if (blocks < 1) blocks = 1;
-    if (prune) k_shadow<true><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, sq, s_count, work, Lo);
-    else k_shadow<false><<<blocks, EZRT_EXTEND_THREADS, 0, st>>>(sc, sq, s_count, work, Lo);
+    if (prune) k_shadow<true><<<blocks, threads, extend_smem(k_shadow<true>, sc), st>>>(sc, sq, s_count, work, Lo);
+    else k_shadow<false><<<blocks, threads, extend_smem(k_shadow<false>, sc), st>>>(sc, sq, s_count, work, Lo);
 }
 void launch_shade(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, int bounce, uint32_t batch_first_frame,
                   PathQueue qin, const uint32_t* in_count, PathQueue qout, uint32_t* out_count, ShadowQueue sq,

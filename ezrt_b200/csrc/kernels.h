@@ -6,12 +6,10 @@
 
 #include "device_scene.h"
 
-// extend/shadow kernels: persistent blocks, EZRT_EXTEND_BLOCKS_PER_SM resident per SM
-#define EZRT_EXTEND_THREADS 128
-#define EZRT_EXTEND_BLOCKS_PER_SM 8
-#ifndef EZRT_EXTEND_MIN_BLOCKS
-#define EZRT_EXTEND_MIN_BLOCKS 8   // register cap 64: 8 x 128 threads resident per SM
-#endif
+// extend/shadow kernels: persistent blocks; the register cap of 64 lets 1024 threads reside per SM
+#define EZRT_EXTEND_MAX_THREADS 1024
+#define EZRT_EXTEND_THREADS 1024
+#define EZRT_EXTEND_BLOCKS_PER_SM 1
 
 void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots, uint32_t batch_first_frame, PathQueue q,
                      uint32_t* q_count, int n_sms, cudaStream_t st);

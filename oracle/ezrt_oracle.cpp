@@ -69,6 +69,7 @@ struct Counters {
     uint64_t hits;       // H     : rays that hit
     uint64_t hdr_lookups;
     uint64_t max_stack;
+    uint64_t innerByDepth[64];  // inner-node visits by tree depth (root = 0)
 };
 
 struct Scene {
@@ -237,13 +238,16 @@ HitResult hitBVH(const Scene& sc, const Ray& ray, Counters& cn, int kind) {
 
     int stack[256];
     float stackT0[256];
+    int stackDepth[256];
     int sp = 0;
     stackT0[sp] = -1.0f;
+    stackDepth[sp] = 0;
     stack[sp++] = 1;
     cn.nodes++;  // the root is fetched once
     while (sp > 0) {
         if ((uint64_t)sp > cn.max_stack) cn.max_stack = (uint64_t)sp;
         int top = stack[--sp];
+        const int depth = stackDepth[sp];
         if (prune && pruned(stackT0[sp], res.distance, slack)) continue;
         BVHNode node = getBVHNode(sc, top);
         if (node.n > 0) {
@@ -255,6 +259,7 @@ HitResult hitBVH(const Scene& sc, const Ray& ray, Counters& cn, int kind) {
         }
         float d1 = EZ_INF, d2 = EZ_INF;
         float e1 = -1.0f, e2 = -1.0f;
+        cn.innerByDepth[depth < 63 ? depth : 63]++;
         if (node.left > 0) {
             BVHNode leftNode = getBVHNode(sc, node.left);
             cn.nodes++;
@@ -270,18 +275,21 @@ HitResult hitBVH(const Scene& sc, const Ray& ray, Counters& cn, int kind) {
             if (h1 && pruned(e1, res.distance, slack)) h1 = false;
             if (h2 && pruned(e2, res.distance, slack)) h2 = false;
             if (h1 && h2) {
-                if (d1 < d2) { stackT0[sp] = e2; stack[sp++] = node.right; stackT0[sp] = e1; stack[sp++] = node.left; }
-                else         { stackT0[sp] = e1; stack[sp++] = node.left;  stackT0[sp] = e2; stack[sp++] = node.right; }
-            } else if (h1) { stackT0[sp] = e1; stack[sp++] = node.left; }
-            else if (h2)   { stackT0[sp] = e2; stack[sp++] = node.right; }
+                if (d1 < d2) { stackT0[sp] = e2; stackDepth[sp] = depth + 1; stack[sp++] = node.right; stackT0[sp] = e1; stackDepth[sp] = depth + 1; stack[sp++] = node.left; }
+                else         { stackT0[sp] = e1; stackDepth[sp] = depth + 1; stack[sp++] = node.left;  stackT0[sp] = e2; stackDepth[sp] = depth + 1; stack[sp++] = node.right; }
+            } else if (h1) { stackT0[sp] = e1; stackDepth[sp] = depth + 1; stack[sp++] = node.left; }
+            else if (h2)   { stackT0[sp] = e2; stackDepth[sp] = depth + 1; stack[sp++] = node.right; }
             continue;
         }
         if (h1 && h2) {
+            stackDepth[sp] = stackDepth[sp + 1] = depth + 1;
             if (d1 < d2) { stack[sp++] = node.right; stack[sp++] = node.left; }
             else         { stack[sp++] = node.left;  stack[sp++] = node.right; }
         } else if (h1) {
+            stackDepth[sp] = depth + 1;
             stack[sp++] = node.left;
         } else if (h2) {
+            stackDepth[sp] = depth + 1;
             stack[sp++] = node.right;
         }
     }
@@ -762,6 +770,8 @@ inline float maxAbsCoord(const float* tris, int n) {
     return m;
 }
 
+uint64_t g_innerByDepth[64];  // accumulated by oracle_render (diagnostic: where traversal time goes)
+
 Scene makeScene(const float* tris, int nTriangles, const float* nodes, int nNodes, const float* hdr,
                 const float* hdrCache, int hdrW, int hdrH, int hdrLinear, const float envColor[3], int mode,
                 int traverse) {
@@ -818,6 +828,7 @@ int oracle_render(const float* tris, int nTriangles, const float* nodes, int nNo
             for (int k = 0; k < 3; k++) total.rays[k] += cn.rays[k];
             total.nodes += cn.nodes; total.tris += cn.tris; total.hits += cn.hits;
             total.hdr_lookups += cn.hdr_lookups;
+            for (int k = 0; k < 64; k++) g_innerByDepth[k] += cn.innerByDepth[k];
             if (cn.max_stack > total.max_stack) total.max_stack = cn.max_stack;
         }
     }
@@ -923,5 +934,9 @@ void oracle_wang_chain(uint32_t seed, int n, uint32_t* hashes, float* rands) {
 float oracle_sobol(uint32_t d, uint32_t i) { return sobol(d, grayCode(i)); }
 void oracle_cp_rotation(float* xy, uint32_t px, uint32_t py) { CranleyPattersonRotation(&xy[0], &xy[1], px, py); }
 float oracle_pi(void) { return EZ_PI; }
+// inner-node visits by depth accumulated over all oracle_render calls since the last reset
+void oracle_depth_hist(uint64_t* out64, int reset) {
+    for (int k = 0; k < 64; k++) { out64[k] = g_innerByDepth[k]; if (reset) g_innerByDepth[k] = 0; }
+}
 
 }  // extern "C"
