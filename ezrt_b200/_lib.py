@@ -76,11 +76,18 @@ class EzrtError(RuntimeError):
 
 def _load():
     path = _build.PRODUCT_SO
+    variant = os.environ.get("EZRT_LIB_VARIANT")
+    if variant:  # experiment copy built by build.build_product(variant=..., defines=...)
+        path = path.replace(".so", "_%s.so" % variant)
+        return _bind(C.CDLL(path))
     # in-tree incremental build (no-op when the .so is newer than its sources); without nvcc a
     # prebuilt .so is used as is, and a missing one raises -- there is no CPU fallback
     if not os.path.exists(path) or _build._nvcc() is not None:
         _build.build_product()
-    lib = C.CDLL(path)
+    return _bind(C.CDLL(path))
+
+
+def _bind(lib):
     for name, (restype, argtypes) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = restype

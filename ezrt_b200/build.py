@@ -61,31 +61,35 @@ def _headers():
     return hs
 
 
-def build_product(force=False, verbose=False):
-    """nvcc + g++ -> ezrt_b200/libezrt_b200.so (cross-compiles for sm_100a without a GPU)."""
+def build_product(force=False, verbose=False, variant=None, defines=()):
+    """nvcc + g++ -> ezrt_b200/libezrt_b200.so (cross-compiles for sm_100a without a GPU).
+    variant/defines build an experiment copy libezrt_b200_<variant>.so with extra -D macros
+    (selected at import time by env EZRT_LIB_VARIANT; used for A/B runs on the GPU box)."""
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libezrt_b200.so")
+    target = PRODUCT_SO if not variant else PRODUCT_SO.replace(".so", "_%s.so" % variant)
     cu = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
     cpp = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cpp"))
-    if not force and not _newer(PRODUCT_SO, cu + cpp + _headers()):
-        return PRODUCT_SO
-    objdir = os.path.join(ROOT, "build", "obj")
+    if not force and not _newer(target, cu + cpp + _headers()):
+        return target
+    objdir = os.path.join(ROOT, "build", "obj" + ("_" + variant if variant else ""))
     os.makedirs(objdir, exist_ok=True)
+    dflags = ["-D" + d for d in defines]
     objs = []
     for src in cu:
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
-        out = _run([nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj],
+        out = _run([nvcc] + NVCC_FLAGS + dflags + ["-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj],
                    log=os.path.join(objdir, os.path.basename(src) + ".ptxas.log"))
         if verbose:
             print(out)
         objs.append(obj)
     for src in cpp:
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
-        _run(["g++"] + HOST_FLAGS + ["-pthread", "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj])
+        _run(["g++"] + HOST_FLAGS + dflags + ["-pthread", "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj])
         objs.append(obj)
-    _run([nvcc, "-shared", "-o", PRODUCT_SO] + objs + ["-Xcompiler", "-pthread", "-cudart", "static"])
-    return PRODUCT_SO
+    _run([nvcc, "-shared", "-o", target] + objs + ["-Xcompiler", "-pthread", "-cudart", "static"])
+    return target
 
 
 def build_oracle(force=False):

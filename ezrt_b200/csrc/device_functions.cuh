@@ -379,11 +379,12 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
         // visits running at 5.8 of 32 lanes, because the warp waited for its longest walk per leaf.
         unsigned busy;
         do {
+            const unsigned m_busy = __ballot_sync(FULL, ray >= 0);  // constant during the inner phase
             while (true) {
                 const bool at_inner = (ray >= 0) && (ref >= 0);
                 const unsigned m_inner = __ballot_sync(FULL, at_inner);
                 if (m_inner == 0u) break;
-                const unsigned m_wait = __ballot_sync(FULL, (ray >= 0) && (ref < 0));
+                const unsigned m_wait = m_busy & ~m_inner;  // busy lanes standing at a leaf (or done)
                 if (m_wait != 0u && (__popc(m_inner) < inner_thresh || __popc(m_wait) >= leaf_thresh)) break;
                 if (at_inner) {
                     NodeVisit nv = node_visit_top<true>(sc, smem_top, top_nodes, ref, rs);

@@ -7,8 +7,10 @@
 #include "device_scene.h"
 
 // extend/shadow kernels: persistent blocks; the register cap of 64 lets 1024 threads reside per SM
+#ifndef EZRT_EXTEND_MAX_THREADS
 #define EZRT_EXTEND_MAX_THREADS 1024
-#define EZRT_EXTEND_THREADS 1024
+#endif
+#define EZRT_EXTEND_THREADS EZRT_EXTEND_MAX_THREADS
 #define EZRT_EXTEND_BLOCKS_PER_SM 1
 
 void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots, uint32_t batch_first_frame, PathQueue q,
