@@ -215,10 +215,12 @@ def main():
     stream = torch.cuda.current_stream()
     d_fb = torch.zeros(max(1, n_local) * C, dtype=torch.float32, device="cuda")
 
+    gatherer = ezdist.FramebufferGather(W, H, C, rank, world, d_fb.device) if world > 1 else None
+
     def device_step(step, profile=0):
         scene.render_device(cfg_for(step, profile), d_fb, stream)
         if world > 1:
-            return ezdist.gather_framebuffer(d_fb, W, H, C, rank, world)
+            return gatherer(d_fb)  # the single NCCL collective of the step
         return None
 
     def barrier():

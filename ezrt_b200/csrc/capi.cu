@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <array>
 #include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -78,7 +80,7 @@ struct ezrt_scene {
     int tree_depth = 0;
     // render state (lazily sized)
     DeviceBuffer tiles_buf, queue_buf[2], shadow_buf, lo_buf, le_buf, counters_buf, totals_buf, fb_buf, sort_buf;
-    int sort_rays = 1;  // env EZRT_SORT_RAYS=0 disables the bounce-ray sort
+    int sort_rays = 0;  // env EZRT_SORT_RAYS=1 enables the bounce-ray sort (measured: no gain with per-lane refill)
     int tiles_key[4] = {-1, -1, -1, -1};
     std::vector<TileDev> tiles;
     cudaStream_t own_stream = nullptr;
@@ -357,7 +359,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.refill_thresh = 24;
     d.inner_thresh = 16;
     d.leaf_thresh = 8;
-    d.work_chunk = 128;
+    d.work_chunk = 32;
     if (const char* e = getenv("EZRT_CHUNK")) d.work_chunk = std::max(32, std::min(65536, atoi(e)));
     if (const char* e = getenv("EZRT_LEAF_T")) d.leaf_thresh = std::max(1, std::min(33, atoi(e)));
     if (const char* e = getenv("EZRT_REFILL_T")) d.refill_thresh = std::max(1, std::min(32, atoi(e)));
@@ -556,18 +558,33 @@ int64_t ezrt_partition_pixels(int width, int height, int rank, int count) {
 int ezrt_partition_scatter(const float* d_compact, float* d_full, int width, int height, int channels, int rank, int count,
                            void* cuda_stream) {
     if (!d_compact || !d_full || channels < 1) return ezrt_set_error(EZRT_ERR_INVALID, "partition_scatter: bad argument");
-    std::vector<TileDev> tiles = partition_tiles(width, height, rank, count);
-    if (tiles.empty()) return EZRT_OK;
+    if (width <= 0 || height <= 0 || count < 1 || rank < 0 || rank >= count) return ezrt_set_error(EZRT_ERR_INVALID, "partition_scatter: bad partition");
+    // device tile lists are cached per (device, image, part): the gather runs every step
+    struct Entry { TileDev* d_tiles; int n; };
+    static std::map<std::array<int, 5>, Entry> cache;
+    static std::mutex mu;
+    int device = 0;
+    CU_CHECK(cudaGetDevice(&device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    TileDev* d_tiles = nullptr;
-    CU_CHECK(cudaMalloc(&d_tiles, sizeof(TileDev) * tiles.size()));
-    cudaError_t e = cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(TileDev) * tiles.size(), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) {
-        launch_partition_scatter(d_compact, d_full, d_tiles, (int)tiles.size(), width, channels, st);
-        e = cudaStreamSynchronize(st);
+    Entry ent;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        std::array<int, 5> key = {device, width, height, rank, count};
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            std::vector<TileDev> tiles = partition_tiles(width, height, rank, count);
+            Entry e{nullptr, (int)tiles.size()};
+            if (!tiles.empty()) {
+                CU_CHECK(cudaMalloc(&e.d_tiles, sizeof(TileDev) * tiles.size()));
+                CU_CHECK(cudaMemcpy(e.d_tiles, tiles.data(), sizeof(TileDev) * tiles.size(), cudaMemcpyHostToDevice));
+            }
+            it = cache.emplace(key, e).first;
+        }
+        ent = it->second;
     }
-    cudaFree(d_tiles);
-    if (e != cudaSuccess) return ezrt_set_error(EZRT_ERR_CUDA, "partition_scatter: %s", cudaGetErrorString(e));
+    if (ent.n == 0) return EZRT_OK;
+    launch_partition_scatter(d_compact, d_full, ent.d_tiles, ent.n, width, channels, st);
+    CU_CHECK(cudaGetLastError());
     return EZRT_OK;
 }
 

@@ -15,32 +15,42 @@ def part_sizes(width, height, world):
     return [api.partition_pixels(width, height, r, world) for r in range(world)]
 
 
-def gather_framebuffer(local, width, height, channels, rank, world, group=None, dst=0):
-    """Gather the compact per-rank buffers (torch tensors, CPU or CUDA, float32, n_local*channels)
-    to rank `dst` and scatter them into a full [height, width, channels] image there.
-    Returns the image on `dst`, None elsewhere.  One collective: torch.distributed.gather."""
-    import torch
-    import torch.distributed as dist
+class FramebufferGather:
+    """Preallocated buffers for the per-step gather: a padded send buffer per rank, the receive list
+    and the assembled image on rank `dst`.  One collective per call: torch.distributed.gather."""
 
-    if world == 1:  # a single part is already the row-major image
-        return local.reshape(-1)[: height * width * channels].reshape(height, width, channels)
-    sizes = part_sizes(width, height, world)
-    n_max = max(sizes) * channels
-    buf = local.new_zeros(n_max)
-    buf[: sizes[rank] * channels] = local.reshape(-1)[: sizes[rank] * channels]
-    parts = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
-    dist.gather(buf, parts, dst=dst, group=group)
-    if rank != dst:
-        return None
-    full = local.new_zeros(height * width * channels)
-    for r in range(world):
-        if local.is_cuda:
-            api.check(api.lib.ezrt_partition_scatter(parts[r].data_ptr(), full.data_ptr(), width, height, channels, r, world,
-                                                     torch.cuda.current_stream().cuda_stream))
-        else:
-            src = parts[r].numpy()[: sizes[r] * channels]
-            api.partition_scatter_host(np.ascontiguousarray(src), full.numpy(), width, height, channels, r, world)
-    return full.reshape(height, width, channels)
+    def __init__(self, width, height, channels, rank, world, device, group=None, dst=0):
+        import torch
+        self.w, self.h, self.c, self.rank, self.world, self.group, self.dst = width, height, channels, rank, world, group, dst
+        self.sizes = part_sizes(width, height, world)
+        n_max = max(self.sizes) * channels
+        self.send = torch.zeros(n_max, dtype=torch.float32, device=device)
+        self.parts = [torch.empty_like(self.send) for _ in range(world)] if (rank == dst and world > 1) else None
+        self.full = torch.zeros(height * width * channels, dtype=torch.float32, device=device) if rank == dst else None
+
+    def __call__(self, local):
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:  # a single part is already the row-major image
+            return local.reshape(-1)[: self.h * self.w * self.c].reshape(self.h, self.w, self.c)
+        n = self.sizes[self.rank] * self.c
+        self.send[:n].copy_(local.reshape(-1)[:n])
+        dist.gather(self.send, self.parts, dst=self.dst, group=self.group)
+        if self.rank != self.dst:
+            return None
+        for r in range(self.world):
+            if self.send.is_cuda:
+                api.check(api.lib.ezrt_partition_scatter(self.parts[r].data_ptr(), self.full.data_ptr(), self.w, self.h, self.c, r, self.world,
+                                                         torch.cuda.current_stream().cuda_stream))
+            else:
+                src = self.parts[r].numpy()[: self.sizes[r] * self.c]
+                api.partition_scatter_host(np.ascontiguousarray(src), self.full.numpy(), self.w, self.h, self.c, r, self.world)
+        return self.full.reshape(self.h, self.w, self.c)
+
+
+def gather_framebuffer(local, width, height, channels, rank, world, group=None, dst=0):
+    """One-shot form of FramebufferGather (allocates its buffers)."""
+    return FramebufferGather(width, height, channels, rank, world, local.device, group, dst)(local)
 
 
 def render_partitioned(scene, cfg, rank, world, group=None, d_local=None):

@@ -1,0 +1,74 @@
+"""world_size-2 gloo test (CPU) of the N>1 path: tile partition -> ONE gather -> de-interleave on rank 0.
+
+No GPU here, so each rank fills its compact part buffer with a function of the pixel coordinates it owns
+(through the same partition helpers the render uses) and rank 0 must reassemble the exact image."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _pixel_value(W, H, C):
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = np.stack([(xx * 3 + yy * 7 + c * 1000).astype(np.float32) for c in range(C)], axis=-1)
+    return img
+
+
+def _worker(rank, world, port, W, H, C, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ezrt_b200 import api
+    from ezrt_b200 import dist as ezdist
+    full = _pixel_value(W, H, C)
+    # this rank's compact part: gather its own pixels in partition order = scatter's inverse
+    n = api.partition_pixels(W, H, rank, world)
+    idx_img = np.arange(W * H, dtype=np.float32).reshape(H, W, 1)
+    # recover the partition order by scattering pixel ids of a ramp through the host scatter
+    probe = np.full((H, W, 1), -1, np.float32)
+    api.partition_scatter_host(np.arange(n, dtype=np.float32).reshape(n, 1), probe, W, H, 1, rank, world)
+    owned = probe[..., 0] >= 0
+    order = np.argsort(probe[..., 0][owned])
+    local = full[owned][order].reshape(-1)
+    assert local.size == n * C
+    img = ezdist.gather_framebuffer(torch.from_numpy(np.ascontiguousarray(local)), W, H, C, rank, world)
+    if rank == 0:
+        np.save(out_path, img.numpy())
+    else:
+        assert img is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,W,H", [(2, 100, 52), (3, 64, 64)])
+def test_gather_framebuffer_gloo(tmp_path, world, W, H):
+    C = 3
+    out = str(tmp_path / "img.npy")
+    mp.spawn(_worker, args=(world, _free_port(), W, H, C, out), nprocs=world, join=True)
+    got = np.load(out)
+    np.testing.assert_array_equal(got, _pixel_value(W, H, C))
+
+
+def test_weak_image_keeps_pixels_per_gpu():
+    sys.path.insert(0, ROOT)
+    import bench
+    for n in (1, 2, 4, 8):
+        w, h = bench.weak_image(1920, 1080, n)
+        assert w * h == 1920 * 1080 * n
+    assert bench.weak_image(1920, 1080, 4) == (3840, 2160)  # BASELINE configs[4] resolution
