@@ -32,6 +32,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per k_extend launch on the C3 workload, mean of the three launch
+# kinds (camera / bounce-1 / bounce-2), from the committed ncu capture profiles/ncu_extend_r1_summary.md
+NCU_DRAM_BYTES_PER_EXTEND_LAUNCH = 354.7e6
+
 METRIC = "Mrays/s (primary+secondary)"
 UNIT = "Mrays/s"
 WORKLOADS = {
@@ -54,7 +58,7 @@ def parse_args():
     ap.add_argument("--pipeline", default="wavefront", choices=["wavefront", "megakernel"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", default="480x270x2", help="oracle sample WxHxSPP used for cpu_baseline and B_ray")
+    ap.add_argument("--cpu-sample", default="960x540x2", help="oracle sample WxHxSPP used for cpu_baseline and B_ray")
     return ap.parse_args()
 
 
@@ -327,7 +331,8 @@ def main():
         rays_rank0 = rays / world  # rank 0's own launches were timed; rays are evenly spread by the tile interleave
         achieved = rays_rank0 * bray_ref / (ext_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "peak_source": peak_kind, "bytes_per_ray": bray_ref, "bytes_per_ray_pruned_policy": bray_pruned,
+                    "traffic": NCU_DRAM_BYTES_PER_EXTEND_LAUNCH, "traffic_unit": "bytes/launch (dram read+write, ncu --set full, profiles/ncu_extend_r1_summary.md)",
+                    "algorithmic_bytes_per_launch": rays_rank0 * bray_ref / max(1, ext_n), "peak_source": peak_kind, "bytes_per_ray": bray_ref, "bytes_per_ray_pruned_policy": bray_pruned,
                     "ray_means": means, "extend_ms_per_launch": ext_ms / max(1, ext_n), "extend_launches": ext_n,
                     "extend_share_of_step": ext_ms / ms,
                     "note": "algorithmic demand bytes on the reference layout/policy, no cross-ray reuse; nodes+positions are L2-resident so frac may exceed 1"}
