@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--spp-per-step", type=int, default=16)
     ap.add_argument("--frames-per-batch", type=int, default=0)
-    ap.add_argument("--traverse", default="pruned", choices=["pruned", "reference"])
+    ap.add_argument("--traverse", default="accel", choices=["accel", "pruned", "reference"])
     ap.add_argument("--pipeline", default="wavefront", choices=["wavefront", "megakernel"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -207,7 +207,7 @@ def main():
     upload_ms = 1e3 * (time.perf_counter() - t0)
     C = 3
     n_local = api.partition_pixels(W, H, rank, world)
-    traverse = api.TRAVERSE_PRUNED if args.traverse == "pruned" else api.TRAVERSE_REFERENCE
+    traverse = {"accel": api.TRAVERSE_ACCEL, "pruned": api.TRAVERSE_PRUNED, "reference": api.TRAVERSE_REFERENCE}[args.traverse]
     pipeline = api.PIPELINE_WAVEFRONT if args.pipeline == "wavefront" else api.PIPELINE_MEGAKERNEL
 
     def cfg_for(step, profile=0):

@@ -30,6 +30,7 @@ class Counters(C.Structure):
     _fields_ = [
         ("rays", C.c_uint64), ("primary_rays", C.c_uint64), ("bounce_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
         ("samples", C.c_uint64), ("kernel_launches", C.c_uint64), ("device_ms", C.c_double),
+        ("deferred_rays", C.c_uint64),
     ]
 
 

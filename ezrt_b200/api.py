@@ -20,8 +20,9 @@ MODE_DISNEY_SOBOL_P5 = 2
 MODE_DISNEY_IS_MIS_P5 = 3
 MODES = {"diffuse_p3": 0, "disney_aniso_p4": 1, "disney_sobol_p5": 2, "disney_is_mis_p5": 3}
 
-TRAVERSE_PRUNED = 0
+TRAVERSE_ACCEL = 0
 TRAVERSE_REFERENCE = 1
+TRAVERSE_PRUNED = 2
 PIPELINE_WAVEFRONT = 0
 PIPELINE_MEGAKERNEL = 1
 
@@ -174,7 +175,7 @@ class RenderConfig:
     eye: tuple = (0.0, 0.0, 4.0)
     camera_rotate: tuple = tuple(np.eye(4, dtype=np.float32).reshape(-1))
     env_color: tuple = (0.0, 0.0, 0.0)
-    traverse: int = TRAVERSE_PRUNED
+    traverse: int = TRAVERSE_ACCEL
     pipeline: int = PIPELINE_WAVEFRONT
     out_channels: int = 3
     part_rank: int = 0
@@ -255,7 +256,7 @@ class Scene:
         check(lib.ezrt_get_kernel_times(self._h, ms, n))
         return {k: (ms[i], int(n[i])) for i, k in enumerate(("extend", "shade", "shadow", "other"))}
 
-    def trace_rays(self, origins, dirs, traverse=TRAVERSE_PRUNED, any_hit=False, p3_normal_fudge=False):
+    def trace_rays(self, origins, dirs, traverse=TRAVERSE_ACCEL, any_hit=False, p3_normal_fudge=False):
         """hitBVH for n rays on the device (P5/fsh:254-306)."""
         o = _f32(origins, (-1, 3))
         d = _f32(dirs, (-1, 3))

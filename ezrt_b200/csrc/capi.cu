@@ -76,6 +76,8 @@ struct ezrt_scene {
     int n_sms = 148;
     SceneDev dev{};
     DeviceBuffer nodes, tri_geo, tri_shade, materials, hdr, hdr_cache;
+    DeviceBuffer acc_nodes, acc_tri_geo, acc_tri_ref, tri_leaf, leaf_box, defer_buf;
+    int acc_depth = 0;
     int n_materials = 0;
     int tree_depth = 0;
     // render state (lazily sized)
@@ -251,20 +253,32 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         if (hn[c].n > 0) return (int)(EZRT_LEAF_FLAG | ((uint32_t)hn[c].index << 7) | (uint32_t)hn[c].n);
         return inner_id[c];
     };
+    auto pack_node = [](float4* g, const float* LA, const float* LB, const float* RA, const float* RB, int rl, int rr) {
+        float fl, fr;
+        memcpy(&fl, &rl, 4);
+        memcpy(&fr, &rr, 4);
+        g[0] = make_float4(LA[0], LA[1], LB[0], LB[1]);  // left : AA.x AA.y | BB.x BB.y
+        g[1] = make_float4(RA[0], RA[1], RB[0], RB[1]);  // right: AA.x AA.y | BB.x BB.y
+        g[2] = make_float4(LA[2], LB[2], RA[2], RB[2]);  // left AA.z BB.z  | right AA.z BB.z
+        g[3] = make_float4(fl, fr, 0.0f, 0.0f);          // child references
+    };
     std::vector<float4> gnodes((size_t)std::max(1, n_inner) * 4);
     for (int i = 1; i < n_nodes; i++) {
         if (inner_id[i] < 0) continue;
         const float* L = nodes + (size_t)hn[i].left * EZRT_BVHNODE_FLOATS;
         const float* R = nodes + (size_t)hn[i].right * EZRT_BVHNODE_FLOATS;
-        float4* g = &gnodes[(size_t)inner_id[i] * 4];
-        int rl = child_ref(hn[i].left), rr = child_ref(hn[i].right);
-        float fl, fr;
-        memcpy(&fl, &rl, 4);
-        memcpy(&fr, &rr, 4);
-        g[0] = make_float4(L[6], L[7], L[9], L[10]);   // left : AA.x AA.y | BB.x BB.y
-        g[1] = make_float4(R[6], R[7], R[9], R[10]);   // right: AA.x AA.y | BB.x BB.y
-        g[2] = make_float4(L[8], L[11], R[8], R[11]);  // left AA.z BB.z  | right AA.z BB.z
-        g[3] = make_float4(fl, fr, 0.0f, 0.0f);        // child references
+        pack_node(&gnodes[(size_t)inner_id[i] * 4], L + 6, L + 9, R + 6, R + 9, child_ref(hn[i].left), child_ref(hn[i].right));
+    }
+    // reference leaf of every triangle + leaf boxes (accel policy: "does the shader reach this leaf?")
+    std::vector<int> tri_leaf(n_triangles, 0);
+    std::vector<float4> leaf_box;
+    for (int i = 1; i < n_nodes; i++) {
+        if (!seen[i] || hn[i].n <= 0) continue;
+        const float* B = nodes + (size_t)i * EZRT_BVHNODE_FLOATS;
+        int slot = (int)(leaf_box.size() / 2);
+        leaf_box.push_back(make_float4(B[6], B[7], B[8], 0.0f));
+        leaf_box.push_back(make_float4(B[9], B[10], B[11], 0.0f));
+        for (int k = 0; k < hn[i].n; k++) tri_leaf[hn[i].index + k] = slot;
     }
 
     // ---- triangles: geometry records, shading records, de-duplicated material table ----
@@ -309,6 +323,66 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         shade[(size_t)i * 3 + 2] = make_float4(s[15], s[16], s[17], 0.0f);
     }
 
+    // ---- acceleration tree: sentinel-free SAH over the same triangles (DESIGN.md "accel") ----
+    const float prune_delta = max_abs * 1.52587890625e-05f;  // 2^-16 * scene extent
+    std::vector<float4> acc_nodes, acc_geo((size_t)n_triangles * 4);
+    std::vector<uint32_t> acc_order;
+    int acc_root_ref = 0, acc_top = 0, acc_inner = 0, acc_depth = 0;
+    {
+        std::vector<EzrtAccelNode> an;
+        ezrt_build_accel(tris, n_triangles, 8, an, acc_order);
+        const int na = (int)an.size();
+        std::vector<int> aid(na, -1);
+        {   // top levels breadth-first, the rest in pre-order (as for the reference tree)
+            std::vector<int> level, next;
+            if (an[0].n <= 0) level.push_back(0);
+            while (!level.empty() && acc_top + (int)level.size() <= EZRT_TOP_NODES_MAX) {
+                next.clear();
+                for (int i : level) {
+                    aid[i] = acc_top++;
+                    if (an[an[i].left].n <= 0) next.push_back(an[i].left);
+                    if (an[an[i].right].n <= 0) next.push_back(an[i].right);
+                }
+                level.swap(next);
+                acc_depth++;
+            }
+            acc_inner = acc_top;
+            for (int i = 0; i < na; i++)
+                if (an[i].n <= 0 && aid[i] < 0) aid[i] = acc_inner++;
+        }
+        {   // depth (stack bound)
+            std::vector<std::pair<int, int>> stk;
+            stk.push_back({0, 1});
+            int md = 0;
+            while (!stk.empty()) {
+                auto [i, dpt] = stk.back();
+                stk.pop_back();
+                md = std::max(md, dpt);
+                if (an[i].n <= 0) { stk.push_back({an[i].left, dpt + 1}); stk.push_back({an[i].right, dpt + 1}); }
+            }
+            acc_depth = md;
+            if (md + 1 > EZRT_MAX_STACK) return ezrt_set_error(EZRT_ERR_BAD_TREE, "scene_create: acceleration tree depth %d exceeds %d", md, EZRT_MAX_STACK - 1);
+        }
+        auto aref = [&](int c) -> int {
+            if (an[c].n > 0) return (int)(EZRT_LEAF_FLAG | ((uint32_t)an[c].index << 7) | (uint32_t)an[c].n);
+            return aid[c];
+        };
+        // boxes inflated by 2*delta: a hit hitTriangle accepts lies within delta of its triangle's box, so
+        // the inflated boxes of the whole ancestor chain are entered no later than the hit distance
+        const float pad = 2.0f * prune_delta;
+        acc_nodes.resize((size_t)std::max(1, acc_inner) * 4);
+        for (int i = 0; i < na; i++) {
+            if (aid[i] < 0) continue;
+            const EzrtAccelNode &L = an[an[i].left], &R = an[an[i].right];
+            float LA[3], LB[3], RA[3], RB[3];
+            for (int k = 0; k < 3; k++) { LA[k] = L.AA[k] - pad; LB[k] = L.BB[k] + pad; RA[k] = R.AA[k] - pad; RB[k] = R.BB[k] + pad; }
+            pack_node(&acc_nodes[(size_t)aid[i] * 4], LA, LB, RA, RB, aref(an[i].left), aref(an[i].right));
+        }
+        acc_root_ref = aref(0);
+        for (int i = 0; i < n_triangles; i++)
+            for (int k = 0; k < 4; k++) acc_geo[(size_t)i * 4 + k] = geo[(size_t)acc_order[i] * 4 + k];
+    }
+
     ezrt_scene* sc = new (std::nothrow) ezrt_scene();
     if (!sc) return ezrt_set_error(EZRT_ERR_NOMEM, "scene_create: out of host memory");
     sc->device = device;
@@ -326,6 +400,11 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     if (!rc) rc = upload(sc->tri_geo, geo.data(), geo.size() * sizeof(float4));
     if (!rc) rc = upload(sc->tri_shade, shade.data(), shade.size() * sizeof(float4));
     if (!rc) rc = upload(sc->materials, mats.data(), mats.size() * sizeof(float4));
+    if (!rc) rc = upload(sc->acc_nodes, acc_nodes.data(), acc_nodes.size() * sizeof(float4));
+    if (!rc) rc = upload(sc->acc_tri_geo, acc_geo.data(), acc_geo.size() * sizeof(float4));
+    if (!rc) rc = upload(sc->acc_tri_ref, acc_order.data(), acc_order.size() * sizeof(uint32_t));
+    if (!rc) rc = upload(sc->tri_leaf, tri_leaf.data(), tri_leaf.size() * sizeof(int));
+    if (!rc) rc = upload(sc->leaf_box, leaf_box.data(), leaf_box.size() * sizeof(float4));
     if (!rc && hdr) rc = upload(sc->hdr, hdr, sizeof(float) * 3 * (size_t)hdr_w * hdr_h);
     if (!rc && hdr_cache) rc = upload(sc->hdr_cache, hdr_cache, sizeof(float) * 3 * (size_t)hdr_w * hdr_h);
     if (!rc && cudaStreamCreateWithFlags(&sc->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = ezrt_set_error(EZRT_ERR_CUDA, "scene_create: stream");
@@ -345,11 +424,22 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.hdr_cache = hdr_cache ? (const float*)sc->hdr_cache.p : nullptr;
     d.hdr_w = hdr_w; d.hdr_h = hdr_h; d.hdr_linear = hdr_filter_linear ? 1 : 0;
     d.root_ref = child_ref(1);
+    d.acc_nodes = (const float4*)sc->acc_nodes.p;
+    d.acc_tri_geo = (const float4*)sc->acc_tri_geo.p;
+    d.acc_tri_ref = (const uint32_t*)sc->acc_tri_ref.p;
+    d.acc_root_ref = acc_root_ref;
+    d.acc_top_nodes = acc_top;
+    d.tri_leaf = (const int*)sc->tri_leaf.p;
+    d.leaf_box = (const float4*)sc->leaf_box.p;
+    sc->acc_depth = acc_depth;
     d.n_triangles = n_triangles;
     d.n_inner = n_inner;
     d.top_nodes = n_top;
-    if (const char* e = getenv("EZRT_TOP_NODES")) d.top_nodes = std::max(0, std::min(n_top, atoi(e)));
-    d.prune_delta = max_abs * 1.52587890625e-05f;  // 2^-16 * scene extent (DESIGN.md "pruning")
+    if (const char* e = getenv("EZRT_TOP_NODES")) {
+        d.top_nodes = std::max(0, std::min(n_top, atoi(e)));
+        d.acc_top_nodes = std::max(0, std::min(acc_top, atoi(e)));
+    }
+    d.prune_delta = prune_delta;  // 2^-16 * scene extent (DESIGN.md "pruning")
     for (int k = 0; k < 3; k++) {
         d.bmin[k] = bmin[k];
         float ext = bmax[k] - bmin[k];
@@ -373,6 +463,7 @@ int ezrt_scene_destroy(ezrt_scene* s) {
     cudaSetDevice(s->device);
     s->nodes.release(); s->tri_geo.release(); s->tri_shade.release(); s->materials.release();
     s->hdr.release(); s->hdr_cache.release(); s->tiles_buf.release();
+    s->acc_nodes.release(); s->acc_tri_geo.release(); s->acc_tri_ref.release(); s->tri_leaf.release(); s->leaf_box.release(); s->defer_buf.release();
     s->queue_buf[0].release(); s->queue_buf[1].release(); s->shadow_buf.release();
     s->lo_buf.release(); s->le_buf.release(); s->counters_buf.release(); s->totals_buf.release(); s->fb_buf.release(); s->sort_buf.release();
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -394,11 +485,11 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     cudaStream_t st = (cudaStream_t)cuda_stream;
     rc = prepare_tiles(s, p, st);
     if (rc) return rc;
-    rc = s->totals_buf.ensure(sizeof(unsigned long long) * 4);
+    rc = s->totals_buf.ensure(sizeof(unsigned long long) * 8);
     if (rc) return rc;
     unsigned long long* totals = (unsigned long long*)s->totals_buf.p;
     CU_CHECK(cudaEventRecord(s->ev_start, st));
-    CU_CHECK(cudaMemsetAsync(totals, 0, sizeof(unsigned long long) * 4, st));
+    CU_CHECK(cudaMemsetAsync(totals, 0, sizeof(unsigned long long) * 8, st));
     s->launches = 0;
     s->have_timing = true;
     s->profiling = (p->profile != 0);
@@ -406,7 +497,8 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     s->ev_used = 0;
     RenderDev rd = make_render_dev(s, p);
     const TileDev* d_tiles = (const TileDev*)s->tiles_buf.p;
-    const bool prune = (p->traverse == EZRT_TRAVERSE_PRUNED);
+    const bool prune = (p->traverse != EZRT_TRAVERSE_REFERENCE);
+    const bool accel = (p->traverse == EZRT_TRAVERSE_ACCEL);
     if (rd.n_tiles == 0 || p->spp == 0) {
         CU_CHECK(cudaEventRecord(s->ev_stop, st));
         return EZRT_OK;
@@ -437,10 +529,15 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     if ((rc = s->lo_buf.ensure(sizeof(float4) * capacity))) return rc;
     if ((rc = s->le_buf.ensure(sizeof(float4) * capacity))) return rc;
     const int n_stages = p->max_bounce + 2;
-    // counters: [0,n) queue sizes, [n,2n) shadow sizes, [2n,3n) extend work, [3n,4n) shadow work
-    if ((rc = s->counters_buf.ensure(sizeof(uint32_t) * 4 * n_stages))) return rc;
+    // counters: [0,n) queue sizes, [n,2n) shadow sizes, [2n,3n) extend work, [3n,4n) shadow work,
+    // [4n,6n) deferred-ray counts of the accel passes (extend, shadow), [6n,8n) work counters of their exact passes
+    const int n_counters = 8 * n_stages;
+    if ((rc = s->counters_buf.ensure(sizeof(uint32_t) * n_counters))) return rc;
     uint32_t* cnt = (uint32_t*)s->counters_buf.p;
     uint32_t *q_count = cnt, *s_count = cnt + n_stages, *w_ext = cnt + 2 * n_stages, *w_sh = cnt + 3 * n_stages;
+    uint32_t *d_ext = cnt + 4 * n_stages, *d_sh = cnt + 5 * n_stages, *dw_ext = cnt + 6 * n_stages, *dw_sh = cnt + 7 * n_stages;
+    if ((rc = s->defer_buf.ensure(sizeof(uint32_t) * (capacity + 64)))) return rc;
+    uint32_t* defer_list = (uint32_t*)s->defer_buf.p;
     float4* Lo = (float4*)s->lo_buf.p;
     float4* Le = (float4*)s->le_buf.p;
     if ((rc = s->sort_buf.ensure(sizeof(uint32_t) * (2 * capacity + EZRT_SORT_BINS + 64)))) return rc;
@@ -452,7 +549,7 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
         const int nf = std::min(F, p->spp - done);
         const uint32_t n_slots = (uint32_t)(per_frame * (size_t)nf);
         const uint32_t batch_first = p->first_frame + (uint32_t)done;
-        CU_CHECK(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * 4 * n_stages, st));
+        CU_CHECK(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * n_counters, st));
         int sp = s->span_begin(3, st);
         launch_generate(rd, d_tiles, n_slots, batch_first, q[0], &q_count[0], s->n_sms, st);
         s->span_end(sp, st);
@@ -461,7 +558,7 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
             PathQueue& qin = q[b & 1];
             PathQueue& qout = q[(b + 1) & 1];
             const uint32_t* perm = nullptr;
-            if (b > 0 && s->sort_rays) {  // camera rays are coherent as generated; bounce rays are sorted
+            if (b > 0 && s->sort_rays && !accel) {  // optional experiment (exact policies only)
                 sp = s->span_begin(3, st);
                 launch_ray_sort(s->dev, qin, &q_count[b], sort_keys, sort_bins, sort_perm, n_slots, s->n_sms, st);
                 s->span_end(sp, st);
@@ -469,7 +566,12 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
                 perm = sort_perm;
             }
             sp = s->span_begin(0, st);
-            launch_extend(s->dev, prune, qin, &q_count[b], &w_ext[b], perm, n_slots, s->n_sms, st);
+            if (accel) {
+                launch_extend_accel(s->dev, false, qin, &q_count[b], &w_ext[b], defer_list, &d_ext[b], &dw_ext[b], n_slots, s->n_sms, st);
+                s->launches++;
+            } else {
+                launch_extend(s->dev, prune, false, qin, &q_count[b], &w_ext[b], perm, n_slots, s->n_sms, st);
+            }
             s->span_end(sp, st);
             sp = s->span_begin(1, st);
             launch_shade(s->dev, rd, d_tiles, b, batch_first, qin, &q_count[b], qout, &q_count[b + 1], sq, &s_count[b], Lo, Le,
@@ -478,14 +580,19 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
             s->launches += 2;
             if (is_mode && b < p->max_bounce) {
                 sp = s->span_begin(2, st);
-                launch_shadow(s->dev, prune, sq, &s_count[b], &w_sh[b], Lo, n_slots, s->n_sms, st);
+                if (accel) {
+                    launch_shadow_accel(s->dev, sq, &s_count[b], &w_sh[b], Lo, defer_list, &d_sh[b], &dw_sh[b], n_slots, s->n_sms, st);
+                    s->launches++;
+                } else {
+                    launch_shadow(s->dev, prune, sq, &s_count[b], &w_sh[b], Lo, nullptr, n_slots, s->n_sms, st);
+                }
                 s->span_end(sp, st);
                 s->launches++;
             }
         }
         sp = s->span_begin(3, st);
         launch_blend(rd, d_tiles, nf, batch_first, Lo, Le, d_fb, st);
-        launch_tally(q_count, s_count, p->max_bounce + 1, totals, st);
+        launch_tally(q_count, s_count, d_ext, d_sh, p->max_bounce + 1, totals, st);
         s->span_end(sp, st);
         s->launches += 2;
     }
@@ -518,8 +625,9 @@ int ezrt_get_counters(ezrt_scene* s, ezrt_counters* out) {
     if (!s->have_timing) return EZRT_OK;
     CU_CHECK(cudaSetDevice(s->device));
     CU_CHECK(cudaEventSynchronize(s->ev_stop));
-    unsigned long long t[4] = {0, 0, 0, 0};
+    unsigned long long t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     CU_CHECK(cudaMemcpy(t, s->totals_buf.p, sizeof(t), cudaMemcpyDeviceToHost));
+    out->deferred_rays = t[4];
     float ms = 0.0f;
     CU_CHECK(cudaEventElapsedTime(&ms, s->ev_start, s->ev_stop));
     out->primary_rays = t[0]; out->bounce_rays = t[1]; out->shadow_rays = t[2];
@@ -610,32 +718,47 @@ int ezrt_trace_rays(ezrt_scene* s, int n, const float* origins, const float* dir
         return ezrt_set_error(EZRT_ERR_INVALID, "trace_rays: null argument");
     if (n == 0) return EZRT_OK;
     CU_CHECK(cudaSetDevice(s->device));
+    // the rays go through the production path: a ray queue traced by the persistent extend kernels
+    std::vector<float4> ho(n), hd(n);
+    for (int i = 0; i < n; i++) {
+        ho[i] = make_float4(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2], 0.0f);
+        hd[i] = make_float4(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], 0.0f);
+    }
     DeviceBuffer buf;
-    size_t fN = sizeof(float) * (size_t)n;
-    int rc = buf.ensure(fN * 3 * 4 + fN * 4 + 256);
+    const size_t N = (size_t)n;
+    int rc = buf.ensure(sizeof(float4) * 2 * N + sizeof(float) * 7 * N + sizeof(int) * 4 * N + 1024);
     if (rc) return rc;
-    float* d_o = (float*)buf.p;
-    float* d_d = d_o + 3 * (size_t)n;
-    float* d_point = d_d + 3 * (size_t)n;
-    float* d_normal = d_point + 3 * (size_t)n;
-    float* d_dist = d_normal + 3 * (size_t)n;
-    int* d_hit = (int*)(d_dist + n);
-    int* d_tri = d_hit + n;
-    int* d_inside = d_tri + n;
+    char* p = (char*)buf.p;
+    PathQueue q{};
+    q.ray_o = (float4*)p; p += sizeof(float4) * N;
+    q.ray_d = (float4*)p; p += sizeof(float4) * N;
+    float* d_point = (float*)p; p += sizeof(float) * 3 * N;
+    float* d_normal = (float*)p; p += sizeof(float) * 3 * N;
+    float* d_dist = (float*)p; p += sizeof(float) * N;
+    int* d_hit = (int*)p; p += sizeof(int) * N;
+    int* d_tri = (int*)p; p += sizeof(int) * N;
+    int* d_inside = (int*)p; p += sizeof(int) * N;
+    uint32_t* d_defer = (uint32_t*)p; p += sizeof(uint32_t) * N;
+    uint32_t* d_cnt = (uint32_t*)p;  // [0] n, [1] work, [2] deferred, [3] deferred work
     cudaStream_t st = s->own_stream;
-    cudaError_t e = cudaMemcpyAsync(d_o, origins, fN * 3, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dirs, fN * 3, cudaMemcpyHostToDevice, st);
+    const uint32_t counters[4] = {(uint32_t)n, 0u, 0u, 0u};
+    cudaError_t e = cudaMemcpyAsync(q.ray_o, ho.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q.ray_d, hd.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_cnt, counters, sizeof(counters), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
-        launch_trace_rays(s->dev, traverse == EZRT_TRAVERSE_PRUNED, any_hit != 0, n, d_o, d_d, p3_normal_fudge, d_hit, d_dist, d_tri,
-                          d_inside, d_point, d_normal, st);
+        if (traverse == EZRT_TRAVERSE_ACCEL)
+            launch_extend_accel(s->dev, any_hit != 0, q, d_cnt, d_cnt + 1, d_defer, d_cnt + 2, d_cnt + 3, (uint32_t)n, s->n_sms, st);
+        else
+            launch_extend(s->dev, traverse != EZRT_TRAVERSE_REFERENCE, any_hit != 0, q, d_cnt, d_cnt + 1, nullptr, (uint32_t)n, s->n_sms, st);
+        launch_trace_finish(s->dev, n, q, p3_normal_fudge, d_hit, d_dist, d_tri, d_inside, d_point, d_normal, st);
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_hit, d_hit, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_distance, d_dist, fN, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_triangle, d_tri, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_inside, d_inside, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_point, d_point, fN * 3, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_normal, d_normal, fN * 3, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_hit, d_hit, sizeof(int) * N, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_distance, d_dist, sizeof(float) * N, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_triangle, d_tri, sizeof(int) * N, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_inside, d_inside, sizeof(int) * N, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_point, d_point, sizeof(float) * 3 * N, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_normal, d_normal, sizeof(float) * 3 * N, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     buf.release();
     if (e != cudaSuccess) return ezrt_set_error(EZRT_ERR_CUDA, "trace_rays: %s", cudaGetErrorString(e));

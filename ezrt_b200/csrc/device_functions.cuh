@@ -140,13 +140,13 @@ __device__ __forceinline__ NodeVisit node_visit(const float4* __restrict__ nd, c
 // record of the top tree levels from shared memory (stride EZRT_TOP_STRIDE float4 = 80 B, so the
 // 16-byte pieces of different records spread over the banks), else from global memory
 template <bool FAST>
-__device__ __forceinline__ NodeVisit node_visit_top(const SceneDev& sc, const float4* smem_top, int top_nodes, int ref, const RaySlab& rs) {
+__device__ __forceinline__ NodeVisit node_visit_top(const float4* __restrict__ nodes, const float4* smem_top, int top_nodes, int ref, const RaySlab& rs) {
     ulonglong2 q0, q1, q2, q3;
     if (ref < top_nodes) {
         const ulonglong2* p = reinterpret_cast<const ulonglong2*>(smem_top + ref * EZRT_TOP_STRIDE);
         q0 = p[0]; q1 = p[1]; q2 = p[2]; q3 = p[3];
     } else {
-        const float4* nd = sc.nodes + (size_t)ref * 4;
+        const float4* nd = nodes + (size_t)ref * 4;
         ldg256_b64(nd, q0, q1);
         ldg256_b64(nd + 2, q2, q3);
     }
@@ -189,16 +189,19 @@ __device__ __forceinline__ NodeVisit node_visit_q(ulonglong2 q0, ulonglong2 q1, 
 
 // Ray/triangle test against the repacked record.  Accepts exactly the hits hitTriangle accepts
 // that are also strictly closer than `best` (the only ones hitArray/hitBVH can keep).
-__device__ __forceinline__ bool tri_test(const float4* __restrict__ rec, vec3 o, vec3 d, float best, float& tout) {
+// TIES (accel policy): a hit at exactly t == best is also reported (return 2) so the caller can
+// detect that two triangles tie and let the exact reference-order traversal decide.
+template <bool TIES>
+__device__ __forceinline__ int tri_test_t(const float4* __restrict__ rec, vec3 o, vec3 d, float best, float& tout) {
     float4 q0, q1, q2, q3;
     ldg256_f32(rec, q0, q1);
     ldg256_f32(rec + 2, q2, q3);
     vec3 N = ez_v3(q0.w, q1.w, q2.w);
     float nd = ez_dot(N, d);
-    if (ez_abs(nd) < 0.00001f) return false;                    // :181 (|dot(+-N,d)| is sign-free)
+    if (ez_abs(nd) < 0.00001f) return 0;                        // :181 (|dot(+-N,d)| is sign-free)
     float t = EZ_DIV(q3.x - ez_dot(o, N), nd);                  // :184 (sign of N cancels exactly)
-    if (t < 0.0005f) return false;                              // :185
-    if (!(t < best)) return false;                              // :245, :273 strict <, first wins
+    if (t < 0.0005f) return 0;                                  // :185
+    if (TIES ? !(t <= best) : !(t < best)) return 0;            // :245, :273 strict <, first wins
     vec3 p1 = f4xyz(q0), p2 = f4xyz(q1), p3 = f4xyz(q2);
     vec3 P = ez_add(o, ez_scale(d, t));                         // :188
     float s1 = ez_dot(ez_cross(ez_sub(p2, p1), ez_sub(P, p1)), N);  // :191-195 (N unflipped: r1/r2 swap)
@@ -206,9 +209,12 @@ __device__ __forceinline__ bool tri_test(const float4* __restrict__ rec, vec3 o,
     float s3 = ez_dot(ez_cross(ez_sub(p1, p3), ez_sub(P, p3)), N);
     bool r1 = (s1 > 0.0f && s2 > 0.0f && s3 > 0.0f);
     bool r2 = (s1 < 0.0f && s2 < 0.0f && s3 < 0.0f);
-    if (!(r1 || r2)) return false;
+    if (!(r1 || r2)) return 0;
     tout = t;
-    return true;
+    return (TIES && t == best) ? 2 : 1;
+}
+__device__ __forceinline__ bool tri_test(const float4* __restrict__ rec, vec3 o, vec3 d, float best, float& tout) {
+    return tri_test_t<false>(rec, o, d, best, tout) != 0;
 }
 
 __device__ __forceinline__ bool prune_test(float t0, float best, float slack) {
@@ -306,9 +312,41 @@ __device__ __forceinline__ HitRec trace_ray(const SceneDev& sc, vec3 o, vec3 d) 
 // ------------------------------------------------------------------------------------------
 #define EZRT_REF_DONE ((int)0x80000000)   // leaf flag with n == 0: no real leaf has this encoding
 
-template <bool PRUNE, bool ANYHIT, class RayIO>
-__device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n, uint32_t* work, RayIO io, const float4* smem_top) {
-    const int top_nodes = sc.top_nodes;
+// the tree a persistent traversal walks: the reference tree or the device's acceleration tree
+struct TreeView {
+    const float4* nodes;
+    const float4* tri_geo;
+    int root_ref;
+    int top_nodes;
+};
+
+// Would the shader's hitBVH have reached the leaf that holds reference triangle `ref_tri`?  Yes iff
+// the leaf's own box passes hitAABB > 0: the fp32 slab values are monotone in the box bounds
+// (rounding is monotone), every ancestor box contains the leaf box, so it passes whenever the leaf
+// does (DESIGN.md "accel").  Exact hitAABB arithmetic; only called for rays with finite 1/d.
+__device__ __forceinline__ bool reference_reaches_leaf(const int* __restrict__ tri_leaf, const float4* __restrict__ leaf_box, int ref_tri, vec3 o,
+                                                       const RaySlab& rs) {
+    const int leaf = __ldg(tri_leaf + ref_tri);
+    const float4 a = ldg4(leaf_box + 2 * (size_t)leaf), b = ldg4(leaf_box + 2 * (size_t)leaf + 1);
+    float ix, iy, iz, iz2;
+    pk2_split(rs.inv_xy, ix, iy);
+    pk2_split(rs.inv_zz, iz, iz2);
+    float fx = (b.x - o.x) * ix, fy = (b.y - o.y) * iy, fz = (b.z - o.z) * iz;
+    float nx = (a.x - o.x) * ix, ny = (a.y - o.y) * iy, nz = (a.z - o.z) * iz;
+    float t1 = fminf(fmaxf(fx, nx), fminf(fmaxf(fy, ny), fmaxf(fz, nz)));
+    float t0 = fmaxf(fminf(fx, nx), fmaxf(fminf(fy, ny), fminf(fz, nz)));
+    float d = (t1 >= t0) ? ((t0 > 0.0f) ? t0 : t1) : -1.0f;
+    return d > 0.0f;
+}
+
+// ACCEL: `tree` is the device's own acceleration tree, not the reference tree: the closest hit it
+// finds is the global minimum over all triangles; ties (two triangles at exactly the same t) and rays
+// with non-finite 1/d are handed to io.defer() and re-traced by the exact reference-order kernel.
+template <bool PRUNE, bool ANYHIT, bool ACCEL, class RayIO>
+__device__ __forceinline__ void extend_persistent(const SceneDev& sc, const TreeView tree, uint32_t n, uint32_t* work, RayIO io,
+                                                  const float4* smem_top) {
+    const int top_nodes = tree.top_nodes;
+    bool tie = false;          // ACCEL: another triangle was accepted at exactly the best distance
     const int refill_thresh = sc.refill_thresh;  // go back to refill when fewer lanes than this are busy
     const int inner_thresh = sc.inner_thresh;    // leave the inner-node phase when fewer lanes than this walk
     const int leaf_thresh = sc.leaf_thresh;      // ... or when at least this many lanes wait at a leaf
@@ -351,12 +389,15 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
                     if ((ax < 3.0e38f) && (ay < 3.0e38f) && (az < 3.0e38f)) {
                         rs = make_ray_slab(o, inv);
                         ray = (int)idx;
-                        ref = sc.root_ref;
+                        ref = tree.root_ref;
                         sp = 0;
                         best = EZ_INF;
                         best_tri = -1;
+                        tie = false;
+                    } else if (ACCEL) {  // exact kernel handles the literal ternary min/max path
+                        io.defer(idx);
                     } else {  // a zero / NaN direction component: literal ternary min/max path (rare)
-                        io.store(idx, trace_impl<PRUNE, ANYHIT, false>(sc, o, d, inv, slack));
+                        io.store(idx, trace_impl<PRUNE, ANYHIT, false>(sc, o, d, inv, slack), false, o, rs);
                     }
                 }
             }
@@ -387,7 +428,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
                 const unsigned m_wait = m_busy & ~m_inner;  // busy lanes standing at a leaf (or done)
                 if (m_wait != 0u && (__popc(m_inner) < inner_thresh || __popc(m_wait) >= leaf_thresh)) break;
                 if (at_inner) {
-                    NodeVisit nv = node_visit_top<true>(sc, smem_top, top_nodes, ref, rs);
+                    NodeVisit nv = node_visit_top<true>(tree.nodes, smem_top, top_nodes, ref, rs);
                     bool h1 = nv.h1, h2 = nv.h2;
                     const float d1 = nv.d1, d2 = nv.d2, e1 = nv.e1, e2 = nv.e2;
                     const int rl = nv.rl, rr = nv.rr;
@@ -441,29 +482,44 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
                 const int rfirst = __shfl_sync(FULL, my_first, src);
                 const int rcnt_all = __shfl_sync(FULL, my_cnt, src);  // every lane must take part in the shuffle
                 const int rcnt = (owner < 0) ? 0 : rcnt_all;
+                bool lane_tie = false;
                 unsigned long long key = 0xffffffffffffffffull;
                 for (int kb = 0; __ballot_sync(FULL, kb < rcnt) != 0u; kb += 8) {
                     const int ti = kb + k;
                     if (ti < rcnt) {
                         float t;
-                        if (tri_test(sc.tri_geo + (size_t)(rfirst + ti) * 4, ro, rdir, rbest, t)) {
+                        if (tri_test_t<ACCEL>(tree.tri_geo + (size_t)(rfirst + ti) * 4, ro, rdir, rbest, t) != 0) {
                             unsigned long long kk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)(rfirst + ti);
+                            if (ACCEL && key != 0xffffffffffffffffull && (unsigned)(kk >> 32) == (unsigned)(key >> 32)) lane_tie = true;
                             key = (kk < key) ? kk : key;
                         }
                     }
                 }
+                const unsigned long long mine = key;
                 // min over the octet
                 for (int off = 1; off < 8; off <<= 1) {
                     unsigned long long other = __shfl_xor_sync(FULL, key, off);
                     key = (other < key) ? other : key;
                 }
+                unsigned tie_mask = 0u;
+                if (ACCEL) {  // a second triangle of this leaf at the winning distance, or the old best tied
+                    const bool t_tie = lane_tie || (mine != 0xffffffffffffffffull && mine != key && (unsigned)(mine >> 32) == (unsigned)(key >> 32)) ||
+                                       (key != 0xffffffffffffffffull && __uint_as_float((unsigned)(key >> 32)) == rbest);
+                    tie_mask = __ballot_sync(FULL, t_tie);
+                }
                 // owners read the result of their octet
                 const int back = (lane == j0) ? 0 : (lane == j1) ? 8 : (lane == j2) ? 16 : (lane == j3) ? 24 : lane;
                 const unsigned long long res = __shfl_sync(FULL, key, back);
-                if (at_leaf && (lane == j0 || lane == j1 || lane == j2 || lane == j3) && res != 0xffffffffffffffffull) {
-                    best = __uint_as_float((unsigned)(res >> 32));
-                    best_tri = (int)(unsigned)(res & 0xffffffffull);
-                    if (ANYHIT) stop = true;
+                if (at_leaf && (lane == j0 || lane == j1 || lane == j2 || lane == j3)) {
+                    if (ACCEL && ((tie_mask >> back) & 0xffu) != 0u) tie = true;
+                    if (res != 0xffffffffffffffffull) {
+                        const float tn = __uint_as_float((unsigned)(res >> 32));
+                        if (!ACCEL || tn < best) {  // ACCEL accepts t == best only to flag the tie
+                            best = tn;
+                            best_tri = (int)(unsigned)(res & 0xffffffffull);
+                        }
+                        if (ANYHIT) stop = true;
+                    }
                 }
             }
             if (at_leaf) {  // pop (hitBVH continues with the next stack entry)
@@ -481,7 +537,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, uint32_t n
                 HitRec h;
                 h.t = best;
                 h.tri = best_tri;
-                io.store((uint32_t)ray, h);
+                io.store((uint32_t)ray, h, tie, o, rs);
                 ray = -1;
             }
             busy = __ballot_sync(FULL, ray >= 0);

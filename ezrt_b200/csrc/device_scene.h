@@ -41,6 +41,16 @@ struct SceneDev {
     const float* hdr_cache;   // W*H*3 or null
     int hdr_w, hdr_h, hdr_linear;
     int root_ref;
+    // acceleration tree (default traversal policy): sentinel-free SAH over the same triangles, boxes
+    // inflated by 2*prune_delta; acc_tri_geo is tri_geo in the tree's own order, acc_tri_ref maps back
+    const float4* acc_nodes;
+    const float4* acc_tri_geo;
+    const uint32_t* acc_tri_ref;
+    int acc_root_ref;
+    int acc_top_nodes;
+    // reference leaf of every reference triangle + the leaves' boxes (AA, BB as float4 pairs)
+    const int* tri_leaf;
+    const float4* leaf_box;
     int n_triangles;
     int n_inner;
     int top_nodes;            // records [0, top_nodes) = the top tree levels, staged in shared memory

@@ -394,6 +394,7 @@ struct FastCtx {
     const std::vector<ez_vec3>* bmax;
     Key* keys;
     int leaf_n;
+    float inf;  // cost sentinel / box seed: EZ_INF (114514, the reference's quirk) or FLT_MAX (accel tree)
 };
 bool kcmpx(const Key& a, const Key& b) { return a.cx < b.cx; }
 bool kcmpy(const Key& a, const Key& b) { return a.cy < b.cy; }
@@ -423,7 +424,8 @@ void build_sah_fast(const FastCtx& cx, int l, int r, std::vector<Node>& out, int
         out[base].index = l;
         return;
     }
-    float Cost = EZ_INF;
+    const float INFV = cx.inf;
+    float Cost = INFV;
     int Axis = 0;
     int Split = (l + r) / 2;
     {
@@ -432,16 +434,16 @@ void build_sah_fast(const FastCtx& cx, int l, int r, std::vector<Node>& out, int
             if (axis == 0) std::sort(keys + l, keys + r + 1, kcmpx);
             if (axis == 1) std::sort(keys + l, keys + r + 1, kcmpy);
             if (axis == 2) std::sort(keys + l, keys + r + 1, kcmpz);
-            ez_vec3 rmax = ez_v3(-EZ_INF, -EZ_INF, -EZ_INF), rmin = ez_v3(EZ_INF, EZ_INF, EZ_INF);
+            ez_vec3 rmax = ez_v3(-INFV, -INFV, -INFV), rmin = ez_v3(INFV, INFV, INFV);
             for (int i = r; i >= l; i--) {
                 rmax = ez_vmax(rmax, bmax[keys[i].id]);
                 rmin = ez_vmin(rmin, bmin[keys[i].id]);
                 rightMax[i - l] = rmax;
                 rightMin[i - l] = rmin;
             }
-            float cost = EZ_INF;
+            float cost = INFV;
             int split = l;
-            ez_vec3 lmax = ez_v3(-EZ_INF, -EZ_INF, -EZ_INF), lmin = ez_v3(EZ_INF, EZ_INF, EZ_INF);
+            ez_vec3 lmax = ez_v3(-INFV, -INFV, -INFV), lmin = ez_v3(INFV, INFV, INFV);
             for (int i = l; i <= r - 1; i++) {
                 lmax = ez_vmax(lmax, bmax[keys[i].id]);
                 lmin = ez_vmin(lmin, bmin[keys[i].id]);
@@ -494,6 +496,38 @@ struct ezrt_trilist {
     std::vector<Tri> tris;
     std::vector<Node> nodes;
 };
+
+// Acceleration tree for the device's default traversal policy (capi.cu): the same exhaustive-sweep
+// SAH as buildBVHwithSAH but WITHOUT the reference's INF = 114514 cost sentinel, so the top levels
+// are real SAH splits instead of median splits on axis 0.  nodes[0] is the root; child links are
+// indices into `nodes` (0 = none); order[i] = index (in `tris`) of the i-th triangle of the tree.
+int ezrt_build_accel(const float* tris, int n_tris, int leaf_n, std::vector<EzrtAccelNode>& nodes_out, std::vector<uint32_t>& order) {
+    std::vector<Key> keys(n_tris);
+    std::vector<ez_vec3> bmin(n_tris), bmax(n_tris);
+    for (int i = 0; i < n_tris; i++) {
+        const float* t = tris + (size_t)i * EZRT_TRIANGLE_FLOATS;
+        Tri tr;
+        tr.p1 = ez_v3(t[0], t[1], t[2]); tr.p2 = ez_v3(t[3], t[4], t[5]); tr.p3 = ez_v3(t[6], t[7], t[8]);
+        ez_vec3 c = centroid(tr);
+        keys[i].cx = c.x; keys[i].cy = c.y; keys[i].cz = c.z; keys[i].id = (unsigned)i;
+        bmin[i] = tri_min(tr);
+        bmax[i] = tri_max(tr);
+    }
+    FastCtx cx;
+    cx.bmin = &bmin; cx.bmax = &bmax; cx.keys = keys.data(); cx.leaf_n = leaf_n; cx.inf = 3.0e38f;
+    std::vector<Node> sub;
+    build_sah_fast(cx, 0, n_tris - 1, sub, 0);
+    nodes_out.resize(sub.size());
+    for (size_t i = 0; i < sub.size(); i++) {
+        EzrtAccelNode& d = nodes_out[i];
+        d.left = sub[i].left; d.right = sub[i].right; d.n = sub[i].n; d.index = sub[i].index;
+        d.AA[0] = sub[i].AA.x; d.AA[1] = sub[i].AA.y; d.AA[2] = sub[i].AA.z;
+        d.BB[0] = sub[i].BB.x; d.BB[1] = sub[i].BB.y; d.BB[2] = sub[i].BB.z;
+    }
+    order.resize(n_tris);
+    for (int i = 0; i < n_tris; i++) order[i] = keys[i].id;
+    return (int)nodes_out.size();
+}
 
 extern "C" {
 
@@ -559,7 +593,7 @@ int ezrt_trilist_build_bvh(ezrt_trilist* list, int leaf_n, int builder) {
         build_sah_literal(list->tris, list->nodes, 0, N - 1, leaf_n);
     } else if (builder == EZRT_BVH_MEDIAN) {
         build_median(list->tris, list->nodes, 0, N - 1, leaf_n);
-    } else if (builder == EZRT_BVH_SAH_FAST) {
+    } else if (builder == EZRT_BVH_SAH_FAST || builder == EZRT_BVH_SAH_NO_SENTINEL) {
         std::vector<Key> keys(N);
         std::vector<ez_vec3> bmin(N), bmax(N);
         for (int i = 0; i < N; i++) {
@@ -570,6 +604,7 @@ int ezrt_trilist_build_bvh(ezrt_trilist* list, int leaf_n, int builder) {
         }
         FastCtx cx;
         cx.bmin = &bmin; cx.bmax = &bmax; cx.keys = keys.data(); cx.leaf_n = leaf_n;
+        cx.inf = (builder == EZRT_BVH_SAH_NO_SENTINEL) ? 3.0e38f : EZ_INF;
         std::vector<Node> sub;
         build_sah_fast(cx, 0, N - 1, sub, 0);
         for (auto nd : sub) {  // relative-to-block-0 -> absolute (dummy node shifts everything by 1)

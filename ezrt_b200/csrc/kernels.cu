@@ -161,14 +161,26 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const uint32_t* __restrict
     }
 }
 
-// the top tree levels, copied from global memory by every persistent block at kernel start
+// the top levels of the tree a kernel walks, copied from global memory by every persistent block at start
 extern __shared__ float4 g_smem_top[];
-__device__ __forceinline__ void stage_top_nodes(const SceneDev& sc) {
-    const int n4 = sc.top_nodes * 4;
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) g_smem_top[(i >> 2) * EZRT_TOP_STRIDE + (i & 3)] = sc.nodes[i];
+__device__ __forceinline__ void stage_top_nodes(const TreeView& tree) {
+    const int n4 = tree.top_nodes * 4;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) g_smem_top[(i >> 2) * EZRT_TOP_STRIDE + (i & 3)] = tree.nodes[i];
     __syncthreads();
 }
+__device__ __forceinline__ TreeView reference_tree(const SceneDev& sc) {
+    TreeView t;
+    t.nodes = sc.nodes; t.tri_geo = sc.tri_geo; t.root_ref = sc.root_ref; t.top_nodes = sc.top_nodes;
+    return t;
+}
+__device__ __forceinline__ TreeView accel_tree(const SceneDev& sc) {
+    TreeView t;
+    t.nodes = sc.acc_nodes; t.tri_geo = sc.acc_tri_geo; t.root_ref = sc.acc_root_ref; t.top_nodes = sc.acc_top_nodes;
+    return t;
+}
 
+// ---- exact kernels: the reference tree in the shader's order (policies REFERENCE and PRUNED, and the
+// fallback pass of the accel policy, which traces only the deferred ray indices in `perm`)
 struct ExtendIO {
     PathQueue q;
     const uint32_t* perm;  // null: trace in queue order
@@ -178,51 +190,141 @@ struct ExtendIO {
         o = ez_v3(o4.x, o4.y, o4.z);
         d = ez_v3(d4.x, d4.y, d4.z);
     }
-    __device__ __forceinline__ void store(uint32_t i, HitRec h) const {
+    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3, const RaySlab&) const {
         const uint32_t j = perm ? perm[i] : i;
         q.ray_o[j].w = h.t;
         q.ray_d[j].w = __int_as_float(h.tri);
     }
+    __device__ __forceinline__ void defer(uint32_t) const {}
 };
 
-template <bool PRUNE>
+template <bool PRUNE, bool ANYHIT>
 __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_extend(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
                                                                 uint32_t* work, const uint32_t* __restrict__ perm) {
     ExtendIO io;
     io.q = q;
     io.perm = perm;
-    stage_top_nodes(sc);
-    extend_persistent<PRUNE, false>(sc, *q_count, work, io, g_smem_top);
+    const TreeView tree = reference_tree(sc);
+    stage_top_nodes(tree);
+    extend_persistent<PRUNE, ANYHIT, false>(sc, tree, *q_count, work, io, g_smem_top);
 }
 
-// shadow rays: any hit; an unoccluded ray adds its precomputed contribution (P5/fsh:829-841).
+// ---- accel kernels: the device's own SAH tree finds the global closest hit G; the result is kept when
+// the shader's traversal provably reaches G's leaf and nothing ties with G, otherwise the ray index is
+// appended to `defer_list` for the exact kernel (DESIGN.md "accel").
+struct AccelIO {
+    PathQueue q;
+    const uint32_t* acc_tri_ref;
+    const int* tri_leaf;
+    const float4* leaf_box;
+    uint32_t* defer_list;
+    uint32_t* defer_count;
+    __device__ __forceinline__ void load(uint32_t i, vec3& o, vec3& d) const {
+        float4 o4 = q.ray_o[i], d4 = q.ray_d[i];
+        o = ez_v3(o4.x, o4.y, o4.z);
+        d = ez_v3(d4.x, d4.y, d4.z);
+    }
+    __device__ __forceinline__ void defer(uint32_t i) const { defer_list[atomicAdd(defer_count, 1u)] = i; }
+    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool tie, vec3 o, const RaySlab& rs) const {
+        int ref_tri = -1;
+        if (h.tri >= 0) {
+            ref_tri = (int)__ldg(acc_tri_ref + h.tri);
+            if (tie || !reference_reaches_leaf(tri_leaf, leaf_box, ref_tri, o, rs)) {
+                defer(i);
+                return;
+            }
+        }
+        q.ray_o[i].w = h.t;
+        q.ray_d[i].w = __int_as_float(ref_tri);
+    }
+};
+
+template <bool ANYHIT>
+__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_extend_accel(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
+                                                                      uint32_t* work, uint32_t* defer_list, uint32_t* defer_count) {
+    AccelIO io;
+    io.q = q;
+    io.acc_tri_ref = sc.acc_tri_ref;
+    io.tri_leaf = sc.tri_leaf;
+    io.leaf_box = sc.leaf_box;
+    io.defer_list = defer_list;
+    io.defer_count = defer_count;
+    const TreeView tree = accel_tree(sc);
+    stage_top_nodes(tree);
+    extend_persistent<true, ANYHIT, true>(sc, tree, *q_count, work, io, g_smem_top);
+}
+
+// ---- shadow rays: any hit; an unoccluded ray adds its precomputed contribution (P5/fsh:829-841).
 // One path per sample slot -> no two lanes touch the same Lo entry.
 struct ShadowIO {
     ShadowQueue sq;
     float4* Lo;
+    const uint32_t* perm;
     __device__ __forceinline__ void load(uint32_t i, vec3& o, vec3& d) const {
-        float4 o4 = sq.ray_o[i], d4 = sq.ray_d[i];
+        const uint32_t j = perm ? perm[i] : i;
+        float4 o4 = sq.ray_o[j], d4 = sq.ray_d[j];
         o = ez_v3(o4.x, o4.y, o4.z);
         d = ez_v3(d4.x, d4.y, d4.z);
     }
-    __device__ __forceinline__ void store(uint32_t i, HitRec h) const {
-        if (h.tri >= 0) return;
-        uint32_t slot = __float_as_uint(sq.ray_o[i].w);
-        float4 c = sq.contrib[i];
+    __device__ __forceinline__ void add(uint32_t j) const {
+        uint32_t slot = __float_as_uint(sq.ray_o[j].w);
+        float4 c = sq.contrib[j];
         float4 lo = Lo[slot];
         lo.x += c.x; lo.y += c.y; lo.z += c.z;
         Lo[slot] = lo;
     }
+    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3, const RaySlab&) const {
+        if (h.tri < 0) add(perm ? perm[i] : i);
+    }
+    __device__ __forceinline__ void defer(uint32_t) const {}
 };
 
 template <bool PRUNE>
 __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_shadow(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count,
-                                                                uint32_t* work, float4* __restrict__ Lo) {
+                                                                uint32_t* work, float4* __restrict__ Lo, const uint32_t* __restrict__ perm) {
     ShadowIO io;
     io.sq = sq;
     io.Lo = Lo;
-    stage_top_nodes(sc);
-    extend_persistent<PRUNE, true>(sc, *s_count, work, io, g_smem_top);
+    io.perm = perm;
+    const TreeView tree = reference_tree(sc);
+    stage_top_nodes(tree);
+    extend_persistent<PRUNE, true, false>(sc, tree, *s_count, work, io, g_smem_top);
+}
+
+struct ShadowAccelIO {
+    ShadowIO base;
+    const uint32_t* acc_tri_ref;
+    const int* tri_leaf;
+    const float4* leaf_box;
+    uint32_t* defer_list;
+    uint32_t* defer_count;
+    __device__ __forceinline__ void load(uint32_t i, vec3& o, vec3& d) const { base.load(i, o, d); }
+    __device__ __forceinline__ void defer(uint32_t i) const { defer_list[atomicAdd(defer_count, 1u)] = i; }
+    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3 o, const RaySlab& rs) const {
+        if (h.tri < 0) {  // nothing accepted anywhere: the shader finds nothing either
+            base.add(i);
+            return;
+        }
+        // occluded if the shader reaches the occluder's leaf; otherwise let the exact kernel decide
+        if (!reference_reaches_leaf(tri_leaf, leaf_box, (int)__ldg(acc_tri_ref + h.tri), o, rs)) defer(i);
+    }
+};
+
+__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_shadow_accel(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count,
+                                                                      uint32_t* work, float4* __restrict__ Lo, uint32_t* defer_list,
+                                                                      uint32_t* defer_count) {
+    ShadowAccelIO io;
+    io.base.sq = sq;
+    io.base.Lo = Lo;
+    io.base.perm = nullptr;
+    io.acc_tri_ref = sc.acc_tri_ref;
+    io.tri_leaf = sc.tri_leaf;
+    io.leaf_box = sc.leaf_box;
+    io.defer_list = defer_list;
+    io.defer_count = defer_count;
+    const TreeView tree = accel_tree(sc);
+    stage_top_nodes(tree);
+    extend_persistent<true, true, true>(sc, tree, *s_count, work, io, g_smem_top);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -317,17 +419,18 @@ __global__ void __launch_bounds__(256) k_blend(RenderDev rd, const TileDev* __re
     if (rd.out_channels == 4) fb[idx + 3] = 1.0f;
 }
 
-// totals[0..2] += primary, bounce, shadow rays of this batch; totals[3] += samples
-__global__ void k_tally(const uint32_t* __restrict__ q_counts, const uint32_t* __restrict__ s_counts, int n_stages,
-                        unsigned long long* totals) {
+// totals[0..2] += primary, bounce, shadow rays of this batch; totals[3] += samples; totals[4] += deferred rays
+__global__ void k_tally(const uint32_t* __restrict__ q_counts, const uint32_t* __restrict__ s_counts, const uint32_t* __restrict__ d_ext,
+                        const uint32_t* __restrict__ d_sh, int n_stages, unsigned long long* totals) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    unsigned long long bounce = 0, shadow = 0;
+    unsigned long long bounce = 0, shadow = 0, deferred = 0;
     for (int b = 1; b < n_stages; b++) bounce += q_counts[b];
-    for (int b = 0; b < n_stages; b++) shadow += s_counts[b];
+    for (int b = 0; b < n_stages; b++) { shadow += s_counts[b]; deferred += d_ext[b] + d_sh[b]; }
     totals[0] += q_counts[0];
     totals[1] += bounce;
     totals[2] += shadow;
     totals[3] += q_counts[0];
+    totals[4] += deferred;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -384,23 +487,24 @@ __global__ void __launch_bounds__(128) k_megakernel(SceneDev sc, RenderDev rd, c
 // ------------------------------------------------------------------------------------------
 // single-function entry points (parity tests)
 // ------------------------------------------------------------------------------------------
-template <bool PRUNE, bool ANYHIT>
-__global__ void k_trace_rays(SceneDev sc, int n, const float* __restrict__ o, const float* __restrict__ d, int p3fudge,
-                             int* hit, float* dist, int* tri, int* inside, float* point, float* normal) {
+// results of a traced ray queue -> the outputs of ezrt_trace_rays (tail of hitTriangle for the final hit)
+__global__ void k_trace_finish(SceneDev sc, int n, PathQueue q, int p3fudge, int* hit, float* dist, int* tri, int* inside, float* point,
+                               float* normal) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    vec3 ro = ez_v3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), rdv = ez_v3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
-    HitRec h = trace_ray<PRUNE, ANYHIT>(sc, ro, rdv);
-    hit[i] = h.tri >= 0;
-    dist[i] = h.t;
-    tri[i] = h.tri;
+    float4 o4 = q.ray_o[i], d4 = q.ray_d[i];
+    vec3 ro = ez_v3(o4.x, o4.y, o4.z), rdv = ez_v3(d4.x, d4.y, d4.z);
+    const int ht = __float_as_int(d4.w);
+    hit[i] = ht >= 0;
+    dist[i] = o4.w;
+    tri[i] = ht;
     vec3 P = splat3(0.0f), N = splat3(0.0f);
     int ins = 0;
-    if (h.tri >= 0) {
-        SurfaceHit s = surface_hit(sc, ro, rdv, h.t, h.tri, p3fudge != 0);
+    if (ht >= 0) {
+        SurfaceHit s = surface_hit(sc, ro, rdv, o4.w, ht, p3fudge != 0);
         P = s.P;
         N = s.N;
-        const float4* g = sc.tri_geo + (size_t)h.tri * 4;
+        const float4* g = sc.tri_geo + (size_t)ht * 4;
         vec3 Ng = ez_v3(ldg4(g).w, ldg4(g + 1).w, ldg4(g + 2).w);
         ins = ez_dot(Ng, rdv) > 0.0f;
     }
@@ -487,26 +591,39 @@ static int extend_blocks_per_sm() {
     }
     return v;
 }
-template <class K>
-static size_t extend_smem(K kernel, const SceneDev& sc) {
-    size_t bytes = (size_t)sc.top_nodes * EZRT_TOP_STRIDE * sizeof(float4);
-    static size_t configured = 0;
-    (void)configured;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bytes, 1024));
-    return bytes;
-}
 void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots, uint32_t batch_first_frame, PathQueue q,
                      uint32_t* q_count, int n_sms, cudaStream_t st) {
     int blocks = std::min(div_up(n_slots, 256), n_sms * 8);
     k_generate<<<blocks, 256, 0, st>>>(rd, tiles, n_slots, batch_first_frame, q, q_count);
 }
-void launch_extend(const SceneDev& sc, bool prune, PathQueue q, const uint32_t* q_count, uint32_t* work, const uint32_t* perm,
-                   uint32_t n_max, int n_sms, cudaStream_t st) {
-    const int threads = extend_threads();
-    int blocks = std::min(div_up(n_max, threads), n_sms * extend_blocks_per_sm());
-    if (blocks < 1) blocks = 1;
-    if (prune) k_extend<true><<<blocks, threads, extend_smem(k_extend<true>, sc), st>>>(sc, q, q_count, work, perm);
-    else k_extend<false><<<blocks, threads, extend_smem(k_extend<false>, sc), st>>>(sc, q, q_count, work, perm);
+template <class K>
+static size_t smem_for(K kernel, int top_nodes) {
+    size_t bytes = (size_t)top_nodes * EZRT_TOP_STRIDE * sizeof(float4);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bytes, 1024));
+    return bytes;
+}
+static int persistent_blocks(uint32_t n_max, int n_sms) {
+    int blocks = std::min(div_up(n_max, extend_threads()), n_sms * extend_blocks_per_sm());
+    return blocks < 1 ? 1 : blocks;
+}
+
+// exact traversal of the reference tree (policies REFERENCE / PRUNED, and the accel policy's fallback pass
+// over the deferred indices in `perm`)
+void launch_extend(const SceneDev& sc, bool prune, bool anyhit, PathQueue q, const uint32_t* q_count, uint32_t* work,
+                   const uint32_t* perm, uint32_t n_max, int n_sms, cudaStream_t st) {
+    const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
+    if (prune && anyhit) k_extend<true, true><<<blocks, threads, smem_for(k_extend<true, true>, sc.top_nodes), st>>>(sc, q, q_count, work, perm);
+    else if (prune) k_extend<true, false><<<blocks, threads, smem_for(k_extend<true, false>, sc.top_nodes), st>>>(sc, q, q_count, work, perm);
+    else if (anyhit) k_extend<false, true><<<blocks, threads, smem_for(k_extend<false, true>, sc.top_nodes), st>>>(sc, q, q_count, work, perm);
+    else k_extend<false, false><<<blocks, threads, smem_for(k_extend<false, false>, sc.top_nodes), st>>>(sc, q, q_count, work, perm);
+}
+// accel policy: acceleration-tree pass, then the exact pass over whatever it deferred
+void launch_extend_accel(const SceneDev& sc, bool anyhit, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t* defer_list,
+                         uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, cudaStream_t st) {
+    const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
+    if (anyhit) k_extend_accel<true><<<blocks, threads, smem_for(k_extend_accel<true>, sc.acc_top_nodes), st>>>(sc, q, q_count, work, defer_list, defer_count);
+    else k_extend_accel<false><<<blocks, threads, smem_for(k_extend_accel<false>, sc.acc_top_nodes), st>>>(sc, q, q_count, work, defer_list, defer_count);
+    launch_extend(sc, true, anyhit, q, defer_count, defer_work, defer_list, std::min<uint32_t>(n_max, 65536u), n_sms, st);
 }
 // counting sort of the queue's ray indices into `perm` (3 kernels; bins must hold EZRT_SORT_BINS counters)
 void launch_ray_sort(const SceneDev& sc, PathQueue q, const uint32_t* q_count, uint32_t* keys, uint32_t* bins, uint32_t* perm,
@@ -518,12 +635,16 @@ void launch_ray_sort(const SceneDev& sc, PathQueue q, const uint32_t* q_count, u
     k_sort_scatter<<<blocks, 256, 0, st>>>(q_count, keys, bins, perm);
 }
 void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo,
-                   uint32_t n_max, int n_sms, cudaStream_t st) {
-    const int threads = extend_threads();
-    int blocks = std::min(div_up(n_max, threads), n_sms * extend_blocks_per_sm());
-    if (blocks < 1) blocks = 1;
-    if (prune) k_shadow<true><<<blocks, threads, extend_smem(k_shadow<true>, sc), st>>>(sc, sq, s_count, work, Lo);
-    else k_shadow<false><<<blocks, threads, extend_smem(k_shadow<false>, sc), st>>>(sc, sq, s_count, work, Lo);
+                   const uint32_t* perm, uint32_t n_max, int n_sms, cudaStream_t st) {
+    const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
+    if (prune) k_shadow<true><<<blocks, threads, smem_for(k_shadow<true>, sc.top_nodes), st>>>(sc, sq, s_count, work, Lo, perm);
+    else k_shadow<false><<<blocks, threads, smem_for(k_shadow<false>, sc.top_nodes), st>>>(sc, sq, s_count, work, Lo, perm);
+}
+void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo, uint32_t* defer_list,
+                         uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, cudaStream_t st) {
+    const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
+    k_shadow_accel<<<blocks, threads, smem_for(k_shadow_accel, sc.acc_top_nodes), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
+    launch_shadow(sc, true, sq, defer_count, defer_work, Lo, defer_list, std::min<uint32_t>(n_max, 65536u), n_sms, st);
 }
 void launch_shade(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, int bounce, uint32_t batch_first_frame,
                   PathQueue qin, const uint32_t* in_count, PathQueue qout, uint32_t* out_count, ShadowQueue sq,
@@ -537,8 +658,9 @@ void launch_blend(const RenderDev& rd, const TileDev* tiles, int nf, uint32_t ba
     uint32_t per_frame = (uint32_t)rd.n_tiles * EZRT_TILE_PIXELS;
     k_blend<<<div_up(per_frame, 256), 256, 0, st>>>(rd, tiles, nf, batch_first_frame, Lo, Le, fb);
 }
-void launch_tally(const uint32_t* q_counts, const uint32_t* s_counts, int n_stages, unsigned long long* totals, cudaStream_t st) {
-    k_tally<<<1, 32, 0, st>>>(q_counts, s_counts, n_stages, totals);
+void launch_tally(const uint32_t* q_counts, const uint32_t* s_counts, const uint32_t* d_ext, const uint32_t* d_sh, int n_stages,
+                  unsigned long long* totals, cudaStream_t st) {
+    k_tally<<<1, 32, 0, st>>>(q_counts, s_counts, d_ext, d_sh, n_stages, totals);
 }
 void launch_megakernel(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, bool prune, int spp, float* fb,
                        unsigned long long* totals, cudaStream_t st) {
@@ -546,13 +668,9 @@ void launch_megakernel(const SceneDev& sc, const RenderDev& rd, const TileDev* t
     if (prune) k_megakernel<true><<<div_up(per_frame, 128), 128, 0, st>>>(sc, rd, tiles, spp, fb, totals);
     else k_megakernel<false><<<div_up(per_frame, 128), 128, 0, st>>>(sc, rd, tiles, spp, fb, totals);
 }
-void launch_trace_rays(const SceneDev& sc, bool prune, bool anyhit, int n, const float* o, const float* d, int p3fudge, int* hit,
-                       float* dist, int* tri, int* inside, float* point, float* normal, cudaStream_t st) {
-    int blocks = div_up(n, 128);
-    if (prune && anyhit) k_trace_rays<true, true><<<blocks, 128, 0, st>>>(sc, n, o, d, p3fudge, hit, dist, tri, inside, point, normal);
-    else if (prune) k_trace_rays<true, false><<<blocks, 128, 0, st>>>(sc, n, o, d, p3fudge, hit, dist, tri, inside, point, normal);
-    else if (anyhit) k_trace_rays<false, true><<<blocks, 128, 0, st>>>(sc, n, o, d, p3fudge, hit, dist, tri, inside, point, normal);
-    else k_trace_rays<false, false><<<blocks, 128, 0, st>>>(sc, n, o, d, p3fudge, hit, dist, tri, inside, point, normal);
+void launch_trace_finish(const SceneDev& sc, int n, PathQueue q, int p3fudge, int* hit, float* dist, int* tri, int* inside, float* point,
+                         float* normal, cudaStream_t st) {
+    k_trace_finish<<<div_up(n, 128), 128, 0, st>>>(sc, n, q, p3fudge, hit, dist, tri, inside, point, normal);
 }
 void launch_eval_brdf(int which, int n, const float* V, const float* N, const float* L, const float* xi, const float* materials,
                       float* out, cudaStream_t st) {

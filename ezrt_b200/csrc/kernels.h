@@ -15,22 +15,27 @@
 
 void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots, uint32_t batch_first_frame, PathQueue q,
                      uint32_t* q_count, int n_sms, cudaStream_t st);
-void launch_extend(const SceneDev& sc, bool prune, PathQueue q, const uint32_t* q_count, uint32_t* work, const uint32_t* perm,
-                   uint32_t n_max, int n_sms, cudaStream_t st);
+void launch_extend(const SceneDev& sc, bool prune, bool anyhit, PathQueue q, const uint32_t* q_count, uint32_t* work,
+                   const uint32_t* perm, uint32_t n_max, int n_sms, cudaStream_t st);
+void launch_extend_accel(const SceneDev& sc, bool anyhit, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t* defer_list,
+                         uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, cudaStream_t st);
 void launch_ray_sort(const SceneDev& sc, PathQueue q, const uint32_t* q_count, uint32_t* keys, uint32_t* bins, uint32_t* perm,
                      uint32_t n_max, int n_sms, cudaStream_t st);
 void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo,
-                   uint32_t n_max, int n_sms, cudaStream_t st);
+                   const uint32_t* perm, uint32_t n_max, int n_sms, cudaStream_t st);
+void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo, uint32_t* defer_list,
+                         uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, cudaStream_t st);
 void launch_shade(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, int bounce, uint32_t batch_first_frame,
                   PathQueue qin, const uint32_t* in_count, PathQueue qout, uint32_t* out_count, ShadowQueue sq,
                   uint32_t* s_count, float4* Lo, float4* Le, uint32_t n_max, int n_sms, cudaStream_t st);
 void launch_blend(const RenderDev& rd, const TileDev* tiles, int nf, uint32_t batch_first_frame, const float4* Lo,
                   const float4* Le, float* fb, cudaStream_t st);
-void launch_tally(const uint32_t* q_counts, const uint32_t* s_counts, int n_stages, unsigned long long* totals, cudaStream_t st);
+void launch_tally(const uint32_t* q_counts, const uint32_t* s_counts, const uint32_t* d_ext, const uint32_t* d_sh, int n_stages,
+                  unsigned long long* totals, cudaStream_t st);
 void launch_megakernel(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, bool prune, int spp, float* fb,
                        unsigned long long* totals, cudaStream_t st);
-void launch_trace_rays(const SceneDev& sc, bool prune, bool anyhit, int n, const float* o, const float* d, int p3fudge, int* hit,
-                       float* dist, int* tri, int* inside, float* point, float* normal, cudaStream_t st);
+void launch_trace_finish(const SceneDev& sc, int n, PathQueue q, int p3fudge, int* hit, float* dist, int* tri, int* inside, float* point,
+                         float* normal, cudaStream_t st);
 void launch_eval_brdf(int which, int n, const float* V, const float* N, const float* L, const float* xi, const float* materials,
                       float* out, cudaStream_t st);
 void launch_eval_math(int which, int n, const float* a, const float* b, float* out, cudaStream_t st);

@@ -53,13 +53,19 @@ typedef enum ezrt_mode {
     EZRT_MODE_DISNEY_IS_MIS_P5 = 3 /* P5/fsh:810-890  BRDF + HDR importance sampling, MIS      */
 } ezrt_mode;
 
-/* BVH traversal policy.  REFERENCE walks every box the ray overlaps (P5/fsh:254-306, no
- * best-distance pruning).  PRUNED additionally skips a subtree when its box entry distance
- * exceeds the current best hit by a conservative margin; it returns bit-identical hits
- * (DESIGN.md "pruning") and is the default. */
+/* BVH traversal policy.  All three return bit-identical hits (tests assert it).
+ * ACCEL (default): the device builds its own acceleration tree over the same triangles (the
+ *   reference's sweep SAH without its INF = 114514 cost cut-off, P5/main.cpp:20,:493), finds the
+ *   global closest hit there, keeps it when the shader's hitBVH provably reaches that triangle's
+ *   leaf in the REFERENCE tree and no other triangle ties, and otherwise re-traces the ray with the
+ *   exact reference-order traversal (DESIGN.md "accel").
+ * REFERENCE walks every box the ray overlaps, exactly as P5/fsh:254-306 (no best-distance pruning).
+ * PRUNED walks the reference tree in the shader's order but skips a sub-tree whose box entry lies
+ *   beyond the current best hit by a conservative margin (DESIGN.md "pruning"). */
 typedef enum ezrt_traverse {
-    EZRT_TRAVERSE_PRUNED = 0,
-    EZRT_TRAVERSE_REFERENCE = 1
+    EZRT_TRAVERSE_ACCEL = 0,
+    EZRT_TRAVERSE_REFERENCE = 1,
+    EZRT_TRAVERSE_PRUNED = 2
 } ezrt_traverse;
 
 typedef enum ezrt_pipeline {
@@ -96,6 +102,7 @@ typedef struct ezrt_counters {
     uint64_t samples;       /* pixel-samples = fragment shader invocations                   */
     uint64_t kernel_launches;
     double device_ms;       /* CUDA-event time of the last render on its stream              */
+    uint64_t deferred_rays; /* accel policy: rays re-traced by the exact reference-order pass */
 } ezrt_counters;
 
 typedef struct ezrt_scene ezrt_scene; /* device-resident scene (replaces the two TBOs + 2 textures) */
@@ -195,7 +202,10 @@ int ezrt_trilist_append_encoded(ezrt_trilist* list, const float* tris, int n);
 typedef enum ezrt_bvh_builder {
     EZRT_BVH_SAH_FAST = 0,    /* same tree as SAH_LITERAL, keys pre-computed, subtrees in parallel */
     EZRT_BVH_SAH_LITERAL = 1, /* buildBVHwithSAH exactly as written (P5/main.cpp:458-589)   */
-    EZRT_BVH_MEDIAN = 2       /* buildBVH (P5/main.cpp:395-455)                              */
+    EZRT_BVH_MEDIAN = 2,      /* buildBVH (P5/main.cpp:395-455)                              */
+    EZRT_BVH_SAH_NO_SENTINEL = 3 /* NOT the reference tree: same sweep SAH without the INF = 114514
+                                    cost cut-off (P5/main.cpp:20,:493); what the device builds
+                                    internally as its acceleration tree (DESIGN.md "accel")      */
 } ezrt_bvh_builder;
 
 /* Sorts the list's triangles in place and builds the node array: nodes{testNode};

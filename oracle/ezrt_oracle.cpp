@@ -233,7 +233,7 @@ HitResult hitBVH(const Scene& sc, const Ray& ray, Counters& cn, int kind) {
     res.triangle = -1;
     res.hitPoint = res.normal = res.viewDir = ez_v3(0, 0, 0);
 
-    const bool prune = (sc.traverse == EZRT_TRAVERSE_PRUNED);
+    const bool prune = (sc.traverse != EZRT_TRAVERSE_REFERENCE);  // the oracle has no accel tree: ACCEL == PRUNED here
     const float slack = prune ? pruneSlack(sc, ray) : 0.0f;
 
     int stack[256];

@@ -110,7 +110,7 @@ def _random_rays(n, seed, extent=3.0):
     return o, d
 
 
-@pytest.mark.parametrize("traverse", [api.TRAVERSE_PRUNED, api.TRAVERSE_REFERENCE])
+@pytest.mark.parametrize("traverse", [api.TRAVERSE_ACCEL, api.TRAVERSE_PRUNED, api.TRAVERSE_REFERENCE])
 @pytest.mark.parametrize("fudge", [False, True])
 def test_trace_rays_match_oracle(oracle, bunny_scene, gpu_bunny, traverse, fudge):
     tris, nodes, eye, cam = bunny_scene
@@ -240,17 +240,51 @@ def test_rgba_output(bunny_scene, gpu_bunny):
 
 
 # ------------------------------------------------------------------ size-independent properties at larger sizes
-def test_pruned_equals_reference_traversal_large(gpu_grid, grid_scene):
-    """Pruning must not change a single bit: full-size property test (no oracle needed)."""
+@pytest.mark.parametrize("policy", [api.TRAVERSE_ACCEL, api.TRAVERSE_PRUNED])
+def test_fast_policies_equal_reference_traversal_large(gpu_grid, grid_scene, policy):
+    """Neither pruning nor the acceleration tree may change a single bit: full-size property test (no oracle needed)."""
     tris, nodes, eye, cam = grid_scene
-    cfg = _cfg(eye, cam, width=640, height=360, spp=4, max_bounce=3, mode=api.MODE_DISNEY_SOBOL_P5)
+    cfg = _cfg(eye, cam, width=640, height=360, spp=4, max_bounce=3, mode=api.MODE_DISNEY_SOBOL_P5, traverse=policy)
     a = gpu_grid.render(cfg)
     ca = gpu_grid.counters()
     cfg.traverse = api.TRAVERSE_REFERENCE
     b = gpu_grid.render(cfg)
     cb = gpu_grid.counters()
-    assert_same_bits(a, b, "pruned vs reference traversal")
+    assert_same_bits(a, b, "policy %d vs reference traversal" % policy)
     assert ca.rays == cb.rays and ca.rays > 640 * 360 * 4
+
+
+def test_accel_policy_defers_ties_to_the_exact_traversal(oracle, bunny_scene):
+    """Every triangle twice (second copy with another material): every hit ties with its twin, the accel pass must
+    defer all of them and the exact reference-order pass must pick the copy the shader picks."""
+    tris, nodes, eye, cam = bunny_scene
+    twin = tris.copy()
+    twin[:, 21:24] = [0.9, 0.2, 0.1]  # baseColor of the copies
+    tl = api.TriangleList()
+    tl.append_encoded(np.concatenate([tris, twin]))
+    tris2, nodes2 = tl.build_bvh(8)
+    sc = api.Scene(tris2, nodes2)
+    try:
+        cfg = _cfg(eye, cam, mode=api.MODE_DISNEY_SOBOL_P5, max_bounce=2, width=64, height=48, spp=2)
+        ref, rc = oracle.render(tris2, nodes2, cfg)
+        got = sc.render(cfg)
+        c = sc.counters()
+        assert_same_bits(got, ref, "twin triangles")
+        assert c.rays == rc["rays"] and c.deferred_rays >= rc["hits"] > 1000
+        o, d = _random_rays(4000, 21)
+        a = sc.trace_rays(o, d, traverse=api.TRAVERSE_ACCEL)
+        b = oracle.trace_rays(tris2, nodes2, o, d, traverse=api.TRAVERSE_REFERENCE)
+        np.testing.assert_array_equal(a["triangle"], b["triangle"])
+        assert_same_bits(a["distance"], b["distance"], "twin distance")
+    finally:
+        sc.close()
+
+
+def test_accel_policy_rarely_defers(gpu_grid, grid_scene):
+    tris, nodes, eye, cam = grid_scene
+    gpu_grid.render(_cfg(eye, cam, width=320, height=180, spp=2, max_bounce=2))
+    c = gpu_grid.counters()
+    assert c.deferred_rays < c.rays // 1000
 
 
 def test_wavefront_equals_megakernel_large(gpu_grid, grid_scene):
