@@ -336,7 +336,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         {   // top levels breadth-first, the rest in pre-order (as for the reference tree)
             std::vector<int> level, next;
             if (an[0].n <= 0) level.push_back(0);
-            while (!level.empty() && acc_top + (int)level.size() <= EZRT_TOP_NODES_MAX) {
+            while (!level.empty() && acc_top + (int)level.size() <= EZRT_ACC_TOP_NODES_MAX) {
                 next.clear();
                 for (int i : level) {
                     aid[i] = acc_top++;
@@ -448,7 +448,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     if (const char* e = getenv("EZRT_SORT_RAYS")) sc->sort_rays = atoi(e);
     d.refill_thresh = 24;
     d.inner_thresh = 16;
-    d.leaf_thresh = 8;
+    d.leaf_thresh = 12;
     d.work_chunk = 32;
     if (const char* e = getenv("EZRT_CHUNK")) d.work_chunk = std::max(32, std::min(65536, atoi(e)));
     if (const char* e = getenv("EZRT_LEAF_T")) d.leaf_thresh = std::max(1, std::min(33, atoi(e)));

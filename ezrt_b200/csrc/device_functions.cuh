@@ -455,16 +455,19 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                     }
                 }
             }
-            // ---- leaf phase, warp-cooperative: the warp takes up to four waiting leaves at a time
-            // and gives each an octet of lanes, one triangle per lane (leaves hold <= 8 triangles in
-            // reference-built trees; longer leaves take several passes).  The owner's ray travels by
-            // shuffle; the octet's hits are min-reduced on the key (t bits, triangle index), which is
-            // hitArray's "strictly closer, first index wins" rule (P5/fsh:242-249).
+            // ---- leaf phase, warp-cooperative: the warp takes up to four waiting leaves at a time and gives
+            // each an octet of lanes, one triangle per lane (leaves hold <= 8 triangles in reference-built
+            // trees; longer leaves take several passes).  The owner's ray travels by shuffle; the octet's
+            // winning distance is a 3-step integer min of the t bits (t > 0, so bit order = value order) and
+            // the winning triangle is the lowest lane holding it -- hitArray's "strictly closer, first
+            // index wins" rule (P5/fsh:242-249); more than one holder, or a hit at exactly the old best,
+            // is a tie (ACCEL).
             const bool at_leaf = (ray >= 0) && (ref < 0) && (ref != EZRT_REF_DONE);
             unsigned m_leaf = __ballot_sync(FULL, at_leaf);
             const uint32_t my_bits = (uint32_t)ref & 0x7fffffffu;
-            const int my_cnt = at_leaf ? (int)(my_bits & 127u) : 0;
-            const int my_first = (int)(my_bits >> 7);
+            int leaf_cnt = at_leaf ? (int)(my_bits & 127u) : 0;
+            int leaf_first = (int)(my_bits >> 7);
+            const bool long_leaves = __ballot_sync(FULL, leaf_cnt > 8) != 0u;
             bool stop = false;
             while (m_leaf != 0u) {
                 int j0 = __ffs(m_leaf) - 1; m_leaf &= m_leaf - 1u;
@@ -479,48 +482,35 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                 ro.x = __shfl_sync(FULL, o.x, src); ro.y = __shfl_sync(FULL, o.y, src); ro.z = __shfl_sync(FULL, o.z, src);
                 rdir.x = __shfl_sync(FULL, d.x, src); rdir.y = __shfl_sync(FULL, d.y, src); rdir.z = __shfl_sync(FULL, d.z, src);
                 const float rbest = __shfl_sync(FULL, best, src);
-                const int rfirst = __shfl_sync(FULL, my_first, src);
-                const int rcnt_all = __shfl_sync(FULL, my_cnt, src);  // every lane must take part in the shuffle
-                const int rcnt = (owner < 0) ? 0 : rcnt_all;
-                bool lane_tie = false;
-                unsigned long long key = 0xffffffffffffffffull;
-                for (int kb = 0; __ballot_sync(FULL, kb < rcnt) != 0u; kb += 8) {
-                    const int ti = kb + k;
-                    if (ti < rcnt) {
-                        float t;
-                        if (tri_test_t<ACCEL>(tree.tri_geo + (size_t)(rfirst + ti) * 4, ro, rdir, rbest, t) != 0) {
-                            unsigned long long kk = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned)(rfirst + ti);
-                            if (ACCEL && key != 0xffffffffffffffffull && (unsigned)(kk >> 32) == (unsigned)(key >> 32)) lane_tie = true;
-                            key = (kk < key) ? kk : key;
-                        }
-                    }
+                const int rfirst = __shfl_sync(FULL, leaf_first, src);
+                const int rcnt = __shfl_sync(FULL, leaf_cnt, src);
+                unsigned tb = 0xffffffffu;  // t bits of this lane's triangle, or "no hit"
+                if (owner >= 0 && k < rcnt) {
+                    float t;
+                    if (tri_test_t<ACCEL>(tree.tri_geo + (size_t)(rfirst + k) * 4, ro, rdir, rbest, t) != 0) tb = __float_as_uint(t);
                 }
-                const unsigned long long mine = key;
-                // min over the octet
-                for (int off = 1; off < 8; off <<= 1) {
-                    unsigned long long other = __shfl_xor_sync(FULL, key, off);
-                    key = (other < key) ? other : key;
-                }
-                unsigned tie_mask = 0u;
-                if (ACCEL) {  // a second triangle of this leaf at the winning distance, or the old best tied
-                    const bool t_tie = lane_tie || (mine != 0xffffffffffffffffull && mine != key && (unsigned)(mine >> 32) == (unsigned)(key >> 32)) ||
-                                       (key != 0xffffffffffffffffull && __uint_as_float((unsigned)(key >> 32)) == rbest);
-                    tie_mask = __ballot_sync(FULL, t_tie);
-                }
-                // owners read the result of their octet
-                const int back = (lane == j0) ? 0 : (lane == j1) ? 8 : (lane == j2) ? 16 : (lane == j3) ? 24 : lane;
-                const unsigned long long res = __shfl_sync(FULL, key, back);
-                if (at_leaf && (lane == j0 || lane == j1 || lane == j2 || lane == j3)) {
-                    if (ACCEL && ((tie_mask >> back) & 0xffu) != 0u) tie = true;
-                    if (res != 0xffffffffffffffffull) {
-                        const float tn = __uint_as_float((unsigned)(res >> 32));
+                unsigned mn = tb;
+                mn = min(mn, __shfl_xor_sync(FULL, mn, 1));
+                mn = min(mn, __shfl_xor_sync(FULL, mn, 2));
+                mn = min(mn, __shfl_xor_sync(FULL, mn, 4));
+                const unsigned win = __ballot_sync(FULL, tb == mn && tb != 0xffffffffu);  // holders of the winning distance
+                const int pos = (lane == j0) ? 0 : (lane == j1) ? 1 : (lane == j2) ? 2 : (lane == j3) ? 3 : -1;
+                const unsigned res = __shfl_sync(FULL, mn, (pos < 0) ? lane : pos * 8);
+                if (pos >= 0) {  // this lane owns one of the leaves just tested
+                    const unsigned mq = (win >> (8 * pos)) & 0xffu;
+                    if (mq != 0u) {
+                        const float tn = __uint_as_float(res);
+                        if (ACCEL && (__popc(mq) > 1 || tn == best)) tie = true;
                         if (!ACCEL || tn < best) {  // ACCEL accepts t == best only to flag the tie
                             best = tn;
-                            best_tri = (int)(unsigned)(res & 0xffffffffull);
+                            best_tri = leaf_first + __ffs(mq) - 1;
                         }
                         if (ANYHIT) stop = true;
                     }
+                    leaf_first += 8;
+                    leaf_cnt -= 8;
                 }
+                if (long_leaves) m_leaf |= __ballot_sync(FULL, pos >= 0 && leaf_cnt > 0 && !stop);  // next pass of a long leaf
             }
             if (at_leaf) {  // pop (hitBVH continues with the next stack entry)
                 ref = EZRT_REF_DONE;

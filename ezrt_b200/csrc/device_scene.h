@@ -26,6 +26,7 @@
 #define EZRT_LEAF_FLAG 0x80000000u
 #define EZRT_LEAF_MAX_N 127
 #define EZRT_TOP_NODES_MAX 1023   // 10 full levels; 80 B each in shared memory (bank-conflict padding)
+#define EZRT_ACC_TOP_NODES_MAX 255 // acceleration tree: 8 levels are enough (its upper levels are real SAH splits)
 #define EZRT_TOP_STRIDE 5         // float4 per shared-memory record
 #define EZRT_TILE 16             // == EZRT_PART_TILE
 #define EZRT_TILE_PIXELS 256
