@@ -516,7 +516,8 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
 
     const size_t per_frame = (size_t)rd.n_tiles * EZRT_TILE_PIXELS;
     int F = p->frames_per_batch;
-    if (F <= 0) F = (int)std::max<size_t>(1, ((size_t)4 << 20) / per_frame);
+    if (F <= 0) F = (int)std::max<size_t>(1, ((size_t)32 << 20) / per_frame);  // ~32 M sample slots per batch (~7.5 GB of state):
+                                                                              // long queues amortise the persistent kernels' ramp-up and tail
     F = std::min(F, p->spp);
     const size_t capacity = per_frame * (size_t)F;
     if (capacity >= ((size_t)1 << 31)) return ezrt_set_error(EZRT_ERR_INVALID, "render: batch too large");
