@@ -76,7 +76,7 @@ struct ezrt_scene {
     int n_sms = 148;
     SceneDev dev{};
     DeviceBuffer nodes, tri_geo, tri_shade, materials, hdr, hdr_cache;
-    DeviceBuffer acc_nodes, acc_tri_geo, acc_tri_ref, tri_leaf, leaf_box, defer_buf;
+    DeviceBuffer acc_nodes, acc_tri_geo, acc_tri_ref, tri_leaf, leaf_box, defer_buf, acc_tri_shade, acc_tri_leaf, ref_to_acc;
     int acc_depth = 0;
     int n_materials = 0;
     int tree_depth = 0;
@@ -116,7 +116,7 @@ struct ezrt_scene {
 namespace {
 
 int carve_queue(DeviceBuffer& buf, size_t capacity, PathQueue& q) {
-    size_t per = sizeof(float4) * 4 + sizeof(uint2);
+    size_t per = sizeof(float4) * 4 + sizeof(uint2) + sizeof(float2);
     int rc = buf.ensure(per * capacity + 256);
     if (rc) return rc;
     char* p = (char*)buf.p;
@@ -124,7 +124,8 @@ int carve_queue(DeviceBuffer& buf, size_t capacity, PathQueue& q) {
     q.ray_d = (float4*)p; p += sizeof(float4) * capacity;
     q.hist = (float4*)p;  p += sizeof(float4) * capacity;
     q.fr = (float4*)p;    p += sizeof(float4) * capacity;
-    q.meta = (uint2*)p;
+    q.meta = (uint2*)p;   p += sizeof(uint2) * capacity;
+    q.hit = (float2*)p;
     return EZRT_OK;
 }
 int carve_shadow(DeviceBuffer& buf, size_t capacity, ShadowQueue& q) {
@@ -174,6 +175,7 @@ RenderDev make_render_dev(const ezrt_scene* s, const ezrt_render_params* p) {
     rd.out_channels = p->out_channels;
     rd.compact_out = (p->part_count > 1) ? 1 : 0;
     rd.n_tiles = (int)s->tiles.size();
+    rd.accel_space = (p->traverse == EZRT_TRAVERSE_ACCEL && p->pipeline == EZRT_PIPELINE_WAVEFRONT) ? 1 : 0;
     return rd;
 }
 
@@ -382,6 +384,16 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         for (int i = 0; i < n_triangles; i++)
             for (int k = 0; k < 4; k++) acc_geo[(size_t)i * 4 + k] = geo[(size_t)acc_order[i] * 4 + k];
     }
+    // shading data and the reference-leaf map in the acceleration tree's order, and the inverse permutation
+    std::vector<float4> acc_shade((size_t)n_triangles * 3);
+    std::vector<int> acc_leaf(n_triangles);
+    std::vector<uint32_t> ref_to_acc(n_triangles);
+    for (int i = 0; i < n_triangles; i++) {
+        const uint32_t r = acc_order[i];
+        for (int k = 0; k < 3; k++) acc_shade[(size_t)i * 3 + k] = shade[(size_t)r * 3 + k];
+        acc_leaf[i] = tri_leaf[r];
+        ref_to_acc[r] = (uint32_t)i;
+    }
 
     ezrt_scene* sc = new (std::nothrow) ezrt_scene();
     if (!sc) return ezrt_set_error(EZRT_ERR_NOMEM, "scene_create: out of host memory");
@@ -405,6 +417,9 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     if (!rc) rc = upload(sc->acc_tri_ref, acc_order.data(), acc_order.size() * sizeof(uint32_t));
     if (!rc) rc = upload(sc->tri_leaf, tri_leaf.data(), tri_leaf.size() * sizeof(int));
     if (!rc) rc = upload(sc->leaf_box, leaf_box.data(), leaf_box.size() * sizeof(float4));
+    if (!rc) rc = upload(sc->acc_tri_shade, acc_shade.data(), acc_shade.size() * sizeof(float4));
+    if (!rc) rc = upload(sc->acc_tri_leaf, acc_leaf.data(), acc_leaf.size() * sizeof(int));
+    if (!rc) rc = upload(sc->ref_to_acc, ref_to_acc.data(), ref_to_acc.size() * sizeof(uint32_t));
     if (!rc && hdr) rc = upload(sc->hdr, hdr, sizeof(float) * 3 * (size_t)hdr_w * hdr_h);
     if (!rc && hdr_cache) rc = upload(sc->hdr_cache, hdr_cache, sizeof(float) * 3 * (size_t)hdr_w * hdr_h);
     if (!rc && cudaStreamCreateWithFlags(&sc->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = ezrt_set_error(EZRT_ERR_CUDA, "scene_create: stream");
@@ -429,6 +444,9 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.acc_tri_ref = (const uint32_t*)sc->acc_tri_ref.p;
     d.acc_root_ref = acc_root_ref;
     d.acc_top_nodes = acc_top;
+    d.acc_tri_shade = (const float4*)sc->acc_tri_shade.p;
+    d.acc_tri_leaf = (const int*)sc->acc_tri_leaf.p;
+    d.ref_to_acc = (const uint32_t*)sc->ref_to_acc.p;
     d.tri_leaf = (const int*)sc->tri_leaf.p;
     d.leaf_box = (const float4*)sc->leaf_box.p;
     sc->acc_depth = acc_depth;
@@ -464,6 +482,7 @@ int ezrt_scene_destroy(ezrt_scene* s) {
     s->nodes.release(); s->tri_geo.release(); s->tri_shade.release(); s->materials.release();
     s->hdr.release(); s->hdr_cache.release(); s->tiles_buf.release();
     s->acc_nodes.release(); s->acc_tri_geo.release(); s->acc_tri_ref.release(); s->tri_leaf.release(); s->leaf_box.release(); s->defer_buf.release();
+    s->acc_tri_shade.release(); s->acc_tri_leaf.release(); s->ref_to_acc.release();
     s->queue_buf[0].release(); s->queue_buf[1].release(); s->shadow_buf.release();
     s->lo_buf.release(); s->le_buf.release(); s->counters_buf.release(); s->totals_buf.release(); s->fb_buf.release(); s->sort_buf.release();
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -571,7 +590,7 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
                 launch_extend_accel(s->dev, false, qin, &q_count[b], &w_ext[b], defer_list, &d_ext[b], &dw_ext[b], n_slots, s->n_sms, st);
                 s->launches++;
             } else {
-                launch_extend(s->dev, prune, false, qin, &q_count[b], &w_ext[b], perm, n_slots, s->n_sms, st);
+                launch_extend(s->dev, prune, false, qin, &q_count[b], &w_ext[b], perm, 0, n_slots, s->n_sms, st);
             }
             s->span_end(sp, st);
             sp = s->span_begin(1, st);
@@ -727,12 +746,13 @@ int ezrt_trace_rays(ezrt_scene* s, int n, const float* origins, const float* dir
     }
     DeviceBuffer buf;
     const size_t N = (size_t)n;
-    int rc = buf.ensure(sizeof(float4) * 2 * N + sizeof(float) * 7 * N + sizeof(int) * 4 * N + 1024);
+    int rc = buf.ensure(sizeof(float4) * 2 * N + sizeof(float2) * N + sizeof(float) * 7 * N + sizeof(int) * 4 * N + 1024);
     if (rc) return rc;
     char* p = (char*)buf.p;
     PathQueue q{};
     q.ray_o = (float4*)p; p += sizeof(float4) * N;
     q.ray_d = (float4*)p; p += sizeof(float4) * N;
+    q.hit = (float2*)p; p += sizeof(float2) * N;
     float* d_point = (float*)p; p += sizeof(float) * 3 * N;
     float* d_normal = (float*)p; p += sizeof(float) * 3 * N;
     float* d_dist = (float*)p; p += sizeof(float) * N;
@@ -750,8 +770,8 @@ int ezrt_trace_rays(ezrt_scene* s, int n, const float* origins, const float* dir
         if (traverse == EZRT_TRAVERSE_ACCEL)
             launch_extend_accel(s->dev, any_hit != 0, q, d_cnt, d_cnt + 1, d_defer, d_cnt + 2, d_cnt + 3, (uint32_t)n, s->n_sms, st);
         else
-            launch_extend(s->dev, traverse != EZRT_TRAVERSE_REFERENCE, any_hit != 0, q, d_cnt, d_cnt + 1, nullptr, (uint32_t)n, s->n_sms, st);
-        launch_trace_finish(s->dev, n, q, p3_normal_fudge, d_hit, d_dist, d_tri, d_inside, d_point, d_normal, st);
+            launch_extend(s->dev, traverse != EZRT_TRAVERSE_REFERENCE, any_hit != 0, q, d_cnt, d_cnt + 1, nullptr, 0, (uint32_t)n, s->n_sms, st);
+        launch_trace_finish(s->dev, n, q, p3_normal_fudge, traverse == EZRT_TRAVERSE_ACCEL, d_hit, d_dist, d_tri, d_inside, d_point, d_normal, st);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_hit, d_hit, sizeof(int) * N, cudaMemcpyDeviceToHost, st);

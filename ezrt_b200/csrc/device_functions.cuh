@@ -324,9 +324,9 @@ struct TreeView {
 // the leaf's own box passes hitAABB > 0: the fp32 slab values are monotone in the box bounds
 // (rounding is monotone), every ancestor box contains the leaf box, so it passes whenever the leaf
 // does (DESIGN.md "accel").  Exact hitAABB arithmetic; only called for rays with finite 1/d.
-__device__ __forceinline__ bool reference_reaches_leaf(const int* __restrict__ tri_leaf, const float4* __restrict__ leaf_box, int ref_tri, vec3 o,
+__device__ __forceinline__ bool reference_reaches_leaf(const int* __restrict__ tri_leaf, const float4* __restrict__ leaf_box, int tri, vec3 o,
                                                        const RaySlab& rs) {
-    const int leaf = __ldg(tri_leaf + ref_tri);
+    const int leaf = __ldg(tri_leaf + tri);  // tri_leaf in the same index space as `tri`
     const float4 a = ldg4(leaf_box + 2 * (size_t)leaf), b = ldg4(leaf_box + 2 * (size_t)leaf + 1);
     float ix, iy, iz, iz2;
     pk2_split(rs.inv_xy, ix, iy);
@@ -567,10 +567,10 @@ struct SurfaceHit {
 
 // Recomputes P and the interpolated normal for (ray, t, tri).  p3fudge selects the P3/P4
 // barycentric denominators (P3/fsh:273-274) instead of P5's "+1e-7" (P5/fsh:206-207).
-__device__ __forceinline__ SurfaceHit surface_hit(const SceneDev& sc, vec3 o, vec3 d, float t, int tri, bool p3fudge) {
-    const float4* g = sc.tri_geo + (size_t)tri * 4;
+__device__ __forceinline__ SurfaceHit surface_hit(const SceneDev& sc, vec3 o, vec3 d, float t, int tri, bool p3fudge, bool accel_space = false) {
+    const float4* g = (accel_space ? sc.acc_tri_geo : sc.tri_geo) + (size_t)tri * 4;
     float4 q0 = ldg4(g), q1 = ldg4(g + 1), q2 = ldg4(g + 2);
-    const float4* s = sc.tri_shade + (size_t)tri * 3;
+    const float4* s = (accel_space ? sc.acc_tri_shade : sc.tri_shade) + (size_t)tri * 3;
     float4 m0 = ldg4(s), m1 = ldg4(s + 1), m2 = ldg4(s + 2);
     vec3 p1 = f4xyz(q0), p2 = f4xyz(q1), p3 = f4xyz(q2);
     vec3 Ng = ez_v3(q0.w, q1.w, q2.w);
@@ -921,7 +921,7 @@ __device__ __forceinline__ bool shade_step(const SceneDev& sc, const RenderDev& 
         }
     }
     const bool fudge = (mode == EZRT_MODE_DIFFUSE_P3 || mode == EZRT_MODE_DISNEY_ANISO_P4);
-    SurfaceHit hit = surface_hit(sc, p.o, p.d, hit_t, hit_tri, fudge);
+    SurfaceHit hit = surface_hit(sc, p.o, p.d, hit_t, hit_tri, fudge, rd.accel_space != 0);
     MaterialDev mat = load_material(sc, hit.matId);
     if (bounce == 0) {
         Le = mat.emissive;  // P5/fsh:936

@@ -46,7 +46,10 @@ struct SceneDev {
     // inflated by 2*prune_delta; acc_tri_geo is tri_geo in the tree's own order, acc_tri_ref maps back
     const float4* acc_nodes;
     const float4* acc_tri_geo;
-    const uint32_t* acc_tri_ref;
+    const uint32_t* acc_tri_ref;   // accel order -> reference triangle index
+    const uint32_t* ref_to_acc;    // reference triangle index -> accel order
+    const float4* acc_tri_shade;   // tri_shade in accel order (shading reads the arrays traversal keeps hot in L2)
+    const int* acc_tri_leaf;       // reference leaf (slot in leaf_box) of every triangle, accel order
     int acc_root_ref;
     int acc_top_nodes;
     // reference leaf of every reference triangle + the leaves' boxes (AA, BB as float4 pairs)
@@ -74,6 +77,7 @@ struct RenderDev {
     uint32_t first_frame;
     int out_channels;
     int compact_out;          // 1: write tile-major compact buffer (part_count > 1)
+    int accel_space;          // 1: hit records hold acceleration-tree triangle indices (accel policy)
     int n_tiles;              // tiles owned by this part
 };
 
@@ -85,8 +89,9 @@ struct TileDev {
 
 // SoA path state of the wavefront pipeline (one set per queue; two queues ping-pong).
 struct PathQueue {
-    float4* ray_o;    // (origin.xyz, hit distance written by extend)
-    float4* ray_d;    // (direction.xyz, hit triangle as int bits written by extend)
+    float4* ray_o;    // (origin.xyz, -)
+    float4* ray_d;    // (direction.xyz, -)
+    float2* hit;      // written by extend: (hit distance, triangle index as int bits; -1 = miss)
     float4* hist;     // (history.xyz, cosine_i)
     float4* fr;       // (f_r.xyz, pdf)   pdf <= 0 marks "break after trace" (P5/fsh:865)
     uint2* meta;      // (rng seed, sample slot)

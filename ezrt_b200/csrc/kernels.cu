@@ -61,9 +61,9 @@ __global__ void __launch_bounds__(256) k_generate(RenderDev rd, const TileDev* _
         uint32_t seed;
         vec3 o, d;
         primary_ray(rd, px, py, batch_first_frame + fib, seed, o, d);
-        q.ray_o[pos] = make_float4(o.x, o.y, o.z, 0.0f);
-        q.ray_d[pos] = make_float4(d.x, d.y, d.z, 0.0f);
-        q.meta[pos] = make_uint2(seed, slot);
+        __stcs(q.ray_o + pos, make_float4(o.x, o.y, o.z, 0.0f));
+        __stcs(q.ray_d + pos, make_float4(d.x, d.y, d.z, 0.0f));
+        __stcs(q.meta + pos, make_uint2(seed, slot));
     }
 }
 
@@ -183,27 +183,30 @@ __device__ __forceinline__ TreeView accel_tree(const SceneDev& sc) {
 // fallback pass of the accel policy, which traces only the deferred ray indices in `perm`)
 struct ExtendIO {
     PathQueue q;
-    const uint32_t* perm;  // null: trace in queue order
+    const uint32_t* perm;      // null: trace in queue order
+    const uint32_t* to_accel;  // non-null (fallback pass of the accel policy): hits are stored as accel-order indices
     __device__ __forceinline__ void load(uint32_t i, vec3& o, vec3& d) const {
         const uint32_t j = perm ? perm[i] : i;
-        float4 o4 = q.ray_o[j], d4 = q.ray_d[j];
+        float4 o4 = __ldcs(q.ray_o + j), d4 = __ldcs(q.ray_d + j);  // queue data streams through the caches
         o = ez_v3(o4.x, o4.y, o4.z);
         d = ez_v3(d4.x, d4.y, d4.z);
     }
     __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3, const RaySlab&) const {
         const uint32_t j = perm ? perm[i] : i;
-        q.ray_o[j].w = h.t;
-        q.ray_d[j].w = __int_as_float(h.tri);
+        int tri = h.tri;
+        if (to_accel && tri >= 0) tri = (int)__ldg(to_accel + tri);
+        __stcs(q.hit + j, make_float2(h.t, __int_as_float(tri)));
     }
     __device__ __forceinline__ void defer(uint32_t) const {}
 };
 
 template <bool PRUNE, bool ANYHIT>
 __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_extend(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
-                                                                uint32_t* work, const uint32_t* __restrict__ perm) {
+                                                                uint32_t* work, const uint32_t* __restrict__ perm, int to_accel) {
     ExtendIO io;
     io.q = q;
     io.perm = perm;
+    io.to_accel = to_accel ? sc.ref_to_acc : nullptr;
     const TreeView tree = reference_tree(sc);
     stage_top_nodes(tree);
     extend_persistent<PRUNE, ANYHIT, false>(sc, tree, *q_count, work, io, g_smem_top);
@@ -214,28 +217,22 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_extend(SceneDev 
 // appended to `defer_list` for the exact kernel (DESIGN.md "accel").
 struct AccelIO {
     PathQueue q;
-    const uint32_t* acc_tri_ref;
-    const int* tri_leaf;
+    const int* acc_tri_leaf;
     const float4* leaf_box;
     uint32_t* defer_list;
     uint32_t* defer_count;
     __device__ __forceinline__ void load(uint32_t i, vec3& o, vec3& d) const {
-        float4 o4 = q.ray_o[i], d4 = q.ray_d[i];
+        float4 o4 = __ldcs(q.ray_o + i), d4 = __ldcs(q.ray_d + i);
         o = ez_v3(o4.x, o4.y, o4.z);
         d = ez_v3(d4.x, d4.y, d4.z);
     }
     __device__ __forceinline__ void defer(uint32_t i) const { defer_list[atomicAdd(defer_count, 1u)] = i; }
     __device__ __forceinline__ void store(uint32_t i, HitRec h, bool tie, vec3 o, const RaySlab& rs) const {
-        int ref_tri = -1;
-        if (h.tri >= 0) {
-            ref_tri = (int)__ldg(acc_tri_ref + h.tri);
-            if (tie || !reference_reaches_leaf(tri_leaf, leaf_box, ref_tri, o, rs)) {
-                defer(i);
-                return;
-            }
+        if (h.tri >= 0 && (tie || !reference_reaches_leaf(acc_tri_leaf, leaf_box, h.tri, o, rs))) {
+            defer(i);
+            return;
         }
-        q.ray_o[i].w = h.t;
-        q.ray_d[i].w = __int_as_float(ref_tri);
+        __stcs(q.hit + i, make_float2(h.t, __int_as_float(h.tri)));  // accel-order triangle index
     }
 };
 
@@ -244,8 +241,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_extend_accel(Sce
                                                                       uint32_t* work, uint32_t* defer_list, uint32_t* defer_count) {
     AccelIO io;
     io.q = q;
-    io.acc_tri_ref = sc.acc_tri_ref;
-    io.tri_leaf = sc.tri_leaf;
+    io.acc_tri_leaf = sc.acc_tri_leaf;
     io.leaf_box = sc.leaf_box;
     io.defer_list = defer_list;
     io.defer_count = defer_count;
@@ -262,7 +258,7 @@ struct ShadowIO {
     const uint32_t* perm;
     __device__ __forceinline__ void load(uint32_t i, vec3& o, vec3& d) const {
         const uint32_t j = perm ? perm[i] : i;
-        float4 o4 = sq.ray_o[j], d4 = sq.ray_d[j];
+        float4 o4 = __ldcs(sq.ray_o + j), d4 = __ldcs(sq.ray_d + j);
         o = ez_v3(o4.x, o4.y, o4.z);
         d = ez_v3(d4.x, d4.y, d4.z);
     }
@@ -293,8 +289,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_shadow(SceneDev 
 
 struct ShadowAccelIO {
     ShadowIO base;
-    const uint32_t* acc_tri_ref;
-    const int* tri_leaf;
+    const int* acc_tri_leaf;
     const float4* leaf_box;
     uint32_t* defer_list;
     uint32_t* defer_count;
@@ -306,7 +301,7 @@ struct ShadowAccelIO {
             return;
         }
         // occluded if the shader reaches the occluder's leaf; otherwise let the exact kernel decide
-        if (!reference_reaches_leaf(tri_leaf, leaf_box, (int)__ldg(acc_tri_ref + h.tri), o, rs)) defer(i);
+        if (!reference_reaches_leaf(acc_tri_leaf, leaf_box, h.tri, o, rs)) defer(i);
     }
 };
 
@@ -317,8 +312,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_shadow_accel(Sce
     io.base.sq = sq;
     io.base.Lo = Lo;
     io.base.perm = nullptr;
-    io.acc_tri_ref = sc.acc_tri_ref;
-    io.tri_leaf = sc.tri_leaf;
+    io.acc_tri_leaf = sc.acc_tri_leaf;
     io.leaf_box = sc.leaf_box;
     io.defer_list = defer_list;
     io.defer_count = defer_count;
@@ -342,8 +336,9 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev sc, RenderDev rd, const 
         sh.valid = false;
         uint32_t slot = 0;
         if (i < n) {
-            float4 o4 = qin.ray_o[i], d4 = qin.ray_d[i];
-            uint2 meta = qin.meta[i];
+            float4 o4 = __ldcs(qin.ray_o + i), d4 = __ldcs(qin.ray_d + i);
+            const float2 hit = __ldcs(qin.hit + i);
+            uint2 meta = __ldcs(qin.meta + i);
             slot = meta.y;
             p.o = ez_v3(o4.x, o4.y, o4.z);
             p.d = ez_v3(d4.x, d4.y, d4.z);
@@ -351,7 +346,7 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev sc, RenderDev rd, const 
             vec3 lo = splat3(0.0f), le = splat3(0.0f);
             bool pmiss = false;
             if (bounce > 0) {
-                float4 h4 = qin.hist[i], f4 = qin.fr[i];
+                float4 h4 = __ldcs(qin.hist + i), f4 = __ldcs(qin.fr + i);
                 p.history = ez_v3(h4.x, h4.y, h4.z);
                 p.cosine_i = h4.w;
                 p.f_r = ez_v3(f4.x, f4.y, f4.z);
@@ -366,24 +361,24 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev sc, RenderDev rd, const 
             }
             uint32_t px, py, fib;
             slot_pixel(rd, tiles, slot, px, py, fib);
-            alive = shade_step(sc, rd, bounce, p, o4.w, __float_as_int(d4.w), px, py, batch_first_frame + fib, lo, le, pmiss, sh);
+            alive = shade_step(sc, rd, bounce, p, hit.x, __float_as_int(hit.y), px, py, batch_first_frame + fib, lo, le, pmiss, sh);
             Lo[slot] = make_float4(lo.x, lo.y, lo.z, pmiss ? 1.0f : 0.0f);
             if (bounce == 0) Le[slot] = make_float4(le.x, le.y, le.z, 0.0f);
         }
         uint32_t pos = warp_append(alive, out_count);
         if (alive) {
-            qout.ray_o[pos] = make_float4(p.o.x, p.o.y, p.o.z, 0.0f);
-            qout.ray_d[pos] = make_float4(p.d.x, p.d.y, p.d.z, 0.0f);
-            qout.hist[pos] = make_float4(p.history.x, p.history.y, p.history.z, p.cosine_i);
-            qout.fr[pos] = make_float4(p.f_r.x, p.f_r.y, p.f_r.z, p.pdf);
-            qout.meta[pos] = make_uint2(p.seed, slot);
+            __stcs(qout.ray_o + pos, make_float4(p.o.x, p.o.y, p.o.z, 0.0f));
+            __stcs(qout.ray_d + pos, make_float4(p.d.x, p.d.y, p.d.z, 0.0f));
+            __stcs(qout.hist + pos, make_float4(p.history.x, p.history.y, p.history.z, p.cosine_i));
+            __stcs(qout.fr + pos, make_float4(p.f_r.x, p.f_r.y, p.f_r.z, p.pdf));
+            __stcs(qout.meta + pos, make_uint2(p.seed, slot));
         }
         if (rd.mode == EZRT_MODE_DISNEY_IS_MIS_P5) {
             uint32_t spos = warp_append(sh.valid, s_count);
             if (sh.valid) {
-                sq.ray_o[spos] = make_float4(sh.o.x, sh.o.y, sh.o.z, __uint_as_float(slot));
-                sq.ray_d[spos] = make_float4(sh.d.x, sh.d.y, sh.d.z, 0.0f);
-                sq.contrib[spos] = make_float4(sh.contrib.x, sh.contrib.y, sh.contrib.z, 0.0f);
+                __stcs(sq.ray_o + spos, make_float4(sh.o.x, sh.o.y, sh.o.z, __uint_as_float(slot)));
+                __stcs(sq.ray_d + spos, make_float4(sh.d.x, sh.d.y, sh.d.z, 0.0f));
+                __stcs(sq.contrib + spos, make_float4(sh.contrib.x, sh.contrib.y, sh.contrib.z, 0.0f));
             }
         }
     }
@@ -488,23 +483,24 @@ __global__ void __launch_bounds__(128) k_megakernel(SceneDev sc, RenderDev rd, c
 // single-function entry points (parity tests)
 // ------------------------------------------------------------------------------------------
 // results of a traced ray queue -> the outputs of ezrt_trace_rays (tail of hitTriangle for the final hit)
-__global__ void k_trace_finish(SceneDev sc, int n, PathQueue q, int p3fudge, int* hit, float* dist, int* tri, int* inside, float* point,
-                               float* normal) {
+__global__ void k_trace_finish(SceneDev sc, int n, PathQueue q, int p3fudge, int accel_space, int* hit, float* dist, int* tri, int* inside,
+                               float* point, float* normal) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 o4 = q.ray_o[i], d4 = q.ray_d[i];
+    const float2 h = q.hit[i];
     vec3 ro = ez_v3(o4.x, o4.y, o4.z), rdv = ez_v3(d4.x, d4.y, d4.z);
-    const int ht = __float_as_int(d4.w);
+    const int ht = __float_as_int(h.y);  // triangle index in the policy's index space
     hit[i] = ht >= 0;
-    dist[i] = o4.w;
-    tri[i] = ht;
+    dist[i] = h.x;
+    tri[i] = (ht >= 0 && accel_space) ? (int)sc.acc_tri_ref[ht] : ht;
     vec3 P = splat3(0.0f), N = splat3(0.0f);
     int ins = 0;
     if (ht >= 0) {
-        SurfaceHit s = surface_hit(sc, ro, rdv, o4.w, ht, p3fudge != 0);
+        SurfaceHit s = surface_hit(sc, ro, rdv, h.x, ht, p3fudge != 0, accel_space != 0);
         P = s.P;
         N = s.N;
-        const float4* g = sc.tri_geo + (size_t)ht * 4;
+        const float4* g = (accel_space ? sc.acc_tri_geo : sc.tri_geo) + (size_t)ht * 4;
         vec3 Ng = ez_v3(ldg4(g).w, ldg4(g + 1).w, ldg4(g + 2).w);
         ins = ez_dot(Ng, rdv) > 0.0f;
     }
@@ -610,12 +606,12 @@ static int persistent_blocks(uint32_t n_max, int n_sms) {
 // exact traversal of the reference tree (policies REFERENCE / PRUNED, and the accel policy's fallback pass
 // over the deferred indices in `perm`)
 void launch_extend(const SceneDev& sc, bool prune, bool anyhit, PathQueue q, const uint32_t* q_count, uint32_t* work,
-                   const uint32_t* perm, uint32_t n_max, int n_sms, cudaStream_t st) {
+                   const uint32_t* perm, int to_accel, uint32_t n_max, int n_sms, cudaStream_t st) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
-    if (prune && anyhit) k_extend<true, true><<<blocks, threads, smem_for(k_extend<true, true>, sc.top_nodes), st>>>(sc, q, q_count, work, perm);
-    else if (prune) k_extend<true, false><<<blocks, threads, smem_for(k_extend<true, false>, sc.top_nodes), st>>>(sc, q, q_count, work, perm);
-    else if (anyhit) k_extend<false, true><<<blocks, threads, smem_for(k_extend<false, true>, sc.top_nodes), st>>>(sc, q, q_count, work, perm);
-    else k_extend<false, false><<<blocks, threads, smem_for(k_extend<false, false>, sc.top_nodes), st>>>(sc, q, q_count, work, perm);
+    if (prune && anyhit) k_extend<true, true><<<blocks, threads, smem_for(k_extend<true, true>, sc.top_nodes), st>>>(sc, q, q_count, work, perm, to_accel);
+    else if (prune) k_extend<true, false><<<blocks, threads, smem_for(k_extend<true, false>, sc.top_nodes), st>>>(sc, q, q_count, work, perm, to_accel);
+    else if (anyhit) k_extend<false, true><<<blocks, threads, smem_for(k_extend<false, true>, sc.top_nodes), st>>>(sc, q, q_count, work, perm, to_accel);
+    else k_extend<false, false><<<blocks, threads, smem_for(k_extend<false, false>, sc.top_nodes), st>>>(sc, q, q_count, work, perm, to_accel);
 }
 // accel policy: acceleration-tree pass, then the exact pass over whatever it deferred
 void launch_extend_accel(const SceneDev& sc, bool anyhit, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t* defer_list,
@@ -623,7 +619,7 @@ void launch_extend_accel(const SceneDev& sc, bool anyhit, PathQueue q, const uin
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
     if (anyhit) k_extend_accel<true><<<blocks, threads, smem_for(k_extend_accel<true>, sc.acc_top_nodes), st>>>(sc, q, q_count, work, defer_list, defer_count);
     else k_extend_accel<false><<<blocks, threads, smem_for(k_extend_accel<false>, sc.acc_top_nodes), st>>>(sc, q, q_count, work, defer_list, defer_count);
-    launch_extend(sc, true, anyhit, q, defer_count, defer_work, defer_list, std::min<uint32_t>(n_max, 65536u), n_sms, st);
+    launch_extend(sc, true, anyhit, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_max, 65536u), n_sms, st);
 }
 // counting sort of the queue's ray indices into `perm` (3 kernels; bins must hold EZRT_SORT_BINS counters)
 void launch_ray_sort(const SceneDev& sc, PathQueue q, const uint32_t* q_count, uint32_t* keys, uint32_t* bins, uint32_t* perm,
@@ -668,9 +664,9 @@ void launch_megakernel(const SceneDev& sc, const RenderDev& rd, const TileDev* t
     if (prune) k_megakernel<true><<<div_up(per_frame, 128), 128, 0, st>>>(sc, rd, tiles, spp, fb, totals);
     else k_megakernel<false><<<div_up(per_frame, 128), 128, 0, st>>>(sc, rd, tiles, spp, fb, totals);
 }
-void launch_trace_finish(const SceneDev& sc, int n, PathQueue q, int p3fudge, int* hit, float* dist, int* tri, int* inside, float* point,
-                         float* normal, cudaStream_t st) {
-    k_trace_finish<<<div_up(n, 128), 128, 0, st>>>(sc, n, q, p3fudge, hit, dist, tri, inside, point, normal);
+void launch_trace_finish(const SceneDev& sc, int n, PathQueue q, int p3fudge, int accel_space, int* hit, float* dist, int* tri, int* inside,
+                         float* point, float* normal, cudaStream_t st) {
+    k_trace_finish<<<div_up(n, 128), 128, 0, st>>>(sc, n, q, p3fudge, accel_space, hit, dist, tri, inside, point, normal);
 }
 void launch_eval_brdf(int which, int n, const float* V, const float* N, const float* L, const float* xi, const float* materials,
                       float* out, cudaStream_t st) {

@@ -16,7 +16,7 @@
 void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots, uint32_t batch_first_frame, PathQueue q,
                      uint32_t* q_count, int n_sms, cudaStream_t st);
 void launch_extend(const SceneDev& sc, bool prune, bool anyhit, PathQueue q, const uint32_t* q_count, uint32_t* work,
-                   const uint32_t* perm, uint32_t n_max, int n_sms, cudaStream_t st);
+                   const uint32_t* perm, int to_accel, uint32_t n_max, int n_sms, cudaStream_t st);
 void launch_extend_accel(const SceneDev& sc, bool anyhit, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t* defer_list,
                          uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, cudaStream_t st);
 void launch_ray_sort(const SceneDev& sc, PathQueue q, const uint32_t* q_count, uint32_t* keys, uint32_t* bins, uint32_t* perm,
@@ -34,8 +34,8 @@ void launch_tally(const uint32_t* q_counts, const uint32_t* s_counts, const uint
                   unsigned long long* totals, cudaStream_t st);
 void launch_megakernel(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, bool prune, int spp, float* fb,
                        unsigned long long* totals, cudaStream_t st);
-void launch_trace_finish(const SceneDev& sc, int n, PathQueue q, int p3fudge, int* hit, float* dist, int* tri, int* inside, float* point,
-                         float* normal, cudaStream_t st);
+void launch_trace_finish(const SceneDev& sc, int n, PathQueue q, int p3fudge, int accel_space, int* hit, float* dist, int* tri, int* inside,
+                         float* point, float* normal, cudaStream_t st);
 void launch_eval_brdf(int which, int n, const float* V, const float* N, const float* L, const float* xi, const float* materials,
                       float* out, cudaStream_t st);
 void launch_eval_math(int which, int n, const float* a, const float* b, float* out, cudaStream_t st);
