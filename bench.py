@@ -330,7 +330,7 @@ def main():
     if bray_ref and ext_ms > 0:
         rays_rank0 = rays / world  # rank 0's own launches were timed; rays are evenly spread by the tile interleave
         achieved = rays_rank0 * bray_ref / (ext_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        roofline = {"bound": "hbm", "kernel": "k_extend_accel" if args.traverse == "accel" else "k_extend", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "traffic": NCU_DRAM_BYTES_PER_EXTEND_LAUNCH, "traffic_unit": "bytes/launch (dram read+write, ncu --set full, profiles/ncu_extend_r1_summary.md)",
                     "algorithmic_bytes_per_launch": rays_rank0 * bray_ref / max(1, ext_n), "peak_source": peak_kind, "bytes_per_ray": bray_ref, "bytes_per_ray_pruned_policy": bray_pruned,
                     "ray_means": means, "extend_ms_per_launch": ext_ms / max(1, ext_n), "extend_launches": ext_n,
