@@ -32,9 +32,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per k_extend launch on the C3 workload, mean of the three launch
+# dram__bytes_read.sum + dram__bytes_write.sum per k_extend_accel launch on the C3 workload (16-frame batch), mean of the three launch
 # kinds (camera / bounce-1 / bounce-2), from the committed ncu capture profiles/ncu_extend_r1_summary.md
-NCU_DRAM_BYTES_PER_EXTEND_LAUNCH = 354.7e6
+NCU_DRAM_BYTES_PER_EXTEND_LAUNCH = 1966e6
 
 METRIC = "Mrays/s (primary+secondary)"
 UNIT = "Mrays/s"
