@@ -40,8 +40,9 @@ METRIC = "Mrays/s (primary+secondary)"
 UNIT = "Mrays/s"
 WORKLOADS = {
     # name: (scene builder name, width, height, mode, max_bounce)
-    "c3": ("s_1m", 1920, 1080, 2, 2),
-    "c2": ("s_bunny", 1024, 1024, 0, 2),
+    "c3": ("s_1m", 1920, 1080, 2, 2),   # configs[2]: 1M tris, 1080p, Disney + Sobol (mode disney_sobol_p5)
+    "c2": ("s_bunny", 1024, 1024, 0, 2),  # configs[1]: bunny-class 5k tris, 1024^2, diffuse-only (mode diffuse_p3)
+    "c4": ("s_1m", 1920, 1080, 3, 2),   # configs[3]: C3 + HDR env-map importance sampling + MIS (mode disney_is_mis_p5)
 }
 
 
@@ -128,8 +129,13 @@ def build_workload(name):
     builder, w, h, mode, bounces = WORKLOADS[name]
     t0 = time.time()
     tris, nodes, eye, cam = getattr(scenes, builder)()
+    hdr = cache = None
+    if mode == 3:  # procedural 2k environment map (the reference's chinese_garden_2k.hdr is not on the GPU box)
+        from ezrt_b200 import api
+        hdr = scenes.synth_hdr(2048, 1024)
+        cache = api.hdr_cache(hdr)
     return dict(tris=tris, nodes=nodes, eye=eye, cam=cam, width=w, height=h, mode=mode, max_bounce=bounces, scene=builder,
-                build_s=time.time() - t0)
+                hdr=hdr, cache=cache, build_s=time.time() - t0)
 
 
 def oracle_sample(wl, sample, traverse, threads=0):
@@ -140,7 +146,7 @@ def oracle_sample(wl, sample, traverse, threads=0):
     cfg = api.RenderConfig(width=w, height=h, spp=spp, max_bounce=wl["max_bounce"], mode=wl["mode"], eye=tuple(wl["eye"]),
                            camera_rotate=tuple(wl["cam"]), env_color=(0.35, 0.45, 0.6), traverse=traverse)
     t0 = time.perf_counter()
-    _, c = oracle.render(wl["tris"], wl["nodes"], cfg, threads=threads)
+    _, c = oracle.render(wl["tris"], wl["nodes"], cfg, hdr=wl.get("hdr"), hdr_cache=wl.get("cache"), threads=threads)
     dt = time.perf_counter() - t0
     return c["rays"] / dt / 1e6, c, dt
 
@@ -203,7 +209,7 @@ def main():
     wl = build_workload(args.workload)
     W, H = weak_image(wl["width"], wl["height"], world)
     t0 = time.perf_counter()
-    scene = api.Scene(wl["tris"], wl["nodes"], device=local_rank)
+    scene = api.Scene(wl["tris"], wl["nodes"], wl.get("hdr"), wl.get("cache"), device=local_rank)
     upload_ms = 1e3 * (time.perf_counter() - t0)
     C = 3
     n_local = api.partition_pixels(W, H, rank, world)

@@ -36,27 +36,44 @@ __device__ __forceinline__ bool slot_pixel(const RenderDev& rd, const TileDev* _
     return ix < t.w && iy < t.h;
 }
 
-// warp-aggregated append: returns this lane's position in the output queue (valid lanes only)
-__device__ __forceinline__ uint32_t warp_append(bool valid, uint32_t* counter) {
-    unsigned mask = __ballot_sync(0xffffffffu, valid);
-    if (mask == 0u) return 0u;
-    int lane = threadIdx.x & 31;
-    int leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+// block-aggregated append: returns this thread's position in the output queue (valid threads only).
+// One atomicAdd per BLOCK: all queue appends of a kernel hit a single counter, and the L2 atomic unit
+// serialises per address (~2 M warp-level atomics per step were a measurable part of k_shade/k_generate).
+// Must be reached by every thread of the block (uniform loop trip counts).
+__device__ __forceinline__ uint32_t block_append(bool valid, uint32_t* counter, uint32_t* s_scan /* [34] */) {
+    const unsigned mask = __ballot_sync(0xffffffffu, valid);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
+    if (lane == 0) s_scan[wid] = (uint32_t)__popc(mask);
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t v = (lane < n_warps) ? s_scan[lane] : 0u;
+        uint32_t incl = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t base = 0;
+        if (lane == 0 && total != 0u) base = atomicAdd(counter, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        s_scan[lane] = base + incl - v;  // start of each warp's range
+    }
+    __syncthreads();
+    const uint32_t pos = s_scan[wid] + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+    __syncthreads();  // s_scan is reused by the next append
+    return pos;
 }
 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_generate(RenderDev rd, const TileDev* __restrict__ tiles, uint32_t n_slots,
                                                   uint32_t batch_first_frame, PathQueue q, uint32_t* q_count) {
+    __shared__ uint32_t s_scan[34];
     uint32_t stride = gridDim.x * blockDim.x;
-    uint32_t n_round = (n_slots + 31u) & ~31u;
+    uint32_t n_round = ((n_slots + blockDim.x - 1u) / blockDim.x) * blockDim.x;
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_round; slot += stride) {
         uint32_t px = 0, py = 0, fib = 0;
         bool valid = (slot < n_slots) && slot_pixel(rd, tiles, slot, px, py, fib);
-        uint32_t pos = warp_append(valid, q_count);
+        uint32_t pos = block_append(valid, q_count, s_scan);
         if (!valid) continue;
         uint32_t seed;
         vec3 o, d;
@@ -326,8 +343,9 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev sc, RenderDev rd, const 
                                                uint32_t batch_first_frame, PathQueue qin, const uint32_t* __restrict__ in_count,
                                                PathQueue qout, uint32_t* out_count, ShadowQueue sq, uint32_t* s_count,
                                                float4* __restrict__ Lo, float4* __restrict__ Le) {
+    __shared__ uint32_t s_scan[34];
     const uint32_t n = *in_count;
-    const uint32_t n_round = (n + 31u) & ~31u;
+    const uint32_t n_round = ((n + blockDim.x - 1u) / blockDim.x) * blockDim.x;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         bool alive = false;
@@ -365,7 +383,7 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev sc, RenderDev rd, const 
             Lo[slot] = make_float4(lo.x, lo.y, lo.z, pmiss ? 1.0f : 0.0f);
             if (bounce == 0) Le[slot] = make_float4(le.x, le.y, le.z, 0.0f);
         }
-        uint32_t pos = warp_append(alive, out_count);
+        uint32_t pos = block_append(alive, out_count, s_scan);
         if (alive) {
             __stcs(qout.ray_o + pos, make_float4(p.o.x, p.o.y, p.o.z, 0.0f));
             __stcs(qout.ray_d + pos, make_float4(p.d.x, p.d.y, p.d.z, 0.0f));
@@ -374,7 +392,7 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev sc, RenderDev rd, const 
             __stcs(qout.meta + pos, make_uint2(p.seed, slot));
         }
         if (rd.mode == EZRT_MODE_DISNEY_IS_MIS_P5) {
-            uint32_t spos = warp_append(sh.valid, s_count);
+            uint32_t spos = block_append(sh.valid, s_count, s_scan);
             if (sh.valid) {
                 __stcs(sq.ray_o + spos, make_float4(sh.o.x, sh.o.y, sh.o.z, __uint_as_float(slot)));
                 __stcs(sq.ray_d + spos, make_float4(sh.d.x, sh.d.y, sh.d.z, 0.0f));
