@@ -336,7 +336,9 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     int acc_root_ref = 0, acc_top = 0, acc_inner = 0, acc_depth = 0;
     {
         std::vector<EzrtAccelNode> an;
-        ezrt_build_accel(tris, n_triangles, 8, an, acc_order);
+        int acc_leaf_n = 8;  // one octet pass per leaf
+        if (const char* e = getenv("EZRT_ACCEL_LEAF")) acc_leaf_n = std::max(1, std::min(64, atoi(e)));
+        ezrt_build_accel(tris, n_triangles, acc_leaf_n, an, acc_order);
         const int na = (int)an.size();
         std::vector<int> aid(na, -1);
         {   // top levels breadth-first, the rest in pre-order (as for the reference tree)

@@ -339,7 +339,10 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_shadow_accel(Sce
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_shade(SceneDev sc, RenderDev rd, const TileDev* __restrict__ tiles, int bounce,
+#ifndef EZRT_SHADE_MIN_BLOCKS
+#define EZRT_SHADE_MIN_BLOCKS 8   // 64 registers: k_shade is latency-bound, 32 resident warps beat 20 despite small spills
+#endif
+__global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev sc, RenderDev rd, const TileDev* __restrict__ tiles, int bounce,
                                                uint32_t batch_first_frame, PathQueue qin, const uint32_t* __restrict__ in_count,
                                                PathQueue qout, uint32_t* out_count, ShadowQueue sq, uint32_t* s_count,
                                                float4* __restrict__ Lo, float4* __restrict__ Le) {
@@ -663,7 +666,7 @@ void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_c
 void launch_shade(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, int bounce, uint32_t batch_first_frame,
                   PathQueue qin, const uint32_t* in_count, PathQueue qout, uint32_t* out_count, ShadowQueue sq,
                   uint32_t* s_count, float4* Lo, float4* Le, uint32_t n_max, int n_sms, cudaStream_t st) {
-    int blocks = std::min(div_up(n_max, 128), n_sms * 16);
+    int blocks = std::min(div_up(n_max, 128), n_sms * 4 * EZRT_SHADE_MIN_BLOCKS);
     if (blocks < 1) blocks = 1;
     k_shade<<<blocks, 128, 0, st>>>(sc, rd, tiles, bounce, batch_first_frame, qin, in_count, qout, out_count, sq, s_count, Lo, Le);
 }
