@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <array>
 #include <map>
 #include <mutex>
@@ -76,7 +77,7 @@ struct ezrt_scene {
     int n_sms = 148;
     SceneDev dev{};
     DeviceBuffer nodes, tri_geo, tri_shade, materials, hdr, hdr_cache;
-    DeviceBuffer acc_nodes, acc_tri_geo, acc_tri_ref, tri_leaf, leaf_box, defer_buf, acc_tri_shade, acc_tri_leaf, ref_to_acc;
+    DeviceBuffer acc_nodes, acc_tri_geo, acc_tri_ref, tri_leaf, leaf_box, defer_buf, acc_tri_shade, acc_tri_leaf, ref_to_acc, acc_wide;
     int acc_depth = 0;
     int n_materials = 0;
     int tree_depth = 0;
@@ -331,7 +332,8 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
 
     // ---- acceleration tree: sentinel-free SAH over the same triangles (DESIGN.md "accel") ----
     const float prune_delta = max_abs * 1.52587890625e-05f;  // 2^-16 * scene extent
-    std::vector<float4> acc_nodes, acc_geo((size_t)n_triangles * 4);
+    std::vector<float4> acc_nodes, acc_geo((size_t)n_triangles * 4), acc_wide;
+    int acc_wide_root = 0;
     std::vector<uint32_t> acc_order;
     int acc_root_ref = 0, acc_top = 0, acc_inner = 0, acc_depth = 0;
     {
@@ -389,6 +391,55 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         acc_root_ref = aref(0);
         for (int i = 0; i < n_triangles; i++)
             for (int k = 0; k < 4; k++) acc_geo[(size_t)i * 4 + k] = geo[(size_t)acc_order[i] * 4 + k];
+
+        // ---- the same tree collapsed to 4-wide nodes: a node's children are its binary children with the
+        // largest inner ones replaced by their own children until four (one dependent fetch per two levels)
+        const char* we = getenv("EZRT_ACCEL_WIDE");
+        if (!(we && atoi(we) == 0) && an[0].n <= 0) {
+            auto area = [&](int c) {
+                float x = an[c].BB[0] - an[c].AA[0], y = an[c].BB[1] - an[c].AA[1], z = an[c].BB[2] - an[c].AA[2];
+                return x * y + x * z + y * z;
+            };
+            int wide_depth = 0;
+            std::function<int(int, int)> build_wide = [&](int b, int depth) -> int {
+                wide_depth = std::max(wide_depth, depth);
+                const int id = (int)(acc_wide.size() / 8);
+                acc_wide.resize(acc_wide.size() + 8, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+                int ch[4] = {an[b].left, an[b].right, -1, -1};
+                int cnt = 2;
+                while (cnt < 4) {
+                    int best = -1;
+                    float ba = -1.0f;
+                    for (int k = 0; k < cnt; k++)
+                        if (an[ch[k]].n <= 0 && area(ch[k]) > ba) { ba = area(ch[k]); best = k; }
+                    if (best < 0) break;
+                    const int c = ch[best];
+                    for (int k = cnt; k > best + 1; k--) ch[k] = ch[k - 1];
+                    ch[best] = an[c].left;
+                    ch[best + 1] = an[c].right;
+                    cnt++;
+                }
+                float rec[32];
+                int refs[4];
+                for (int k = 0; k < 4; k++) {
+                    float AA[3] = {3.0e38f, 3.0e38f, 3.0e38f}, BB[3] = {3.0e38f, 3.0e38f, 3.0e38f};  // absent: a far-away point box
+                    refs[k] = (int)EZRT_LEAF_FLAG;  // EZRT_REF_DONE, never followed
+                    if (k < cnt) {
+                        const EzrtAccelNode& c = an[ch[k]];
+                        for (int a = 0; a < 3; a++) { AA[a] = c.AA[a] - pad; BB[a] = c.BB[a] + pad; }
+                        refs[k] = (c.n > 0) ? (int)(EZRT_LEAF_FLAG | ((uint32_t)c.index << 7) | (uint32_t)c.n) : build_wide(ch[k], depth + 1);
+                    }
+                    rec[4 * k + 0] = AA[0]; rec[4 * k + 1] = AA[1]; rec[4 * k + 2] = BB[0]; rec[4 * k + 3] = BB[1];
+                    rec[16 + 2 * k] = AA[2]; rec[16 + 2 * k + 1] = BB[2];
+                }
+                memcpy(&rec[24], refs, 16);
+                for (int k = 24 + 4; k < 32; k++) rec[k] = 0.0f;
+                memcpy(&acc_wide[(size_t)id * 8], rec, sizeof(rec));
+                return id;
+            };
+            acc_wide_root = build_wide(0, 1);
+            if (3 * wide_depth + 2 > EZRT_MAX_STACK) acc_wide.clear();  // too deep for the traversal stack: keep the binary form
+        }
     }
     // shading data and the reference-leaf map in the acceleration tree's order, and the inverse permutation
     std::vector<float4> acc_shade((size_t)n_triangles * 3);
@@ -438,6 +489,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         sc->hot_bytes = acc_nodes_bytes + acc_geo_bytes + acc_shade_bytes;
     }
     if (!rc) rc = upload(sc->acc_tri_ref, acc_order.data(), acc_order.size() * sizeof(uint32_t));
+    if (!rc && !acc_wide.empty()) rc = upload(sc->acc_wide, acc_wide.data(), acc_wide.size() * sizeof(float4));
     if (!rc) rc = upload(sc->tri_leaf, tri_leaf.data(), tri_leaf.size() * sizeof(int));
     if (!rc) rc = upload(sc->leaf_box, leaf_box.data(), leaf_box.size() * sizeof(float4));
     if (!rc) rc = upload(sc->acc_tri_leaf, acc_leaf.data(), acc_leaf.size() * sizeof(int));
@@ -465,6 +517,8 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.acc_tri_geo = (const float4*)((const char*)sc->acc_nodes.p + acc_nodes_bytes);
     d.acc_tri_ref = (const uint32_t*)sc->acc_tri_ref.p;
     d.acc_root_ref = acc_root_ref;
+    d.acc_wide_nodes = acc_wide.empty() ? nullptr : (const float4*)sc->acc_wide.p;
+    d.acc_wide_root_ref = acc_wide_root;
     d.acc_top_nodes = acc_top;
     d.acc_tri_shade = (const float4*)((const char*)sc->acc_nodes.p + acc_nodes_bytes + acc_geo_bytes);
     d.acc_tri_leaf = (const int*)sc->acc_tri_leaf.p;
@@ -513,7 +567,7 @@ int ezrt_scene_destroy(ezrt_scene* s) {
     s->nodes.release(); s->tri_geo.release(); s->tri_shade.release(); s->materials.release();
     s->hdr.release(); s->hdr_cache.release(); s->tiles_buf.release();
     s->acc_nodes.release(); s->acc_tri_geo.release(); s->acc_tri_ref.release(); s->tri_leaf.release(); s->leaf_box.release(); s->defer_buf.release();
-    s->acc_tri_shade.release(); s->acc_tri_leaf.release(); s->ref_to_acc.release();
+    s->acc_tri_shade.release(); s->acc_tri_leaf.release(); s->ref_to_acc.release(); s->acc_wide.release();
     s->queue_buf[0].release(); s->queue_buf[1].release(); s->shadow_buf.release();
     s->lo_buf.release(); s->le_buf.release(); s->counters_buf.release(); s->totals_buf.release(); s->fb_buf.release(); s->sort_buf.release();
     if (s->own_stream) cudaStreamDestroy(s->own_stream);

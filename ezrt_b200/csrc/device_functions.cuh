@@ -187,6 +187,59 @@ __device__ __forceinline__ NodeVisit node_visit_q(ulonglong2 q0, ulonglong2 q1, 
     return v;
 }
 
+// ---- 4-wide node of the acceleration tree (128-byte record, DESIGN.md "accel"):
+//   q0..q3 : child c = (AA.x, AA.y, BB.x, BB.y)      q4 : (AA.z0, BB.z0, AA.z1, BB.z1)
+//   q5     : (AA.z2, BB.z2, AA.z3, BB.z3)            q6 : the four child references
+// An absent child has an inverted box (never hit).  The acceleration tree is free to visit children
+// in any order, so they are ordered by slab entry distance; one dependent fetch now decides two levels.
+struct WideVisit {
+    float k0, k1, k2, k3;   // entry distance of each child, +inf when missed / pruned
+    int r0, r1, r2, r3;
+};
+__device__ __forceinline__ void slab_xy(pk2 lo, pk2 hi, const RaySlab& rs, float& t0, float& t1) {
+    float nx, ny, fx, fy;
+    pk2_split(pk2_mul(pk2_add(lo, rs.no_xy), rs.inv_xy), nx, ny);
+    pk2_split(pk2_mul(pk2_add(hi, rs.no_xy), rs.inv_xy), fx, fy);
+    t0 = fmaxf(fminf(fx, nx), fminf(fy, ny));
+    t1 = fminf(fmaxf(fx, nx), fmaxf(fy, ny));
+}
+__device__ __forceinline__ float wide_key(float t0, float t1, float nz, float fz, float limit) {
+    t0 = fmaxf(t0, fminf(fz, nz));
+    t1 = fminf(t1, fmaxf(fz, nz));
+    const bool ok = (t1 >= t0) && (t1 > 0.0f) && !(t0 > limit);  // hitAABB > 0 and not beyond the best hit
+    return ok ? t0 : 3.0e38f;
+}
+__device__ __forceinline__ WideVisit wide_visit(const float4* __restrict__ nd, const RaySlab& rs, float limit) {
+    ulonglong2 q0, q1, q2, q3, q4, q5;
+    ldg256_b64(nd, q0, q1);
+    ldg256_b64(nd + 2, q2, q3);
+    ldg256_b64(nd + 4, q4, q5);
+    const int4 refs = __ldg(reinterpret_cast<const int4*>(nd + 6));
+    float a0, b0, a1, b1, a2, b2, a3, b3;
+    slab_xy(q0.x, q0.y, rs, a0, b0);
+    slab_xy(q1.x, q1.y, rs, a1, b1);
+    slab_xy(q2.x, q2.y, rs, a2, b2);
+    slab_xy(q3.x, q3.y, rs, a3, b3);
+    float z0n, z0f, z1n, z1f, z2n, z2f, z3n, z3f;
+    pk2_split(pk2_mul(pk2_add(q4.x, rs.no_zz), rs.inv_zz), z0n, z0f);
+    pk2_split(pk2_mul(pk2_add(q4.y, rs.no_zz), rs.inv_zz), z1n, z1f);
+    pk2_split(pk2_mul(pk2_add(q5.x, rs.no_zz), rs.inv_zz), z2n, z2f);
+    pk2_split(pk2_mul(pk2_add(q5.y, rs.no_zz), rs.inv_zz), z3n, z3f);
+    WideVisit v;
+    v.k0 = wide_key(a0, b0, z0n, z0f, limit);
+    v.k1 = wide_key(a1, b1, z1n, z1f, limit);
+    v.k2 = wide_key(a2, b2, z2n, z2f, limit);
+    v.k3 = wide_key(a3, b3, z3n, z3f, limit);
+    v.r0 = refs.x; v.r1 = refs.y; v.r2 = refs.z; v.r3 = refs.w;
+    return v;
+}
+__device__ __forceinline__ void cswap(float& ka, int& ra, float& kb, int& rb) {  // ascending by key
+    const bool sw = kb < ka;
+    const float tk = sw ? kb : ka, uk = sw ? ka : kb;
+    const int tr = sw ? rb : ra, ur = sw ? ra : rb;
+    ka = tk; kb = uk; ra = tr; rb = ur;
+}
+
 // Ray/triangle test against the repacked record.  Accepts exactly the hits hitTriangle accepts
 // that are also strictly closer than `best` (the only ones hitArray/hitBVH can keep).
 // TIES (accel policy): a hit at exactly t == best is also reported (return 2) so the caller can
@@ -314,10 +367,11 @@ __device__ __forceinline__ HitRec trace_ray(const SceneDev& sc, vec3 o, vec3 d) 
 
 // the tree a persistent traversal walks: the reference tree or the device's acceleration tree
 struct TreeView {
-    const float4* nodes;
+    const float4* nodes;     // binary records (64 B), or 4-wide records (128 B) when `wide`
     const float4* tri_geo;
     int root_ref;
     int top_nodes;
+    int wide;
 };
 
 // Would the shader's hitBVH have reached the leaf that holds reference triangle `ref_tri`?  Yes iff
@@ -342,7 +396,7 @@ __device__ __forceinline__ bool reference_reaches_leaf(const int* __restrict__ t
 // ACCEL: `tree` is the device's own acceleration tree, not the reference tree: the closest hit it
 // finds is the global minimum over all triangles; ties (two triangles at exactly the same t) and rays
 // with non-finite 1/d are handed to io.defer() and re-traced by the exact reference-order kernel.
-template <bool PRUNE, bool ANYHIT, bool ACCEL, class RayIO>
+template <bool PRUNE, bool ANYHIT, bool ACCEL, bool WIDE, class RayIO>
 __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const TreeView tree, uint32_t n, uint32_t* work, RayIO io,
                                                   const float4* smem_top) {
     const int top_nodes = tree.top_nodes;
@@ -427,7 +481,31 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                 if (m_inner == 0u) break;
                 const unsigned m_wait = m_busy & ~m_inner;  // busy lanes standing at a leaf (or done)
                 if (m_wait != 0u && (__popc(m_inner) < inner_thresh || __popc(m_wait) >= leaf_thresh)) break;
-                if (at_inner) {
+                if (WIDE) {
+                    if (at_inner) {  // 4-wide acceleration-tree node: nearest child next, the others pushed far-to-near
+                        const float limit = best + (best * 0.000244140625f + slack);
+                        WideVisit w = wide_visit(tree.nodes + (size_t)ref * 8, rs, limit);
+                        cswap(w.k0, w.r0, w.k1, w.r1);
+                        cswap(w.k2, w.r2, w.k3, w.r3);
+                        cswap(w.k0, w.r0, w.k2, w.r2);
+                        cswap(w.k1, w.r1, w.k3, w.r3);
+                        cswap(w.k1, w.r1, w.k2, w.r2);
+                        if (w.k3 < 3.0e38f) stack[sp++] = make_int2(w.r3, __float_as_int(w.k3));
+                        if (w.k2 < 3.0e38f) stack[sp++] = make_int2(w.r2, __float_as_int(w.k2));
+                        if (w.k1 < 3.0e38f) stack[sp++] = make_int2(w.r1, __float_as_int(w.k1));
+                        if (w.k0 < 3.0e38f) {
+                            ref = w.r0;
+                        } else {  // pop
+                            ref = EZRT_REF_DONE;
+                            while (sp > 0) {
+                                const int2 e = stack[--sp];
+                                if (prune_test(__int_as_float(e.y), best, slack)) continue;
+                                ref = e.x;
+                                break;
+                            }
+                        }
+                    }
+                } else if (at_inner) {
                     NodeVisit nv = node_visit_top<true>(tree.nodes, smem_top, top_nodes, ref, rs);
                     bool h1 = nv.h1, h2 = nv.h2;
                     const float d1 = nv.d1, d2 = nv.d2, e1 = nv.e1, e2 = nv.e2;

@@ -52,6 +52,8 @@ struct SceneDev {
     const int* acc_tri_leaf;       // reference leaf (slot in leaf_box) of every triangle, accel order
     int acc_root_ref;
     int acc_top_nodes;
+    const float4* acc_wide_nodes;  // the same tree collapsed to 4-wide nodes (128 B records); null = use the binary form
+    int acc_wide_root_ref;
     // reference leaf of every reference triangle + the leaves' boxes (AA, BB as float4 pairs)
     const int* tri_leaf;
     const float4* leaf_box;

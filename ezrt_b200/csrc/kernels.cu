@@ -187,12 +187,12 @@ __device__ __forceinline__ void stage_top_nodes(const TreeView& tree) {
 }
 __device__ __forceinline__ TreeView reference_tree(const SceneDev& sc) {
     TreeView t;
-    t.nodes = sc.nodes; t.tri_geo = sc.tri_geo; t.root_ref = sc.root_ref; t.top_nodes = sc.top_nodes;
+    t.nodes = sc.nodes; t.tri_geo = sc.tri_geo; t.root_ref = sc.root_ref; t.top_nodes = sc.top_nodes; t.wide = 0;
     return t;
 }
 __device__ __forceinline__ TreeView accel_tree(const SceneDev& sc) {
     TreeView t;
-    t.nodes = sc.acc_nodes; t.tri_geo = sc.acc_tri_geo; t.root_ref = sc.acc_root_ref; t.top_nodes = sc.acc_top_nodes;
+    t.nodes = sc.acc_nodes; t.tri_geo = sc.acc_tri_geo; t.root_ref = sc.acc_root_ref; t.top_nodes = sc.acc_top_nodes; t.wide = 0;
     return t;
 }
 
@@ -218,7 +218,7 @@ struct ExtendIO {
 };
 
 template <bool PRUNE, bool ANYHIT>
-__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_extend(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
+__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
                                                                 uint32_t* work, const uint32_t* __restrict__ perm, int to_accel) {
     ExtendIO io;
     io.q = q;
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_extend(SceneDev 
     io.to_accel = to_accel ? sc.ref_to_acc : nullptr;
     const TreeView tree = reference_tree(sc);
     stage_top_nodes(tree);
-    extend_persistent<PRUNE, ANYHIT, false>(sc, tree, *q_count, work, io, g_smem_top);
+    extend_persistent<PRUNE, ANYHIT, false, false>(sc, tree, *q_count, work, io, g_smem_top);
 }
 
 // ---- accel kernels: the device's own SAH tree finds the global closest hit G; the result is kept when
@@ -253,8 +253,8 @@ struct AccelIO {
     }
 };
 
-template <bool ANYHIT>
-__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_extend_accel(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
+template <bool ANYHIT, bool WIDE>
+__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend_accel(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
                                                                       uint32_t* work, uint32_t* defer_list, uint32_t* defer_count) {
     AccelIO io;
     io.q = q;
@@ -262,9 +262,16 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_extend_accel(Sce
     io.leaf_box = sc.leaf_box;
     io.defer_list = defer_list;
     io.defer_count = defer_count;
-    const TreeView tree = accel_tree(sc);
-    stage_top_nodes(tree);
-    extend_persistent<true, ANYHIT, true>(sc, tree, *q_count, work, io, g_smem_top);
+    TreeView tree = accel_tree(sc);
+    if (WIDE) {  // 4-wide records, read straight from global memory / L1
+        tree.nodes = sc.acc_wide_nodes;
+        tree.root_ref = sc.acc_wide_root_ref;
+        tree.top_nodes = 0;
+        tree.wide = 1;
+    } else {
+        stage_top_nodes(tree);
+    }
+    extend_persistent<true, ANYHIT, true, WIDE>(sc, tree, *q_count, work, io, g_smem_top);
 }
 
 // ---- shadow rays: any hit; an unoccluded ray adds its precomputed contribution (P5/fsh:829-841).
@@ -293,7 +300,7 @@ struct ShadowIO {
 };
 
 template <bool PRUNE>
-__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_shadow(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count,
+__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_shadow(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count,
                                                                 uint32_t* work, float4* __restrict__ Lo, const uint32_t* __restrict__ perm) {
     ShadowIO io;
     io.sq = sq;
@@ -301,7 +308,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_shadow(SceneDev 
     io.perm = perm;
     const TreeView tree = reference_tree(sc);
     stage_top_nodes(tree);
-    extend_persistent<PRUNE, true, false>(sc, tree, *s_count, work, io, g_smem_top);
+    extend_persistent<PRUNE, true, false, false>(sc, tree, *s_count, work, io, g_smem_top);
 }
 
 struct ShadowAccelIO {
@@ -322,7 +329,8 @@ struct ShadowAccelIO {
     }
 };
 
-__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_shadow_accel(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count,
+template <bool WIDE>
+__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_shadow_accel(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count,
                                                                       uint32_t* work, float4* __restrict__ Lo, uint32_t* defer_list,
                                                                       uint32_t* defer_count) {
     ShadowAccelIO io;
@@ -333,9 +341,16 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, 1) k_shadow_accel(Sce
     io.leaf_box = sc.leaf_box;
     io.defer_list = defer_list;
     io.defer_count = defer_count;
-    const TreeView tree = accel_tree(sc);
-    stage_top_nodes(tree);
-    extend_persistent<true, true, true>(sc, tree, *s_count, work, io, g_smem_top);
+    TreeView tree = accel_tree(sc);
+    if (WIDE) {
+        tree.nodes = sc.acc_wide_nodes;
+        tree.root_ref = sc.acc_wide_root_ref;
+        tree.top_nodes = 0;
+        tree.wide = 1;
+    } else {
+        stage_top_nodes(tree);
+    }
+    extend_persistent<true, true, true, WIDE>(sc, tree, *s_count, work, io, g_smem_top);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -638,8 +653,14 @@ void launch_extend(const SceneDev& sc, bool prune, bool anyhit, PathQueue q, con
 void launch_extend_accel(const SceneDev& sc, bool anyhit, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t* defer_list,
                          uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, cudaStream_t st) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
-    if (anyhit) k_extend_accel<true><<<blocks, threads, smem_for(k_extend_accel<true>, sc.acc_top_nodes), st>>>(sc, q, q_count, work, defer_list, defer_count);
-    else k_extend_accel<false><<<blocks, threads, smem_for(k_extend_accel<false>, sc.acc_top_nodes), st>>>(sc, q, q_count, work, defer_list, defer_count);
+    if (sc.acc_wide_nodes) {
+        if (anyhit) k_extend_accel<true, true><<<blocks, threads, 0, st>>>(sc, q, q_count, work, defer_list, defer_count);
+        else k_extend_accel<false, true><<<blocks, threads, 0, st>>>(sc, q, q_count, work, defer_list, defer_count);
+    } else if (anyhit) {
+        k_extend_accel<true, false><<<blocks, threads, smem_for(k_extend_accel<true, false>, sc.acc_top_nodes), st>>>(sc, q, q_count, work, defer_list, defer_count);
+    } else {
+        k_extend_accel<false, false><<<blocks, threads, smem_for(k_extend_accel<false, false>, sc.acc_top_nodes), st>>>(sc, q, q_count, work, defer_list, defer_count);
+    }
     launch_extend(sc, true, anyhit, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_max, 65536u), n_sms, st);
 }
 // counting sort of the queue's ray indices into `perm` (3 kernels; bins must hold EZRT_SORT_BINS counters)
@@ -660,7 +681,8 @@ void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_
 void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo, uint32_t* defer_list,
                          uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, cudaStream_t st) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
-    k_shadow_accel<<<blocks, threads, smem_for(k_shadow_accel, sc.acc_top_nodes), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
+    if (sc.acc_wide_nodes) k_shadow_accel<true><<<blocks, threads, 0, st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
+    else k_shadow_accel<false><<<blocks, threads, smem_for(k_shadow_accel<false>, sc.acc_top_nodes), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
     launch_shadow(sc, true, sq, defer_count, defer_work, Lo, defer_list, std::min<uint32_t>(n_max, 65536u), n_sms, st);
 }
 void launch_shade(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, int bounce, uint32_t batch_first_frame,

@@ -11,6 +11,9 @@
 #define EZRT_EXTEND_MAX_THREADS 1024
 #endif
 #define EZRT_EXTEND_THREADS EZRT_EXTEND_MAX_THREADS
+#ifndef EZRT_EXTEND_LB_BLOCKS
+#define EZRT_EXTEND_LB_BLOCKS 1
+#endif
 #define EZRT_EXTEND_BLOCKS_PER_SM 1
 
 void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots, uint32_t batch_first_frame, PathQueue q,
