@@ -52,6 +52,8 @@ SIGNATURES = {
                                   c_int32_p, c_int32_p, c_float_p, c_float_p]),
     "ezrt_eval_brdf": (C.c_int, [C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p]),
     "ezrt_eval_math": (C.c_int, [C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, c_float_p]),
+    "ezrt_post_tonemap": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
+    "ezrt_write_png": (C.c_int, [C.c_char_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ezrt_trilist_create": (C.c_void_p, []),
     "ezrt_trilist_destroy": (None, [C.c_void_p]),
     "ezrt_trilist_size": (C.c_int, [C.c_void_p]),

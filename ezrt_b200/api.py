@@ -269,6 +269,25 @@ class Scene:
         return dict(hit=hit, distance=dist, triangle=tri, inside=inside, point=point, normal=normal)
 
 
+def post_tonemap(d_in, d_out=None, limit=1.5, stream=None):
+    """pass3 (P5/shaders/pass3.fsh:14-25) on a device framebuffer (torch CUDA tensor [..., 3|4]) -> [..., 3]."""
+    import torch
+    channels = d_in.shape[-1]
+    n = d_in.numel() // channels
+    if d_out is None:
+        d_out = torch.empty(tuple(d_in.shape[:-1]) + (3,), dtype=torch.float32, device=d_in.device)
+    st = torch.cuda.current_stream() if stream is None else stream
+    check(lib.ezrt_post_tonemap(C.c_void_p(d_in.data_ptr()), channels, C.c_void_p(d_out.data_ptr()), n, float(limit), C.c_void_p(st.cuda_stream)))
+    return d_out
+
+
+def write_png(path, framebuffer, tonemap=True):
+    """Write a linear framebuffer [H, W, 3|4] (row 0 = bottom) as an 8-bit PNG (pass3 tone map + gamma when tonemap)."""
+    fb = _f32(framebuffer)
+    h, w, c = fb.shape
+    check(lib.ezrt_write_png(str(path).encode(), _fp(fb), w, h, c, int(bool(tonemap))))
+
+
 def eval_brdf(which, V, N, L, xi, materials, device=0):
     V = _f32(V, (-1, 3)); N = _f32(N, (-1, 3))
     L = None if L is None else _f32(L, (-1, 3))

@@ -833,6 +833,16 @@ int ezrt_partition_scatter_host(const float* compact, float* full, int width, in
 }
 
 // ------------------------------------------------------------------------------------------
+// post pass
+// ------------------------------------------------------------------------------------------
+int ezrt_post_tonemap(const float* d_in, int channels, float* d_out, int64_t n_pixels, float limit, void* cuda_stream) {
+    if (!d_in || !d_out || (channels != 3 && channels != 4) || n_pixels < 0) return ezrt_set_error(EZRT_ERR_INVALID, "post_tonemap: bad argument");
+    launch_tonemap(d_in, channels, d_out, (long long)n_pixels, limit, (cudaStream_t)cuda_stream);
+    CU_CHECK(cudaGetLastError());
+    return EZRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // single-function entry points (parity tests)
 // ------------------------------------------------------------------------------------------
 int ezrt_trace_rays(ezrt_scene* s, int n, const float* origins, const float* dirs, int traverse, int any_hit, int p3_normal_fudge,

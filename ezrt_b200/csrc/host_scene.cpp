@@ -812,6 +812,87 @@ int ezrt_hdr_cache(const float* HDR, int width, int height, float* cache) {
     return EZRT_OK;
 }
 
+// ---- PNG output (role of P1's imshow + svpng, P1/main.cpp:173-194): 8-bit RGB, zlib "stored" blocks --
+namespace {
+struct PngOut {
+    FILE* f;
+    uint32_t crc;
+    void raw(const unsigned char* p, size_t n) { fwrite(p, 1, n, f); }
+    void u32(uint32_t v) { unsigned char b[4] = {(unsigned char)(v >> 24), (unsigned char)(v >> 16), (unsigned char)(v >> 8), (unsigned char)v}; raw(b, 4); }
+    void crc_bytes(const unsigned char* p, size_t n) {
+        static uint32_t table[256];
+        static bool init = false;
+        if (!init) {
+            for (uint32_t i = 0; i < 256; i++) {
+                uint32_t c = i;
+                for (int k = 0; k < 8; k++) c = (c & 1u) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
+                table[i] = c;
+            }
+            init = true;
+        }
+        for (size_t i = 0; i < n; i++) crc = table[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+    }
+    void chunk(const char* tag, const std::vector<unsigned char>& data) {
+        u32((uint32_t)data.size());
+        crc = 0xffffffffu;
+        crc_bytes((const unsigned char*)tag, 4);
+        raw((const unsigned char*)tag, 4);
+        if (!data.empty()) { crc_bytes(data.data(), data.size()); raw(data.data(), data.size()); }
+        u32(crc ^ 0xffffffffu);
+    }
+};
+}  // namespace
+
+int ezrt_write_png(const char* path, const float* fb, int width, int height, int channels, int tonemap) {
+    if (!path || !fb || width <= 0 || height <= 0 || (channels != 3 && channels != 4)) return ezrt_set_error(EZRT_ERR_INVALID, "write_png: bad argument");
+    // scanlines top row first (framebuffer row 0 is the bottom row), filter byte 0, quantised as imshow()
+    const size_t stride = (size_t)width * 3 + 1;
+    std::vector<unsigned char> rawimg(stride * height);
+    for (int y = 0; y < height; y++) {
+        unsigned char* row = &rawimg[(size_t)y * stride];
+        row[0] = 0;
+        const float* src = fb + (size_t)(height - 1 - y) * width * channels;
+        for (int x = 0; x < width; x++) {
+            ez_vec3 c = ez_v3(src[(size_t)x * channels], src[(size_t)x * channels + 1], src[(size_t)x * channels + 2]);
+            if (tonemap) c = ez_tonemap_pass3(c, 1.5f);
+            const float v[3] = {c.x, c.y, c.z};
+            for (int k = 0; k < 3; k++) {
+                float q = v[k] * 255.0f;
+                q = (q != q) ? 0.0f : ez_min(ez_max(q, 0.0f), 255.0f);
+                row[1 + 3 * x + k] = (unsigned char)q;
+            }
+        }
+    }
+    std::vector<unsigned char> z;
+    z.push_back(0x78); z.push_back(0x01);  // zlib header, no compression
+    uint32_t a = 1, b = 0;                 // adler32
+    for (unsigned char c : rawimg) { a = (a + c) % 65521u; b = (b + a) % 65521u; }
+    size_t pos = 0;
+    while (pos < rawimg.size()) {
+        size_t n = std::min<size_t>(65535, rawimg.size() - pos);
+        z.push_back(pos + n == rawimg.size() ? 1 : 0);
+        z.push_back((unsigned char)(n & 0xff)); z.push_back((unsigned char)(n >> 8));
+        z.push_back((unsigned char)(~n & 0xff)); z.push_back((unsigned char)((~n >> 8) & 0xff));
+        z.insert(z.end(), rawimg.begin() + pos, rawimg.begin() + pos + n);
+        pos += n;
+    }
+    const uint32_t adler = (b << 16) | a;
+    z.push_back((unsigned char)(adler >> 24)); z.push_back((unsigned char)(adler >> 16)); z.push_back((unsigned char)(adler >> 8)); z.push_back((unsigned char)adler);
+    FILE* f = fopen(path, "wb");
+    if (!f) return ezrt_set_error(EZRT_ERR_IO, "write_png: cannot open %s", path);
+    PngOut out{f, 0};
+    const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    out.raw(sig, 8);
+    std::vector<unsigned char> ihdr = {(unsigned char)(width >> 24), (unsigned char)(width >> 16), (unsigned char)(width >> 8), (unsigned char)width,
+                                       (unsigned char)(height >> 24), (unsigned char)(height >> 16), (unsigned char)(height >> 8), (unsigned char)height,
+                                       8, 2, 0, 0, 0};
+    out.chunk("IHDR", ihdr);
+    out.chunk("IDAT", z);
+    out.chunk("IEND", std::vector<unsigned char>());
+    fclose(f);
+    return EZRT_OK;
+}
+
 // ---- display() camera, P5/main.cpp:710-713 -------------------------------------------------
 void ezrt_camera_orbit(float rotatAngle, float upAngle, float r, float eye_out[3], float camera_rotate[16]) {
     float ra = rotatAngle * kDegToRad, ua = upAngle * kDegToRad;

@@ -587,6 +587,15 @@ __global__ void k_eval_math(int which, int n, const float* a, const float* b, fl
     out[i] = r;
 }
 
+// pass3: tone map + gamma (P5/shaders/pass3.fsh:14-25)
+__global__ void __launch_bounds__(256) k_tonemap(const float* __restrict__ in, int channels, float* __restrict__ out, long long n, float limit) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vec3 c = ez_v3(in[i * channels], in[i * channels + 1], in[i * channels + 2]);
+    c = ez_tonemap_pass3(c, limit);
+    out[i * 3] = c.x; out[i * 3 + 1] = c.y; out[i * 3 + 2] = c.z;
+}
+
 // compact tile-major part buffer -> full row-major framebuffer
 __global__ void k_partition_scatter(const float* __restrict__ compact, float* __restrict__ full, const TileDev* __restrict__ tiles,
                                     int n_tiles, int width, int channels) {
@@ -717,6 +726,10 @@ void launch_eval_brdf(int which, int n, const float* V, const float* N, const fl
 }
 void launch_eval_math(int which, int n, const float* a, const float* b, float* out, cudaStream_t st) {
     k_eval_math<<<div_up(n, 256), 256, 0, st>>>(which, n, a, b, out);
+}
+void launch_tonemap(const float* in, int channels, float* out, long long n, float limit, cudaStream_t st) {
+    if (n <= 0) return;
+    k_tonemap<<<div_up(n, 256), 256, 0, st>>>(in, channels, out, n, limit);
 }
 void launch_partition_scatter(const float* compact, float* full, const TileDev* tiles, int n_tiles, int width, int channels,
                               cudaStream_t st) {

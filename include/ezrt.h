@@ -173,6 +173,19 @@ int ezrt_eval_brdf(int device, int which, int n, const float* V, const float* N,
 int ezrt_eval_math(int device, int which, int n, const float* a, const float* b, float* out);
 
 /* ----------------------------------------------------------------------------------------
+ * Post pass (SURVEY.md 8f "next" row 3): what the user sees.
+ * -------------------------------------------------------------------------------------- */
+
+/* pass3 (P5/shaders/pass3.fsh:14-25): toneMapping(c, limit) = c * 1.0 / (1.0 + lum/limit) with
+ * lum = 0.3 r + 0.6 g + 0.1 b (limit = 1.5 in the shader), then pow(c, 1/2.2).  Device kernel:
+ * d_in has `channels` (3 or 4) floats per pixel, d_out 3 floats per pixel. */
+int ezrt_post_tonemap(const float* d_in, int channels, float* d_out, int64_t n_pixels, float limit, void* cuda_stream);
+/* Host: write a linear framebuffer (row 0 = bottom, as ezrt_render returns it) as an 8-bit RGB PNG, top row
+ * first; tonemap = 1 applies pass3 first; quantisation is P1's imshow(): (unsigned char)clamp(v*255, 0, 255)
+ * (P1/main.cpp:173-194; P1 wrote its PNG with the vendored svpng.inc, this is an independent writer). */
+int ezrt_write_png(const char* path, const float* framebuffer, int width, int height, int channels, int tonemap);
+
+/* ----------------------------------------------------------------------------------------
  * Host side: the scene pipeline that feeds the path (stays on the CPU, north_star).
  * -------------------------------------------------------------------------------------- */
 

@@ -287,4 +287,14 @@ EZ_HD float ez_asin(float xx) {
     return (sign < 0.0f) ? -z : z;
 }
 
+/* ------------------------------------------------------------------ post pass */
+/* pass3.fsh:14-25: toneMapping(c, limit) = c * 1.0 / (1.0 + lum / limit), then pow(c, vec3(1.0/2.2)) */
+EZ_HD ez_vec3 ez_tonemap_pass3(ez_vec3 c, float limit) {
+    float luminance = 0.3f * c.x + 0.6f * c.y + 0.1f * c.z;
+    float den = 1.0f + EZ_DIV(luminance, limit);
+    ez_vec3 t = ez_v3(EZ_DIV(c.x * 1.0f, den), EZ_DIV(c.y * 1.0f, den), EZ_DIV(c.z * 1.0f, den));
+    const float g = EZ_DIV(1.0f, 2.2f);
+    return ez_v3(ez_pow(t.x, g), ez_pow(t.y, g), ez_pow(t.z, g));
+}
+
 #endif /* EZRT_MATH_H */

@@ -934,6 +934,13 @@ void oracle_wang_chain(uint32_t seed, int n, uint32_t* hashes, float* rands) {
 float oracle_sobol(uint32_t d, uint32_t i) { return sobol(d, grayCode(i)); }
 void oracle_cp_rotation(float* xy, uint32_t px, uint32_t py) { CranleyPattersonRotation(&xy[0], &xy[1], px, py); }
 float oracle_pi(void) { return EZ_PI; }
+// pass3.fsh:14-25 on n pixels (`channels` floats in, 3 floats out)
+void oracle_tonemap(const float* in, int channels, float* out, long long n, float limit) {
+    for (long long i = 0; i < n; i++) {
+        vec3 c = ez_tonemap_pass3(ez_v3(in[i * channels], in[i * channels + 1], in[i * channels + 2]), limit);
+        out[i * 3] = c.x; out[i * 3 + 1] = c.y; out[i * 3 + 2] = c.z;
+    }
+}
 // inner-node visits by depth accumulated over all oracle_render calls since the last reset
 void oracle_depth_hist(uint64_t* out64, int reset) {
     for (int k = 0; k < 64; k++) { out64[k] = g_innerByDepth[k]; if (reset) g_innerByDepth[k] = 0; }

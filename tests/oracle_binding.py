@@ -109,5 +109,17 @@ def cp_rotation(x, y, px, py):
     return float(xy[0]), float(xy[1])
 
 
+_o.oracle_tonemap.restype = None
+_o.oracle_tonemap.argtypes = [_fp, C.c_int, _fp, C.c_longlong, C.c_float]
+
+
+def tonemap(fb, limit=1.5):
+    fb = _f32(fb)
+    ch = fb.shape[-1]
+    out = np.zeros(fb.shape[:-1] + (3,), np.float32)
+    _o.oracle_tonemap(_f(fb), ch, _f(out), fb.size // ch, float(limit))
+    return out
+
+
 def pi():
     return float(_o.oracle_pi())

@@ -326,3 +326,76 @@ def test_errors_are_reported_not_fatal(bunny_scene):
             sc.render(_cfg(eye, cam, mode=api.MODE_DISNEY_IS_MIS_P5))  # no HDR map
     finally:
         sc.close()
+
+
+# ------------------------------------------------------------------ committed golden fixtures + edge cases
+def test_golden_p3_scene_images(small_hdr):
+    """The reference's own P3 scene (real Stanford bunny, arrays committed in tests/golden/p3_scene.npz together
+    with the oracle's images): the GPU must reproduce the committed images bit for bit, in all four modes."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "p3_scene.npz"))
+    hdr, cache = small_hdr
+    sc = api.Scene(g["tris"], g["nodes"], hdr, cache)
+    try:
+        for mode, bounces in ((0, 3), (1, 4), (2, 2), (3, 2)):
+            for policy in (api.TRAVERSE_ACCEL, api.TRAVERSE_REFERENCE):
+                cfg = api.RenderConfig(width=48, height=32, spp=2, max_bounce=bounces, mode=mode, eye=tuple(g["eye"]),
+                                       camera_rotate=tuple(g["cam"]), env_color=(0.35, 0.45, 0.6), traverse=policy)
+                if mode != 3:  # the golden images of modes 0-2 were rendered without an environment map
+                    sc2 = api.Scene(g["tris"], g["nodes"])
+                    try:
+                        got = sc2.render(cfg)
+                        c = sc2.counters()
+                    finally:
+                        sc2.close()
+                else:
+                    got = sc.render(cfg)
+                    c = sc.counters()
+                assert_same_bits(got, g["img_mode%d" % mode], "golden P3 scene, mode %d policy %d" % (mode, policy))
+                assert [c.primary_rays, c.bounce_rays, c.shadow_rays] == list(g["rays_mode%d" % mode][:3])
+    finally:
+        sc.close()
+
+
+@pytest.mark.parametrize("policy", [api.TRAVERSE_ACCEL, api.TRAVERSE_PRUNED, api.TRAVERSE_REFERENCE])
+def test_long_leaves_and_single_leaf_trees(oracle, bunny_scene, policy):
+    """Caller-provided trees: leaves of up to 20 triangles (several octet passes) and a scene that is one leaf."""
+    tris, nodes, eye, cam = bunny_scene
+    tl = api.TriangleList()
+    tl.append_encoded(tris)
+    t20, n20 = tl.build_bvh(20)
+    assert n20[:, 3].max() > 8
+    sc = api.Scene(t20, n20)
+    try:
+        cfg = _cfg(eye, cam, mode=api.MODE_DISNEY_SOBOL_P5, width=64, height=48, spp=2, traverse=policy)
+        ref, rc = oracle.render(t20, n20, cfg)
+        assert_same_bits(sc.render(cfg), ref, "20-triangle leaves")
+        assert sc.counters().rays == rc["rays"]
+    finally:
+        sc.close()
+    tl = api.TriangleList()
+    tl.append_encoded(tris[-5:])  # five triangles of the emissive sphere: the root is a leaf
+    t1, n1 = tl.build_bvh(8)
+    assert n1.shape[0] == 2 and n1[1, 3] == 5
+    sc = api.Scene(t1, n1)
+    try:
+        cfg = _cfg(eye, cam, mode=api.MODE_DIFFUSE_P3, width=48, height=32, spp=2, traverse=policy)
+        ref, rc = oracle.render(t1, n1, cfg)
+        assert_same_bits(sc.render(cfg), ref, "single-leaf tree")
+        o, d = _random_rays(2000, 5, extent=1.5)
+        a = sc.trace_rays(o, d, traverse=policy)
+        b = oracle.trace_rays(t1, n1, o, d, traverse=api.TRAVERSE_REFERENCE)
+        np.testing.assert_array_equal(a["triangle"], b["triangle"])
+    finally:
+        sc.close()
+
+
+def test_zero_bounces_and_zero_spp(oracle, bunny_scene, gpu_bunny):
+    tris, nodes, eye, cam = bunny_scene
+    cfg = _cfg(eye, cam, max_bounce=0, spp=2)
+    ref, rc = oracle.render(tris, nodes, cfg)
+    assert_same_bits(gpu_bunny.render(cfg), ref, "max_bounce = 0")
+    assert gpu_bunny.counters().rays == rc["rays"] == 96 * 64 * 2
+    fb = np.full((64 * 96, 3), 7.0, np.float32)
+    out = gpu_bunny.render(_cfg(eye, cam, spp=0, first_frame=3), framebuffer=fb)
+    assert (out == 7.0).all()  # spp = 0 leaves lastFrame untouched
