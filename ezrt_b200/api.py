@@ -152,6 +152,16 @@ def hdr_cache(hdr):
     return out
 
 
+def hdr_cache_device(hdr, device=0):
+    """calculateHdrCache on the GPU (bit-identical to hdr_cache).  Returns (cache, kernel milliseconds)."""
+    hdr = _f32(hdr)
+    h, w = hdr.shape[0], hdr.shape[1]
+    out = np.zeros((h, w, 3), dtype=np.float32)
+    ms = C.c_double(0.0)
+    check(lib.ezrt_hdr_cache_device(int(device), _fp(hdr), w, h, _fp(out), C.byref(ms)))
+    return out, ms.value
+
+
 def partition_pixels(width, height, rank, count):
     return int(check(lib.ezrt_partition_pixels(width, height, rank, count)))
 

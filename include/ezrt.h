@@ -236,6 +236,10 @@ int ezrt_hdr_load(const char* path, int* width, int* height, float* cols);
 /* calculateHdrCache (P5/main.cpp:592-689): (sample_x, sample_y, pdf) lookup texture. */
 int ezrt_hdr_cache(const float* hdr, int width, int height, float* cache_out);
 
+/* calculateHdrCache on the GPU `device`: same bits as ezrt_hdr_cache -- every fp32
+ * sum keeps the reference's order -- host arrays in and out; device_ms (nullable) = kernel time. */
+int ezrt_hdr_cache_device(int device, const float* hdr, int width, int height, float* cache_out, double* device_ms);
+
 /* Camera of display() (P5/main.cpp:710-713): orbit angles in degrees + radius ->
  * eye, cameraRotate = inverse(lookAt(eye, 0, +y)), column-major. */
 void ezrt_camera_orbit(float rotate_angle_deg, float up_angle_deg, float r, float eye[3],

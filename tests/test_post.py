@@ -62,3 +62,18 @@ def test_gpu_tonemap_matches_oracle(oracle):
         fb[:4] = 0.0
         got = api.post_tonemap(torch.from_numpy(fb).cuda()).cpu().numpy()
         assert got.tobytes() == oracle.tonemap(fb).tobytes()
+
+
+@pytest.mark.gpu
+def test_gpu_hdr_cache_equals_host():
+    """calculateHdrCache on the GPU keeps every fp32 sum in the reference's order -> identical bits."""
+    import time
+    from ezrt_b200 import scenes
+    for w, h in ((128, 64), (2048, 1024)):
+        hdr = scenes.synth_hdr(w, h)
+        t0 = time.perf_counter()
+        host = api.hdr_cache(hdr)
+        host_ms = 1e3 * (time.perf_counter() - t0)
+        dev, dev_ms = api.hdr_cache_device(hdr)
+        assert dev.tobytes() == host.tobytes()
+        print("hdr cache %dx%d: host %.1f ms, device kernels %.2f ms" % (w, h, host_ms, dev_ms))
