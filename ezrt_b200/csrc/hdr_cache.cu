@@ -21,16 +21,36 @@ __global__ void k_lum(const float* __restrict__ hdr, float* __restrict__ pdf, si
     float R = hdr[3 * k], G = hdr[3 * k + 1], B = hdr[3 * k + 2];
     pdf[k] = 0.2f * R + 0.7f * G + 0.1f * B;  // :604
 }
-__global__ void k_lum_sum(const float* __restrict__ pdf, size_t n, float* out) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// The ordered sum: the block stages 4096-float chunks in shared memory (coalesced loads), thread 0 adds them
+// in order from there (the add chain, ~4 cycles per element, is the floor: fp32 addition is not associative).
+__global__ void __launch_bounds__(1024) k_lum_sum(const float* __restrict__ pdf, size_t n, float* out) {
+    __shared__ float buf[2][4096];
     float s = 0.0f;
-    size_t k = 0;
-    for (; k + 8 <= n; k += 8) {  // loads first (independent), then the ordered add chain
-        float v0 = pdf[k], v1 = pdf[k + 1], v2 = pdf[k + 2], v3 = pdf[k + 3], v4 = pdf[k + 4], v5 = pdf[k + 5], v6 = pdf[k + 6], v7 = pdf[k + 7];
-        s += v0; s += v1; s += v2; s += v3; s += v4; s += v5; s += v6; s += v7;
+    const size_t n_chunks = (n + 4095) / 4096;
+    for (int k = threadIdx.x; k < 4096; k += 1024) buf[0][k] = ((size_t)k < n) ? pdf[k] : 0.0f;
+    __syncthreads();
+    for (size_t c = 0; c < n_chunks; c++) {
+        const int cur = (int)(c & 1);
+        if (threadIdx.x == 0) {  // ordered adds of chunk c ...
+            const size_t left = n - c * 4096;
+            const int m = left < 4096 ? (int)left : 4096;
+            const float* b = buf[cur];
+            int k = 0;
+            for (; k + 16 <= m; k += 16) {
+                float v[16];
+#pragma unroll
+                for (int u = 0; u < 16; u++) v[u] = b[k + u];
+#pragma unroll
+                for (int u = 0; u < 16; u++) s += v[u];
+            }
+            for (; k < m; k++) s += b[k];
+        } else if (c + 1 < n_chunks) {  // ... while the other threads fetch chunk c+1
+            const size_t base = (c + 1) * 4096;
+            for (int k = threadIdx.x - 1; k < 4096; k += 1023) buf[cur ^ 1][k] = (base + k < n) ? pdf[base + k] : 0.0f;
+        }
+        __syncthreads();
     }
-    for (; k < n; k++) s += pdf[k];
-    *out = s;  // :606
+    if (threadIdx.x == 0) *out = s;  // :606
 }
 __global__ void k_normalise(float* __restrict__ pdf, size_t n, const float* __restrict__ lum_sum) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -118,7 +138,7 @@ extern "C" int ezrt_hdr_cache_device(int device, const float* hdr, int width, in
         const unsigned gn = (unsigned)((n + T - 1) / T), gw = (unsigned)((width + T - 1) / T);
         cudaEventRecord(e0);
         k_lum<<<gn, T>>>(d_hdr, d_pdf, n);
-        k_lum_sum<<<1, 32>>>(d_pdf, n, d_sum);
+        k_lum_sum<<<1, 1024>>>(d_pdf, n, d_sum);
         k_normalise<<<gn, T>>>(d_pdf, n, d_sum);
         k_margin<<<gw, T>>>(d_pdf, width, height, d_margin);
         k_cdf_x<<<1, 32>>>(d_margin, width, d_cdf_x);
