@@ -86,7 +86,8 @@ def _load():
         return _bind(C.CDLL(path))
     # in-tree incremental build (no-op when the .so is newer than its sources); without nvcc a
     # prebuilt .so is used as is, and a missing one raises -- there is no CPU fallback
-    if not os.path.exists(path) or _build._nvcc() is not None:
+    # (ranks launched by torchrun never rebuild a library that exists: the launcher built/imported it first)
+    if not os.path.exists(path) or (_build._nvcc() is not None and "RANK" not in os.environ and os.environ.get("EZRT_AUTO_BUILD", "1") != "0"):
         _build.build_product()
     return _bind(C.CDLL(path))
 

@@ -75,6 +75,20 @@ def build_product(force=False, verbose=False, variant=None, defines=()):
         return target
     objdir = os.path.join(ROOT, "build", "obj" + ("_" + variant if variant else ""))
     os.makedirs(objdir, exist_ok=True)
+    # one builder at a time (several ranks / pytest workers may import the package at once)
+    import fcntl
+    lock = open(os.path.join(ROOT, "build", ".lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and not _newer(target, cu + cpp + _headers()):
+            return target
+        return _build_product_locked(nvcc, target, cu, cpp, objdir, defines, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_product_locked(nvcc, target, cu, cpp, objdir, defines, verbose):
     dflags = ["-D" + d for d in defines]
     objs = []
     for src in cu:
@@ -88,7 +102,9 @@ def build_product(force=False, verbose=False, variant=None, defines=()):
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
         _run(["g++"] + HOST_FLAGS + dflags + ["-pthread", "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj])
         objs.append(obj)
-    _run([nvcc, "-shared", "-o", target] + objs + ["-Xcompiler", "-pthread", "-cudart", "static"])
+    tmp = target + ".tmp%d" % os.getpid()
+    _run([nvcc, "-shared", "-o", tmp] + objs + ["-Xcompiler", "-pthread", "-cudart", "static"])
+    os.replace(tmp, target)  # atomic: a concurrent import never sees a half-written library
     return target
 
 
