@@ -399,3 +399,72 @@ def test_zero_bounces_and_zero_spp(oracle, bunny_scene, gpu_bunny):
     fb = np.full((64 * 96, 3), 7.0, np.float32)
     out = gpu_bunny.render(_cfg(eye, cam, spp=0, first_frame=3), framebuffer=fb)
     assert (out == 7.0).all()  # spp = 0 leaves lastFrame untouched
+
+
+# ------------------------------------------------------------------ hostile geometry
+def _soup(n, seed):
+    """Random overlapping triangles incl. zero-area, sliver and duplicated-vertex ones, three materials."""
+    rng = np.random.default_rng(seed)
+    t = np.zeros((n, 36), np.float32)
+    c = rng.uniform(-2, 2, (n, 1, 3))
+    p = c + rng.normal(scale=0.35, size=(n, 3, 3))
+    p[::17, 2] = p[::17, 1]                      # zero-area: p3 == p2  (N = NaN)
+    p[5::23, 2] = p[5::23, 0] + 1e-6 * (p[5::23, 1] - p[5::23, 0])  # slivers
+    p[7::29] = np.round(p[7::29], 1)             # axis-aligned-ish coordinates: exact plane hits
+    t[:, :9] = p.reshape(n, 9)
+    nrm = rng.normal(size=(n, 3, 3))
+    nrm /= np.linalg.norm(nrm, axis=2, keepdims=True)
+    t[:, 9:18] = nrm.reshape(n, 9)
+    mats = [api.Material(baseColor=(0.8, 0.3, 0.2), roughness=0.4).as_array(),
+            api.Material(baseColor=(0.2, 0.6, 0.9), metallic=0.8, roughness=0.2, clearcoat=1.0).as_array(),
+            api.Material(emissive=(4, 3, 2)).as_array()]
+    for k in range(3):
+        t[k::3, 18:] = mats[k]
+    return t
+
+
+@pytest.mark.parametrize("policy", [api.TRAVERSE_ACCEL, api.TRAVERSE_PRUNED, api.TRAVERSE_REFERENCE])
+def test_triangle_soup_with_degenerate_geometry(oracle, policy):
+    tl = api.TriangleList()
+    tl.append_encoded(_soup(3000, 4))
+    tris, nodes = tl.build_bvh(8)
+    sc = api.Scene(tris, nodes)
+    try:
+        o, d = _random_rays(30000, 17, extent=2.5)
+        o[:200] = np.round(o[:200], 1)  # origins on the rounded coordinate planes
+        got = sc.trace_rays(o, d, traverse=policy)
+        ref = oracle.trace_rays(tris, nodes, o, d, traverse=api.TRAVERSE_REFERENCE)
+        assert ref["hit"].sum() > 5000
+        np.testing.assert_array_equal(got["triangle"], ref["triangle"])
+        assert_same_bits(got["distance"], ref["distance"], "soup distance")
+        assert_same_bits(got["normal"], ref["normal"], "soup normal")
+        eye, cam = api.camera_orbit(30.0, 20.0, 6.0)
+        cfg = _cfg(eye, cam, mode=api.MODE_DISNEY_ANISO_P4, max_bounce=3, width=64, height=48, spp=2, traverse=policy)
+        ref_img, rc = oracle.render(tris, nodes, cfg)
+        assert_same_bits(sc.render(cfg), ref_img, "soup image")
+        assert sc.counters().rays == rc["rays"]
+    finally:
+        sc.close()
+
+
+def test_p5_style_scene_with_huge_floor(oracle, small_hdr):
+    """P5's own set-up scales the floor by 13000 (P5/main.cpp:818-819): the INF = 114514 sentinel turns the upper
+    tree levels into median splits and the scene extent (hence the pruning slack) is huge."""
+    hdr, cache = small_hdr
+    tl = api.TriangleList()
+    m = api.Material(baseColor=(1, 0.73, 0.25), roughness=0.5, specular=1.0, metallic=1.0, clearcoat=1.0, clearcoatGloss=0.0)
+    tl.read_obj_text(scenes.blob_obj(3), m, api.transform_matrix((0, 0, 0), (0, -0.1, 0), (0.75, 0.75, 0.75)), True)
+    m = api.Material(baseColor=(1, 1, 1), roughness=0.01, metallic=0.1, specular=1.0)
+    tl.read_obj_text(scenes.box_obj(), m, api.transform_matrix((0, 0, 0), (0, -0.5, 0), (13000.0, 0.01, 13000.0)), False)
+    tris, nodes = tl.build_bvh(8)
+    eye, cam = api.camera_orbit(90.0, 10.0, 2.0)  # P5/main.cpp:796-798
+    sc = api.Scene(tris, nodes, hdr, cache)
+    try:
+        for policy in (api.TRAVERSE_ACCEL, api.TRAVERSE_PRUNED):
+            cfg = _cfg(eye, cam, mode=api.MODE_DISNEY_IS_MIS_P5, max_bounce=2, width=72, height=48, spp=2, traverse=policy)
+            ref, rc = oracle.render(tris, nodes, cfg, hdr=hdr, hdr_cache=cache)
+            assert_same_bits(sc.render(cfg), ref, "P5-style scene, policy %d" % policy)
+            c = sc.counters()
+            assert (c.primary_rays, c.bounce_rays, c.shadow_rays) == (rc["rays_primary"], rc["rays_bounce"], rc["rays_shadow"])
+    finally:
+        sc.close()
