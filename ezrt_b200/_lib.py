@@ -65,6 +65,7 @@ SIGNATURES = {
     "ezrt_trilist_node_count": (C.c_int, [C.c_void_p]),
     "ezrt_trilist_encode_triangles": (C.c_int, [C.c_void_p, c_float_p]),
     "ezrt_trilist_encode_nodes": (C.c_int, [C.c_void_p, c_float_p]),
+    "ezrt_scene_file_load": (C.c_int, [C.c_char_p, C.c_void_p, c_float_p, C.c_char_p, C.c_size_t]),
     "ezrt_hdr_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), c_float_p]),
     "ezrt_hdr_cache": (C.c_int, [c_float_p, C.c_int, C.c_int, c_float_p]),
     "ezrt_hdr_cache_device": (C.c_int, [C.c_int, c_float_p, C.c_int, C.c_int, c_float_p, C.POINTER(C.c_double)]),

@@ -102,12 +102,12 @@ class TriangleList:
 
     def read_obj(self, path, material, trans, smooth_normal):
         """readObj(filepath, triangles, material, trans, smoothNormal), P5/main.cpp:274-392."""
-        check(lib.ezrt_trilist_read_obj(self._h, str(path).encode(), _fp(material.as_array()), _fp(_f32(trans)), int(bool(smooth_normal))))
+        check(lib.ezrt_trilist_read_obj(self._h, str(path).encode(), _fp(material.as_array()), _fp(_f32(trans)), int(smooth_normal)))
         return self
 
     def read_obj_text(self, text, material, trans, smooth_normal):
         data = text.encode() if isinstance(text, str) else bytes(text)
-        check(lib.ezrt_trilist_read_obj_text(self._h, data, len(data), _fp(material.as_array()), _fp(_f32(trans)), int(bool(smooth_normal))))
+        check(lib.ezrt_trilist_read_obj_text(self._h, data, len(data), _fp(material.as_array()), _fp(_f32(trans)), int(smooth_normal)))
         return self
 
     def append_encoded(self, tris):
@@ -132,6 +132,19 @@ class TriangleList:
         out = np.zeros((n_nodes, BVHNODE_FLOATS), dtype=np.float32)
         check(lib.ezrt_trilist_encode_nodes(self._h, _fp(out)))
         return out
+
+
+OBJ_HARDENED = 2
+
+
+def load_scene_file(path):
+    """Scene description file -> (TriangleList, (rotatAngle, upAngle, r), hdr path or None); see include/ezrt.h."""
+    tl = TriangleList()
+    cam = np.zeros(3, dtype=np.float32)
+    buf = C.create_string_buffer(4096)
+    check(lib.ezrt_scene_file_load(str(path).encode(), tl._h, _fp(cam), buf, 4096))
+    hdr = buf.value.decode() or None
+    return tl, tuple(float(x) for x in cam), hdr
 
 
 def hdr_load(path):

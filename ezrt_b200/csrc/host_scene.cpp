@@ -187,7 +187,7 @@ Mat4 mat_look_at(ez_vec3 eye, ez_vec3 center, ez_vec3 up) {
 // readObj, P5/main.cpp:274-392
 // ------------------------------------------------------------------------------------------
 int read_obj_stream(std::istream& fin, std::vector<Tri>& triangles, const float material[EZRT_MATERIAL_FLOATS],
-                    const Mat4& trans, bool smoothNormal) {
+                    const Mat4& trans, bool smoothNormal, bool hardened = false) {
     std::vector<ez_vec3> vertices;
     std::vector<unsigned> indices;
 
@@ -210,15 +210,23 @@ int read_obj_stream(std::istream& fin, std::vector<Tri>& triangles, const float 
         if (type == "f") {
             // "v", "v/vt", "v/vt/vn" (and, hardened, "v//vn"): the leading integer of each
             // of the first three vertex tokens; extra vertices are ignored as in the reference.
-            int v[3] = {1, 1, 1};
-            for (int k = 0; k < 3; k++) {
-                std::string tok;
-                if (!(sin >> tok)) return EZRT_ERR_IO;
-                v[k] = (int)std::strtol(tok.c_str(), nullptr, 10);
+            // Hardened mode (EZRT_OBJ_HARDENED): negative (relative) indices, and polygons are
+            // triangulated as a fan instead of being cut to their first three vertices.
+            std::vector<int> fv;
+            std::string tok;
+            while (sin >> tok) {
+                int idx = (int)std::strtol(tok.c_str(), nullptr, 10);
+                if (hardened && idx < 0) idx = (int)vertices.size() + 1 + idx;
+                fv.push_back(idx);
+                if (!hardened && fv.size() == 3) break;
             }
-            for (int k = 0; k < 3; k++) {
-                if (v[k] < 1 || (size_t)v[k] > vertices.size()) return EZRT_ERR_IO;
-                indices.push_back((unsigned)(v[k] - 1));
+            if (fv.size() < 3) return EZRT_ERR_IO;
+            for (int idx : fv)
+                if (idx < 1 || (size_t)idx > vertices.size()) return EZRT_ERR_IO;
+            for (size_t k = 2; k < fv.size(); k++) {
+                indices.push_back((unsigned)(fv[0] - 1));
+                indices.push_back((unsigned)(fv[k - 1] - 1));
+                indices.push_back((unsigned)(fv[k] - 1));
             }
         }
     }
@@ -548,7 +556,7 @@ int ezrt_trilist_read_obj(ezrt_trilist* list, const char* path, const float mate
     if (!fin.is_open()) return ezrt_set_error(EZRT_ERR_IO, "read_obj: cannot open %s", path);
     Mat4 m;
     memcpy(m.c, trans, sizeof(float) * 16);
-    int rc = read_obj_stream(fin, list->tris, material, m, smooth_normal != 0);
+    int rc = read_obj_stream(fin, list->tris, material, m, (smooth_normal & 1) != 0, (smooth_normal & EZRT_OBJ_HARDENED) != 0);
     if (rc) return ezrt_set_error(rc, "read_obj: malformed face in %s", path);
     return EZRT_OK;
 }
@@ -559,7 +567,7 @@ int ezrt_trilist_read_obj_text(ezrt_trilist* list, const char* text, size_t len,
     std::istringstream fin(std::string(text, len));
     Mat4 m;
     memcpy(m.c, trans, sizeof(float) * 16);
-    int rc = read_obj_stream(fin, list->tris, material, m, smooth_normal != 0);
+    int rc = read_obj_stream(fin, list->tris, material, m, (smooth_normal & 1) != 0, (smooth_normal & EZRT_OBJ_HARDENED) != 0);
     if (rc) return ezrt_set_error(rc, "read_obj_text: malformed face");
     return EZRT_OK;
 }
@@ -809,6 +817,85 @@ int ezrt_hdr_cache(const float* HDR, int width, int height, float* cache) {
             cache[3 * (i * W + j) + 1] = (float)y / (float)height;
             cache[3 * (i * W + j) + 2] = pdf[i * W + j];
         }
+    return EZRT_OK;
+}
+
+// ---- scene description file: replaces the hard-coded scene blocks of main()
+// (P3/main.cpp:688-701, P4/main.cpp:687-729, P5/main.cpp:795-823).  Line oriented, '#' comments:
+//   set <field> <values...>   field of the current Material (emissive, baseColor: 3 floats; others: 1)
+//   reset                     back to the reference's default Material (P5/main.cpp:27-42)
+//   mesh <obj path> smooth|flat [hardened] rotate rx ry rz translate tx ty tz scale sx sy sz
+//   camera <rotatAngle> <upAngle> <r>          (P5/main.cpp:796-798)
+//   hdr <path>
+// Relative paths are resolved against the scene file's directory.
+int ezrt_scene_file_load(const char* path, ezrt_trilist* list, float camera[3], char* hdr_path, size_t hdr_path_cap) {
+    if (!path || !list) return ezrt_set_error(EZRT_ERR_INVALID, "scene_file_load: null argument");
+    std::ifstream fin(path);
+    if (!fin.is_open()) return ezrt_set_error(EZRT_ERR_IO, "scene_file_load: cannot open %s", path);
+    std::string dir(path);
+    size_t slash = dir.find_last_of('/');
+    dir = (slash == std::string::npos) ? std::string() : dir.substr(0, slash + 1);
+    auto resolve = [&](const std::string& p) { return (!p.empty() && p[0] == '/') ? p : dir + p; };
+    const float defaults[EZRT_MATERIAL_FLOATS] = {0, 0, 0, 1, 1, 1, 0.0f, 0.0f, 0.5f, 0.0f, 0.5f, 0.0f, 0.0f, 0.5f, 0.0f, 1.0f, 1.0f, 0.0f};
+    float mat[EZRT_MATERIAL_FLOATS];
+    memcpy(mat, defaults, sizeof(mat));
+    static const char* names[] = {"subsurface", "metallic", "specular", "specularTint", "roughness", "anisotropic", "sheen", "sheenTint",
+                                  "clearcoat", "clearcoatGloss", "IOR", "transmission"};
+    if (camera) { camera[0] = 0.0f; camera[1] = 0.0f; camera[2] = 4.0f; }  // rotatAngle, upAngle, r defaults (P5/main.cpp:149-151)
+    if (hdr_path && hdr_path_cap) hdr_path[0] = 0;
+    std::string line;
+    int lineno = 0;
+    while (std::getline(fin, line)) {
+        lineno++;
+        size_t hash = line.find('#');
+        if (hash != std::string::npos) line = line.substr(0, hash);
+        std::istringstream sin(line);
+        std::string cmd;
+        if (!(sin >> cmd)) continue;
+        if (cmd == "reset") {
+            memcpy(mat, defaults, sizeof(mat));
+        } else if (cmd == "set") {
+            std::string field;
+            sin >> field;
+            if (field == "emissive" || field == "baseColor") {
+                float* dst = mat + (field == "emissive" ? 0 : 3);
+                if (!(sin >> dst[0] >> dst[1] >> dst[2])) return ezrt_set_error(EZRT_ERR_IO, "%s:%d: set %s needs 3 numbers", path, lineno, field.c_str());
+            } else {
+                int k = -1;
+                for (int i = 0; i < 12; i++)
+                    if (field == names[i]) k = i;
+                if (k < 0 || !(sin >> mat[6 + k])) return ezrt_set_error(EZRT_ERR_IO, "%s:%d: bad material field '%s'", path, lineno, field.c_str());
+            }
+        } else if (cmd == "mesh") {
+            std::string file, mode, key;
+            if (!(sin >> file >> mode) || (mode != "smooth" && mode != "flat")) return ezrt_set_error(EZRT_ERR_IO, "%s:%d: mesh <path> smooth|flat ...", path, lineno);
+            float rot[3] = {0, 0, 0}, tr[3] = {0, 0, 0}, sc[3] = {1, 1, 1};
+            int flags = (mode == "smooth") ? 1 : 0;
+            while (sin >> key) {
+                float* dst = (key == "rotate") ? rot : (key == "translate") ? tr : (key == "scale") ? sc : nullptr;
+                if (key == "hardened") { flags |= EZRT_OBJ_HARDENED; continue; }
+                if (!dst || !(sin >> dst[0] >> dst[1] >> dst[2])) return ezrt_set_error(EZRT_ERR_IO, "%s:%d: bad mesh option '%s'", path, lineno, key.c_str());
+            }
+            float m16[16];
+            ezrt_transform_matrix(rot, tr, sc, m16);
+            int rc = ezrt_trilist_read_obj(list, resolve(file).c_str(), mat, m16, flags);
+            if (rc) return rc;
+        } else if (cmd == "camera") {
+            float c[3];
+            if (!(sin >> c[0] >> c[1] >> c[2])) return ezrt_set_error(EZRT_ERR_IO, "%s:%d: camera <rotatAngle> <upAngle> <r>", path, lineno);
+            if (camera) memcpy(camera, c, sizeof(c));
+        } else if (cmd == "hdr") {
+            std::string file;
+            if (!(sin >> file)) return ezrt_set_error(EZRT_ERR_IO, "%s:%d: hdr <path>", path, lineno);
+            std::string full = resolve(file);
+            if (hdr_path && hdr_path_cap) {
+                if (full.size() + 1 > hdr_path_cap) return ezrt_set_error(EZRT_ERR_INVALID, "%s:%d: hdr path too long", path, lineno);
+                memcpy(hdr_path, full.c_str(), full.size() + 1);
+            }
+        } else {
+            return ezrt_set_error(EZRT_ERR_IO, "%s:%d: unknown directive '%s'", path, lineno, cmd.c_str());
+        }
+    }
     return EZRT_OK;
 }
 

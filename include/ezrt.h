@@ -205,6 +205,10 @@ void ezrt_transform_matrix(const float rotate_deg[3], const float translate[3], 
  * sheenTint, clearcoat, clearcoatGloss, IOR, transmission). */
 int ezrt_trilist_read_obj(ezrt_trilist* list, const char* path, const float material[EZRT_MATERIAL_FLOATS],
                           const float trans[16], int smooth_normal);
+/* smooth_normal is a flag word: bit 0 = smoothNormal; EZRT_OBJ_HARDENED additionally accepts negative
+ * (relative) vertex indices and fan-triangulates polygons -- the reference cuts a polygon to its first three
+ * vertices (P5/main.cpp:321-336), which stays the default behaviour. */
+#define EZRT_OBJ_HARDENED 2
 /* Same parser on an in-memory OBJ text (synthetic meshes). */
 int ezrt_trilist_read_obj_text(ezrt_trilist* list, const char* text, size_t len,
                                const float material[EZRT_MATERIAL_FLOATS], const float trans[16],
@@ -229,6 +233,12 @@ int ezrt_trilist_node_count(const ezrt_trilist* list);
 /* Encode as P5/main.cpp:843-871 into caller buffers (36 floats/triangle, 12 floats/node). */
 int ezrt_trilist_encode_triangles(const ezrt_trilist* list, float* tris_out);
 int ezrt_trilist_encode_nodes(const ezrt_trilist* list, float* nodes_out);
+
+/* Scene description file in place of the hard-coded scene blocks of main()
+ * (P3/main.cpp:688-701, P4/main.cpp:687-729, P5/main.cpp:795-823): directives `set <field> ...`, `reset`,
+ * `mesh <obj> smooth|flat [hardened] rotate.. translate.. scale..`, `camera <rotatAngle> <upAngle> <r>`,
+ * `hdr <path>`; appends the meshes to `list`; camera[3] and hdr_path (nullable) receive the other settings. */
+int ezrt_scene_file_load(const char* path, ezrt_trilist* list, float camera[3], char* hdr_path, size_t hdr_path_cap);
 
 /* HDRLoader::load (P5/lib/hdrloader.cpp:29-97): Radiance .hdr -> float RGB rows.  Call with
  * cols = NULL to query width/height. */

@@ -310,3 +310,50 @@ def test_hdr_cache_properties(small_hdr):
         s = np.float32(s + v)
     pdf = pdf / s
     np.testing.assert_array_equal(cache[..., 2], pdf)
+
+
+# ---------------------------------------------------------------- hardened OBJ reader + scene files (8f row 4)
+def test_hardened_obj_reader_triangulates_polygons_and_relative_indices():
+    quad = "v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\n"
+    tl = api.TriangleList()
+    tl.read_obj_text(quad, api.Material(), api.transform_matrix(), 0)
+    assert len(tl) == 1  # reference behaviour: the polygon is cut to its first three vertices
+    tl = api.TriangleList()
+    tl.read_obj_text(quad, api.Material(), api.transform_matrix(), api.OBJ_HARDENED)
+    t = tl.encode_triangles()
+    assert t.shape[0] == 2 and np.allclose(t[1, :9], [0, 0, 0, 1, 1, 0, 0, 1, 0])  # fan (1,3,4)
+    rel = "v 0 0 0\nv 1 0 0\nv 0 1 0\nf -3 -2 -1\n"
+    tl2 = api.TriangleList()
+    tl2.read_obj_text(rel, api.Material(), api.transform_matrix(), api.OBJ_HARDENED)
+    tl3 = api.TriangleList()
+    tl3.read_obj_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n", api.Material(), api.transform_matrix(), 0)
+    assert np.array_equal(tl2.encode_triangles(), tl3.encode_triangles())
+    with pytest.raises(api.EzrtError):
+        tl3.read_obj_text(rel, api.Material(), api.transform_matrix(), 0)  # not hardened: negative index rejected
+
+
+def test_scene_file_reproduces_programmatic_scene(tmp_path):
+    (tmp_path / "blob.obj").write_text(scenes.blob_obj(2))
+    (tmp_path / "box.obj").write_text(scenes.box_obj())
+    (tmp_path / "scene.txt").write_text("""# P3-style scene
+set baseColor 1 1 1
+mesh blob.obj smooth rotate 0 0 0 translate 0.3 -0.65 0 scale 1.5 1.5 1.5
+set baseColor 0.725 0.71 0.68
+set roughness 0.3
+mesh box.obj flat translate 0 -1.4 0 scale 18.83 0.01 18.83
+reset
+set emissive 30 20 10
+mesh blob.obj flat translate 0 0.9 0
+camera 90 10 2
+hdr env.hdr
+""")
+    tl, cam, hdr = api.load_scene_file(tmp_path / "scene.txt")
+    assert cam == (90.0, 10.0, 2.0) and hdr == str(tmp_path / "env.hdr")
+    ref = api.TriangleList()
+    ref.read_obj_text(scenes.blob_obj(2), api.Material(baseColor=(1, 1, 1)), api.transform_matrix((0, 0, 0), (0.3, -0.65, 0), (1.5, 1.5, 1.5)), 1)
+    ref.read_obj_text(scenes.box_obj(), api.Material(baseColor=(0.725, 0.71, 0.68), roughness=0.3), api.transform_matrix((0, 0, 0), (0, -1.4, 0), (18.83, 0.01, 18.83)), 0)
+    ref.read_obj_text(scenes.blob_obj(2), api.Material(emissive=(30, 20, 10)), api.transform_matrix((0, 0, 0), (0, 0.9, 0), (1, 1, 1)), 0)
+    assert np.array_equal(tl.encode_triangles(), ref.encode_triangles())
+    (tmp_path / "bad.txt").write_text("mesh nothere.obj smooth")
+    with pytest.raises(api.EzrtError):
+        api.load_scene_file(tmp_path / "bad.txt")
