@@ -87,6 +87,7 @@ struct ezrt_scene {
     size_t hot_bytes = 0;
     size_t l2_persist_bytes = 0;
     size_t max_window_bytes = 0;  // persisting L2 set-aside granted by the device (0 = feature off)
+    bool regular_tree = true;  // false: only the literal REFERENCE traversal is valid for this tree
     int sort_rays = 0;  // env EZRT_SORT_RAYS=1 enables the bounce-ray sort (measured: no gain with per-lane refill)
     int tiles_key[4] = {-1, -1, -1, -1};
     std::vector<TileDev> tiles;
@@ -180,7 +181,7 @@ RenderDev make_render_dev(const ezrt_scene* s, const ezrt_render_params* p) {
     rd.out_channels = p->out_channels;
     rd.compact_out = (p->part_count > 1) ? 1 : 0;
     rd.n_tiles = (int)s->tiles.size();
-    rd.accel_space = (p->traverse == EZRT_TRAVERSE_ACCEL && p->pipeline == EZRT_PIPELINE_WAVEFRONT) ? 1 : 0;
+    rd.accel_space = (s->regular_tree && p->traverse == EZRT_TRAVERSE_ACCEL && p->pipeline == EZRT_PIPELINE_WAVEFRONT) ? 1 : 0;
     return rd;
 }
 
@@ -235,6 +236,34 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         }
     }
     if (max_depth + 1 > EZRT_MAX_STACK) return ezrt_set_error(EZRT_ERR_BAD_TREE, "scene_create: tree depth %d exceeds %d", max_depth, EZRT_MAX_STACK - 1);
+    // The ACCEL and PRUNED policies rely on what buildBVH* guarantees: every triangle in exactly one leaf,
+    // leaf boxes bounding their triangles, child boxes inside their parent's.  A caller-supplied tree that
+    // breaks any of these is only ever walked literally (REFERENCE policy), whatever the params ask for.
+    bool regular_tree = true;
+    {
+        std::vector<unsigned char> cover(n_triangles, 0);
+        for (int i = 1; i < n_nodes && regular_tree; i++) {
+            if (!seen[i]) continue;
+            const float* B = nodes + (size_t)i * EZRT_BVHNODE_FLOATS;
+            if (hn[i].n > 0) {
+                for (int k = 0; k < hn[i].n && regular_tree; k++) {
+                    const int t = hn[i].index + k;
+                    if (cover[t]++) regular_tree = false;
+                    const float* v = tris + (size_t)t * EZRT_TRIANGLE_FLOATS;
+                    for (int c = 0; c < 9; c++)
+                        if (!(v[c] >= B[6 + c % 3] && v[c] <= B[9 + c % 3])) regular_tree = false;
+                }
+            } else {
+                for (int c : {hn[i].left, hn[i].right}) {
+                    const float* C = nodes + (size_t)c * EZRT_BVHNODE_FLOATS;
+                    for (int a = 0; a < 3; a++)
+                        if (!(C[6 + a] >= B[6 + a] && C[9 + a] <= B[9 + a])) regular_tree = false;
+                }
+            }
+        }
+        for (int t = 0; t < n_triangles && regular_tree; t++)
+            if (cover[t] != 1) regular_tree = false;
+    }
     // Record numbering: the top of the tree level by level (these records are staged in shared memory
     // by the traversal kernels: 61% of all inner-node visits hit depth <= 9 on the 1M-triangle scene),
     // whole levels while they fit EZRT_TOP_NODES_MAX; everything below in the builder's pre-order.
@@ -503,6 +532,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         return rc;
     }
     sc->n_materials = (int)mat_ids.size();
+    sc->regular_tree = regular_tree;
     sc->tree_depth = max_depth;
     SceneDev& d = sc->dev;
     d.nodes = (const float4*)sc->nodes.p;
@@ -601,8 +631,8 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     s->ev_used = 0;
     RenderDev rd = make_render_dev(s, p);
     const TileDev* d_tiles = (const TileDev*)s->tiles_buf.p;
-    const bool prune = (p->traverse != EZRT_TRAVERSE_REFERENCE);
-    const bool accel = (p->traverse == EZRT_TRAVERSE_ACCEL);
+    const bool prune = s->regular_tree && (p->traverse != EZRT_TRAVERSE_REFERENCE);
+    const bool accel = s->regular_tree && (p->traverse == EZRT_TRAVERSE_ACCEL);
     if (rd.n_tiles == 0 || p->spp == 0) {
         CU_CHECK(cudaEventRecord(s->ev_stop, st));
         return EZRT_OK;
@@ -875,6 +905,7 @@ int ezrt_trace_rays(ezrt_scene* s, int n, const float* origins, const float* dir
     int* d_inside = (int*)p; p += sizeof(int) * N;
     uint32_t* d_defer = (uint32_t*)p; p += sizeof(uint32_t) * N;
     uint32_t* d_cnt = (uint32_t*)p;  // [0] n, [1] work, [2] deferred, [3] deferred work
+    if (!s->regular_tree) traverse = EZRT_TRAVERSE_REFERENCE;
     cudaStream_t st = s->own_stream;
     const uint32_t counters[4] = {(uint32_t)n, 0u, 0u, 0u};
     cudaError_t e = cudaMemcpyAsync(q.ray_o, ho.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, st);

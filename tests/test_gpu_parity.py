@@ -468,3 +468,26 @@ def test_p5_style_scene_with_huge_floor(oracle, small_hdr):
             assert (c.primary_rays, c.bounce_rays, c.shadow_rays) == (rc["rays_primary"], rc["rays_bounce"], rc["rays_shadow"])
     finally:
         sc.close()
+
+
+@pytest.mark.parametrize("policy", [api.TRAVERSE_ACCEL, api.TRAVERSE_PRUNED])
+def test_irregular_caller_tree_is_walked_literally(oracle, bunny_scene, policy):
+    """A caller-supplied tree whose leaf boxes do not bound their triangles (here: every leaf box shrunk) defeats
+    the assumptions of the accel/pruned policies; the library must then reproduce the shader's literal walk."""
+    tris, nodes, eye, cam = bunny_scene
+    bad = nodes.copy()
+    leaf = bad[:, 3] > 0
+    leaf[0] = False
+    centre = 0.5 * (bad[leaf, 6:9] + bad[leaf, 9:12])
+    bad[leaf, 6:9] = centre + 0.6 * (bad[leaf, 6:9] - centre)
+    bad[leaf, 9:12] = centre + 0.6 * (bad[leaf, 9:12] - centre)
+    sc = api.Scene(tris, bad)
+    try:
+        cfg = _cfg(eye, cam, mode=api.MODE_DISNEY_SOBOL_P5, width=64, height=48, spp=2, traverse=policy)
+        ref, rc = oracle.render(tris, bad, _cfg(eye, cam, mode=api.MODE_DISNEY_SOBOL_P5, width=64, height=48, spp=2, traverse=api.TRAVERSE_REFERENCE))
+        good, _ = oracle.render(tris, nodes, cfg)
+        assert ref.tobytes() != good.tobytes()  # the shrunk boxes really change what the shader sees
+        assert_same_bits(sc.render(cfg), ref, "irregular tree")
+        assert sc.counters().rays == rc["rays"]
+    finally:
+        sc.close()
