@@ -363,6 +363,9 @@ __device__ __forceinline__ HitRec trace_ray(const SceneDev& sc, vec3 o, vec3 d) 
 // of trace_impl / the shader's hitBVH.
 //   io.load(i, o, d) fetches ray i; io.store(i, hit) receives its result.
 // ------------------------------------------------------------------------------------------
+#ifndef EZRT_SMEM_STACK
+#define EZRT_SMEM_STACK 0   // stack entries kept in shared memory (experiment; 0 = all in local memory)
+#endif
 #define EZRT_REF_DONE ((int)0x80000000)   // leaf flag with n == 0: no real leaf has this encoding
 
 // the tree a persistent traversal walks: the reference tree or the device's acceleration tree
@@ -407,7 +410,19 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    int2 stack[EZRT_MAX_STACK];  // (child reference, slab entry distance bits): one 8-byte local store / load
+    // stack of (child reference, slab entry distance bits).  Entries below EZRT_SMEM_STACK live in shared
+    // memory at [entry][thread] (a lane always hits its own banks: 2 wavefronts per warp access however the
+    // lanes' stack pointers differ), deeper ones in local memory.
+    int2 stack_local[EZRT_MAX_STACK];
+#if EZRT_SMEM_STACK > 0
+    int2* const stack_sm = reinterpret_cast<int2*>(const_cast<float4*>(smem_top) + (size_t)tree.top_nodes * EZRT_TOP_STRIDE) + threadIdx.x;
+    const int stack_stride = blockDim.x;
+#define STACK_PUSH(e) do { const int2 e__ = (e); if (sp < EZRT_SMEM_STACK) stack_sm[sp * stack_stride] = e__; else stack_local[sp] = e__; ++sp; } while (0)
+#define STACK_POP() ((--sp < EZRT_SMEM_STACK) ? stack_sm[sp * stack_stride] : stack_local[sp])
+#else
+#define STACK_PUSH(e) do { stack_local[sp++] = (e); } while (0)
+#define STACK_POP() (stack_local[--sp])
+#endif
     int sp = 0;
     int ray = -1;              // index of the ray this lane is tracing, -1 = idle
     int ref = EZRT_REF_DONE;
@@ -490,15 +505,15 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                         cswap(w.k0, w.r0, w.k2, w.r2);
                         cswap(w.k1, w.r1, w.k3, w.r3);
                         cswap(w.k1, w.r1, w.k2, w.r2);
-                        if (w.k3 < 3.0e38f) stack[sp++] = make_int2(w.r3, __float_as_int(w.k3));
-                        if (w.k2 < 3.0e38f) stack[sp++] = make_int2(w.r2, __float_as_int(w.k2));
-                        if (w.k1 < 3.0e38f) stack[sp++] = make_int2(w.r1, __float_as_int(w.k1));
+                        if (w.k3 < 3.0e38f) STACK_PUSH(make_int2(w.r3, __float_as_int(w.k3)));
+                        if (w.k2 < 3.0e38f) STACK_PUSH(make_int2(w.r2, __float_as_int(w.k2)));
+                        if (w.k1 < 3.0e38f) STACK_PUSH(make_int2(w.r1, __float_as_int(w.k1)));
                         if (w.k0 < 3.0e38f) {
                             ref = w.r0;
                         } else {  // pop
                             ref = EZRT_REF_DONE;
                             while (sp > 0) {
-                                const int2 e = stack[--sp];
+                                const int2 e = STACK_POP();
                                 if (prune_test(__int_as_float(e.y), best, slack)) continue;
                                 ref = e.x;
                                 break;
@@ -516,7 +531,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                     }
                     if (h1 && h2) {
                         bool leftFirst = d1 < d2;
-                        stack[sp++] = make_int2(leftFirst ? rr : rl, __float_as_int(leftFirst ? e2 : e1));
+                        STACK_PUSH(make_int2(leftFirst ? rr : rl, __float_as_int(leftFirst ? e2 : e1)));
                         ref = leftFirst ? rl : rr;
                     } else if (h1) {
                         ref = rl;
@@ -525,7 +540,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                     } else {  // pop
                         ref = EZRT_REF_DONE;
                         while (sp > 0) {
-                            const int2 e = stack[--sp];
+                            const int2 e = STACK_POP();
                             if (PRUNE && prune_test(__int_as_float(e.y), best, slack)) continue;
                             ref = e.x;
                             break;
@@ -594,7 +609,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                 ref = EZRT_REF_DONE;
                 if (!stop) {
                     while (sp > 0) {
-                        const int2 e = stack[--sp];
+                        const int2 e = STACK_POP();
                         if (PRUNE && prune_test(__int_as_float(e.y), best, slack)) continue;
                         ref = e.x;
                         break;
@@ -612,6 +627,9 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
         } while (busy != 0u && (exhausted || __popc(busy) >= refill_thresh));
     }
 }
+
+#undef STACK_PUSH
+#undef STACK_POP
 
 // ------------------------------------------------------------------------------------------
 // hit geometry + material for the final closest hit (tail of hitTriangle :198-214, getMaterial :110-135)

@@ -3,9 +3,12 @@
 // Pipeline per batch of `nf` frames (= display() calls, P5/main.cpp:697-748) x owned pixels:
 //   k_generate : camera rays (main(), P5/fsh:920-925)                     -> queue 0
 //   per bounce b = 0..maxBounce:
-//     k_extend : hitBVH for every queued ray (persistent warps, dynamic fetch)
-//     k_shade  : account the hit/miss, NEE + BRDF sampling, warp-ballot compaction -> queue b+1
-//     k_shadow : any-hit trace of the environment shadow rays (IS mode only)
+//     k_extend_accel : hitBVH for every queued ray on the device's 4-wide acceleration tree (persistent warps,
+//                      per-lane refill, vote-driven inner / leaf phases); rays it cannot decide exactly are
+//                      deferred to  k_extend  = the exact reference-order traversal (also the whole extend
+//                      stage under the REFERENCE / PRUNED policies)
+//     k_shade        : account the hit/miss, NEE + BRDF sampling, block-aggregated compaction -> queue b+1
+//     k_shadow_accel / k_shadow : any-hit trace of the environment shadow rays (IS mode only)
 //   k_blend    : running mean into the framebuffer in frame order (P5/fsh:942-947)
 // No host synchronisation inside a render: queue sizes live in device counters.
 #include "kernels.h"
@@ -639,7 +642,7 @@ void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots
 }
 template <class K>
 static size_t smem_for(K kernel, int top_nodes) {
-    size_t bytes = (size_t)top_nodes * EZRT_TOP_STRIDE * sizeof(float4);
+    size_t bytes = (size_t)top_nodes * EZRT_TOP_STRIDE * sizeof(float4) + (size_t)EZRT_SMEM_STACK * sizeof(int2) * extend_threads();
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bytes, 1024));
     return bytes;
 }
@@ -663,8 +666,8 @@ void launch_extend_accel(const SceneDev& sc, bool anyhit, PathQueue q, const uin
                          uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, cudaStream_t st) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
     if (sc.acc_wide_nodes) {
-        if (anyhit) k_extend_accel<true, true><<<blocks, threads, 0, st>>>(sc, q, q_count, work, defer_list, defer_count);
-        else k_extend_accel<false, true><<<blocks, threads, 0, st>>>(sc, q, q_count, work, defer_list, defer_count);
+        if (anyhit) k_extend_accel<true, true><<<blocks, threads, smem_for(k_extend_accel<true, true>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count);
+        else k_extend_accel<false, true><<<blocks, threads, smem_for(k_extend_accel<false, true>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count);
     } else if (anyhit) {
         k_extend_accel<true, false><<<blocks, threads, smem_for(k_extend_accel<true, false>, sc.acc_top_nodes), st>>>(sc, q, q_count, work, defer_list, defer_count);
     } else {
@@ -690,7 +693,7 @@ void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_
 void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo, uint32_t* defer_list,
                          uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, cudaStream_t st) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
-    if (sc.acc_wide_nodes) k_shadow_accel<true><<<blocks, threads, 0, st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
+    if (sc.acc_wide_nodes) k_shadow_accel<true><<<blocks, threads, smem_for(k_shadow_accel<true>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
     else k_shadow_accel<false><<<blocks, threads, smem_for(k_shadow_accel<false>, sc.acc_top_nodes), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
     launch_shadow(sc, true, sq, defer_count, defer_work, Lo, defer_list, std::min<uint32_t>(n_max, 65536u), n_sms, st);
 }
