@@ -4,6 +4,8 @@
   oracle/libezrt_oracle.so    the CPU oracle (test infrastructure, see oracle/README.md)
   oracle/_ref/libhdrloader_ref.so   the one reference translation unit that compiles stand-alone
                                      (P5/lib/hdrloader.cpp), built only where /root/reference exists
+  oracle/_ref/libezrt_refshader.so  the reference's own fragment shaders (P3/P4/P5 fshader.fsh) transpiled
+                                     to C++ from where they lie (oracle/ref_shader/), same condition
 
 Parity needs bit-identical fp32 arithmetic on host and device, hence
   host  : -ffp-contract=off -mfma      (FMA only where ezrt_math.h spells it)
@@ -21,7 +23,11 @@ PRODUCT_SO = os.path.join(ROOT, "ezrt_b200", "libezrt_b200.so")
 ORACLE_SO = os.path.join(ROOT, "oracle", "libezrt_oracle.so")
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 REF_HDR_SO = os.path.join(REF_DIR, "libhdrloader_ref.so")
-REFERENCE_P5 = "/root/reference/part 5 -- Importance Sampling & Low Discrepancy Sequence/source code"
+REF_SHADER_SO = os.path.join(REF_DIR, "libezrt_refshader.so")
+REFERENCE_ROOT = "/root/reference"
+REFERENCE_PARTS = ("part 3 -- OpenGL Raytracing", "part 4 -- Disney Principle BRDF",
+                   "part 5 -- Importance Sampling & Low Discrepancy Sequence")
+REFERENCE_P5 = os.path.join(REFERENCE_ROOT, REFERENCE_PARTS[2], "source code")
 
 HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-mfma", "-Wall"]
 NVCC_FLAGS = [
@@ -133,10 +139,32 @@ def build_reference_hdrloader(force=False):
     return REF_HDR_SO
 
 
+def build_reference_shaders(force=False):
+    """oracle/_ref: the reference's own fragment shaders (P3/P4/P5 shaders/fshader.fsh), transpiled from
+    where they lie by oracle/ref_shader/transpile.py and compiled against oracle/ref_shader/glsl_emul.h.
+    Test infrastructure: pins the hand-written oracle to the reference's statements (tests/test_ref_shader.py)."""
+    rs = os.path.join(ROOT, "oracle", "ref_shader")
+    srcs = [os.path.join(REFERENCE_ROOT, part, "source code", "shaders", "fshader.fsh") for part in REFERENCE_PARTS]
+    if not all(os.path.exists(s) for s in srcs):
+        return REF_SHADER_SO if os.path.exists(REF_SHADER_SO) else None
+    os.makedirs(REF_DIR, exist_ok=True)
+    deps = srcs + [os.path.join(rs, f) for f in ("transpile.py", "glsl_emul.h", "ref_shader_host.cpp")] + [os.path.join(INCLUDE, "ezrt_math.h"), os.path.join(INCLUDE, "ezrt.h")]
+    if force or _newer(REF_SHADER_SO, deps):
+        _run([sys.executable, os.path.join(rs, "transpile.py"), REFERENCE_ROOT, REF_DIR])
+        tmp = REF_SHADER_SO + ".tmp%d" % os.getpid()
+        _run(["g++"] + HOST_FLAGS + ["-fopenmp", "-w", "-shared", "-I", INCLUDE, "-I", rs, "-I", REF_DIR, os.path.join(rs, "ref_shader_host.cpp"), "-o", tmp])
+        os.replace(tmp, REF_SHADER_SO)
+        for f in os.listdir(REF_DIR):  # the transpiled text is a build intermediate: keep only the binary
+            if f.startswith("shader_") and f.endswith(".inc"):
+                os.remove(os.path.join(REF_DIR, f))
+    return REF_SHADER_SO
+
+
 def build_all(force=False, verbose=False):
     build_product(force=force, verbose=verbose)
     build_oracle(force=force)
     build_reference_hdrloader(force=force)
+    build_reference_shaders(force=force)
 
 
 if __name__ == "__main__":

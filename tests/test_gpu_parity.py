@@ -329,6 +329,32 @@ def test_errors_are_reported_not_fatal(bunny_scene):
 
 
 # ------------------------------------------------------------------ committed golden fixtures + edge cases
+@pytest.mark.parametrize("name", ["p3", "bunny", "grid"])
+def test_reference_shader_golden_frames(name):
+    """tests/golden/refshader.npz holds frames rendered by THE REFERENCE'S OWN SHADER SOURCE (P3/P4/P5 fshader.fsh
+    transpiled to C++, tests/golden/make_golden_refshader.py).  The CUDA path must reproduce them bit for bit
+    through the C ABI, under every traversal policy and both pipelines."""
+    from tests import refshader_cases as cases
+    g = cases.load()
+    hdr, cache = cases.environment()
+    tris, nodes, eye, cam = cases.scene(name)
+    built = {}
+    try:
+        for case in cases.CASES:
+            key, mode, mb, lin, first, spp = case
+            if lin not in built:
+                built[lin] = api.Scene(tris, nodes, hdr, cache, hdr_filter_linear=lin)
+            want = g["%s_%s" % (name, key)]
+            for policy, pipeline in ((api.TRAVERSE_ACCEL, api.PIPELINE_WAVEFRONT), (api.TRAVERSE_REFERENCE, api.PIPELINE_WAVEFRONT),
+                                     (api.TRAVERSE_PRUNED, api.PIPELINE_WAVEFRONT), (api.TRAVERSE_PRUNED, api.PIPELINE_MEGAKERNEL)):
+                fb = g["%s_m3" % name].reshape(-1, 3).copy() if first else None
+                got = built[lin].render(cases.config(case, eye, cam, traverse=policy, pipeline=pipeline), framebuffer=fb)
+                assert_same_bits(got, want, "reference shader frame %s_%s policy %d pipeline %d" % (name, key, policy, pipeline))
+    finally:
+        for sc in built.values():
+            sc.close()
+
+
 def test_golden_p3_scene_images(small_hdr):
     """The reference's own P3 scene (real Stanford bunny, arrays committed in tests/golden/p3_scene.npz together
     with the oracle's images): the GPU must reproduce the committed images bit for bit, in all four modes."""
