@@ -4,6 +4,8 @@
   oracle/libezrt_oracle.so    the CPU oracle (test infrastructure, see oracle/README.md)
   oracle/_ref/libhdrloader_ref.so   the one reference translation unit that compiles stand-alone
                                      (P5/lib/hdrloader.cpp), built only where /root/reference exists
+  oracle/_ref/libezrt_refhost.so    the reference's own host code (P5 main.cpp + hdrloader.cpp) compiled from where
+                                     it lies against stand-in GL/GLUT/glm headers (oracle/ref_stubs/), same condition
   oracle/_ref/libezrt_refshader.so  the reference's own fragment shaders (P3/P4/P5 fshader.fsh) transpiled
                                      to C++ from where they lie (oracle/ref_shader/), same condition
 
@@ -24,6 +26,7 @@ ORACLE_SO = os.path.join(ROOT, "oracle", "libezrt_oracle.so")
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 REF_HDR_SO = os.path.join(REF_DIR, "libhdrloader_ref.so")
 REF_SHADER_SO = os.path.join(REF_DIR, "libezrt_refshader.so")
+REF_HOST_SO = os.path.join(REF_DIR, "libezrt_refhost.so")
 REFERENCE_ROOT = "/root/reference"
 REFERENCE_PARTS = ("part 3 -- OpenGL Raytracing", "part 4 -- Disney Principle BRDF",
                    "part 5 -- Importance Sampling & Low Discrepancy Sequence")
@@ -160,11 +163,40 @@ def build_reference_shaders(force=False):
     return REF_SHADER_SO
 
 
+def build_reference_host(force=False):
+    """oracle/_ref: the reference's own host code (P5 main.cpp: readObj, buildBVH, buildBVHwithSAH,
+    calculateHdrCache, main()'s scene set-up and uploads), compiled from where it lies together with its
+    hdrloader.cpp; GL/GLUT/glm come from the stand-ins in oracle/ref_stubs/.  Test infrastructure
+    (tests/test_ref_host.py)."""
+    main_cpp = os.path.join(REFERENCE_P5, "main.cpp")
+    hdr_cpp = os.path.join(REFERENCE_P5, "lib", "hdrloader.cpp")
+    if not (os.path.exists(main_cpp) and os.path.exists(hdr_cpp)):
+        return REF_HOST_SO if os.path.exists(REF_HOST_SO) else None
+    os.makedirs(REF_DIR, exist_ok=True)
+    orc = os.path.join(ROOT, "oracle")
+    stubs = os.path.join(orc, "ref_stubs")
+    shim, hshim, prefix = (os.path.join(orc, f) for f in ("ref_host_shim.cpp", "ref_hdrloader_shim.cpp", "ref_hdrloader_prefix.h"))
+    deps = [main_cpp, hdr_cpp, shim, hshim, prefix, os.path.join(INCLUDE, "ezrt_math.h")]
+    for d, _, files in os.walk(stubs):
+        deps += [os.path.join(d, f) for f in files]
+    if force or _newer(REF_HOST_SO, deps):
+        obj = os.path.join(REF_DIR, "hdrloader_host.o")
+        _run(["g++", "-O2", "-fPIC", "-w", "-include", prefix, "-I", os.path.join(REFERENCE_P5, "lib"), "-c", hdr_cpp, "-o", obj])
+        tmp = REF_HOST_SO + ".tmp%d" % os.getpid()
+        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-mfma", "-w", "-Dmain=ezrt_ref_main",
+              '-DEZRT_REF_MAIN_CPP="%s"' % main_cpp, "-I", stubs, "-I", INCLUDE, "-I", REFERENCE_P5, "-I", os.path.join(REFERENCE_P5, "lib"),
+              "-shared", shim, obj, hshim, "-o", tmp])
+        os.replace(tmp, REF_HOST_SO)
+        os.remove(obj)
+    return REF_HOST_SO
+
+
 def build_all(force=False, verbose=False):
     build_product(force=force, verbose=verbose)
     build_oracle(force=force)
     build_reference_hdrloader(force=force)
     build_reference_shaders(force=force)
+    build_reference_host(force=force)
 
 
 if __name__ == "__main__":

@@ -19,7 +19,7 @@ __global__ void k_lum(const float* __restrict__ hdr, float* __restrict__ pdf, si
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     float R = hdr[3 * k], G = hdr[3 * k + 1], B = hdr[3 * k + 2];
-    pdf[k] = 0.2f * R + 0.7f * G + 0.1f * B;  // :604
+    pdf[k] = (float)((0.2 * (double)R + 0.7 * (double)G) + 0.1 * (double)B);  // :604 -- the literals are doubles (fp64, -fmad=false)
 }
 // The ordered sum: the block stages 4096-float chunks in shared memory (coalesced loads), thread 0 adds them
 // in order from there (the add chain, ~4 cycles per element, is the floor: fp32 addition is not associative).

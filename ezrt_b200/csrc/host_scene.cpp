@@ -785,7 +785,7 @@ int ezrt_hdr_cache(const float* HDR, int width, int height, float* cache) {
     for (size_t i = 0; i < H; i++)
         for (size_t j = 0; j < W; j++) {
             float R = HDR[3 * (i * W + j)], G = HDR[3 * (i * W + j) + 1], B = HDR[3 * (i * W + j) + 2];
-            float lum = 0.2f * R + 0.7f * G + 0.1f * B;
+            float lum = (float)((0.2 * (double)R + 0.7 * (double)G) + 0.1 * (double)B);  // :604 -- the literals are doubles
             pdf[i * W + j] = lum;
             lumSum += lum;
         }

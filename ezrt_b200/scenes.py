@@ -121,24 +121,30 @@ MATERIAL_PRESETS = [
 ]
 
 
+def bunny_meshes():
+    """P3's scene with the blob in place of the bunny (P3/main.cpp:688-701) as readObj calls:
+    [(obj text, Material, trans, smooth)]"""
+    return [
+        (blob_obj(), Material(baseColor=(1, 1, 1)), transform_matrix((0, 0, 0), (0.3, -0.65, 0.0), (1.5, 1.5, 1.5)), True),
+        (box_obj(), Material(baseColor=(0.725, 0.71, 0.68)), transform_matrix((0, 0, 0), (0, -1.4, 0), (18.83, 0.01, 18.83)), False),
+        (sphere_obj(), Material(baseColor=(1, 1, 1), emissive=(30, 20, 10)), transform_matrix((0, 0, 0), (0.0, 0.9, 0.0), (1, 1, 1)), False),
+    ]
+
+
 def s_bunny(builder=api.BVH_SAH_FAST):
-    """P3's scene with the blob in place of the bunny (P3/main.cpp:688-701).  Returns (tris, nodes, eye, cam)."""
+    """bunny_meshes() built with the default leaf size.  Returns (tris, nodes, eye, cam)."""
     tl = TriangleList()
-    m = Material(baseColor=(1, 1, 1))
-    tl.read_obj_text(blob_obj(), m, transform_matrix((0, 0, 0), (0.3, -0.65, 0.0), (1.5, 1.5, 1.5)), True)
-    m = Material(baseColor=(0.725, 0.71, 0.68))
-    tl.read_obj_text(box_obj(), m, transform_matrix((0, 0, 0), (0, -1.4, 0), (18.83, 0.01, 18.83)), False)
-    m = Material(baseColor=(1, 1, 1), emissive=(30, 20, 10))
-    tl.read_obj_text(sphere_obj(), m, transform_matrix((0, 0, 0), (0.0, 0.9, 0.0), (1, 1, 1)), False)
+    for text, m, trans, smooth in bunny_meshes():
+        tl.read_obj_text(text, m, trans, smooth)
     tris, nodes = tl.build_bvh(8, builder)
     eye, cam = api.camera_orbit(0.0, 0.0, 4.0)  # P3/main.cpp:148-150
     return tris, nodes, eye, cam
 
 
-def s_grid(nx, nz, n_lights=4, builder=api.BVH_SAH_FAST, pitch=1.2):
+def grid_meshes(nx, nz, n_lights=4, pitch=1.2):
     """nx*nz blob instances on a grid (y-rotation and scale from wang_hash, material preset id%8),
-    `n_lights` emissive spheres above it and a floor box.  Returns (tris, nodes, eye, cam)."""
-    tl = TriangleList()
+    `n_lights` emissive spheres above it and a floor box, as readObj calls: [(obj text, Material, trans, smooth)]"""
+    out = []
     text = blob_obj()
     inst = 0
     for iz in range(nz):
@@ -149,7 +155,7 @@ def s_grid(nx, nz, n_lights=4, builder=api.BVH_SAH_FAST, pitch=1.2):
             x = (ix - (nx - 1) / 2.0) * pitch
             z = (iz - (nz - 1) / 2.0) * pitch
             m = MATERIAL_PRESETS[inst % 8]
-            tl.read_obj_text(text, m, transform_matrix((0, rot, 0), (x, -1.4 + 0.6 * sc, z), (sc, sc, sc)), True)
+            out.append((text, m, transform_matrix((0, rot, 0), (x, -1.4 + 0.6 * sc, z), (sc, sc, sc)), True))
             inst += 1
     light = Material(baseColor=(1, 1, 1), emissive=(20, 20, 20))
     sph = sphere_obj()
@@ -157,12 +163,20 @@ def s_grid(nx, nz, n_lights=4, builder=api.BVH_SAH_FAST, pitch=1.2):
     for k in range(n_lights):
         lx = (((k % 2) * 2 - 1) * 0.25) * span_x
         lz = (((k // 2) * 2 - 1) * 0.25) * span_z
-        tl.read_obj_text(sph, light, transform_matrix((0, 0, 0), (lx, 2.5, lz), (1.5, 1.5, 1.5)), False)
+        out.append((sph, light, transform_matrix((0, 0, 0), (lx, 2.5, lz), (1.5, 1.5, 1.5)), False))
     floor = Material(baseColor=(0.725, 0.71, 0.68), roughness=0.3, metallic=0.1)
     ext = max(span_x, span_z) * 1.5 + 4.0
-    tl.read_obj_text(box_obj(), floor, transform_matrix((0, 0, 0), (0, -1.4, 0), (ext, 0.01, ext)), False)
+    out.append((box_obj(), floor, transform_matrix((0, 0, 0), (0, -1.4, 0), (ext, 0.01, ext)), False))
+    return out
+
+
+def s_grid(nx, nz, n_lights=4, builder=api.BVH_SAH_FAST, pitch=1.2):
+    """grid_meshes() built with the default leaf size.  Returns (tris, nodes, eye, cam)."""
+    tl = TriangleList()
+    for text, m, trans, smooth in grid_meshes(nx, nz, n_lights, pitch):
+        tl.read_obj_text(text, m, trans, smooth)
     tris, nodes = tl.build_bvh(8, builder)
-    r = 0.62 * max(span_x, span_z) + 3.0
+    r = 0.62 * max(nx * pitch, nz * pitch) + 3.0
     eye, cam = api.camera_orbit(30.0, 25.0, r)
     return tris, nodes, eye, cam
 

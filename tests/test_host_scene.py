@@ -304,7 +304,8 @@ def test_hdr_cache_properties(small_hdr):
     sampled = lum[np.clip(ys, 0, h - 1), xs]
     assert sampled.mean() > 5 * lum.mean()
     # literal re-statement in numpy (float32 accumulation order as the C++ loops)
-    pdf = (np.float32(0.2) * hdr[..., 0] + np.float32(0.7) * hdr[..., 1] + np.float32(0.1) * hdr[..., 2]).astype(np.float32)
+    # (the luminance weights are double literals in the reference, P5/main.cpp:604: fp64 sum, rounded once)
+    pdf = ((0.2 * hdr[..., 0].astype(np.float64) + 0.7 * hdr[..., 1].astype(np.float64)) + 0.1 * hdr[..., 2].astype(np.float64)).astype(np.float32)
     s = np.float32(0)
     for v in pdf.reshape(-1):
         s = np.float32(s + v)
