@@ -163,15 +163,17 @@ def build_reference_shaders(force=False):
     return REF_SHADER_SO
 
 
-def build_reference_host(force=False):
-    """oracle/_ref: the reference's own host code (P5 main.cpp: readObj, buildBVH, buildBVHwithSAH,
-    calculateHdrCache, main()'s scene set-up and uploads), compiled from where it lies together with its
-    hdrloader.cpp; GL/GLUT/glm come from the stand-ins in oracle/ref_stubs/.  Test infrastructure
-    (tests/test_ref_host.py)."""
-    main_cpp = os.path.join(REFERENCE_P5, "main.cpp")
-    hdr_cpp = os.path.join(REFERENCE_P5, "lib", "hdrloader.cpp")
+def build_reference_host(force=False, part=5):
+    """oracle/_ref: the reference's own host code (main.cpp of tutorial part 3, 4 or 5: readObj, buildBVH,
+    buildBVHwithSAH, calculateHdrCache (P5), main()'s scene set-up and uploads), compiled from where it lies
+    together with its hdrloader.cpp; GL/GLUT/glm come from the stand-ins in oracle/ref_stubs/.  Test
+    infrastructure (tests/test_ref_host.py)."""
+    src_dir = os.path.join(REFERENCE_ROOT, REFERENCE_PARTS[part - 3], "source code")
+    target = REF_HOST_SO if part == 5 else REF_HOST_SO.replace(".so", "_p%d.so" % part)
+    main_cpp = os.path.join(src_dir, "main.cpp")
+    hdr_cpp = os.path.join(src_dir, "lib", "hdrloader.cpp")
     if not (os.path.exists(main_cpp) and os.path.exists(hdr_cpp)):
-        return REF_HOST_SO if os.path.exists(REF_HOST_SO) else None
+        return target if os.path.exists(target) else None
     os.makedirs(REF_DIR, exist_ok=True)
     orc = os.path.join(ROOT, "oracle")
     stubs = os.path.join(orc, "ref_stubs")
@@ -179,16 +181,16 @@ def build_reference_host(force=False):
     deps = [main_cpp, hdr_cpp, shim, hshim, prefix, os.path.join(INCLUDE, "ezrt_math.h")]
     for d, _, files in os.walk(stubs):
         deps += [os.path.join(d, f) for f in files]
-    if force or _newer(REF_HOST_SO, deps):
-        obj = os.path.join(REF_DIR, "hdrloader_host.o")
-        _run(["g++", "-O2", "-fPIC", "-w", "-include", prefix, "-I", os.path.join(REFERENCE_P5, "lib"), "-c", hdr_cpp, "-o", obj])
-        tmp = REF_HOST_SO + ".tmp%d" % os.getpid()
-        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-mfma", "-w", "-Dmain=ezrt_ref_main",
-              '-DEZRT_REF_MAIN_CPP="%s"' % main_cpp, "-I", stubs, "-I", INCLUDE, "-I", REFERENCE_P5, "-I", os.path.join(REFERENCE_P5, "lib"),
+    if force or _newer(target, deps):
+        obj = os.path.join(REF_DIR, "hdrloader_host_p%d.o" % part)
+        _run(["g++", "-O2", "-fPIC", "-w", "-include", prefix, "-I", os.path.join(src_dir, "lib"), "-c", hdr_cpp, "-o", obj])
+        tmp = target + ".tmp%d" % os.getpid()
+        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-mfma", "-w", "-Dmain=ezrt_ref_main", "-DEZRT_REF_PART=%d" % part,
+              '-DEZRT_REF_MAIN_CPP="%s"' % main_cpp, "-I", stubs, "-I", INCLUDE, "-I", src_dir, "-I", os.path.join(src_dir, "lib"),
               "-shared", shim, obj, hshim, "-o", tmp])
-        os.replace(tmp, REF_HOST_SO)
+        os.replace(tmp, target)
         os.remove(obj)
-    return REF_HOST_SO
+    return target
 
 
 def build_all(force=False, verbose=False):
@@ -196,7 +198,8 @@ def build_all(force=False, verbose=False):
     build_oracle(force=force)
     build_reference_hdrloader(force=force)
     build_reference_shaders(force=force)
-    build_reference_host(force=force)
+    for part in (3, 4, 5):
+        build_reference_host(force=force, part=part)
 
 
 if __name__ == "__main__":

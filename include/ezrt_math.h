@@ -4,7 +4,7 @@
  * The reference (AKGWSB/EzRT) runs this path as GLSL (P5/shaders/fshader.fsh) on top of
  * driver-implemented built-ins (normalize, cross, mix, sin, cos, atan, asin, log, pow ...)
  * and glm on the host; neither is bit-specified, and the reference ships no test that pins
- * them ("parity unpinned").  This header therefore DEFINES every such
+ * them (how parity is pinned nevertheless: DESIGN.md section 2).  This header therefore DEFINES every such
  * operation as a fixed sequence of IEEE-754 binary32  + - * / sqrt fma  operations, so the
  * same source gives bit-identical results under g++ (host, -ffp-contract=off -mfma) and
  * nvcc (device, -fmad=false, default -prec-div/-prec-sqrt/-ftz=false).

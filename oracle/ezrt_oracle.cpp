@@ -3,15 +3,22 @@
 // *** TEST INFRASTRUCTURE, NOT PRODUCT.  Only tests/, __graft_entry__.smoke() and bench.py's
 // *** cpu_baseline / --impl reference legs may load this library.  ezrt_b200 never does.
 //
-// PARITY UNPINNED: the reference (AKGWSB/EzRT @51cf8774) ships no test, golden vector or
-// known-answer value for this path, its hot path is a GLSL fragment shader
-// that needs an OpenGL 4.3 context plus glm/GLEW/freeglut (none installed, no network), so it
-// cannot be compiled or run here.  This file is a plain scalar C++ restatement of the
-// reference's algorithm, function by function, each citing the file:line it follows
+// PARITY PIN.  The reference (AKGWSB/EzRT @51cf8774) ships no test, golden vector or known-answer
+// value for this path and its hot path is a GLSL fragment shader that needs an
+// OpenGL 4.3 context plus glm/GLEW/freeglut (none installed, no network).  What pins this file:
+//   1. the reference's OWN SHADER SOURCE run on the CPU: oracle/ref_shader/ transpiles
+//      P3|P4|P5/shaders/fshader.fsh from where they lie (literal suffixes, swizzle accessors,
+//      qualifiers -- statements, expression order, control flow, constants and tables untouched)
+//      and this file must equal it bit for bit in all four integrator modes
+//      (tests/test_ref_shader.py; frames committed in tests/golden/refshader.npz);
+//   2. constants: wang_hash chain, Sobol/Joe-Kuo points, PI literal (tests/test_kat.py), and the one
+//      ray of P2/main.cpp:581-586 (BVH result == brute force).
+// What stays OURS by definition, because GLSL does not specify it bit-wise: the built-in functions
+// (-> include/ezrt_math.h), texture filtering, the rasteriser's `pix` and the left-to-right
+// evaluation of call arguments (list below).  Both sides of pin 1 share those definitions.
+// This file is a plain scalar C++ restatement of the reference's algorithm, function by function,
+// each citing the file:line it follows
 // (P2/ P3/ P4/ P5/ = "source code" directory of tutorial part 2..5, fsh = shaders/fshader.fsh).
-// The only reference-derived values it can be pinned against are the constants in
-// tests/test_kat.py (wang_hash chain, Sobol/Joe-Kuo points, PI literal) and the one ray of
-// P2/main.cpp:581-586 (BVH result == brute force).
 //
 // Arithmetic is the normative fp32 definition of include/ezrt_math.h (GLSL built-ins are not
 // bit-specified), compiled with -ffp-contract=off -mfma so it is comparable bit-for-bit with

@@ -1,4 +1,5 @@
-// ref_host_shim.cpp -- calls the reference's own host code (P5 main.cpp, compiled from where it lies).
+// ref_host_shim.cpp -- calls the reference's own host code (main.cpp of part 3, 4 or 5 -- EZRT_REF_PART --
+// compiled from where it lies; the functions below are the same in all three parts, line numbers are P5's).
 //
 // *** TEST INFRASTRUCTURE (oracle/), NOT PRODUCT.  Builds into oracle/_ref/libezrt_refhost.so, only where
 // *** /root/reference exists.  Nothing of the reference is copied: this translation unit #includes
@@ -85,16 +86,18 @@ void refhost_encode(float* tris36, float* nodes12) {
     }
 }
 
-// calculateHdrCache (P5/main.cpp:591-683)
+#if EZRT_REF_PART == 5
+// calculateHdrCache (P5/main.cpp:591-683; parts 3 and 4 have no importance sampling)
 void refhost_hdr_cache(const float* hdr, int w, int h, float* out) {
     float* c = calculateHdrCache(const_cast<float*>(hdr), w, h);
     memcpy(out, c, sizeof(float) * 3 * (size_t)w * h);
     delete[] c;
 }
+#endif
 
 // Runs the reference's main() in `source_dir` (it opens models/, HDR/ and shaders/ relative to the cwd) up to
 // glutMainLoop(), which the stand-in returns from.  Returns the number of captured uploads; in call order they
-// are: triangle texture buffer, BVH texture buffer, HDR map, HDR sampling cache (P5/main.cpp:843-868).
+// are: triangle texture buffer, BVH texture buffer, HDR map and (part 5) HDR sampling cache (P5/main.cpp:843-868).
 int refhost_run_main(const char* source_dir) {
     char cwd[4096];
     if (!getcwd(cwd, sizeof(cwd))) return -1;

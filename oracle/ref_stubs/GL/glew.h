@@ -27,7 +27,7 @@ typedef ptrdiff_t GLintptr;
 enum {
     GL_FALSE = 0, GL_TRUE = 1, GL_TRIANGLES = 4, GL_DEPTH_BUFFER_BIT = 0x100, GL_COLOR_BUFFER_BIT = 0x4000,
     GL_DEPTH_TEST = 0x0B71, GL_TEXTURE_2D = 0x0DE1, GL_FLOAT = 0x1406, GL_RGB = 0x1907, GL_RGBA = 0x1908,
-    GL_LINEAR = 0x2601, GL_TEXTURE_MAG_FILTER = 0x2800, GL_TEXTURE_MIN_FILTER = 0x2801, GL_TEXTURE_WRAP_S = 0x2802,
+    GL_NEAREST = 0x2600, GL_LINEAR = 0x2601, GL_TEXTURE_MAG_FILTER = 0x2800, GL_TEXTURE_MIN_FILTER = 0x2801, GL_TEXTURE_WRAP_S = 0x2802,
     GL_TEXTURE_WRAP_T = 0x2803, GL_CLAMP_TO_EDGE = 0x812F, GL_TEXTURE0 = 0x84C0, GL_TEXTURE1, GL_TEXTURE2, GL_TEXTURE3,
     GL_TEXTURE4, GL_RGBA32F = 0x8814, GL_RGB32F = 0x8815, GL_ARRAY_BUFFER = 0x8892, GL_STATIC_DRAW = 0x88E4,
     GL_FRAGMENT_SHADER = 0x8B30, GL_VERTEX_SHADER = 0x8B31, GL_COMPILE_STATUS = 0x8B81, GL_TEXTURE_BUFFER = 0x8C2A,

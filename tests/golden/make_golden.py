@@ -7,8 +7,8 @@
                  48x32, 2 spp.  GPU tests re-render these arrays and must reproduce the images bit for bit;
                  CPU tests re-run the oracle and the literal BVH builder against them.
   synth.npz    : crc32 of the synthetic scenes' arrays + oracle images (platform-independent scene builders).
-The parity of the oracle itself is unpinned by the reference (no golden vectors exist there, SURVEY.md 4);
-these files pin OUR restatement against accidental drift.
+The reference holds no golden vectors; these files freeze OUR restatement against accidental drift.
+The frames that pin it to the reference's own shader source are in refshader.npz (make_golden_refshader.py).
 """
 import os
 import sys

@@ -11,18 +11,22 @@ from ezrt_b200 import build as _build
 
 SOURCE_DIR = _build.REFERENCE_P5
 _fp = C.POINTER(C.c_float)
-_lib = None
+_libs = {}
 
 
-def _load():
-    global _lib
-    if _lib is None:
-        so = _build.build_reference_host()
+def source_dir(part):
+    return os.path.join(_build.REFERENCE_ROOT, _build.REFERENCE_PARTS[part - 3], "source code")
+
+
+def _load(part=5):
+    if part not in _libs:
+        so = _build.build_reference_host(part=part)
         if so is None or not os.path.exists(so):
             return None
-        _lib = C.CDLL(so)
-        _lib.refhost_upload_info.restype = C.c_longlong
-    return _lib
+        lib = C.CDLL(so)
+        lib.refhost_upload_info.restype = C.c_longlong
+        _libs[part] = lib
+    return _libs[part]
 
 
 def available():
@@ -63,12 +67,13 @@ def hdr_cache(hdr):
     return out
 
 
-def run_main():
-    """the reference's main() up to glutMainLoop(): returns its four uploads
-    (triangle texture buffer, BVH texture buffer, HDR map [h,w,3], HDR sampling cache [h,w,3])"""
-    lib = _load()
-    n = lib.refhost_run_main(os.fsencode(SOURCE_DIR))
-    assert n == 4, n
+def run_main(part=5, cwd=None):
+    """the reference's main() (of tutorial part 3, 4 or 5) up to glutMainLoop(), run in `cwd` (default: its own
+    source directory -- it opens models/, HDR/ and shaders/ relative to the cwd).  Returns its uploads in call
+    order: triangle texture buffer [n,36], BVH texture buffer [m,12], HDR map [h,w,3] and (part 5) the HDR sampling cache."""
+    lib = _load(part)
+    n = lib.refhost_run_main(os.fsencode(cwd or source_dir(part)))
+    assert n == (4 if part == 5 else 3), n
     out = []
     for i in range(n):
         w, h, tg = C.c_int(), C.c_int(), C.c_uint()
@@ -76,4 +81,4 @@ def run_main():
         a = np.zeros(size // 4, np.float32)
         lib.refhost_upload_copy(i, a.ctypes.data_as(C.c_void_p))
         out.append(a.reshape(h.value, w.value, 3) if w.value else a)
-    return out[0].reshape(-1, 36), out[1].reshape(-1, 12), out[2], out[3]
+    return [out[0].reshape(-1, 36), out[1].reshape(-1, 12)] + out[2:]

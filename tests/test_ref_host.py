@@ -52,6 +52,47 @@ def test_reference_main_uploads_are_reproduced_byte_for_byte():
     assert same_bytes(api.hdr_cache(hdr), r_cache), "calculateHdrCache"
 
 
+@needs_reference
+def test_reference_p4_main_uploads_are_reproduced_byte_for_byte():
+    """P4/main.cpp:689-743: one golden teapot, SAH tree, 1024x512 map"""
+    r_tris, r_nodes, r_hdr = refhost.run_main(4)
+    src = refhost.source_dir(4)
+    tl = api.TriangleList()
+    m = api.Material(baseColor=(0.75, 0.7, 0.15), roughness=0.15, metallic=1.0, clearcoat=1.0, subsurface=1.0)
+    tl.read_obj(src + "/models/teapot.obj", m, api.transform_matrix((0, 0, 0), (0, -0.4, 0), (1.75, 1.75, 1.75)), True)
+    tris, nodes = tl.build_bvh(8, api.BVH_SAH_FAST)
+    assert same_bytes(tris, r_tris) and same_bytes(nodes, r_nodes)
+    assert same_bytes(api.hdr_load(src + "/HDR/peppermint_powerplant_4k.hdr"), r_hdr)
+
+
+@needs_reference
+def test_reference_p3_main_uploads_equal_the_committed_p3_scene(tmp_path):
+    """P3/main.cpp:688-715 (Stanford bunny + floor + emissive sphere).  Its main() opens ./HDR/sunset.hdr, which the
+    reference does not ship: it is run in a directory whose HDR/sunset.hdr points at the map P3 does ship.
+    tests/golden/p3_scene.npz (the scene the golden frames are rendered from) holds the same geometry and tree;
+    only the Disney parameters differ, which P3's Material defaults to 0 (P3/main.cpp:28-43) and its shader never reads."""
+    src = refhost.source_dir(3)
+    os.symlink(src + "/models", tmp_path / "models")
+    os.symlink(src + "/shaders", tmp_path / "shaders")
+    os.mkdir(tmp_path / "HDR")
+    os.symlink(src + "/HDR/circus_arena_4k.hdr", tmp_path / "HDR" / "sunset.hdr")
+    r_tris, r_nodes, r_hdr = refhost.run_main(3, str(tmp_path))
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "p3_scene.npz"))
+    assert same_bytes(g["nodes"], r_nodes)
+    assert same_bytes(g["tris"][:, :24], r_tris[:, :24])  # positions, normals, emissive, baseColor
+    p3_defaults = dict(specular=0.0, roughness=0.0, sheenTint=0.0, clearcoatGloss=0.0)
+    tl = api.TriangleList()
+    tl.read_obj(src + "/models/Stanford Bunny.obj", api.Material(baseColor=(1, 1, 1), **p3_defaults),
+                api.transform_matrix((0, 0, 0), (0.3, -1.6, 0), (1.5, 1.5, 1.5)), True)
+    tl.read_obj(src + "/models/quad.obj", api.Material(baseColor=(0.725, 0.71, 0.68), **p3_defaults),
+                api.transform_matrix((0, 0, 0), (0, -1.4, 0), (18.83, 0.01, 18.83)), False)
+    tl.read_obj(src + "/models/sphere.obj", api.Material(baseColor=(1, 1, 1), emissive=(30, 20, 10), **p3_defaults),
+                api.transform_matrix((0, 0, 0), (0.0, 0.9, 0.0), (1, 1, 1)), False)
+    tris, nodes = tl.build_bvh(8, api.BVH_SAH_LITERAL)
+    assert same_bytes(tris, r_tris) and same_bytes(nodes, r_nodes)
+    assert same_bytes(api.hdr_load(src + "/HDR/circus_arena_4k.hdr"), r_hdr)
+
+
 def _write(tmp_path, name, text):
     p = tmp_path / name
     p.write_text(text)
