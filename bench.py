@@ -2,7 +2,7 @@
 """bench.py -- Mrays/s (primary + secondary) of the path-tracing hot path on N B200s.
 
   python bench.py --gpus N --steps K --warmup W          (N > 1: launched by torch.distributed.run)
-  python bench.py --impl reference ...                   (the CPU oracle on the host cores, same config)
+  python bench.py --impl reference ...                   (the reference shader source / CPU oracle on the host cores, same config)
 
 Workload (BASELINE.json): N = 1 is configs[2] "C3" -- the ~1M-triangle synthetic scene
 (ezrt_b200.scenes.s_1m: 999,692 triangles), 1920x1080, Disney BRDF + Sobol (mode disney_sobol_p5),
@@ -59,7 +59,7 @@ def parse_args():
     ap.add_argument("--pipeline", default="wavefront", choices=["wavefront", "megakernel"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", default="960x540x2", help="oracle sample WxHxSPP used for cpu_baseline and B_ray")
+    ap.add_argument("--cpu-sample", default="1920x1080x1", help="oracle sample WxHxSPP used for cpu_baseline and B_ray")
     return ap.parse_args()
 
 
@@ -146,9 +146,34 @@ def oracle_sample(wl, sample, traverse, threads=0):
     cfg = api.RenderConfig(width=w, height=h, spp=spp, max_bounce=wl["max_bounce"], mode=wl["mode"], eye=tuple(wl["eye"]),
                            camera_rotate=tuple(wl["cam"]), env_color=(0.35, 0.45, 0.6), traverse=traverse)
     t0 = time.perf_counter()
-    _, c = oracle.render(wl["tris"], wl["nodes"], cfg, hdr=wl.get("hdr"), hdr_cache=wl.get("cache"), threads=threads)
+    img, c = oracle.render(wl["tris"], wl["nodes"], cfg, hdr=wl.get("hdr"), hdr_cache=wl.get("cache"), threads=threads)
     dt = time.perf_counter() - t0
+    c["image"] = img
     return c["rays"] / dt / 1e6, c, dt
+
+
+def reference_shader_sample(wl, sample, check_against=None):
+    """Time the REFERENCE'S OWN SHADER SOURCE (oracle/_ref/libezrt_refshader.so: P3/P4/P5 fshader.fsh transpiled to C++
+    in the authoring container, oracle/ref_shader/) on the same bounded sample, all host threads.  Returns seconds, or
+    None when the library is not there.  A scene without an environment map gets a 1x1 map of the constant colour
+    (GL_NEAREST), which is what env_color means to the shader."""
+    import numpy as np
+    from ezrt_b200 import api
+    from tests import refshader_binding as refshader  # CPU baseline leg only, like oracle_binding
+    if not refshader.available():
+        return None
+    w, h, spp = [int(x) for x in sample.lower().split("x")]
+    cfg = api.RenderConfig(width=w, height=h, spp=spp, max_bounce=wl["max_bounce"], mode=wl["mode"], eye=tuple(wl["eye"]),
+                           camera_rotate=tuple(wl["cam"]), env_color=(0.35, 0.45, 0.6), traverse=1)
+    hdr, cache, linear = wl.get("hdr"), wl.get("cache"), True
+    if hdr is None:
+        hdr, cache, linear = np.array([[[0.35, 0.45, 0.6]]], np.float32), None, False
+    t0 = time.perf_counter()
+    img = refshader.render(wl["tris"], wl["nodes"], cfg, hdr, cache, hdr_linear=linear)
+    dt = time.perf_counter() - t0
+    if check_against is not None:  # the port and the reference shader must agree bit for bit
+        assert img.tobytes() == check_against.tobytes(), "oracle port and transpiled reference shader disagree"
+    return dt
 
 
 def b_ray(c):
@@ -157,29 +182,33 @@ def b_ray(c):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path = the oracle port, all host threads."""
+    """--impl reference: the reference's own implementation of the path on the host cores, all threads: the transpiled
+    reference shaders (oracle/_ref, kind "reference") when that library travelled here, else the oracle port."""
     if rank != 0:
         return
     wl = build_workload(args.workload)
     cores = os.cpu_count() or 1
     sample = args.cpu_sample
-    rates = []
+    _, c, _ = oracle_sample(wl, sample, 1)  # ray count of the sample (the shader library does not count; same paths, same image)
+    kind = "reference" if reference_shader_sample(wl, "64x36x1") is not None else "port"
+    t_start = time.perf_counter()
     for i in range(args.warmup + args.steps):
         if i == args.warmup:
             t_start = time.perf_counter()
-        rate, c, dt = oracle_sample(wl, sample, 1)
-        if i >= args.warmup:
-            rates.append((c["rays"], dt))
-    total_rays = sum(r for r, _ in rates)
+        if kind == "reference":
+            reference_shader_sample(wl, sample, check_against=c["image"] if i == 0 else None)
+        else:
+            oracle_sample(wl, sample, 1)
     total_s = time.perf_counter() - t_start
-    value = total_rays / total_s / 1e6
+    value = c["rays"] * args.steps / total_s / 1e6
+    what = ("reference shader source (P3|P4|P5 fshader.fsh of the mode, transpiled to C++, oracle/_ref)" if kind == "reference" else "oracle port")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "scene": wl["scene"], "triangles": int(wl["tris"].shape[0]), "mode": wl["mode"],
-                   "max_bounce": wl["max_bounce"], "step": "oracle render of sample " + sample + " (reference traversal policy)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + " (WxHxspp) of the workload per step"},
+                   "max_bounce": wl["max_bounce"], "step": what + " renders sample " + sample + " (literal hitBVH traversal)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample + " (WxHxspp) of the workload per step"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -331,6 +360,11 @@ def main():
                  "n_node_pruned": c_pr["n_node"] / c_pr["rays"], "n_tri_pruned": c_pr["n_tri"] / c_pr["rays"]}
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                         "sample": "oracle render of %s (WxHxspp) of the workload, reference traversal, %.1f s" % (args.cpu_sample, dt)}
+        dt_ref = reference_shader_sample(wl, args.cpu_sample, check_against=c_ref["image"])
+        if dt_ref is not None:  # the reference's own shader source compiled for the CPU travelled here: report that one
+            cpu_baseline = {"value": c_ref["rays"] / dt_ref / 1e6, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference",
+                            "sample": "reference shader source (fshader.fsh transpiled to C++, oracle/_ref) renders %s (WxHxspp) of the workload, "
+                                      "%.1f s; image bit-identical to the oracle port's, which runs it at %.2f %s" % (args.cpu_sample, dt_ref, rate, UNIT)}
     ext_ms, ext_n = ktimes["extend"]
     roofline = None
     if bray_ref and ext_ms > 0:

@@ -30,7 +30,8 @@ def _load(part=5):
 
 
 def available():
-    return _load() is not None
+    """the library AND the reference's data files (models/, HDR/) its tests read"""
+    return os.path.isdir(source_dir(5)) and _load() is not None
 
 
 def _f(a):
