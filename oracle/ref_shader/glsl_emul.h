@@ -106,6 +106,7 @@ inline float cos(float x) { return ez_cos(x); }
 inline float log(float x) { return ez_log(x); }
 inline float exp(float x) { return ez_exp(x); }
 inline float pow(float x, float y) { return ez_pow(x, y); }
+inline vec3 pow(vec3 x, vec3 y) { return vec3(ez_pow(x.x, y.x), ez_pow(x.y, y.y), ez_pow(x.z, y.z)); }
 inline float asin(float x) { return ez_asin(x); }
 inline float atan(float y, float x) { return ez_atan2(y, x); }
 inline float min(float a, float b) { return ez_min(a, b); }
@@ -161,6 +162,7 @@ struct Uniforms {
     int nTriangles, nNodes, width, height, hdrResolution;
     samplerBuffer triangles, nodes;
     sampler2D lastFrame, hdrMap, hdrCache;
+    sampler2D texPass0, texPass1, texPass2, texPass3, texPass4, texPass5, texPass6;  // pass2/pass3 inputs (RenderPass::draw)
     vec3 eye;
     mat4 cameraRotate;
 };

@@ -65,6 +65,10 @@ EZRT_SHADER_STRUCT(Shader_p5is, 0)
 #undef SIZE_BVHNODE
 // clang-format on
 
+EZRT_SHADER_STRUCT(Shader_pass3, 0)
+#include "shader_pass3.inc"
+};
+
 template <class S>
 static vec3 run_fragment(const Uniforms& U, vec3 pix, int max_bounce) {
     S s(U, pix, max_bounce);
@@ -129,6 +133,26 @@ int refshader_render(const float* tris, int nTriangles, const float* nodes, int 
         for (int k = 0; k < 3; k++) framebuffer[i * C + k] = last[3 * i + k];
         if (C == 4) framebuffer[i * C + 3] = 1.0f;
     }
+    return 0;
+}
+
+// pass3.fsh (tone mapping + gamma) over a W x H image with `channels` floats per pixel; out: 3 floats per pixel.
+// texPass0 is sampled at the pixel's own texel (GL_NEAREST stand-in for the screen-sized attachment).
+int refshader_pass3(const float* in, int channels, int W, int H, float* out) {
+    using namespace glsl;
+    if (!in || !out || channels < 3) return -1;
+    Uniforms U;
+    memset(&U, 0, sizeof(U));
+    U.texPass0 = sampler2D{in, W, H, channels, 0};
+#pragma omp parallel for
+    for (int py = 0; py < H; py++)
+        for (int px = 0; px < W; px++) {
+            vec3 pix(((float)px + 0.5f) / (float)W * 2.0f - 1.0f, ((float)py + 0.5f) / (float)H * 2.0f - 1.0f, 0.0f);
+            Shader_pass3 s(U, pix, 0);
+            s.shader_main();
+            float* d = out + ((size_t)py * W + px) * 3;
+            d[0] = s.fragColor.x; d[1] = s.fragColor.y; d[2] = s.fragColor.z;
+        }
     return 0;
 }
 

@@ -3,7 +3,7 @@
 
 *** TEST INFRASTRUCTURE (oracle/), NOT PRODUCT.
 
-Reads  <reference>/part {3,4,5} .../source code/shaders/fshader.fsh  WHERE THEY LIE (read-only) and
+Reads  <reference>/part {3,4,5} .../source code/shaders/fshader.fsh  (and P5's pass3.fsh)  WHERE THEY LIE (read-only) and
 writes  oracle/_ref/shader_<variant>.inc  (git-ignored build output, never committed): the shader's
 own text with only the mechanical edits GLSL -> C++ needs.  ref_shader_host.cpp #includes each .inc
 inside `struct Shader_<variant> { ... }` and runs main() per pixel against oracle/ref_shader/glsl_emul.h.
@@ -97,6 +97,24 @@ def transpile(src, variant):
     return t
 
 
+def transpile_pass3(src):
+    """shaders/pass3.fsh (tone mapping + gamma, identical in parts 3, 4 and 5): edits 1-6 only"""
+    t = src.lstrip("\ufeff")
+    t, n = re.subn(r"^#version[^\n]*\n", "\n", t, count=1, flags=re.M)
+    assert n == 1, "#version"
+    t = FLOAT_LIT.sub(lambda m: m.group(1) + "f", t)
+    t = re.sub(r"\.(xyz|rgb|xy|rg)\b(?!\s*\()", r".\1()", t)
+    t = re.sub(r"([(,]\s*)in\s+(?=\w+\s+\w+\s*[,)])", r"\1", t)
+    t, n = re.subn(r"^uniform\s+(\w+)\s+(\w+)\s*;", r"\1 \2 = U.\2;", t, flags=re.M)
+    assert n == 7, "texPass uniforms"
+    t = sub_once(t, "in vec3 pix;", "vec3 pix = pix_in;", "in vec3 pix")
+    t = sub_once(t, "out vec4 fragColor;", "vec4 fragColor;", "out vec4 fragColor")
+    t = sub_once(t, "void main() {", "void shader_main() {", "main")
+    if re.search(r"^\s*(uniform|in|out|inout)\s", t, flags=re.M):
+        raise SystemExit("transpile: a storage qualifier survived")
+    return t
+
+
 def main():
     ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     out_dir = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "_ref")
@@ -113,6 +131,14 @@ def main():
             f.write(body)
         os.replace(tmp, dst)
         print(f"transpile: {variant}: {len(src.splitlines())} lines -> {dst}")
+    path = os.path.join(ref, PARTS["p5"], "source code", "shaders", "pass3.fsh")
+    with open(path, encoding="utf-8") as f:
+        body = transpile_pass3(f.read())
+    dst = os.path.join(out_dir, "shader_pass3.inc")
+    with open(dst, "w", encoding="utf-8") as f:
+        f.write(f"// GENERATED by oracle/ref_shader/transpile.py from {path}\n// build output -- do not commit\n")
+        f.write(body)
+    print(f"transpile: pass3 -> {dst}")
 
 
 if __name__ == "__main__":

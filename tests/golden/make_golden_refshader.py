@@ -37,6 +37,8 @@ def main():
             fb = d["%s_m3" % name].copy() if first else None
             d["%s_%s" % (name, key)] = refshader.render(tris, nodes, cases.config(case, eye, cam), hdr, cache, hdr_linear=lin, framebuffer=fb)
         print(name, "done")
+    from tests.test_ref_shader import _hdr_frame
+    d["pass3_out"] = refshader.pass3(_hdr_frame())  # shaders/pass3.fsh on a fixed HDR frame
     np.savez_compressed(os.path.join(HERE, "refshader.npz"), **d)
 
 

@@ -47,3 +47,15 @@ def render(tris, nodes, cfg, hdr, hdr_cache=None, hdr_linear=True, framebuffer=N
     if rc != 0:
         raise RuntimeError("refshader_render failed (%d)" % rc)
     return fb
+
+
+def pass3(image):
+    """shaders/pass3.fsh (tone mapping + gamma) on an [H,W,C>=3] float image -> [H,W,3]"""
+    lib = _load()
+    lib.refshader_pass3.restype = C.c_int
+    lib.refshader_pass3.argtypes = [_fp, C.c_int, C.c_int, C.c_int, _fp]
+    image = np.ascontiguousarray(image, np.float32)
+    h, w, c = image.shape
+    out = np.zeros((h, w, 3), np.float32)
+    assert lib.refshader_pass3(image.ctypes.data_as(_fp), c, w, h, out.ctypes.data_as(_fp)) == 0
+    return out

@@ -65,6 +65,27 @@ def test_gpu_tonemap_matches_oracle(oracle):
 
 
 @pytest.mark.gpu
+def test_gpu_tonemap_reproduces_reference_pass3_golden():
+    """tests/golden/refshader.npz: output of the reference's own shaders/pass3.fsh (transpiled) for a fixed HDR frame"""
+    import torch
+    from tests import refshader_cases as cases
+    from tests.test_ref_shader import _hdr_frame
+    got = api.post_tonemap(torch.from_numpy(_hdr_frame()).cuda()).cpu().numpy()
+    assert got.tobytes() == cases.load()["pass3_out"].tobytes()
+
+
+@pytest.mark.gpu
+def test_gpu_hdr_cache_reproduces_reference_computed_golden():
+    """tests/golden/refhost.npz: the cache the reference's own calculateHdrCache computed (P5/main.cpp compiled in the
+    authoring container) for the synthetic environment; the GPU kernels must produce the same bytes."""
+    import os
+    from ezrt_b200 import scenes
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refhost.npz"))
+    got = api.hdr_cache_device(scenes.synth_hdr(128, 64))
+    assert np.ascontiguousarray(got, np.float32).tobytes() == g["cache_128x64"].tobytes()
+
+
+@pytest.mark.gpu
 def test_gpu_hdr_cache_equals_host():
     """calculateHdrCache on the GPU keeps every fp32 sum in the reference's order -> identical bits."""
     import time

@@ -97,3 +97,26 @@ def test_oracle_equals_transpiled_shader_inside_a_box(oracle):
         want = refshader.render(tris, nodes, cfg, hdr, cache, hdr_linear=lin)
         got, _ = oracle.render(tris, nodes, cfg, hdr=hdr, hdr_cache=cache, hdr_linear=lin)
         assert same_bits(got, want), mode
+
+
+def _hdr_frame(seed=5, h=24, w=40, c=3):
+    rng = np.random.default_rng(seed)
+    fb = (rng.uniform(0, 1, (h, w, c)) ** 4 * 40.0).astype(np.float32)  # HDR range, many dark texels
+    fb[0, 0, :3] = 0.0
+    fb[0, 1, :3] = (1e-30, 1.0, 3e4)
+    return fb
+
+
+@needs_reference
+@pytest.mark.parametrize("channels", [3, 4])
+def test_tonemap_equals_transpiled_pass3_shader(oracle, channels):
+    """shaders/pass3.fsh (identical in parts 3, 4, 5): toneMapping(c, 1.5) then pow(c, 1/2.2)"""
+    fb = _hdr_frame(c=channels)
+    want = refshader.pass3(fb)
+    assert same_bits(oracle.tonemap(fb), want)
+
+
+def test_tonemap_reproduces_reference_pass3_golden(oracle):
+    """runs everywhere: pass3 output of the reference shader for a fixed frame, committed in refshader.npz"""
+    g = cases.load()
+    assert same_bits(oracle.tonemap(_hdr_frame()), g["pass3_out"])
