@@ -81,7 +81,7 @@ def test_gpu_hdr_cache_reproduces_reference_computed_golden():
     import os
     from ezrt_b200 import scenes
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refhost.npz"))
-    got = api.hdr_cache_device(scenes.synth_hdr(128, 64))
+    got, _ = api.hdr_cache_device(scenes.synth_hdr(128, 64))
     assert np.ascontiguousarray(got, np.float32).tobytes() == g["cache_128x64"].tobytes()
 
 
