@@ -364,11 +364,12 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     std::vector<float4> acc_nodes, acc_geo((size_t)n_triangles * 4), acc_wide;
     int acc_wide_root = 0;
     std::vector<uint32_t> acc_order;
-    int acc_root_ref = 0, acc_top = 0, acc_inner = 0, acc_depth = 0;
+    int acc_root_ref = 0, acc_top = 0, acc_inner = 0, acc_depth = 0, acc_leaf_lanes = 8;
     {
         std::vector<EzrtAccelNode> an;
-        int acc_leaf_n = 8;  // one octet pass per leaf
+        int acc_leaf_n = 4;  // one quad of lanes per leaf, eight leaves per pass (EZRT_ACCEL_LEAF=8: octets, four per pass)
         if (const char* e = getenv("EZRT_ACCEL_LEAF")) acc_leaf_n = std::max(1, std::min(64, atoi(e)));
+        acc_leaf_lanes = (acc_leaf_n <= 4) ? 4 : 8;
         ezrt_build_accel(tris, n_triangles, acc_leaf_n, an, acc_order);
         const int na = (int)an.size();
         std::vector<int> aid(na, -1);
@@ -549,6 +550,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.acc_root_ref = acc_root_ref;
     d.acc_wide_nodes = acc_wide.empty() ? nullptr : (const float4*)sc->acc_wide.p;
     d.acc_wide_root_ref = acc_wide_root;
+    d.acc_leaf_lanes = acc_leaf_lanes;
     d.acc_top_nodes = acc_top;
     d.acc_tri_shade = (const float4*)((const char*)sc->acc_nodes.p + acc_nodes_bytes + acc_geo_bytes);
     d.acc_tri_leaf = (const int*)sc->acc_tri_leaf.p;

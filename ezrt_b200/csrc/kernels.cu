@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     io.to_accel = to_accel ? sc.ref_to_acc : nullptr;
     const TreeView tree = reference_tree(sc);
     stage_top_nodes(tree);
-    extend_persistent<PRUNE, ANYHIT, false, false>(sc, tree, *q_count, work, io, g_smem_top);
+    extend_persistent<PRUNE, ANYHIT, false, false, 8>(sc, tree, *q_count, work, io, g_smem_top);
 }
 
 // ---- accel kernels: the device's own SAH tree finds the global closest hit G; the result is kept when
@@ -256,7 +256,8 @@ struct AccelIO {
     }
 };
 
-template <bool ANYHIT, bool WIDE>
+// LL = lanes per leaf in the cooperative leaf phase: 4 when the acceleration tree was built with leaves <= 4
+template <bool ANYHIT, bool WIDE, int LL>
 __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend_accel(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
                                                                       uint32_t* work, uint32_t* defer_list, uint32_t* defer_count) {
     AccelIO io;
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     } else {
         stage_top_nodes(tree);
     }
-    extend_persistent<true, ANYHIT, true, WIDE>(sc, tree, *q_count, work, io, g_smem_top);
+    extend_persistent<true, ANYHIT, true, WIDE, LL>(sc, tree, *q_count, work, io, g_smem_top);
 }
 
 // ---- shadow rays: any hit; an unoccluded ray adds its precomputed contribution (P5/fsh:829-841).
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     io.perm = perm;
     const TreeView tree = reference_tree(sc);
     stage_top_nodes(tree);
-    extend_persistent<PRUNE, true, false, false>(sc, tree, *s_count, work, io, g_smem_top);
+    extend_persistent<PRUNE, true, false, false, 8>(sc, tree, *s_count, work, io, g_smem_top);
 }
 
 struct ShadowAccelIO {
@@ -332,7 +333,7 @@ struct ShadowAccelIO {
     }
 };
 
-template <bool WIDE>
+template <bool WIDE, int LL>
 __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_shadow_accel(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count,
                                                                       uint32_t* work, float4* __restrict__ Lo, uint32_t* defer_list,
                                                                       uint32_t* defer_count) {
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     } else {
         stage_top_nodes(tree);
     }
-    extend_persistent<true, true, true, WIDE>(sc, tree, *s_count, work, io, g_smem_top);
+    extend_persistent<true, true, true, WIDE, LL>(sc, tree, *s_count, work, io, g_smem_top);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -665,14 +666,16 @@ void launch_extend(const SceneDev& sc, bool prune, bool anyhit, PathQueue q, con
 void launch_extend_accel(const SceneDev& sc, bool anyhit, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t* defer_list,
                          uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, cudaStream_t st) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
+#define EZRT_LAUNCH_EA(AH, W, L, TOP) k_extend_accel<AH, W, L><<<blocks, threads, smem_for(k_extend_accel<AH, W, L>, TOP), st>>>(sc, q, q_count, work, defer_list, defer_count)
     if (sc.acc_wide_nodes) {
-        if (anyhit) k_extend_accel<true, true><<<blocks, threads, smem_for(k_extend_accel<true, true>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count);
-        else k_extend_accel<false, true><<<blocks, threads, smem_for(k_extend_accel<false, true>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count);
+        if (sc.acc_leaf_lanes == 4) { if (anyhit) EZRT_LAUNCH_EA(true, true, 4, 0); else EZRT_LAUNCH_EA(false, true, 4, 0); }
+        else { if (anyhit) EZRT_LAUNCH_EA(true, true, 8, 0); else EZRT_LAUNCH_EA(false, true, 8, 0); }
     } else if (anyhit) {
-        k_extend_accel<true, false><<<blocks, threads, smem_for(k_extend_accel<true, false>, sc.acc_top_nodes), st>>>(sc, q, q_count, work, defer_list, defer_count);
+        EZRT_LAUNCH_EA(true, false, 8, sc.acc_top_nodes);
     } else {
-        k_extend_accel<false, false><<<blocks, threads, smem_for(k_extend_accel<false, false>, sc.acc_top_nodes), st>>>(sc, q, q_count, work, defer_list, defer_count);
+        EZRT_LAUNCH_EA(false, false, 8, sc.acc_top_nodes);
     }
+#undef EZRT_LAUNCH_EA
     launch_extend(sc, true, anyhit, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_max, 65536u), n_sms, st);
 }
 // counting sort of the queue's ray indices into `perm` (3 kernels; bins must hold EZRT_SORT_BINS counters)
@@ -693,8 +696,12 @@ void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_
 void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo, uint32_t* defer_list,
                          uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, cudaStream_t st) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
-    if (sc.acc_wide_nodes) k_shadow_accel<true><<<blocks, threads, smem_for(k_shadow_accel<true>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
-    else k_shadow_accel<false><<<blocks, threads, smem_for(k_shadow_accel<false>, sc.acc_top_nodes), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
+    if (sc.acc_wide_nodes && sc.acc_leaf_lanes == 4)
+        k_shadow_accel<true, 4><<<blocks, threads, smem_for(k_shadow_accel<true, 4>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
+    else if (sc.acc_wide_nodes)
+        k_shadow_accel<true, 8><<<blocks, threads, smem_for(k_shadow_accel<true, 8>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
+    else
+        k_shadow_accel<false, 8><<<blocks, threads, smem_for(k_shadow_accel<false, 8>, sc.acc_top_nodes), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
     launch_shadow(sc, true, sq, defer_count, defer_work, Lo, defer_list, std::min<uint32_t>(n_max, 65536u), n_sms, st);
 }
 void launch_shade(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, int bounce, uint32_t batch_first_frame,
