@@ -77,7 +77,7 @@ struct ezrt_scene {
     int n_sms = 148;
     SceneDev dev{};
     DeviceBuffer nodes, tri_geo, tri_shade, materials, hdr, hdr_cache;
-    DeviceBuffer acc_nodes, acc_tri_geo, acc_tri_ref, tri_leaf, leaf_box, defer_buf, acc_tri_shade, acc_tri_leaf, ref_to_acc, acc_wide, acc_quad;
+    DeviceBuffer acc_nodes, acc_tri_geo, acc_tri_ref, tri_leaf, leaf_box, defer_buf, acc_tri_shade, acc_tri_leaf, ref_to_acc, acc_wide;
     int acc_depth = 0;
     int n_materials = 0;
     int tree_depth = 0;
@@ -361,7 +361,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
 
     // ---- acceleration tree: sentinel-free SAH over the same triangles (DESIGN.md "accel") ----
     const float prune_delta = max_abs * 1.52587890625e-05f;  // 2^-16 * scene extent
-    std::vector<float4> acc_nodes, acc_geo((size_t)n_triangles * 4), acc_wide, acc_quad;
+    std::vector<float4> acc_nodes, acc_geo((size_t)n_triangles * 4), acc_wide;
     int acc_wide_root = 0;
     std::vector<uint32_t> acc_order;
     int acc_root_ref = 0, acc_top = 0, acc_inner = 0, acc_depth = 0, acc_leaf_lanes = 8;
@@ -465,21 +465,10 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
                 memcpy(&rec[24], refs, 16);
                 for (int k = 24 + 4; k < 32; k++) rec[k] = 0.0f;
                 memcpy(&acc_wide[(size_t)id * 8], rec, sizeof(rec));
-                // quad layout of the same node (quad-per-ray kernels): child k = (AA.x, AA.y, AA.z, BB.x), (BB.y, BB.z, ref, 0)
-                if (acc_quad.size() < acc_wide.size()) acc_quad.resize(acc_wide.size(), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
-                for (int k = 0; k < 4; k++) {
-                    float4 lo = make_float4(rec[4 * k + 0], rec[4 * k + 1], rec[16 + 2 * k], rec[4 * k + 2]);
-                    float4 hi = make_float4(rec[4 * k + 3], rec[16 + 2 * k + 1], 0.0f, 0.0f);
-                    memcpy(&hi.z, &refs[k], 4);
-                    acc_quad[(size_t)id * 8 + 2 * k] = lo;
-                    acc_quad[(size_t)id * 8 + 2 * k + 1] = hi;
-                }
                 return id;
             };
             acc_wide_root = build_wide(0, 1);
             if (3 * wide_depth + 2 > EZRT_MAX_STACK) acc_wide.clear();  // too deep for the traversal stack: keep the binary form
-            const char* qe = getenv("EZRT_ACCEL_QUAD");
-            if (acc_wide.empty() || acc_leaf_lanes != 4 || (qe && atoi(qe) == 0)) acc_quad.clear();
         }
     }
     // shading data and the reference-leaf map in the acceleration tree's order, and the inverse permutation
@@ -531,7 +520,6 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     }
     if (!rc) rc = upload(sc->acc_tri_ref, acc_order.data(), acc_order.size() * sizeof(uint32_t));
     if (!rc && !acc_wide.empty()) rc = upload(sc->acc_wide, acc_wide.data(), acc_wide.size() * sizeof(float4));
-    if (!rc && !acc_quad.empty()) rc = upload(sc->acc_quad, acc_quad.data(), acc_quad.size() * sizeof(float4));
     if (!rc) rc = upload(sc->tri_leaf, tri_leaf.data(), tri_leaf.size() * sizeof(int));
     if (!rc) rc = upload(sc->leaf_box, leaf_box.data(), leaf_box.size() * sizeof(float4));
     if (!rc) rc = upload(sc->acc_tri_leaf, acc_leaf.data(), acc_leaf.size() * sizeof(int));
@@ -562,7 +550,6 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.acc_root_ref = acc_root_ref;
     d.acc_wide_nodes = acc_wide.empty() ? nullptr : (const float4*)sc->acc_wide.p;
     d.acc_wide_root_ref = acc_wide_root;
-    d.acc_quad_nodes = acc_quad.empty() ? nullptr : (const float4*)sc->acc_quad.p;
     d.acc_leaf_lanes = acc_leaf_lanes;
     d.acc_top_nodes = acc_top;
     d.acc_tri_shade = (const float4*)((const char*)sc->acc_nodes.p + acc_nodes_bytes + acc_geo_bytes);
@@ -612,7 +599,7 @@ int ezrt_scene_destroy(ezrt_scene* s) {
     s->nodes.release(); s->tri_geo.release(); s->tri_shade.release(); s->materials.release();
     s->hdr.release(); s->hdr_cache.release(); s->tiles_buf.release();
     s->acc_nodes.release(); s->acc_tri_geo.release(); s->acc_tri_ref.release(); s->tri_leaf.release(); s->leaf_box.release(); s->defer_buf.release();
-    s->acc_tri_shade.release(); s->acc_tri_leaf.release(); s->ref_to_acc.release(); s->acc_wide.release(); s->acc_quad.release();
+    s->acc_tri_shade.release(); s->acc_tri_leaf.release(); s->ref_to_acc.release(); s->acc_wide.release();
     s->queue_buf[0].release(); s->queue_buf[1].release(); s->shadow_buf.release();
     s->lo_buf.release(); s->le_buf.release(); s->counters_buf.release(); s->totals_buf.release(); s->fb_buf.release(); s->sort_buf.release();
     if (s->own_stream) cudaStreamDestroy(s->own_stream);

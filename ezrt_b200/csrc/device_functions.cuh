@@ -658,204 +658,6 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
 #undef STACK_POP
 
 // ------------------------------------------------------------------------------------------
-// Quad-per-ray traversal of the 4-wide acceleration tree (accel policy, leaves <= 4).
-// Four adjacent lanes trace ONE ray: at an inner node lane j tests child j (the node's 128-byte record
-// is one cache line read by the four lanes, 32 bytes each -- a quarter of the L1 wavefronts of the
-// lane-per-ray kernel, where every lane reads its own line); at a leaf lane j tests triangle j.  No
-// ray data has to be shuffled to helper lanes, and a warp diverges over 8 rays instead of 32.
-// The quad's stack lives in shared memory, [entry][quad], EZRT_QUAD_STACK entries; a ray that would
-// overflow it is handed to the exact kernel (io.defer), like ties and non-finite directions.
-//   qnodes: child j of node i at float4 [8 i + 2 j] = (AA.x, AA.y, AA.z, BB.x), (BB.y, BB.z, ref bits, 0)
-// Same result contract as extend_persistent<.., ACCEL = true, ..>.
-// ------------------------------------------------------------------------------------------
-#ifndef EZRT_QUAD_STACK
-#define EZRT_QUAD_STACK 24
-#endif
-// 32-bit shared-window addressing (a generic pointer costs an S2R + LEA per access)
-__device__ __forceinline__ void sts64(uint32_t addr, int2 v) { asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory"); }
-__device__ __forceinline__ int2 lds64(uint32_t addr) {
-    int2 v;
-    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
-    return v;
-}
-template <bool ANYHIT, class RayIO>
-__device__ __forceinline__ void extend_quad(const SceneDev& sc, const float4* __restrict__ qnodes, const int root_ref,
-                                            const float4* __restrict__ tri_geo, uint32_t n, uint32_t* work, RayIO io, int2* smem_stack) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, sub = lane & 3, qbase = lane & ~3;
-    const unsigned qmask = 0xFu << qbase;
-    const unsigned below_q = ((1u << qbase) - 1u) & 0x11111111u;  // one bit per lower quad
-    const int n_quads = blockDim.x >> 2;
-    const uint32_t stack = (uint32_t)__cvta_generic_to_shared(smem_stack + (threadIdx.x >> 2));  // entry e at stack + e * stride
-    const uint32_t stride = (uint32_t)n_quads * (uint32_t)sizeof(int2);
-    const int refill_thresh = sc.refill_thresh, inner_thresh = sc.inner_thresh, leaf_thresh = sc.leaf_thresh;
-    int sp = 0;
-    int ray = -1;
-    int ref = EZRT_REF_DONE;
-    vec3 o = splat3(0.0f), d = splat3(0.0f), inv = splat3(0.0f);
-    float slack = 0.0f, best = EZ_INF;
-    int best_tri = -1;
-    bool tie = false, overflow = false;
-    bool exhausted = false;
-    uint32_t chunk_pos = 0, chunk_end = 0;
-    const uint32_t chunk = (uint32_t)sc.work_chunk;
-
-    while (true) {
-        // ---------------- refill idle quads (one ray index per quad) ----------------
-        const unsigned need = __ballot_sync(FULL, ray < 0);
-        if (need != 0u && !exhausted) {
-            if (chunk_pos >= chunk_end) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(work, chunk);
-                base = __shfl_sync(FULL, base, 0);
-                chunk_pos = base;
-                chunk_end = (base + chunk < n) ? base + chunk : n;
-                if (base >= n) exhausted = true;
-            }
-            if (!exhausted && ray < 0) {
-                const uint32_t idx = chunk_pos + (uint32_t)__popc(need & below_q);
-                if (idx < chunk_end) {
-                    io.load(idx, o, d);  // the four lanes read the same words (one broadcast transaction)
-                    inv = ez_v3(EZ_DIV(1.0f, d.x), EZ_DIV(1.0f, d.y), EZ_DIV(1.0f, d.z));
-                    const float ax = ez_abs(inv.x), ay = ez_abs(inv.y), az = ez_abs(inv.z);
-                    slack = sc.prune_delta * ez_max(ax, ez_max(ay, az));
-                    if ((ax < 3.0e38f) && (ay < 3.0e38f) && (az < 3.0e38f)) {
-                        ray = (int)idx;
-                        ref = root_ref;
-                        sp = 0;
-                        best = EZ_INF;
-                        best_tri = -1;
-                        tie = false;
-                        overflow = false;
-                    } else if (sub == 0) {  // the exact kernel handles the literal ternary min/max path
-                        io.defer(idx);
-                    }
-                }
-            }
-            if (!exhausted) {
-                const uint32_t take = (uint32_t)__popc(need & 0x11111111u);
-                chunk_pos = (chunk_pos + take < chunk_end) ? chunk_pos + take : chunk_end;
-            }
-        }
-        if (__ballot_sync(FULL, ray >= 0) == 0u) {
-            if (exhausted) break;
-            continue;
-        }
-        unsigned busy;
-        do {
-            // ---------------- inner phase: quads standing at an inner node visit it ----------------
-            const unsigned m_busy = __ballot_sync(FULL, ray >= 0);
-            while (true) {
-                const bool at_inner = (ray >= 0) && (ref >= 0);
-                const unsigned m_inner = __ballot_sync(FULL, at_inner);
-                if (m_inner == 0u) break;
-                const unsigned m_wait = m_busy & ~m_inner;
-                if (m_wait != 0u && (__popc(m_inner) < inner_thresh || __popc(m_wait) >= leaf_thresh)) break;
-                // the warp-wide votes and shuffles run unconditionally (full mask: no MATCH/WARPSYNC on per-quad masks);
-                // quads not standing at an inner node carry a missed child through them
-                bool ok = false;
-                float key = 3.0e38f;
-                int cref = EZRT_REF_DONE;
-                if (at_inner) {
-                    float4 a, b;
-                    ldg256_f32(qnodes + (size_t)ref * 8 + sub * 2, a, b);
-                    const float nx = (a.x - o.x) * inv.x, ny = (a.y - o.y) * inv.y, nz = (a.z - o.z) * inv.z;
-                    const float fx = (a.w - o.x) * inv.x, fy = (b.x - o.y) * inv.y, fz = (b.y - o.z) * inv.z;
-                    const float t0 = fmaxf(fmaxf(fminf(fx, nx), fminf(fy, ny)), fminf(fz, nz));
-                    const float t1 = fminf(fminf(fmaxf(fx, nx), fmaxf(fy, ny)), fmaxf(fz, nz));
-                    const float limit = best + (best * 0.000244140625f + slack);
-                    ok = (t1 >= t0) && (t1 > 0.0f) && !(t0 > limit);  // hitAABB > 0 and not beyond the best hit
-                    key = ok ? t0 : 3.0e38f;
-                    cref = __float_as_int(b.z);
-                }
-                // rank of this child among the four by entry distance (ties: lower lane first)
-                const float k1 = __shfl_xor_sync(FULL, key, 1), k2 = __shfl_xor_sync(FULL, key, 2), k3 = __shfl_xor_sync(FULL, key, 3);
-                const int rank = (int)((k1 < key) || (k1 == key && (sub ^ 1) < sub)) + (int)((k2 < key) || (k2 == key && (sub ^ 2) < sub)) +
-                                 (int)((k3 < key) || (k3 == key && (sub ^ 3) < sub));
-                const int nh = __popc(__ballot_sync(FULL, ok) & qmask);
-                const unsigned zb = __ballot_sync(FULL, ok && rank == 0) & qmask;
-                const int nearest = __shfl_sync(FULL, cref, (zb != 0u) ? __ffs(zb) - 1 : lane);
-                if (at_inner) {
-                    if (nh > 0) {
-                        if (sp + nh - 1 > EZRT_QUAD_STACK) {  // no room: give the ray to the exact kernel
-                            overflow = true;
-                            ref = EZRT_REF_DONE;
-                            sp = 0;
-                        } else {
-                            if (ok && rank > 0) sts64(stack + (uint32_t)(sp + (nh - 1 - rank)) * stride, make_int2(cref, __float_as_int(key)));  // nearest on top
-                            sp += nh - 1;
-                            ref = nearest;
-                        }
-                    } else {  // pop
-                        ref = EZRT_REF_DONE;
-                        while (sp > 0) {
-                            const int2 e = lds64(stack + (uint32_t)(--sp) * stride);
-                            if (prune_test(__int_as_float(e.y), best, slack)) continue;
-                            ref = e.x;
-                            break;
-                        }
-                    }
-                }
-                __syncwarp();  // this step's pushes are visible to the quad before anyone pops
-            }
-            // ---------------- leaf phase: every quad standing at a leaf tests its triangles, four per pass ----------------
-            // (the acceleration tree is built with leaves <= 4 for this kernel: one pass)
-            const bool at_leaf = (ray >= 0) && (ref < 0) && (ref != EZRT_REF_DONE);
-            const uint32_t bits = (uint32_t)ref & 0x7fffffffu;
-            int cnt = at_leaf ? (int)(bits & 127u) : 0;
-            int first = (int)(bits >> 7);
-            bool stop = false;
-            while (__ballot_sync(FULL, cnt > 0) != 0u) {
-                unsigned tb = 0xffffffffu;
-                if (sub < cnt) {
-                    float t;
-                    if (tri_test_t<true>(tri_geo + (size_t)(first + sub) * 4, o, d, best, t) != 0) tb = __float_as_uint(t);
-                }
-                unsigned mn = min(tb, __shfl_xor_sync(FULL, tb, 1));
-                mn = min(mn, __shfl_xor_sync(FULL, mn, 2));
-                const unsigned win = (__ballot_sync(FULL, tb == mn && tb != 0xffffffffu) >> qbase) & 0xFu;
-                if (win != 0u) {
-                    const float tn = __uint_as_float(mn);
-                    if (__popc(win) > 1 || tn == best) tie = true;
-                    if (tn < best) {
-                        best = tn;
-                        best_tri = first + __ffs(win) - 1;
-                    }
-                    if (ANYHIT) stop = true;
-                }
-                first += 4;
-                cnt = stop ? 0 : cnt - 4;
-            }
-            if (at_leaf) {
-                ref = EZRT_REF_DONE;
-                if (!stop) {
-                    while (sp > 0) {
-                        const int2 e = lds64(stack + (uint32_t)(--sp) * stride);
-                        if (prune_test(__int_as_float(e.y), best, slack)) continue;
-                        ref = e.x;
-                        break;
-                    }
-                }
-            }
-            if (ray >= 0 && ref == EZRT_REF_DONE) {  // ray finished
-                if (sub == 0) {
-                    if (overflow) {
-                        io.defer((uint32_t)ray);
-                    } else {
-                        HitRec h;
-                        h.t = best;
-                        h.tri = best_tri;
-                        io.store((uint32_t)ray, h, tie, o, make_ray_slab(o, inv));
-                    }
-                }
-                ray = -1;
-            }
-            busy = __ballot_sync(FULL, ray >= 0);
-        } while (busy != 0u && (exhausted || __popc(busy) >= refill_thresh));
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // hit geometry + material for the final closest hit (tail of hitTriangle :198-214, getMaterial :110-135)
 // ------------------------------------------------------------------------------------------
 struct MaterialDev {

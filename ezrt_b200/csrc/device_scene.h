@@ -54,7 +54,6 @@ struct SceneDev {
     int acc_top_nodes;
     const float4* acc_wide_nodes;  // the same tree collapsed to 4-wide nodes (128 B records); null = use the binary form
     int acc_wide_root_ref;
-    const float4* acc_quad_nodes;  // the 4-wide tree in quad layout (child j = 32 contiguous bytes) for the quad-per-ray kernels; null = not used
     int acc_leaf_lanes;      // lanes per leaf in the cooperative leaf phase of the accel kernels: 4 (leaves <= 4) or 8
     // reference leaf of every reference triangle + the leaves' boxes (AA, BB as float4 pairs)
     const int* tri_leaf;

@@ -278,19 +278,6 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     extend_persistent<true, ANYHIT, true, WIDE, LL>(sc, tree, *q_count, work, io, g_smem_top);
 }
 
-// quad-per-ray form of k_extend_accel (device_functions.cuh extend_quad): four lanes per ray, child j / triangle j per lane
-template <bool ANYHIT>
-__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend_quad(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
-                                                                     uint32_t* work, uint32_t* defer_list, uint32_t* defer_count) {
-    AccelIO io;
-    io.q = q;
-    io.acc_tri_leaf = sc.acc_tri_leaf;
-    io.leaf_box = sc.leaf_box;
-    io.defer_list = defer_list;
-    io.defer_count = defer_count;
-    extend_quad<ANYHIT>(sc, sc.acc_quad_nodes, sc.acc_wide_root_ref, sc.acc_tri_geo, *q_count, work, io, reinterpret_cast<int2*>(g_smem_top));
-}
-
 // ---- shadow rays: any hit; an unoccluded ray adds its precomputed contribution (P5/fsh:829-841).
 // One path per sample slot -> no two lanes touch the same Lo entry.
 struct ShadowIO {
@@ -368,20 +355,6 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
         stage_top_nodes(tree);
     }
     extend_persistent<true, true, true, WIDE, LL>(sc, tree, *s_count, work, io, g_smem_top);
-}
-
-__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_shadow_quad(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count,
-                                                                     uint32_t* work, float4* __restrict__ Lo, uint32_t* defer_list,
-                                                                     uint32_t* defer_count) {
-    ShadowAccelIO io;
-    io.base.sq = sq;
-    io.base.Lo = Lo;
-    io.base.perm = nullptr;
-    io.acc_tri_leaf = sc.acc_tri_leaf;
-    io.leaf_box = sc.leaf_box;
-    io.defer_list = defer_list;
-    io.defer_count = defer_count;
-    extend_quad<true>(sc, sc.acc_quad_nodes, sc.acc_wide_root_ref, sc.acc_tri_geo, *s_count, work, io, reinterpret_cast<int2*>(g_smem_top));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -674,11 +647,6 @@ static size_t smem_for(K kernel, int top_nodes) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bytes, 1024));
     return bytes;
 }
-static size_t quad_smem(int threads) { return (size_t)EZRT_QUAD_STACK * (size_t)(threads / 4) * sizeof(int2); }
-template <class K>
-static void set_smem(K kernel, size_t bytes) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bytes, 1024));
-}
 static int persistent_blocks(uint32_t n_max, int n_sms) {
     int blocks = std::min(div_up(n_max, extend_threads()), n_sms * extend_blocks_per_sm());
     return blocks < 1 ? 1 : blocks;
@@ -698,13 +666,6 @@ void launch_extend(const SceneDev& sc, bool prune, bool anyhit, PathQueue q, con
 void launch_extend_accel(const SceneDev& sc, bool anyhit, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t* defer_list,
                          uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, cudaStream_t st) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
-    if (sc.acc_quad_nodes) {  // quad-per-ray kernel: the stack of every quad lives in shared memory
-        const size_t smem = quad_smem(threads);
-        if (anyhit) { set_smem(k_extend_quad<true>, smem); k_extend_quad<true><<<blocks, threads, smem, st>>>(sc, q, q_count, work, defer_list, defer_count); }
-        else { set_smem(k_extend_quad<false>, smem); k_extend_quad<false><<<blocks, threads, smem, st>>>(sc, q, q_count, work, defer_list, defer_count); }
-        launch_extend(sc, true, anyhit, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_max, 65536u), n_sms, st);
-        return;
-    }
 #define EZRT_LAUNCH_EA(AH, W, L, TOP) k_extend_accel<AH, W, L><<<blocks, threads, smem_for(k_extend_accel<AH, W, L>, TOP), st>>>(sc, q, q_count, work, defer_list, defer_count)
     if (sc.acc_wide_nodes) {
         if (sc.acc_leaf_lanes == 4) { if (anyhit) EZRT_LAUNCH_EA(true, true, 4, 0); else EZRT_LAUNCH_EA(false, true, 4, 0); }
@@ -735,11 +696,7 @@ void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_
 void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo, uint32_t* defer_list,
                          uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, cudaStream_t st) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
-    if (sc.acc_quad_nodes) {
-        const size_t smem = quad_smem(threads);
-        set_smem(k_shadow_quad, smem);
-        k_shadow_quad<<<blocks, threads, smem, st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
-    } else if (sc.acc_wide_nodes && sc.acc_leaf_lanes == 4)
+    if (sc.acc_wide_nodes && sc.acc_leaf_lanes == 4)
         k_shadow_accel<true, 4><<<blocks, threads, smem_for(k_shadow_accel<true, 4>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
     else if (sc.acc_wide_nodes)
         k_shadow_accel<true, 8><<<blocks, threads, smem_for(k_shadow_accel<true, 8>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
