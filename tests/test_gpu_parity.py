@@ -517,3 +517,42 @@ def test_irregular_caller_tree_is_walked_literally(oracle, bunny_scene, policy):
         assert sc.counters().rays == rc["rays"]
     finally:
         sc.close()
+
+
+# ------------------------------------------------------------------ BASELINE.json's full-size configuration
+def test_c3_full_size_scene_matches_oracle_and_policies_agree(oracle):
+    """The 999,692-triangle scene of configs[2] (C3) itself: (i) a small image of it against the CPU oracle, bit for
+    bit, in the Sobol and the IS/MIS mode; (ii) the full 1920x1080 frame under the three traversal policies --
+    identical bits (a checksum of checksums over rows) and identical ray counts; (iii) 2 x 1 spp == 1 x 2 spp."""
+    import zlib
+    tris, nodes, eye, cam = scenes.s_1m()
+    hdr = scenes.synth_hdr(256, 128)
+    cache = api.hdr_cache(hdr)
+    sc = api.Scene(tris, nodes, hdr, cache)
+    try:
+        for mode in (api.MODE_DISNEY_SOBOL_P5, api.MODE_DISNEY_IS_MIS_P5):
+            cfg = _cfg(eye, cam, mode=mode, max_bounce=2, width=96, height=54, spp=2)
+            ref, rc = oracle.render(tris, nodes, cfg, hdr=hdr, hdr_cache=cache)
+            got = sc.render(cfg)
+            assert_same_bits(got, ref, "1M-triangle scene, mode %d" % mode)
+            assert sc.counters().rays == rc["rays"]
+        sums, rays = [], []
+        for policy in (api.TRAVERSE_ACCEL, api.TRAVERSE_PRUNED, api.TRAVERSE_REFERENCE):
+            cfg = _cfg(eye, cam, mode=api.MODE_DISNEY_SOBOL_P5, max_bounce=2, width=1920, height=1080, spp=1, traverse=policy)
+            img = sc.render(cfg)
+            assert np.isfinite(img).all()
+            sums.append(zlib.crc32(np.array([zlib.crc32(np.ascontiguousarray(row).tobytes()) for row in img], np.uint32).tobytes()))
+            rays.append(sc.counters().rays)
+            if policy == api.TRAVERSE_ACCEL:
+                first = img
+                c = sc.counters()
+                assert c.deferred_rays < 0.01 * c.rays, "the accel policy defers only ties / unreachable leaves"
+        assert sums[0] == sums[1] == sums[2] and rays[0] == rays[1] == rays[2]
+        # accumulation: frame 0 then frame 1 on top == two frames at once
+        cfg2 = _cfg(eye, cam, mode=api.MODE_DISNEY_SOBOL_P5, max_bounce=2, width=1920, height=1080, spp=2)
+        both = sc.render(cfg2)
+        cfg1 = _cfg(eye, cam, mode=api.MODE_DISNEY_SOBOL_P5, max_bounce=2, width=1920, height=1080, spp=1, first_frame=1)
+        step = sc.render(cfg1, framebuffer=first.reshape(-1, 3).copy())
+        assert_same_bits(step, both, "frame-by-frame accumulation at full size")
+    finally:
+        sc.close()
