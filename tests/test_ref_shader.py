@@ -120,3 +120,39 @@ def test_tonemap_reproduces_reference_pass3_golden(oracle):
     """runs everywhere: pass3 output of the reference shader for a fixed frame, committed in refshader.npz"""
     g = cases.load()
     assert same_bits(oracle.tonemap(_hdr_frame()), g["pass3_out"])
+
+
+@needs_reference
+def test_oracle_equals_transpiled_shader_on_degenerate_soup(oracle):
+    """zero-area triangles (NaN normals), slivers, duplicated vertices, axis-aligned coordinates: the NaN / tie
+    behaviour of the oracle is the shader's, statement by statement"""
+    from tests.test_gpu_parity import _soup
+    tl = api.TriangleList()
+    tl.append_encoded(_soup(3000, 4))
+    tris, nodes = tl.build_bvh(8)
+    hdr, cache = cases.environment()
+    eye, cam = api.camera_orbit(30.0, 20.0, 6.0)
+    for mode, mb, lin in ((0, 3, False), (1, 3, False), (2, 2, True), (3, 2, True)):
+        cfg = api.RenderConfig(width=64, height=48, spp=2, max_bounce=mb, mode=mode, eye=tuple(eye), camera_rotate=tuple(cam),
+                               traverse=api.TRAVERSE_REFERENCE)
+        want = refshader.render(tris, nodes, cfg, hdr, cache, hdr_linear=lin)
+        got, _ = oracle.render(tris, nodes, cfg, hdr=hdr, hdr_cache=cache, hdr_linear=lin)
+        assert same_bits(got, want), mode
+
+
+@needs_reference
+def test_oracle_equals_transpiled_shader_on_the_reference_p5_scene(oracle):
+    """the reference's own shipped P5 set-up, end to end: its main() (compiled here, tests/refhost_binding.py) supplies
+    the texture buffers, the HDR map and the sampling cache; its shader (transpiled) renders them with its own camera
+    (P5/main.cpp:796-798) at a reduced size; the oracle must agree bit for bit"""
+    from tests import refhost_binding as refhost
+    if not refhost.available():
+        pytest.skip("reference host sources not present")
+    tris, nodes, hdr, cache = refhost.run_main()
+    eye, cam = api.camera_orbit(90.0, 10.0, 2.0)
+    cfg = api.RenderConfig(width=64, height=64, spp=2, max_bounce=2, mode=api.MODE_DISNEY_IS_MIS_P5, eye=tuple(eye), camera_rotate=tuple(cam),
+                           traverse=api.TRAVERSE_REFERENCE)
+    want = refshader.render(tris, nodes, cfg, hdr, cache, hdr_linear=True)
+    got, c = oracle.render(tris, nodes, cfg, hdr=hdr, hdr_cache=cache, hdr_linear=True)
+    assert c["rays_shadow"] > 0 and float(want.mean()) > 0.01
+    assert same_bits(got, want)
