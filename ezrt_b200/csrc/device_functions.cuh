@@ -93,8 +93,15 @@ __device__ __forceinline__ pk2 pk2_mul(pk2 a, pk2 b) {
 }
 
 // 256-bit read-only global loads (32-byte aligned)
+#ifndef EZRT_NODE_L1_POLICY
+#define EZRT_NODE_L1_POLICY 0   // 1: node records are loaded with L1::evict_last (experiment: no difference, profiles/sweep_nodepol_r1.txt)
+#endif
 __device__ __forceinline__ void ldg256_b64(const void* p, ulonglong2& a, ulonglong2& b) {
+#if EZRT_NODE_L1_POLICY == 1
+    asm("ld.global.nc.L1::evict_last.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a.x), "=l"(a.y), "=l"(b.x), "=l"(b.y) : "l"(p));
+#else
     asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a.x), "=l"(a.y), "=l"(b.x), "=l"(b.y) : "l"(p));
+#endif
 }
 #ifndef EZRT_TRI_L1_POLICY
 #define EZRT_TRI_L1_POLICY 1   // 1: triangle records are read without allocating in L1 (64 MB streamed once per ray: the L1 is kept
