@@ -383,6 +383,10 @@ __device__ __forceinline__ HitRec trace_ray(const SceneDev& sc, vec3 o, vec3 d) 
 #ifndef EZRT_SMEM_STACK
 #define EZRT_SMEM_STACK 0   // stack entries kept in shared memory (experiment; 0 = all in local memory)
 #endif
+#ifndef EZRT_NODE_PREFETCH
+#define EZRT_NODE_PREFETCH 0   // 1: prefetch the next 4-wide node into L1 as soon as it is chosen (experiment: 1.3 % slower,
+                               // profiles/sweep_prefetch_r1.txt)
+#endif
 #ifndef EZRT_WIDE_SORT
 #define EZRT_WIDE_SORT 1    // 1: fully sort the children of a 4-wide node before pushing; 0: nearest first, the others
                             // unsorted (CPU model: +1 % visits, 20 instructions less per visit; measured 4 % slower on B200)
@@ -545,6 +549,9 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
 #endif
                         if (descend) {
                             ref = next;
+#if EZRT_NODE_PREFETCH
+                            if (next >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(tree.nodes + (size_t)next * 8));  // the whole 128-byte record
+#endif
                         } else {  // pop
                             ref = EZRT_REF_DONE;
                             while (sp > 0) {
