@@ -551,6 +551,8 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.acc_wide_nodes = acc_wide.empty() ? nullptr : (const float4*)sc->acc_wide.p;
     d.acc_wide_root_ref = acc_wide_root;
     d.acc_leaf_lanes = acc_leaf_lanes;
+    d.tri_l1_bypass = ((size_t)n_triangles * 64 > ((size_t)4 << 20)) ? 1 : 0;  // > 4 MB of triangle records: stream them past L1
+    if (const char* e = getenv("EZRT_TRI_L1_BYPASS")) d.tri_l1_bypass = atoi(e) != 0;
     d.acc_top_nodes = acc_top;
     d.acc_tri_shade = (const float4*)((const char*)sc->acc_nodes.p + acc_nodes_bytes + acc_geo_bytes);
     d.acc_tri_leaf = (const int*)sc->acc_tri_leaf.p;

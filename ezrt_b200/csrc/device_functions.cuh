@@ -103,18 +103,15 @@ __device__ __forceinline__ void ldg256_b64(const void* p, ulonglong2& a, ulonglo
     asm("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a.x), "=l"(a.y), "=l"(b.x), "=l"(b.y) : "l"(p));
 #endif
 }
-#ifndef EZRT_TRI_L1_POLICY
-#define EZRT_TRI_L1_POLICY 1   // 1: triangle records are read without allocating in L1 (64 MB streamed once per ray: the L1 is kept
-                               // for node records; +0.7 % on C3, profiles/sweep_l1pol_r1.txt); 2: evict_first; 0: default policy
-#endif
 __device__ __forceinline__ void ldg256_f32(const void* p, float4& a, float4& b) {
-#if EZRT_TRI_L1_POLICY == 1
-    asm("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-#elif EZRT_TRI_L1_POLICY == 2
-    asm("ld.global.nc.L1::evict_first.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-#else
     asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-#endif
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+// the same without allocating the line in L1 (LDG.NA): triangle records of a large scene are touched once per ray,
+// the L1 is better spent on node records (+0.7 % on the 1M-triangle scene, profiles/sweep_l1pol_r1.txt; a scene
+// whose triangles fit in L1/L2-near caches loses 20 % with it, so SceneDev::tri_l1_bypass is set by size)
+__device__ __forceinline__ void ldg256_f32_na(const void* p, float4& a, float4& b) {
+    asm("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
         : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
 
@@ -262,10 +259,15 @@ __device__ __forceinline__ void cswap(float& ka, int& ra, float& kb, int& rb) { 
 // TIES (accel policy): a hit at exactly t == best is also reported (return 2) so the caller can
 // detect that two triangles tie and let the exact reference-order traversal decide.
 template <bool TIES>
-__device__ __forceinline__ int tri_test_t(const float4* __restrict__ rec, vec3 o, vec3 d, float best, float& tout) {
+__device__ __forceinline__ int tri_test_t(const float4* __restrict__ rec, vec3 o, vec3 d, float best, float& tout, const bool l1_bypass = false) {
     float4 q0, q1, q2, q3;
-    ldg256_f32(rec, q0, q1);
-    ldg256_f32(rec + 2, q2, q3);
+    if (l1_bypass) {  // warp-uniform
+        ldg256_f32_na(rec, q0, q1);
+        ldg256_f32_na(rec + 2, q2, q3);
+    } else {
+        ldg256_f32(rec, q0, q1);
+        ldg256_f32(rec + 2, q2, q3);
+    }
     vec3 N = ez_v3(q0.w, q1.w, q2.w);
     float nd = ez_dot(N, d);
     if (ez_abs(nd) < 0.00001f) return 0;                        // :181 (|dot(+-N,d)| is sign-free)
@@ -428,6 +430,7 @@ template <bool PRUNE, bool ANYHIT, bool ACCEL, bool WIDE, int LL, class RayIO>
 __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const TreeView tree, uint32_t n, uint32_t* work, RayIO io,
                                                   const float4* smem_top) {
     const int top_nodes = tree.top_nodes;
+    const bool tri_na = sc.tri_l1_bypass != 0;
     bool tie = false;          // ACCEL: another triangle was accepted at exactly the best distance
     const int refill_thresh = sc.refill_thresh;  // go back to refill when fewer lanes than this are busy
     const int inner_thresh = sc.inner_thresh;    // leave the inner-node phase when fewer lanes than this walk
@@ -630,7 +633,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                 unsigned tb = 0xffffffffu;  // t bits of this lane's triangle, or "no hit"
                 if (owner >= 0 && k < rcnt) {
                     float t;
-                    if (tri_test_t<ACCEL>(tree.tri_geo + (size_t)(rfirst + k) * 4, ro, rdir, rbest, t) != 0) tb = __float_as_uint(t);
+                    if (tri_test_t<ACCEL>(tree.tri_geo + (size_t)(rfirst + k) * 4, ro, rdir, rbest, t, tri_na) != 0) tb = __float_as_uint(t);
                 }
                 unsigned mn = tb;
                 mn = min(mn, __shfl_xor_sync(FULL, mn, 1));

@@ -59,6 +59,7 @@ struct SceneDev {
     const int* tri_leaf;
     const float4* leaf_box;
     int n_triangles;
+    int tri_l1_bypass;        // triangle records are read with LDG.NA (set for scenes whose geometry exceeds a few MB)
     int n_inner;
     int top_nodes;            // records [0, top_nodes) = the top tree levels, staged in shared memory
     float prune_delta;        // 2^-16 * max |vertex coordinate|
