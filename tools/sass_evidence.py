@@ -26,7 +26,7 @@ def main():
     print("| kernel | instructions | " + " | ".join(c for c, _ in COLS) + " |")
     print("|---|---|" + "---|" * len(COLS))
     for (name, ins), dm in zip(kernels, demangled):
-        short = re.sub(r"\(.*", "", dm).replace("void ", "").replace("(anonymous namespace)::", "")
+        short = re.sub(r"\(.*", "", dm.replace("(anonymous namespace)::", "")).replace("void ", "")
         counts = [sum(1 for l in ins if re.search(rx, l)) for _, rx in COLS]
         print("| `%s` | %d | %s |" % (short, len(ins), " | ".join(str(c) for c in counts)))
     print("\nFADD2/FMUL2 = packed fp32x2 slab arithmetic (same bits as two scalar IEEE operations); LDG.E.ENL2.256 = 256-bit read-only loads of node "
