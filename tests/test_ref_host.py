@@ -153,3 +153,49 @@ def test_synthetic_scenes_equal_reference_built_golden(bunny_scene, grid_scene):
     for name, sc in (("bunny", bunny_scene), ("grid", grid_scene)):
         tris, nodes = sc[0], sc[1]
         assert (crc(tris), crc(nodes)) == (int(g[name + "_crc_tris"]), int(g[name + "_crc_nodes"])), name
+
+
+@needs_reference
+@pytest.mark.parametrize("form", ["v", "v/vt", "v/vt/vn"])
+def test_read_obj_face_forms_equal_reference(tmp_path, form):
+    """the three `f` forms the reference's parser distinguishes by counting slashes (P5/main.cpp:306-333), among vt / vn /
+    comment / blank lines and trailing spaces -- same triangles and tree as the reference's own parser.  (`v//vn` makes the
+    reference read uninitialised indices -- it crashes here; the product reads the leading integer of every token, see
+    test_read_obj_tolerates_the_form_the_reference_cannot_parse.)"""
+    base = scenes.blob_obj(2, 5).splitlines()
+    rng = np.random.default_rng(len(form))
+    out = ["# a comment", "", "vt 0.5 0.5", "vn 0 1 0"]
+    for ln in base:
+        if ln.startswith("f "):
+            ids = ln.split()[1:]
+            if form == "v":
+                tok = ids
+            elif form == "v/vt":
+                tok = ["%s/1" % i for i in ids]
+            elif form == "v/vt/vn":
+                tok = ["%s/1/1" % i for i in ids]
+            else:
+                tok = ["%s//1" % i for i in ids]
+            out.append("f " + " ".join(tok) + ("  " if rng.uniform() < 0.2 else ""))
+        else:
+            out.append(ln)
+    path = _write(tmp_path, "forms.obj", "\n".join(out) + "\n")
+    mat = api.Material(baseColor=(0.3, 0.5, 0.7))
+    trans = api.transform_matrix((10, 20, 30), (0.1, -0.2, 0.3), (1.5, 0.5, 1.0))
+    for smooth in (False, True):
+        r_tris, r_nodes = refhost.build_scene([(path, mat.as_array(), trans, smooth)], 8, True)
+        tl = api.TriangleList()
+        tl.read_obj(path, mat, trans, smooth)
+        tris, nodes = tl.build_bvh(8, api.BVH_SAH_FAST)
+        assert same_bytes(tris, r_tris) and same_bytes(nodes, r_nodes), (form, smooth)
+
+
+def test_read_obj_tolerates_the_form_the_reference_cannot_parse():
+    plain = "v 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nf 1 2 3\nf 1 3 4\n"
+    vn = "v 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nvn 0 0 1\nf 1//1 2//1 3//1\nf 1//1 3//1 4//1\n"
+    out = []
+    for text in (plain, vn):
+        tl = api.TriangleList()
+        tl.read_obj_text(text, api.Material(), api.transform_matrix(), False)
+        out.append(tl.build_bvh(8, api.BVH_SAH_LITERAL))
+    assert same_bytes(out[0][0], out[1][0]) and same_bytes(out[0][1], out[1][1])
