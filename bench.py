@@ -397,7 +397,10 @@ def main():
                     "traffic_frac_of_peak": NCU_DRAM_BYTES_PER_EXTEND_LAUNCH / (ext_ms * 1e-3 / max(1, ext_n)) / 1e9 / hbm_peak,
                     "ray_means": means, "extend_ms_per_launch": ext_ms / max(1, ext_n), "extend_launches": ext_n,
                     "extend_share_of_step": ext_ms / ms,
-                    "note": "achieved/frac = ALGORITHMIC demand bytes of the reference layout and traversal policy (SURVEY 8d: 48 N_node + 72 N_tri + 72 H + 24 per ray, oracle counters) with no cross-ray reuse; the kernel walks its own acceleration tree out of L2/L1, so frac >> 1 is expected. traffic_* = measured DRAM bytes (ncu): the kernel is bound by the L1 data pipe (~80 % of peak wavefronts) and issue slots (~65 %), not by HBM."}
+                    "note": "achieved/frac = ALGORITHMIC demand bytes of the reference layout and traversal policy (SURVEY 8d: 48 N_node + 72 N_tri + 72 H + 24 per ray, oracle counters) with no cross-ray reuse; the kernel walks its own acceleration tree out of L2/L1, so frac >> 1 is expected. traffic_* = measured DRAM bytes (ncu): the kernel is bound by the L1 data pipe and issue slots, not by HBM (measured_limiter).",
+                    "measured_limiter": {"source": "profiles/ncu_extend_r1_summary.md (ncu --set full, three launches of one batch)",
+                                         "l1tex_data_pipe_lsu_wavefronts_pct": [71.2, 82.5, 84.7], "issue_active_pct": [72.0, 63.4, 59.8],
+                                         "dram_throughput_pct": [3.5, 3.8, 4.7], "launches": ["camera rays", "bounce 1", "bounce 2"]}}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
