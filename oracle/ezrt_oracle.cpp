@@ -231,6 +231,9 @@ inline bool pruned(float t0, float best, float slack) {
 // ---------------------------------------------------------------- hitBVH, P5/fsh:254-306
 // (identical in P3/fsh:319-371 and P4/fsh:243-295).  P2's recursive C++ twin (P2/main.cpp:
 // 466-485) swaps n/index in its leaf call (:471); that bug is documented, not reproduced.
+float* g_rayDump = nullptr;  // see oracle_set_ray_dump
+uint64_t g_rayDumpCap = 0, g_rayDumpCount = 0;
+
 HitResult hitBVH(const Scene& sc, const Ray& ray, Counters& cn, int kind) {
     cn.rays[kind]++;
     HitResult res;
@@ -239,6 +242,15 @@ HitResult hitBVH(const Scene& sc, const Ray& ray, Counters& cn, int kind) {
     res.distance = EZ_INF;
     res.triangle = -1;
     res.hitPoint = res.normal = res.viewDir = ez_v3(0, 0, 0);
+
+    if (g_rayDump) {  // development aid (tools/accel_stats.cpp): record the rays a render traces, kind = 0 primary, 1 bounce, 2 shadow
+        const uint64_t k = __atomic_fetch_add(&g_rayDumpCount, 1, __ATOMIC_RELAXED);
+        if (k < g_rayDumpCap) {
+            float* r = g_rayDump + 7 * k;
+            r[0] = ray.startPoint.x; r[1] = ray.startPoint.y; r[2] = ray.startPoint.z;
+            r[3] = ray.direction.x; r[4] = ray.direction.y; r[5] = ray.direction.z; r[6] = (float)kind;
+        }
+    }
 
     const bool prune = (sc.traverse != EZRT_TRAVERSE_REFERENCE);  // the oracle has no accel tree: ACCEL == PRUNED here
     const float slack = prune ? pruneSlack(sc, ray) : 0.0f;
@@ -948,6 +960,16 @@ void oracle_tonemap(const float* in, int channels, float* out, long long n, floa
         out[i * 3] = c.x; out[i * 3 + 1] = c.y; out[i * 3 + 2] = c.z;
     }
 }
+// development aid: while `buf` is set, every hitBVH call appends (origin, direction, kind) -- 7 floats -- to it (up to `cap`
+// rays); returns the number of rays seen since the previous call and resets the counter
+uint64_t oracle_set_ray_dump(float* buf, uint64_t cap) {
+    const uint64_t seen = g_rayDumpCount;
+    g_rayDump = buf;
+    g_rayDumpCap = cap;
+    g_rayDumpCount = 0;
+    return seen;
+}
+
 // inner-node visits by depth accumulated over all oracle_render calls since the last reset
 void oracle_depth_hist(uint64_t* out64, int reset) {
     for (int k = 0; k < 64; k++) { out64[k] = g_innerByDepth[k]; if (reset) g_innerByDepth[k] = 0; }

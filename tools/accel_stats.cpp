@@ -31,10 +31,23 @@ int main(int argc, char** argv) {
     FILE* f = fopen(argv[1], "rb");
     if (fread(tris.data(), 4, tris.size(), f) != tris.size()) return 1;
     fclose(f);
-    // rays: bounce rays from random surface points, cosine-ish hemisphere
-    const int NR = 200000;
-    std::vector<V> ro(NR), rd(NR);
-    for (int i = 0; i < NR; i++) {
+    // rays: argv[3] = file of (o, d, kind) 7-float records dumped by the oracle (oracle_set_ray_dump), argv[4] = kind filter;
+    // otherwise synthetic bounce rays from random surface points, cosine-ish hemisphere
+    int NR = 200000;
+    std::vector<V> ro, rd;
+    if (argc > 3) {
+        FILE* rf = fopen(argv[3], "rb");
+        const int want = argc > 4 ? atoi(argv[4]) : -1;
+        float r[7];
+        while (fread(r, 4, 7, rf) == 7)
+            if (want < 0 || (int)r[6] == want) { ro.push_back({r[0], r[1], r[2]}); rd.push_back({r[3], r[4], r[5]}); }
+        fclose(rf);
+        NR = (int)ro.size();
+        printf("replaying %d recorded rays (kind %d)\n", NR, want);
+    } else {
+        ro.resize(NR); rd.resize(NR);
+    }
+    for (int i = 0; argc <= 3 && i < NR; i++) {
         int t = (int)(rnd() * n) % n;
         const float* p = &tris[(size_t)t * 36];
         V a{p[0], p[1], p[2]}, b{p[3], p[4], p[5]}, c{p[6], p[7], p[8]};
@@ -50,13 +63,13 @@ int main(int argc, char** argv) {
         ro[i] = {P.x + 1e-3f * N.x, P.y + 1e-3f * N.y, P.z + 1e-3f * N.z};
         rd[i] = d;
     }
-    for (int leaf_n : {4}) {
+    for (int leaf_n : {8, 4}) {
         std::vector<EzrtAccelNode> an;
         std::vector<uint32_t> order;
         ezrt_build_accel(tris.data(), n, leaf_n, an, order);
         std::vector<float> geo((size_t)n * 9);
         for (int i = 0; i < n; i++) memcpy(&geo[(size_t)i * 9], &tris[(size_t)order[i] * 36], 36);
-        for (int width : {4, 8}) for (int order_mode : {0, 1, 2}) {
+        for (int width : {4, 8}) for (int order_mode : {0, 1}) {
             // collapse
             std::vector<WNode> wn;
             std::vector<Leaf> leaves;
@@ -85,8 +98,8 @@ int main(int argc, char** argv) {
             };
             build(0);
             // traverse
-            double nv = 0, lv = 0, tt = 0, hits = 0, maxsp = 0, pushes = 0;
-#pragma omp parallel for reduction(+ : nv, lv, tt, hits, pushes) reduction(max : maxsp)
+            double nv = 0, lv = 0, tt = 0, hits = 0, maxsp = 0, pushes = 0, multi = 0;
+#pragma omp parallel for reduction(+ : nv, lv, tt, hits, pushes, multi) reduction(max : maxsp)
             for (int r = 0; r < NR; r++) {
                 V o = ro[r], d = rd[r];
                 float inv[3] = {1 / d.x, 1 / d.y, 1 / d.z}, oo[3] = {o.x, o.y, o.z};
@@ -121,6 +134,7 @@ int main(int argc, char** argv) {
                             std::swap(hit[nh - 1], hit[f]);
                         } else if (nh == 2 && hit[1].t < hit[0].t) std::swap(hit[0], hit[1]);
                         for (int k = nh - 1; k >= 1; k--) { st[sp++] = hit[k]; pushes += 1; }
+                        if (nh >= 3) multi += 1;
                         if ((double)sp > maxsp) maxsp = sp;
                         if (nh) { cur = hit[0].ref; continue; }
                     } else {
@@ -145,8 +159,8 @@ int main(int argc, char** argv) {
                 }
                 if (best < 1e30f) hits += 1;
             }
-            printf("leaf<=%d width %d order %d: wide nodes %zu leaves %zu | per ray: node visits %.1f leaf visits %.2f tri tests %.1f pushes %.1f hit %.2f maxsp %.0f | node bytes/ray %.0f (128B/64B/80B)\n",
-                   leaf_n, width, order_mode, wn.size(), leaves.size(), nv / NR, lv / NR, tt / NR, pushes / NR, hits / NR, maxsp,
+            printf("leaf<=%d width %d order %d: wide nodes %zu leaves %zu | per ray: node visits %.1f leaf visits %.2f tri tests %.1f pushes %.1f visits with >=3 children hit %.1f%% hit %.2f maxsp %.0f | node bytes/ray %.0f (128B/64B/80B)\n",
+                   leaf_n, width, order_mode, wn.size(), leaves.size(), nv / NR, lv / NR, tt / NR, pushes / NR, 100.0 * multi / nv, hits / NR, maxsp,
                    nv / NR * (width == 2 ? 64 : width == 4 ? 128 : 80));
         }
     }
