@@ -193,9 +193,24 @@ def build_reference_host(force=False, part=5):
     return target
 
 
+EXAMPLE_BIN = os.path.join(ROOT, "examples", "ezrt_main")
+
+
+def build_example(force=False):
+    """examples/ezrt_main: the reference's main() + display() as a C++ host over the C ABI (links libezrt_b200.so)."""
+    src = os.path.join(ROOT, "examples", "ezrt_main.cpp")
+    if force or _newer(EXAMPLE_BIN, [src, PRODUCT_SO, os.path.join(INCLUDE, "ezrt.h")]):
+        tmp = EXAMPLE_BIN + ".tmp%d" % os.getpid()
+        _run(["g++", "-O2", "-std=c++17", "-Wall", "-I", INCLUDE, src, "-L", os.path.dirname(PRODUCT_SO), "-lezrt_b200",
+              "-Wl,-rpath,$ORIGIN/../ezrt_b200", "-o", tmp])
+        os.replace(tmp, EXAMPLE_BIN)
+    return EXAMPLE_BIN
+
+
 def build_all(force=False, verbose=False):
     build_product(force=force, verbose=verbose)
     build_oracle(force=force)
+    build_example(force=force)
     build_reference_hdrloader(force=force)
     build_reference_shaders(force=force)
     for part in (3, 4, 5):
