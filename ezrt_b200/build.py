@@ -117,80 +117,29 @@ def _build_product_locked(nvcc, target, cu, cpp, objdir, defines, verbose):
     return target
 
 
+def _oracle_recipes():
+    """oracle/build_ref.py -- the recipes of the checker libraries live under oracle/ (test infrastructure)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ezrt_oracle_build_ref", os.path.join(ROOT, "oracle", "build_ref.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def build_oracle(force=False):
-    src = os.path.join(ROOT, "oracle", "ezrt_oracle.cpp")
-    deps = [src] + [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
-    if force or _newer(ORACLE_SO, deps):
-        _run(["g++"] + HOST_FLAGS + ["-fopenmp", "-Wno-misleading-indentation", "-shared", "-I", INCLUDE, src, "-o", ORACLE_SO])
-    return ORACLE_SO
+    return _oracle_recipes().build_oracle(force)
 
 
 def build_reference_hdrloader(force=False):
-    """oracle/_ref: compile the reference's own hdrloader.cpp where it lies (never copied)."""
-    src = os.path.join(REFERENCE_P5, "lib", "hdrloader.cpp")
-    shim = os.path.join(ROOT, "oracle", "ref_hdrloader_shim.cpp")
-    if not os.path.exists(src):
-        return REF_HDR_SO if os.path.exists(REF_HDR_SO) else None
-    os.makedirs(REF_DIR, exist_ok=True)
-    if force or _newer(REF_HDR_SO, [src, shim]):
-        # the prefix header reroutes the source's sscanf("%ld" into int) call, which is UB on LP64
-        prefix = os.path.join(ROOT, "oracle", "ref_hdrloader_prefix.h")
-        obj = os.path.join(REF_DIR, "hdrloader.o")
-        _run(["g++", "-O2", "-fPIC", "-w", "-include", prefix, "-I", os.path.join(REFERENCE_P5, "lib"), "-c", src, "-o", obj])
-        _run(["g++", "-O2", "-fPIC", "-shared", "-w", "-I", os.path.join(REFERENCE_P5, "lib"), obj, shim, "-o", REF_HDR_SO])
-        os.remove(obj)
-    return REF_HDR_SO
+    return _oracle_recipes().build_reference_hdrloader(force)
 
 
 def build_reference_shaders(force=False):
-    """oracle/_ref: the reference's own fragment shaders (P3/P4/P5 shaders/fshader.fsh), transpiled from
-    where they lie by oracle/ref_shader/transpile.py and compiled against oracle/ref_shader/glsl_emul.h.
-    Test infrastructure: pins the hand-written oracle to the reference's statements (tests/test_ref_shader.py)."""
-    rs = os.path.join(ROOT, "oracle", "ref_shader")
-    srcs = [os.path.join(REFERENCE_ROOT, part, "source code", "shaders", "fshader.fsh") for part in REFERENCE_PARTS]
-    if not all(os.path.exists(s) for s in srcs):
-        return REF_SHADER_SO if os.path.exists(REF_SHADER_SO) else None
-    os.makedirs(REF_DIR, exist_ok=True)
-    deps = srcs + [os.path.join(rs, f) for f in ("transpile.py", "glsl_emul.h", "ref_shader_host.cpp")] + [os.path.join(INCLUDE, "ezrt_math.h"), os.path.join(INCLUDE, "ezrt.h")]
-    if force or _newer(REF_SHADER_SO, deps):
-        _run([sys.executable, os.path.join(rs, "transpile.py"), REFERENCE_ROOT, REF_DIR])
-        tmp = REF_SHADER_SO + ".tmp%d" % os.getpid()
-        _run(["g++"] + HOST_FLAGS + ["-fopenmp", "-w", "-shared", "-I", INCLUDE, "-I", rs, "-I", REF_DIR, os.path.join(rs, "ref_shader_host.cpp"), "-o", tmp])
-        os.replace(tmp, REF_SHADER_SO)
-        for f in os.listdir(REF_DIR):  # the transpiled text is a build intermediate: keep only the binary
-            if f.startswith("shader_") and f.endswith(".inc"):
-                os.remove(os.path.join(REF_DIR, f))
-    return REF_SHADER_SO
+    return _oracle_recipes().build_reference_shaders(force)
 
 
 def build_reference_host(force=False, part=5):
-    """oracle/_ref: the reference's own host code (main.cpp of tutorial part 3, 4 or 5: readObj, buildBVH,
-    buildBVHwithSAH, calculateHdrCache (P5), main()'s scene set-up and uploads), compiled from where it lies
-    together with its hdrloader.cpp; GL/GLUT/glm come from the stand-ins in oracle/ref_stubs/.  Test
-    infrastructure (tests/test_ref_host.py)."""
-    src_dir = os.path.join(REFERENCE_ROOT, REFERENCE_PARTS[part - 3], "source code")
-    target = REF_HOST_SO if part == 5 else REF_HOST_SO.replace(".so", "_p%d.so" % part)
-    main_cpp = os.path.join(src_dir, "main.cpp")
-    hdr_cpp = os.path.join(src_dir, "lib", "hdrloader.cpp")
-    if not (os.path.exists(main_cpp) and os.path.exists(hdr_cpp)):
-        return target if os.path.exists(target) else None
-    os.makedirs(REF_DIR, exist_ok=True)
-    orc = os.path.join(ROOT, "oracle")
-    stubs = os.path.join(orc, "ref_stubs")
-    shim, hshim, prefix = (os.path.join(orc, f) for f in ("ref_host_shim.cpp", "ref_hdrloader_shim.cpp", "ref_hdrloader_prefix.h"))
-    deps = [main_cpp, hdr_cpp, shim, hshim, prefix, os.path.join(INCLUDE, "ezrt_math.h")]
-    for d, _, files in os.walk(stubs):
-        deps += [os.path.join(d, f) for f in files]
-    if force or _newer(target, deps):
-        obj = os.path.join(REF_DIR, "hdrloader_host_p%d.o" % part)
-        _run(["g++", "-O2", "-fPIC", "-w", "-include", prefix, "-I", os.path.join(src_dir, "lib"), "-c", hdr_cpp, "-o", obj])
-        tmp = target + ".tmp%d" % os.getpid()
-        _run(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-mfma", "-w", "-Dmain=ezrt_ref_main", "-DEZRT_REF_PART=%d" % part,
-              '-DEZRT_REF_MAIN_CPP="%s"' % main_cpp, "-I", stubs, "-I", INCLUDE, "-I", src_dir, "-I", os.path.join(src_dir, "lib"),
-              "-shared", shim, obj, hshim, "-o", tmp])
-        os.replace(tmp, target)
-        os.remove(obj)
-    return target
+    return _oracle_recipes().build_reference_host(force, part)
 
 
 EXAMPLE_BIN = os.path.join(ROOT, "examples", "ezrt_main")
