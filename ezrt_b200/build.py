@@ -156,6 +156,21 @@ def build_example(force=False):
     return EXAMPLE_BIN
 
 
+W8_MODEL_BIN = os.path.join(ROOT, "build", "w8_model")
+
+
+def build_w8_model(force=False):
+    """build/w8_model: CPU model of the W8 acceleration-tree traversal (tools/w8_model.cpp) over the PRODUCT tree builders --
+    the not-gpu check that the quantised tree is conservative (closest hits equal brute force)."""
+    srcs = [os.path.join(ROOT, "tools", "w8_model.cpp")] + [os.path.join(CSRC, f) for f in ("host_scene.cpp", "accel_w8.cpp", "errors.cpp")]
+    if force or _newer(W8_MODEL_BIN, srcs + _headers()):
+        os.makedirs(os.path.dirname(W8_MODEL_BIN), exist_ok=True)
+        tmp = W8_MODEL_BIN + ".tmp%d" % os.getpid()
+        _run(["g++"] + [f for f in HOST_FLAGS if f != "-fPIC"] + ["-fopenmp", "-pthread", "-I", INCLUDE, "-I", CSRC] + srcs + ["-o", tmp])
+        os.replace(tmp, W8_MODEL_BIN)
+    return W8_MODEL_BIN
+
+
 def build_all(force=False, verbose=False):
     build_product(force=force, verbose=verbose)
     build_oracle(force=force)

@@ -19,6 +19,7 @@
 #include "ezrt_internal.h"
 #include "ezrt_math.h"
 #include "kernels.h"
+#include "w8_node.h"
 
 #define CU_CHECK(call)                                                                                  \
     do {                                                                                                \
@@ -87,7 +88,8 @@ struct ezrt_scene {
     size_t hot_bytes = 0;
     size_t l2_persist_bytes = 0;
     size_t max_window_bytes = 0;  // persisting L2 set-aside granted by the device (0 = feature off)
-    bool regular_tree = true;  // false: only the literal REFERENCE traversal is valid for this tree
+    bool regular_tree = true;  // false: only the literal REFERENCE traversal is valid for the caller's tree
+    bool have_accel = true;    // false: no acceleration tree (irregular caller tree, or a degenerate one too deep for the stacks): ACCEL runs as PRUNED
     int sort_rays = 0;  // env EZRT_SORT_RAYS=1 enables the bounce-ray sort (measured: no gain with per-lane refill)
     int tiles_key[4] = {-1, -1, -1, -1};
     std::vector<TileDev> tiles;
@@ -181,7 +183,7 @@ RenderDev make_render_dev(const ezrt_scene* s, const ezrt_render_params* p) {
     rd.out_channels = p->out_channels;
     rd.compact_out = (p->part_count > 1) ? 1 : 0;
     rd.n_tiles = (int)s->tiles.size();
-    rd.accel_space = (s->regular_tree && p->traverse == EZRT_TRAVERSE_ACCEL && p->pipeline == EZRT_PIPELINE_WAVEFRONT) ? 1 : 0;
+    rd.accel_space = (s->regular_tree && s->have_accel && p->traverse == EZRT_TRAVERSE_ACCEL && p->pipeline == EZRT_PIPELINE_WAVEFRONT) ? 1 : 0;
     return rd;
 }
 
@@ -359,73 +361,42 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         shade[(size_t)i * 3 + 2] = make_float4(s[15], s[16], s[17], 0.0f);
     }
 
-    // ---- acceleration tree: sentinel-free SAH over the same triangles (DESIGN.md "accel") ----
+    // ---- acceleration tree: sentinel-free SAH over the same triangles (DESIGN.md "accel"), collapsed to 8-wide
+    // quantised nodes (accel_w8.cpp, w8_node.h).  A tree too deep for the traversal stacks (degenerate input) is
+    // dropped: the scene then renders with the PRUNED policy on the caller's tree, as for an irregular tree.
     const float prune_delta = max_abs * 1.52587890625e-05f;  // 2^-16 * scene extent
-    std::vector<float4> acc_nodes, acc_geo((size_t)n_triangles * 4), acc_wide;
+    std::vector<float4> acc_geo((size_t)n_triangles * 4), acc_wide;
+    std::vector<uint32_t> w8_words;
     int acc_wide_root = 0;
     std::vector<uint32_t> acc_order;
-    int acc_root_ref = 0, acc_top = 0, acc_inner = 0, acc_depth = 0, acc_leaf_lanes = 8;
+    int acc_depth = 0, w8_depth = 0, w8_near_bit[3] = {0, 1, 2};
+    bool have_accel = true;
     {
         std::vector<EzrtAccelNode> an;
-        int acc_leaf_n = 4;  // one quad of lanes per leaf, eight leaves per pass (EZRT_ACCEL_LEAF=8: octets, four per pass)
-        if (const char* e = getenv("EZRT_ACCEL_LEAF")) acc_leaf_n = std::max(1, std::min(64, atoi(e)));
-        acc_leaf_lanes = (acc_leaf_n <= 4) ? 4 : 8;
-        ezrt_build_accel(tris, n_triangles, acc_leaf_n, an, acc_order);
-        const int na = (int)an.size();
-        std::vector<int> aid(na, -1);
-        {   // top levels breadth-first, the rest in pre-order (as for the reference tree)
-            std::vector<int> level, next;
-            if (an[0].n <= 0) level.push_back(0);
-            while (!level.empty() && acc_top + (int)level.size() <= EZRT_ACC_TOP_NODES_MAX) {
-                next.clear();
-                for (int i : level) {
-                    aid[i] = acc_top++;
-                    if (an[an[i].left].n <= 0) next.push_back(an[i].left);
-                    if (an[an[i].right].n <= 0) next.push_back(an[i].right);
-                }
-                level.swap(next);
-                acc_depth++;
-            }
-            acc_inner = acc_top;
-            for (int i = 0; i < na; i++)
-                if (an[i].n <= 0 && aid[i] < 0) aid[i] = acc_inner++;
-        }
-        {   // depth (stack bound)
-            std::vector<std::pair<int, int>> stk;
-            stk.push_back({0, 1});
-            int md = 0;
-            while (!stk.empty()) {
-                auto [i, dpt] = stk.back();
-                stk.pop_back();
-                md = std::max(md, dpt);
-                if (an[i].n <= 0) { stk.push_back({an[i].left, dpt + 1}); stk.push_back({an[i].right, dpt + 1}); }
-            }
-            acc_depth = md;
-            if (md + 1 > EZRT_MAX_STACK) return ezrt_set_error(EZRT_ERR_BAD_TREE, "scene_create: acceleration tree depth %d exceeds %d", md, EZRT_MAX_STACK - 1);
-        }
-        auto aref = [&](int c) -> int {
-            if (an[c].n > 0) return (int)(EZRT_LEAF_FLAG | ((uint32_t)an[c].index << 7) | (uint32_t)an[c].n);
-            return aid[c];
-        };
+        std::vector<uint32_t> order_bin;
+        ezrt_build_accel(tris, n_triangles, W8_MAX_LEAF_TRIS, an, order_bin);
         // boxes inflated by 2*delta: a hit hitTriangle accepts lies within delta of its triangle's box, so
         // the inflated boxes of the whole ancestor chain are entered no later than the hit distance
         const float pad = 2.0f * prune_delta;
-        acc_nodes.resize((size_t)std::max(1, acc_inner) * 4);
-        for (int i = 0; i < na; i++) {
-            if (aid[i] < 0) continue;
-            const EzrtAccelNode &L = an[an[i].left], &R = an[an[i].right];
-            float LA[3], LB[3], RA[3], RB[3];
-            for (int k = 0; k < 3; k++) { LA[k] = L.AA[k] - pad; LB[k] = L.BB[k] + pad; RA[k] = R.AA[k] - pad; RB[k] = R.BB[k] + pad; }
-            pack_node(&acc_nodes[(size_t)aid[i] * 4], LA, LB, RA, RB, aref(an[i].left), aref(an[i].right));
+        EzrtW8Tree w8;
+        ezrt_w8_axis_bits(bmin, bmax, w8_near_bit);
+        const int wrc = ezrt_build_w8(an, order_bin, pad, max_abs, w8_near_bit, w8);
+        if (wrc != 0 || w8.depth > EZRT_W8_SMEM_STACK + W8_LOCAL_STACK) {
+            have_accel = false;
+            acc_order.resize(n_triangles);
+            for (int i = 0; i < n_triangles; i++) acc_order[i] = (uint32_t)i;
+        } else {
+            acc_order = w8.tri_order;
+            w8_words.swap(w8.nodes);
+            w8_depth = w8.depth;
         }
-        acc_root_ref = aref(0);
         for (int i = 0; i < n_triangles; i++)
             for (int k = 0; k < 4; k++) acc_geo[(size_t)i * 4 + k] = geo[(size_t)acc_order[i] * 4 + k];
 
-        // ---- the same tree collapsed to 4-wide nodes: a node's children are its binary children with the
-        // largest inner ones replaced by their own children until four (one dependent fetch per two levels)
-        const char* we = getenv("EZRT_ACCEL_WIDE");
-        if (!(we && atoi(we) == 0) && an[0].n <= 0) {
+        // ---- the round-1 form of the same tree (env EZRT_ACCEL=4, kept for A/B measurements): 4-wide nodes with exact
+        // boxes; a node's children are its binary children with the largest inner ones replaced by their own children
+        const char* we = getenv("EZRT_ACCEL");
+        if (have_accel && we && atoi(we) == 4 && an[0].n <= 0) {
             auto area = [&](int c) {
                 float x = an[c].BB[0] - an[c].AA[0], y = an[c].BB[1] - an[c].AA[1], z = an[c].BB[2] - an[c].AA[2];
                 return x * y + x * z + y * z;
@@ -452,12 +423,12 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
                 float rec[32];
                 int refs[4];
                 for (int k = 0; k < 4; k++) {
-                    float AA[3] = {3.0e38f, 3.0e38f, 3.0e38f}, BB[3] = {3.0e38f, 3.0e38f, 3.0e38f};  // absent: a far-away point box
+                    float AA[3] = {3.0e38f, 3.0e38f, 3.0e38f}, BB[3] = {-3.0e38f, -3.0e38f, -3.0e38f};  // absent: an inverted box, never hit
                     refs[k] = (int)EZRT_LEAF_FLAG;  // EZRT_REF_DONE, never followed
                     if (k < cnt) {
                         const EzrtAccelNode& c = an[ch[k]];
                         for (int a = 0; a < 3; a++) { AA[a] = c.AA[a] - pad; BB[a] = c.BB[a] + pad; }
-                        refs[k] = (c.n > 0) ? (int)(EZRT_LEAF_FLAG | ((uint32_t)c.index << 7) | (uint32_t)c.n) : build_wide(ch[k], depth + 1);
+                        refs[k] = (c.n > 0) ? (int)(EZRT_LEAF_FLAG | ((uint32_t)w8.leaf_first[ch[k]] << 7) | (uint32_t)c.n) : build_wide(ch[k], depth + 1);
                     }
                     rec[4 * k + 0] = AA[0]; rec[4 * k + 1] = AA[1]; rec[4 * k + 2] = BB[0]; rec[4 * k + 3] = BB[1];
                     rec[16 + 2 * k] = AA[2]; rec[16 + 2 * k + 1] = BB[2];
@@ -468,7 +439,8 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
                 return id;
             };
             acc_wide_root = build_wide(0, 1);
-            if (3 * wide_depth + 2 > EZRT_MAX_STACK) acc_wide.clear();  // too deep for the traversal stack: keep the binary form
+            acc_depth = wide_depth;
+            if (3 * wide_depth + 2 > EZRT_MAX_STACK) acc_wide.clear();  // too deep for its stack: the W8 kernel serves
         }
     }
     // shading data and the reference-leaf map in the acceleration tree's order, and the inverse permutation
@@ -505,13 +477,13 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     if (!rc) rc = upload(sc->materials, mats.data(), mats.size() * sizeof(float4));
     // acceleration tree nodes | triangle geometry | shading records in ONE allocation: the window the
     // L2 persisting-access policy is set on while a render runs (the data every ray touches at random)
-    const size_t acc_nodes_bytes = ((acc_nodes.size() * sizeof(float4) + 255) / 256) * 256;
+    const size_t acc_nodes_bytes = ((std::max<size_t>(w8_words.size(), 4) * sizeof(uint32_t) + 255) / 256) * 256;
     const size_t acc_geo_bytes = ((acc_geo.size() * sizeof(float4) + 255) / 256) * 256;
     const size_t acc_shade_bytes = ((acc_shade.size() * sizeof(float4) + 255) / 256) * 256;
     if (!rc) rc = sc->acc_nodes.ensure(acc_nodes_bytes + acc_geo_bytes + acc_shade_bytes);
     if (!rc) {
         char* base = (char*)sc->acc_nodes.p;
-        cudaError_t e = cudaMemcpy(base, acc_nodes.data(), acc_nodes.size() * sizeof(float4), cudaMemcpyHostToDevice);
+        cudaError_t e = w8_words.empty() ? cudaSuccess : cudaMemcpy(base, w8_words.data(), w8_words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(base + acc_nodes_bytes, acc_geo.data(), acc_geo.size() * sizeof(float4), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(base + acc_nodes_bytes + acc_geo_bytes, acc_shade.data(), acc_shade.size() * sizeof(float4), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) rc = ezrt_set_error(EZRT_ERR_CUDA, "scene_create: upload failed: %s", cudaGetErrorString(e));
@@ -534,6 +506,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     }
     sc->n_materials = (int)mat_ids.size();
     sc->regular_tree = regular_tree;
+    sc->have_accel = have_accel;
     sc->tree_depth = max_depth;
     SceneDev& d = sc->dev;
     d.nodes = (const float4*)sc->nodes.p;
@@ -544,16 +517,18 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.hdr_cache = hdr_cache ? (const float*)sc->hdr_cache.p : nullptr;
     d.hdr_w = hdr_w; d.hdr_h = hdr_h; d.hdr_linear = hdr_filter_linear ? 1 : 0;
     d.root_ref = child_ref(1);
-    d.acc_nodes = (const float4*)sc->acc_nodes.p;
+    d.w8_nodes = w8_words.empty() ? nullptr : (const uint4*)sc->acc_nodes.p;
+    for (int k = 0; k < 3; k++) d.w8_near_bit[k] = w8_near_bit[k];
+    d.w8_stack_entries = std::max(1, std::min(w8_depth, EZRT_W8_SMEM_STACK));
+    d.w8_origin_limit = W8_ORIGIN_LIMIT_REL * max_abs;
+    d.w8_decode_bits = W8_DECODE_BITS;
+    if (!acc_wide.empty()) d.w8_nodes = nullptr;   // EZRT_ACCEL=4: the round-1 kernel
     d.acc_tri_geo = (const float4*)((const char*)sc->acc_nodes.p + acc_nodes_bytes);
     d.acc_tri_ref = (const uint32_t*)sc->acc_tri_ref.p;
-    d.acc_root_ref = acc_root_ref;
     d.acc_wide_nodes = acc_wide.empty() ? nullptr : (const float4*)sc->acc_wide.p;
     d.acc_wide_root_ref = acc_wide_root;
-    d.acc_leaf_lanes = acc_leaf_lanes;
     d.tri_l1_bypass = ((size_t)n_triangles * 64 > ((size_t)4 << 20)) ? 1 : 0;  // > 4 MB of triangle records: stream them past L1
     if (const char* e = getenv("EZRT_TRI_L1_BYPASS")) d.tri_l1_bypass = atoi(e) != 0;
-    d.acc_top_nodes = acc_top;
     d.acc_tri_shade = (const float4*)((const char*)sc->acc_nodes.p + acc_nodes_bytes + acc_geo_bytes);
     d.acc_tri_leaf = (const int*)sc->acc_tri_leaf.p;
     d.ref_to_acc = (const uint32_t*)sc->ref_to_acc.p;
@@ -565,7 +540,6 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.top_nodes = n_top;
     if (const char* e = getenv("EZRT_TOP_NODES")) {
         d.top_nodes = std::max(0, std::min(n_top, atoi(e)));
-        d.acc_top_nodes = std::max(0, std::min(acc_top, atoi(e)));
     }
     d.prune_delta = prune_delta;  // 2^-16 * scene extent (DESIGN.md "pruning")
     for (int k = 0; k < 3; k++) {
@@ -630,13 +604,13 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     CU_CHECK(cudaMemsetAsync(totals, 0, sizeof(unsigned long long) * 8, st));
     s->launches = 0;
     s->have_timing = true;
-    s->profiling = (p->profile != 0);
+    s->profiling = (p->profile == 1);
     s->spans.clear();
     s->ev_used = 0;
     RenderDev rd = make_render_dev(s, p);
     const TileDev* d_tiles = (const TileDev*)s->tiles_buf.p;
     const bool prune = s->regular_tree && (p->traverse != EZRT_TRAVERSE_REFERENCE);
-    const bool accel = s->regular_tree && (p->traverse == EZRT_TRAVERSE_ACCEL);
+    const bool accel = s->regular_tree && s->have_accel && (p->traverse == EZRT_TRAVERSE_ACCEL);
     if (rd.n_tiles == 0 || p->spp == 0) {
         CU_CHECK(cudaEventRecord(s->ev_stop, st));
         return EZRT_OK;
@@ -684,6 +658,7 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     uint32_t* sort_perm = sort_keys + capacity;
     uint32_t* sort_bins = sort_perm + capacity;
 
+    unsigned long long* const count_ptr = (p->profile == 2) ? totals + 5 : nullptr;  // node visits, triangle tests of the W8 kernels
     const bool l2_window = accel && s->l2_persist_bytes > 0 && s->hot_bytes > 0;
     if (l2_window) {
         cudaStreamAttrValue attr;
@@ -718,7 +693,7 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
             }
             sp = s->span_begin(0, st);
             if (accel) {
-                launch_extend_accel(s->dev, false, qin, &q_count[b], &w_ext[b], defer_list, &d_ext[b], &dw_ext[b], n_slots, s->n_sms, st);
+                launch_extend_accel(s->dev, qin, &q_count[b], &w_ext[b], defer_list, &d_ext[b], &dw_ext[b], n_slots, s->n_sms, count_ptr, st);
                 s->launches++;
             } else {
                 launch_extend(s->dev, prune, false, qin, &q_count[b], &w_ext[b], perm, 0, n_slots, s->n_sms, st);
@@ -732,7 +707,7 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
             if (is_mode && b < p->max_bounce) {
                 sp = s->span_begin(2, st);
                 if (accel) {
-                    launch_shadow_accel(s->dev, sq, &s_count[b], &w_sh[b], Lo, defer_list, &d_sh[b], &dw_sh[b], n_slots, s->n_sms, st);
+                    launch_shadow_accel(s->dev, sq, &s_count[b], &w_sh[b], Lo, defer_list, &d_sh[b], &dw_sh[b], n_slots, s->n_sms, count_ptr, st);
                     s->launches++;
                 } else {
                     launch_shadow(s->dev, prune, sq, &s_count[b], &w_sh[b], Lo, nullptr, n_slots, s->n_sms, st);
@@ -786,6 +761,10 @@ int ezrt_get_counters(ezrt_scene* s, ezrt_counters* out) {
     unsigned long long t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     CU_CHECK(cudaMemcpy(t, s->totals_buf.p, sizeof(t), cudaMemcpyDeviceToHost));
     out->deferred_rays = t[4];
+    out->node_visits = t[5];
+    out->tri_tests = t[6];
+    out->node_record_bytes = s->dev.w8_nodes ? W8_NODE_BYTES : (s->dev.acc_wide_nodes ? 128 : 64);
+    out->tri_record_bytes = 64;
     float ms = 0.0f;
     CU_CHECK(cudaEventElapsedTime(&ms, s->ev_start, s->ev_stop));
     out->primary_rays = t[0]; out->bounce_rays = t[1]; out->shadow_rays = t[2];
@@ -910,6 +889,7 @@ int ezrt_trace_rays(ezrt_scene* s, int n, const float* origins, const float* dir
     uint32_t* d_defer = (uint32_t*)p; p += sizeof(uint32_t) * N;
     uint32_t* d_cnt = (uint32_t*)p;  // [0] n, [1] work, [2] deferred, [3] deferred work
     if (!s->regular_tree) traverse = EZRT_TRAVERSE_REFERENCE;
+    else if (traverse == EZRT_TRAVERSE_ACCEL && (!s->have_accel || any_hit)) traverse = EZRT_TRAVERSE_PRUNED;  // any-hit probes take the exact kernel
     cudaStream_t st = s->own_stream;
     const uint32_t counters[4] = {(uint32_t)n, 0u, 0u, 0u};
     cudaError_t e = cudaMemcpyAsync(q.ray_o, ho.data(), sizeof(float4) * N, cudaMemcpyHostToDevice, st);
@@ -917,7 +897,7 @@ int ezrt_trace_rays(ezrt_scene* s, int n, const float* origins, const float* dir
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_cnt, counters, sizeof(counters), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         if (traverse == EZRT_TRAVERSE_ACCEL)
-            launch_extend_accel(s->dev, any_hit != 0, q, d_cnt, d_cnt + 1, d_defer, d_cnt + 2, d_cnt + 3, (uint32_t)n, s->n_sms, st);
+            launch_extend_accel(s->dev, q, d_cnt, d_cnt + 1, d_defer, d_cnt + 2, d_cnt + 3, (uint32_t)n, s->n_sms, nullptr, st);
         else
             launch_extend(s->dev, traverse != EZRT_TRAVERSE_REFERENCE, any_hit != 0, q, d_cnt, d_cnt + 1, nullptr, 0, (uint32_t)n, s->n_sms, st);
         launch_trace_finish(s->dev, n, q, p3_normal_fudge, traverse == EZRT_TRAVERSE_ACCEL, d_hit, d_dist, d_tri, d_inside, d_point, d_normal, st);

@@ -10,6 +10,7 @@
 #include "device_scene.h"
 #include "ezrt.h"
 #include "ezrt_math.h"
+#include "w8_node.h"
 
 __constant__ uint32_t c_sobolV[8 * 32] = {
 #include "ezrt_sobol_table.inc"
@@ -423,6 +424,17 @@ __device__ __forceinline__ bool reference_reaches_leaf(const int* __restrict__ t
     return d > 0.0f;
 }
 
+__device__ __forceinline__ bool reference_reaches_leaf_inv(const int* __restrict__ tri_leaf, const float4* __restrict__ leaf_box, int tri, vec3 o, vec3 inv) {
+    const int leaf = __ldg(tri_leaf + tri);
+    const float4 a = ldg4(leaf_box + 2 * (size_t)leaf), b = ldg4(leaf_box + 2 * (size_t)leaf + 1);
+    float fx = (b.x - o.x) * inv.x, fy = (b.y - o.y) * inv.y, fz = (b.z - o.z) * inv.z;
+    float nx = (a.x - o.x) * inv.x, ny = (a.y - o.y) * inv.y, nz = (a.z - o.z) * inv.z;
+    float t1 = fminf(fmaxf(fx, nx), fminf(fmaxf(fy, ny), fmaxf(fz, nz)));
+    float t0 = fmaxf(fminf(fx, nx), fmaxf(fminf(fy, ny), fminf(fz, nz)));
+    float d = (t1 >= t0) ? ((t0 > 0.0f) ? t0 : t1) : -1.0f;
+    return d > 0.0f;
+}
+
 // ACCEL: `tree` is the device's own acceleration tree, not the reference tree: the closest hit it
 // finds is the global minimum over all triangles; ties (two triangles at exactly the same t) and rays
 // with non-finite 1/d are handed to io.defer() and re-traced by the exact reference-order kernel.
@@ -683,6 +695,248 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
 
 #undef STACK_PUSH
 #undef STACK_POP
+
+// ------------------------------------------------------------------------------------------
+// W8: the default traversal of the accel policy.  8-wide nodes with 8-bit quantised child boxes (96-byte records,
+// three 256-bit loads; layout, decode arithmetic and error bound in w8_node.h), children visited in octant order
+// from a hit bit mask -- no distance sort, at most one stack push per node visit -- and a per-lane stack of
+// (child base | slot masks) groups in SHARED memory at [entry][thread].  The triangles of all hit leaf slots of a node
+// are collected in a bit mask and tested one per lane per iteration in a separate warp-synchronous phase.
+// Like the 4-wide kernel it only has to find the globally closest accepted triangle (and notice ties); what it
+// cannot decide exactly goes to io.defer().  Measured ceiling for its access pattern: one
+// divergent load instruction per lane per cycle per SM (tools/gather_bench.cu, profiles/gather_peak_r2.json).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+// byte K of `w` -> the float 2^15 + q (w8_node.h "Decode").  `bias` = W8_DECODE_BITS held in a REGISTER so that the
+// selector can be the instruction's immediate (with the constant as immediate ptxas moves 46 selectors per node visit
+// through registers).
+template <int K>
+__device__ __forceinline__ float w8_plane(uint32_t w, uint32_t bias) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(bias), "n"(0x7604 | (K << 4)));
+    return __uint_as_float(r);
+}
+// one slot: entry / exit distances from the six decoded planes; hit iff the clamped interval is non-empty
+template <int K>
+__device__ __forceinline__ bool w8_slot_hit(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, float Bx, float By, float Bz,
+                                            float Ax, float Ay, float Az, float limit, uint32_t bias) {
+    const float tnx = __fmaf_rn(w8_plane<K>(nx, bias), Bx, Ax), tny = __fmaf_rn(w8_plane<K>(ny, bias), By, Ay), tnz = __fmaf_rn(w8_plane<K>(nz, bias), Bz, Az);
+    const float tfx = __fmaf_rn(w8_plane<K>(fx, bias), Bx, Ax), tfy = __fmaf_rn(w8_plane<K>(fy, bias), By, Ay), tfz = __fmaf_rn(w8_plane<K>(fz, bias), Bz, Az);
+    const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+    const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, limit));
+    return tmin <= tmax;
+}
+
+struct W8Counts {   // COUNT instantiations only (bench.py roofline: records fetched on the kernel's own layout)
+    unsigned long long* node_visits;
+    unsigned long long* tri_tests;
+};
+
+// s_perm: 8 x 256 bytes in shared memory, s_perm[m * 256 + x] = the bits of x moved from position s to position s ^ m
+// stack : uint2 [entries][blockDim.x] in shared memory
+template <bool ANYHIT, bool COUNT, class RayIO>
+__device__ __forceinline__ void extend_w8(const SceneDev& sc, uint32_t n, uint32_t* work, RayIO io, const unsigned char* s_perm, uint2* stack_sm,
+                                          W8Counts counts) {
+    const bool tri_na = sc.tri_l1_bypass != 0;
+    const int refill_thresh = sc.refill_thresh, inner_thresh = sc.inner_thresh, leaf_thresh = sc.leaf_thresh;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int stack_stride = blockDim.x;
+    const int stack_cap = sc.w8_stack_entries;
+    uint2 stack_local[W8_LOCAL_STACK];   // entries beyond the shared-memory part (trees deeper than the smem stack)
+    uint2* const my_stack = stack_sm + threadIdx.x;
+    const uint4* __restrict__ nodes = sc.w8_nodes;
+    const float origin_limit = sc.w8_origin_limit;
+    const uint32_t bias = sc.w8_decode_bits;   // = W8_DECODE_BITS; a run-time value so that ptxas keeps it in a register (see w8_plane)
+
+    int ray = -1;                 // index of the ray this lane traces, -1 = idle
+    int node = -1;                // next node to visit, -1 = none (waiting for the triangle phase, or idle)
+    int sp = 0;
+    vec3 o = splat3(0.0f), d = splat3(0.0f), inv = splat3(0.0f);
+    float slack = 0.0f, best = EZ_INF;
+    int best_tri = -1;
+    bool tie = false;
+    uint32_t near_mask = 0;       // bit of axis a set iff d_a >= 0 (children towards -a come first)
+    uint32_t g_base = 0, g_bits = 0;   // current group: first inner child | imask (bits 0..7), unvisited hit slots in priority positions (bits 8..15)
+    uint32_t t_base = 0, t_mask = 0;   // pending triangles of the node just visited
+    unsigned long long n_visits = 0, n_tests = 0;
+    bool exhausted = false;
+    uint32_t chunk_pos = 0, chunk_end = 0;
+    const uint32_t chunk = (uint32_t)sc.work_chunk;
+
+#define W8_PUSH(e) do { const uint2 e__ = (e); if (sp < stack_cap) my_stack[sp * stack_stride] = e__; else stack_local[sp - stack_cap] = e__; ++sp; } while (0)
+#define W8_POP() ((--sp < stack_cap) ? my_stack[sp * stack_stride] : stack_local[sp - stack_cap])
+    // next node of this lane's ray from the current group / the stack; finishes the ray when nothing is left
+    auto select_next = [&]() {
+        if ((g_bits >> 8) == 0u) {
+            if (sp == 0) {  // ray finished
+                HitRec h;
+                h.t = best;
+                h.tri = best_tri;
+                io.store((uint32_t)ray, h, tie, o, inv);
+                ray = -1;
+                node = -1;
+                return;
+            }
+            const uint2 e = W8_POP();
+            g_base = e.x;
+            g_bits = e.y;
+        }
+        const int p = 23 - __clz(g_bits);                  // highest priority position among bits 8..15
+        g_bits ^= 0x100u << p;
+        const uint32_t slot = (uint32_t)p ^ near_mask;
+        node = (int)(g_base + __popc(g_bits & 0xffu & ((1u << slot) - 1u)));
+    };
+
+    while (true) {
+        // ---------------- refill idle lanes (per-warp chunks of the global work counter, as extend_persistent) ----------------
+        unsigned need = __ballot_sync(FULL, ray < 0);
+        if (need != 0u && !exhausted) {
+            if (chunk_pos >= chunk_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(work, chunk);
+                base = __shfl_sync(FULL, base, 0);
+                chunk_pos = base;
+                chunk_end = (base + chunk < n) ? base + chunk : n;
+                if (base >= n) exhausted = true;
+            }
+            if (!exhausted && ray < 0) {
+                uint32_t idx = chunk_pos + (uint32_t)__popc(need & lt_mask);
+                if (idx < chunk_end && io.load(idx, o, d)) {
+                    inv = ez_v3(EZ_DIV(1.0f, d.x), EZ_DIV(1.0f, d.y), EZ_DIV(1.0f, d.z));
+                    const float ax = ez_abs(inv.x), ay = ez_abs(inv.y), az = ez_abs(inv.z);
+                    const float ao = fmaxf(ez_abs(o.x), fmaxf(ez_abs(o.y), ez_abs(o.z)));
+                    const float amin = fminf(ax, fminf(ay, az)), amax = fmaxf(ax, fmaxf(ay, az));
+                    if ((amax <= W8_INV_LIMIT) && (amin >= W8_INV_MIN) && (ao <= origin_limit)) {  // false for inf / NaN
+                        slack = sc.prune_delta * ez_max(ax, ez_max(ay, az));
+                        near_mask = (d.x >= 0.0f ? (1u << sc.w8_near_bit[0]) : 0u) | (d.y >= 0.0f ? (1u << sc.w8_near_bit[1]) : 0u) |
+                                    (d.z >= 0.0f ? (1u << sc.w8_near_bit[2]) : 0u);
+                        ray = (int)idx;
+                        node = 0;
+                        sp = 0;
+                        g_bits = 0u;
+                        t_mask = 0u;
+                        best = EZ_INF;
+                        best_tri = -1;
+                        tie = false;
+                    } else {  // outside the decode error bound: the exact kernel traces it
+                        io.defer(idx);
+                    }
+                }
+            }
+            if (!exhausted) {
+                uint32_t take = (uint32_t)__popc(need);
+                chunk_pos = (chunk_pos + take < chunk_end) ? chunk_pos + take : chunk_end;
+            }
+        }
+        if (__ballot_sync(FULL, ray >= 0) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        unsigned busy;
+        do {
+            // ---------------- node phase: lanes holding a node visit it, one node per iteration, while enough of them do ----------------
+            const unsigned m_busy = __ballot_sync(FULL, ray >= 0);
+            while (true) {
+                const bool at_node = node >= 0;
+                const unsigned m_node = __ballot_sync(FULL, at_node);
+                if (m_node == 0u) break;
+                const unsigned m_wait = m_busy & ~m_node;   // lanes waiting with triangles to test
+                if (m_wait != 0u && (__popc(m_node) < inner_thresh || __popc(m_wait) >= leaf_thresh)) break;
+                if (at_node) {
+                    const uint4* nd = nodes + (size_t)node * 6;
+                    uint4 h0, h1, l0, l1, u0, u1;
+                    {
+                        ulonglong2 a, b;
+                        ldg256_b64(nd, a, b);
+                        h0 = make_uint4((uint32_t)a.x, (uint32_t)(a.x >> 32), (uint32_t)a.y, (uint32_t)(a.y >> 32));
+                        h1 = make_uint4((uint32_t)b.x, (uint32_t)(b.x >> 32), (uint32_t)b.y, (uint32_t)(b.y >> 32));
+                        ldg256_b64(nd + 2, a, b);
+                        l0 = make_uint4((uint32_t)a.x, (uint32_t)(a.x >> 32), (uint32_t)a.y, (uint32_t)(a.y >> 32));
+                        l1 = make_uint4((uint32_t)b.x, (uint32_t)(b.x >> 32), (uint32_t)b.y, (uint32_t)(b.y >> 32));
+                        ldg256_b64(nd + 4, a, b);
+                        u0 = make_uint4((uint32_t)a.x, (uint32_t)(a.x >> 32), (uint32_t)a.y, (uint32_t)(a.y >> 32));
+                        u1 = make_uint4((uint32_t)b.x, (uint32_t)(b.x >> 32), (uint32_t)b.y, (uint32_t)(b.y >> 32));
+                    }
+                    if (COUNT) n_visits++;
+                    const float limit = best + (best * 0.000244140625f + slack);
+                    // B = scale * inv, A = fma(-2^15, B, (origin - o) * inv)
+                    const float Bx = __uint_as_float(h0.w) * inv.x, By = __uint_as_float(h1.x) * inv.y, Bz = __uint_as_float(h1.y) * inv.z;
+                    const float Ax = __fmaf_rn(-W8_DECODE_BIAS, Bx, (__uint_as_float(h0.x) - o.x) * inv.x);
+                    const float Ay = __fmaf_rn(-W8_DECODE_BIAS, By, (__uint_as_float(h0.y) - o.y) * inv.y);
+                    const float Az = __fmaf_rn(-W8_DECODE_BIAS, Bz, (__uint_as_float(h0.z) - o.z) * inv.z);
+                    // near / far plane words per axis (slots 0..3 | 4..7): low planes are near iff d >= 0
+                    const bool px = d.x >= 0.0f, py = d.y >= 0.0f, pz = d.z >= 0.0f;
+                    const uint32_t nx0 = px ? l0.x : u0.x, nx1 = px ? l0.y : u0.y, fx0 = px ? u0.x : l0.x, fx1 = px ? u0.y : l0.y;
+                    const uint32_t ny0 = py ? l0.z : u0.z, ny1 = py ? l0.w : u0.w, fy0 = py ? u0.z : l0.z, fy1 = py ? u0.w : l0.w;
+                    const uint32_t nz0 = pz ? l1.x : u1.x, nz1 = pz ? l1.y : u1.y, fz0 = pz ? u1.x : l1.x, fz1 = pz ? u1.y : l1.y;
+                    uint32_t hits = 0u;
+                    if (w8_slot_hit<0>(nx0, ny0, nz0, fx0, fy0, fz0, Bx, By, Bz, Ax, Ay, Az, limit, bias)) hits |= 1u;
+                    if (w8_slot_hit<1>(nx0, ny0, nz0, fx0, fy0, fz0, Bx, By, Bz, Ax, Ay, Az, limit, bias)) hits |= 2u;
+                    if (w8_slot_hit<2>(nx0, ny0, nz0, fx0, fy0, fz0, Bx, By, Bz, Ax, Ay, Az, limit, bias)) hits |= 4u;
+                    if (w8_slot_hit<3>(nx0, ny0, nz0, fx0, fy0, fz0, Bx, By, Bz, Ax, Ay, Az, limit, bias)) hits |= 8u;
+                    if (w8_slot_hit<0>(nx1, ny1, nz1, fx1, fy1, fz1, Bx, By, Bz, Ax, Ay, Az, limit, bias)) hits |= 16u;
+                    if (w8_slot_hit<1>(nx1, ny1, nz1, fx1, fy1, fz1, Bx, By, Bz, Ax, Ay, Az, limit, bias)) hits |= 32u;
+                    if (w8_slot_hit<2>(nx1, ny1, nz1, fx1, fy1, fz1, Bx, By, Bz, Ax, Ay, Az, limit, bias)) hits |= 64u;
+                    if (w8_slot_hit<3>(nx1, ny1, nz1, fx1, fy1, fz1, Bx, By, Bz, Ax, Ay, Az, limit, bias)) hits |= 128u;
+                    const uint32_t imask = u1.z & 0xffu;
+                    const uint32_t inner = hits & imask;
+                    uint32_t leaf = hits & ~imask;
+                    // the rest of the group this node came from waits on the stack
+                    if ((g_bits >> 8) != 0u) W8_PUSH(make_uint2(g_base, g_bits));
+                    g_base = h1.z;
+                    g_bits = imask | ((uint32_t)s_perm[near_mask * 256u + inner] << 8);
+                    // triangles of the hit leaf slots: meta byte = (count << 5) | offset
+                    t_base = h1.w;
+                    t_mask = 0u;
+                    while (leaf != 0u) {
+                        const int s = __ffs(leaf) - 1;
+                        leaf &= leaf - 1u;
+                        const uint32_t mb = ((s < 4 ? l1.z : l1.w) >> ((s & 3) * 8)) & 0xffu;
+                        t_mask |= ((1u << (mb >> 5)) - 1u) << (mb & 31u);
+                    }
+                    node = -1;
+                    if (t_mask == 0u) select_next();
+                }
+            }
+            // ---------------- triangle phase: every lane with pending triangles tests one per iteration ----------------
+            while (true) {
+                const bool has = t_mask != 0u;
+                const unsigned m_tri = __ballot_sync(FULL, has);
+                if (m_tri == 0u) break;
+                if (has) {
+                    const int k = __ffs(t_mask) - 1;
+                    t_mask &= t_mask - 1u;
+                    const int tri = (int)t_base + k;
+                    if (COUNT) n_tests++;
+                    float t;
+                    const int r = tri_test_t<true>(sc.acc_tri_geo + (size_t)tri * 4, o, d, best, t, tri_na);
+                    if (r == 2) {
+                        tie = true;              // a second triangle at exactly the best distance: visit order would decide
+                    } else if (r == 1) {
+                        best = t;
+                        best_tri = tri;
+                        tie = false;
+                        if (ANYHIT) { t_mask = 0u; g_bits = 0u; sp = 0; }   // any accepted hit ends a shadow ray
+                    }
+                    if (t_mask == 0u) select_next();
+                }
+            }
+            busy = __ballot_sync(FULL, ray >= 0);
+        } while (busy != 0u && (exhausted || __popc(busy) >= refill_thresh));
+    }
+#undef W8_PUSH
+#undef W8_POP
+    if (COUNT) {
+        atomicAdd(counts.node_visits, n_visits);
+        atomicAdd(counts.tri_tests, n_tests);
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // hit geometry + material for the final closest hit (tail of hitTriangle :198-214, getMaterial :110-135)

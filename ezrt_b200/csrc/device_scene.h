@@ -27,6 +27,7 @@
 #define EZRT_LEAF_MAX_N 127
 #define EZRT_TOP_NODES_MAX 1023   // 10 full levels; 80 B each in shared memory (bank-conflict padding)
 #define EZRT_ACC_TOP_NODES_MAX 255 // acceleration tree: 8 levels are enough (its upper levels are real SAH splits)
+#define EZRT_W8_SMEM_STACK 16      // per-lane W8 stack entries held in shared memory (8 B each x 1024 threads = 128 KB at most)
 #define EZRT_TOP_STRIDE 5         // float4 per shared-memory record
 #define EZRT_TILE 16             // == EZRT_PART_TILE
 #define EZRT_TILE_PIXELS 256
@@ -44,17 +45,18 @@ struct SceneDev {
     int root_ref;
     // acceleration tree (default traversal policy): sentinel-free SAH over the same triangles, boxes
     // inflated by 2*prune_delta; acc_tri_geo is tri_geo in the tree's own order, acc_tri_ref maps back
-    const float4* acc_nodes;
     const float4* acc_tri_geo;
     const uint32_t* acc_tri_ref;   // accel order -> reference triangle index
     const uint32_t* ref_to_acc;    // reference triangle index -> accel order
     const float4* acc_tri_shade;   // tri_shade in accel order (shading reads the arrays traversal keeps hot in L2)
     const int* acc_tri_leaf;       // reference leaf (slot in leaf_box) of every triangle, accel order
-    int acc_root_ref;
-    int acc_top_nodes;
-    const float4* acc_wide_nodes;  // the same tree collapsed to 4-wide nodes (128 B records); null = use the binary form
+    const uint4* w8_nodes;         // the tree as 8-wide nodes with 8-bit quantised child boxes (96 B records, w8_node.h); null = none
+    int w8_near_bit[3];            // significance of axis a in the slot index (octant order)
+    int w8_stack_entries;          // per-lane stack entries kept in shared memory (>= depth of the 8-wide tree, or the smem cap)
+    uint32_t w8_decode_bits;       // W8_DECODE_BITS (passed as data: see w8_plane in device_functions.cuh)
+    float w8_origin_limit;         // rays starting further out than this (any |coordinate|) go to the exact kernel (decode error bound)
+    const float4* acc_wide_nodes;  // the same tree collapsed to 4-wide nodes with exact boxes (128 B records): round-1 kernel, env EZRT_ACCEL=4
     int acc_wide_root_ref;
-    int acc_leaf_lanes;      // lanes per leaf in the cooperative leaf phase of the accel kernels: 4 (leaves <= 4) or 8
     // reference leaf of every reference triangle + the leaves' boxes (AA, BB as float4 pairs)
     const int* tri_leaf;
     const float4* leaf_box;

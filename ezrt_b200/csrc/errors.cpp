@@ -19,6 +19,6 @@ int ezrt_set_error(int code, const char* fmt, ...) {
 
 const char* ezrt_last_error(void) { return g_error; }
 
-int ezrt_version(void) { return 100; }
+int ezrt_version(void) { return 200; }  // 200: ezrt_counters grew (node_visits ...), params.profile = 2
 
 }  // extern "C"

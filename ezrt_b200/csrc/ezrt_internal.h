@@ -29,6 +29,21 @@ struct EzrtAccelNode {
 };
 // host_scene.cpp: sentinel-free SAH tree over the triangles of a Triangle_encoded array
 int ezrt_build_accel(const float* tris, int n_tris, int leaf_n, std::vector<EzrtAccelNode>& nodes, std::vector<uint32_t>& order);
+
+// accel_w8.cpp: the same tree collapsed to 8-wide nodes with 8-bit quantised child boxes (w8_node.h)
+struct EzrtW8Tree {
+    std::vector<uint32_t> nodes;       // W8_NODE_WORDS words per node; node 0 = root; breadth-first numbering
+    std::vector<uint32_t> tri_order;   // triangle i of the tree = tri_order[i] of the caller's triangle array
+    std::vector<int> leaf_first;       // per binary node: first triangle (new order) of that leaf, -1 for inner nodes
+    int depth;                         // levels of 8-wide nodes
+    int n_nodes;
+    long long n_children;              // occupied slots over all nodes (fill statistics)
+};
+// `order_in`: triangle order of the binary tree (ezrt_build_accel); `pad`: box inflation (2 * prune_delta);
+// axis_bit[a]: significance (0..2) of axis a in the slot index (largest scene extent -> bit 2).  Returns 0 or < 0.
+void ezrt_w8_axis_bits(const float bmin[3], const float bmax[3], int axis_bit[3]);
+int ezrt_build_w8(const std::vector<EzrtAccelNode>& an, const std::vector<uint32_t>& order_in, float pad, float max_abs_coord,
+                  const int axis_bit[3], EzrtW8Tree& out);
 #endif
 
 // Image partition shared by host and device code (ezrt_render_params.part_rank/part_count):

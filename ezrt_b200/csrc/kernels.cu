@@ -193,9 +193,9 @@ __device__ __forceinline__ TreeView reference_tree(const SceneDev& sc) {
     t.nodes = sc.nodes; t.tri_geo = sc.tri_geo; t.root_ref = sc.root_ref; t.top_nodes = sc.top_nodes; t.wide = 0;
     return t;
 }
-__device__ __forceinline__ TreeView accel_tree(const SceneDev& sc) {
+__device__ __forceinline__ TreeView accel_tree(const SceneDev& sc) {  // the 4-wide exact-box form (round-1 kernel, env EZRT_ACCEL=4)
     TreeView t;
-    t.nodes = sc.acc_nodes; t.tri_geo = sc.acc_tri_geo; t.root_ref = sc.acc_root_ref; t.top_nodes = sc.acc_top_nodes; t.wide = 0;
+    t.nodes = sc.acc_wide_nodes; t.tri_geo = sc.acc_tri_geo; t.root_ref = sc.acc_wide_root_ref; t.top_nodes = 0; t.wide = 1;
     return t;
 }
 
@@ -205,11 +205,12 @@ struct ExtendIO {
     PathQueue q;
     const uint32_t* perm;      // null: trace in queue order
     const uint32_t* to_accel;  // non-null (fallback pass of the accel policy): hits are stored as accel-order indices
-    __device__ __forceinline__ void load(uint32_t i, vec3& o, vec3& d) const {
+    __device__ __forceinline__ bool load(uint32_t i, vec3& o, vec3& d) const {
         const uint32_t j = perm ? perm[i] : i;
         float4 o4 = __ldcs(q.ray_o + j), d4 = __ldcs(q.ray_d + j);  // queue data streams through the caches
         o = ez_v3(o4.x, o4.y, o4.z);
         d = ez_v3(d4.x, d4.y, d4.z);
+        return true;
     }
     __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3, const RaySlab&) const {
         const uint32_t j = perm ? perm[i] : i;
@@ -241,10 +242,11 @@ struct AccelIO {
     const float4* leaf_box;
     uint32_t* defer_list;
     uint32_t* defer_count;
-    __device__ __forceinline__ void load(uint32_t i, vec3& o, vec3& d) const {
+    __device__ __forceinline__ bool load(uint32_t i, vec3& o, vec3& d) const {
         float4 o4 = __ldcs(q.ray_o + i), d4 = __ldcs(q.ray_d + i);
         o = ez_v3(o4.x, o4.y, o4.z);
         d = ez_v3(d4.x, d4.y, d4.z);
+        return true;
     }
     __device__ __forceinline__ void defer(uint32_t i) const { defer_list[atomicAdd(defer_count, 1u)] = i; }
     __device__ __forceinline__ void store(uint32_t i, HitRec h, bool tie, vec3 o, const RaySlab& rs) const {
@@ -266,15 +268,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     io.leaf_box = sc.leaf_box;
     io.defer_list = defer_list;
     io.defer_count = defer_count;
-    TreeView tree = accel_tree(sc);
-    if (WIDE) {  // 4-wide records, read straight from global memory / L1
-        tree.nodes = sc.acc_wide_nodes;
-        tree.root_ref = sc.acc_wide_root_ref;
-        tree.top_nodes = 0;
-        tree.wide = 1;
-    } else {
-        stage_top_nodes(tree);
-    }
+    const TreeView tree = accel_tree(sc);  // 4-wide records, read straight from global memory / L1
     extend_persistent<true, ANYHIT, true, WIDE, LL>(sc, tree, *q_count, work, io, g_smem_top);
 }
 
@@ -284,11 +278,12 @@ struct ShadowIO {
     ShadowQueue sq;
     float4* Lo;
     const uint32_t* perm;
-    __device__ __forceinline__ void load(uint32_t i, vec3& o, vec3& d) const {
+    __device__ __forceinline__ bool load(uint32_t i, vec3& o, vec3& d) const {
         const uint32_t j = perm ? perm[i] : i;
         float4 o4 = __ldcs(sq.ray_o + j), d4 = __ldcs(sq.ray_d + j);
         o = ez_v3(o4.x, o4.y, o4.z);
         d = ez_v3(d4.x, d4.y, d4.z);
+        return true;
     }
     __device__ __forceinline__ void add(uint32_t j) const {
         uint32_t slot = __float_as_uint(sq.ray_o[j].w);
@@ -321,7 +316,7 @@ struct ShadowAccelIO {
     const float4* leaf_box;
     uint32_t* defer_list;
     uint32_t* defer_count;
-    __device__ __forceinline__ void load(uint32_t i, vec3& o, vec3& d) const { base.load(i, o, d); }
+    __device__ __forceinline__ bool load(uint32_t i, vec3& o, vec3& d) const { return base.load(i, o, d); }
     __device__ __forceinline__ void defer(uint32_t i) const { defer_list[atomicAdd(defer_count, 1u)] = i; }
     __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3 o, const RaySlab& rs) const {
         if (h.tri < 0) {  // nothing accepted anywhere: the shader finds nothing either
@@ -345,16 +340,96 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     io.leaf_box = sc.leaf_box;
     io.defer_list = defer_list;
     io.defer_count = defer_count;
-    TreeView tree = accel_tree(sc);
-    if (WIDE) {
-        tree.nodes = sc.acc_wide_nodes;
-        tree.root_ref = sc.acc_wide_root_ref;
-        tree.top_nodes = 0;
-        tree.wide = 1;
-    } else {
-        stage_top_nodes(tree);
-    }
+    const TreeView tree = accel_tree(sc);
     extend_persistent<true, true, true, WIDE, LL>(sc, tree, *s_count, work, io, g_smem_top);
+}
+
+// ---- W8 kernels (default accel policy): extend_w8 on the 8-wide quantised tree, per-lane stacks and the octant
+// permutation table in shared memory.  Same deferral rule as k_extend_accel.
+__device__ __forceinline__ void w8_smem_setup(unsigned char*& s_perm, uint2*& stack_sm) {
+    unsigned char* base = reinterpret_cast<unsigned char*>(g_smem_top);
+    s_perm = base;
+    stack_sm = reinterpret_cast<uint2*>(base + 2048);
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+        const int m = i >> 8, x = i & 255;
+        int y = 0;
+        for (int b = 0; b < 8; b++)
+            if ((x >> b) & 1) y |= 1 << (b ^ m);
+        s_perm[i] = (unsigned char)y;
+    }
+    __syncthreads();
+}
+
+struct W8ExtendIO {
+    PathQueue q;
+    const int* acc_tri_leaf;
+    const float4* leaf_box;
+    uint32_t* defer_list;
+    uint32_t* defer_count;
+    __device__ __forceinline__ bool load(uint32_t i, vec3& o, vec3& d) const {
+        float4 o4 = __ldcs(q.ray_o + i), d4 = __ldcs(q.ray_d + i);
+        o = ez_v3(o4.x, o4.y, o4.z);
+        d = ez_v3(d4.x, d4.y, d4.z);
+        return true;
+    }
+    __device__ __forceinline__ void defer(uint32_t i) const { defer_list[atomicAdd(defer_count, 1u)] = i; }
+    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool tie, vec3 o, vec3 inv) const {
+        if (h.tri >= 0 && (tie || !reference_reaches_leaf_inv(acc_tri_leaf, leaf_box, h.tri, o, inv))) {
+            defer(i);
+            return;
+        }
+        __stcs(q.hit + i, make_float2(h.t, __int_as_float(h.tri)));  // accel-order triangle index
+    }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend_w8(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count, uint32_t* work,
+                                                                   uint32_t* defer_list, uint32_t* defer_count, W8Counts counts) {
+    unsigned char* s_perm;
+    uint2* stack_sm;
+    w8_smem_setup(s_perm, stack_sm);
+    W8ExtendIO io;
+    io.q = q;
+    io.acc_tri_leaf = sc.acc_tri_leaf;
+    io.leaf_box = sc.leaf_box;
+    io.defer_list = defer_list;
+    io.defer_count = defer_count;
+    extend_w8<false, COUNT>(sc, *q_count, work, io, s_perm, stack_sm, counts);
+}
+
+struct W8ShadowIO {
+    ShadowIO base;
+    const int* acc_tri_leaf;
+    const float4* leaf_box;
+    uint32_t* defer_list;
+    uint32_t* defer_count;
+    __device__ __forceinline__ bool load(uint32_t i, vec3& o, vec3& d) const { return base.load(i, o, d); }
+    __device__ __forceinline__ void defer(uint32_t i) const { defer_list[atomicAdd(defer_count, 1u)] = i; }
+    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3 o, vec3 inv) const {
+        if (h.tri < 0) {  // nothing accepted anywhere: the shader finds nothing either
+            base.add(i);
+            return;
+        }
+        // occluded if the shader reaches the occluder's leaf; otherwise the exact kernel decides
+        if (!reference_reaches_leaf_inv(acc_tri_leaf, leaf_box, h.tri, o, inv)) defer(i);
+    }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_shadow_w8(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count, uint32_t* work,
+                                                                   float4* __restrict__ Lo, uint32_t* defer_list, uint32_t* defer_count, W8Counts counts) {
+    unsigned char* s_perm;
+    uint2* stack_sm;
+    w8_smem_setup(s_perm, stack_sm);
+    W8ShadowIO io;
+    io.base.sq = sq;
+    io.base.Lo = Lo;
+    io.base.perm = nullptr;
+    io.acc_tri_leaf = sc.acc_tri_leaf;
+    io.leaf_box = sc.leaf_box;
+    io.defer_list = defer_list;
+    io.defer_count = defer_count;
+    extend_w8<true, COUNT>(sc, *s_count, work, io, s_perm, stack_sm, counts);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -662,21 +737,27 @@ void launch_extend(const SceneDev& sc, bool prune, bool anyhit, PathQueue q, con
     else if (anyhit) k_extend<false, true><<<blocks, threads, smem_for(k_extend<false, true>, sc.top_nodes), st>>>(sc, q, q_count, work, perm, to_accel);
     else k_extend<false, false><<<blocks, threads, smem_for(k_extend<false, false>, sc.top_nodes), st>>>(sc, q, q_count, work, perm, to_accel);
 }
-// accel policy: acceleration-tree pass, then the exact pass over whatever it deferred
-void launch_extend_accel(const SceneDev& sc, bool anyhit, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t* defer_list,
-                         uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, cudaStream_t st) {
+template <class K>
+static size_t w8_smem_for(K kernel, const SceneDev& sc) {
+    size_t bytes = 2048 + (size_t)sc.w8_stack_entries * sizeof(uint2) * extend_threads();
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return bytes;
+}
+// accel policy: acceleration-tree pass (W8, or the round-1 4-wide kernel when the scene carries no W8 tree), then the
+// exact pass over whatever it deferred.  counts != null selects the counting instantiation (params.profile = 2).
+void launch_extend_accel(const SceneDev& sc, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t* defer_list,
+                         uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, unsigned long long* counts, cudaStream_t st) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
-#define EZRT_LAUNCH_EA(AH, W, L, TOP) k_extend_accel<AH, W, L><<<blocks, threads, smem_for(k_extend_accel<AH, W, L>, TOP), st>>>(sc, q, q_count, work, defer_list, defer_count)
-    if (sc.acc_wide_nodes) {
-        if (sc.acc_leaf_lanes == 4) { if (anyhit) EZRT_LAUNCH_EA(true, true, 4, 0); else EZRT_LAUNCH_EA(false, true, 4, 0); }
-        else { if (anyhit) EZRT_LAUNCH_EA(true, true, 8, 0); else EZRT_LAUNCH_EA(false, true, 8, 0); }
-    } else if (anyhit) {
-        EZRT_LAUNCH_EA(true, false, 8, sc.acc_top_nodes);
+    if (sc.w8_nodes) {
+        W8Counts c;
+        c.node_visits = counts;
+        c.tri_tests = counts ? counts + 1 : nullptr;
+        if (counts) k_extend_w8<true><<<blocks, threads, w8_smem_for(k_extend_w8<true>, sc), st>>>(sc, q, q_count, work, defer_list, defer_count, c);
+        else k_extend_w8<false><<<blocks, threads, w8_smem_for(k_extend_w8<false>, sc), st>>>(sc, q, q_count, work, defer_list, defer_count, c);
     } else {
-        EZRT_LAUNCH_EA(false, false, 8, sc.acc_top_nodes);
+        k_extend_accel<false, true, 4><<<blocks, threads, smem_for(k_extend_accel<false, true, 4>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count);
     }
-#undef EZRT_LAUNCH_EA
-    launch_extend(sc, true, anyhit, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_max, 65536u), n_sms, st);
+    launch_extend(sc, true, false, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_max, 65536u), n_sms, st);
 }
 // counting sort of the queue's ray indices into `perm` (3 kernels; bins must hold EZRT_SORT_BINS counters)
 void launch_ray_sort(const SceneDev& sc, PathQueue q, const uint32_t* q_count, uint32_t* keys, uint32_t* bins, uint32_t* perm,
@@ -694,14 +775,17 @@ void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_
     else k_shadow<false><<<blocks, threads, smem_for(k_shadow<false>, sc.top_nodes), st>>>(sc, sq, s_count, work, Lo, perm);
 }
 void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo, uint32_t* defer_list,
-                         uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, cudaStream_t st) {
+                         uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, unsigned long long* counts, cudaStream_t st) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
-    if (sc.acc_wide_nodes && sc.acc_leaf_lanes == 4)
+    if (sc.w8_nodes) {
+        W8Counts c;
+        c.node_visits = counts;
+        c.tri_tests = counts ? counts + 1 : nullptr;
+        if (counts) k_shadow_w8<true><<<blocks, threads, w8_smem_for(k_shadow_w8<true>, sc), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count, c);
+        else k_shadow_w8<false><<<blocks, threads, w8_smem_for(k_shadow_w8<false>, sc), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count, c);
+    } else {
         k_shadow_accel<true, 4><<<blocks, threads, smem_for(k_shadow_accel<true, 4>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
-    else if (sc.acc_wide_nodes)
-        k_shadow_accel<true, 8><<<blocks, threads, smem_for(k_shadow_accel<true, 8>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
-    else
-        k_shadow_accel<false, 8><<<blocks, threads, smem_for(k_shadow_accel<false, 8>, sc.acc_top_nodes), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
+    }
     launch_shadow(sc, true, sq, defer_count, defer_work, Lo, defer_list, std::min<uint32_t>(n_max, 65536u), n_sms, st);
 }
 void launch_shade(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, int bounce, uint32_t batch_first_frame,

@@ -1,14 +1,22 @@
 """Synthetic scenes for the benchmark configurations of BASELINE.json.
 
-/root/reference (and with it the Stanford bunny OBJ) does not exist on the GPU box, so the
-"bunny" here is a procedural stand-in of the same size class: a bumpy icosphere with 5120
-triangles ("blob"), emitted as OBJ text and pushed through the same readObj() parser, unit-box
-normalisation, transform and smooth-normal code as the reference's meshes.  Geometry uses
-only + - * / sqrt and integer hashing, so the OBJ text is identical on every machine.
+The named scenes use the Stanford bunny.  /root/reference (and its OBJ files) does not exist on the GPU box, so the
+bunny travels as an indexed mesh asset (ezrt_b200/data/bunny.npz, 2503 vertices / 4968 faces, recovered from the
+committed P3 scene arrays by tests/golden/make_bunny_asset.py); it is emitted as OBJ text and pushed through the same
+readObj() parser, unit-box normalisation, transform and smooth-normal code as any mesh file.  sphere.obj (320
+triangles) and quad.obj (a 12-triangle box) are regenerated procedurally with the same triangle counts.
 
-  s_bunny()  ~ P3/main.cpp:690-701: blob (5120) + floor box (12) + emissive sphere (320) = 5452 tris
-  s_1m()     ~ "1M-triangle merged scene": 195 blobs on a 15x13 grid + 4 emissive spheres + floor = 999,692 tris
+  s_p3_bunny()   P3/main.cpp:690-701: bunny (4968) + floor (12) + emissive sphere (320) = 5300 tris     [C1, C2]
+  s_1m_bunny()   SURVEY 8(d) "S-1M": 201 bunnies in the first 201 slots of a 15x14 grid + 4 emissive spheres + floor
+                 = 201*4968 + 1280 + 12 = 999,860 triangles                                              [C3, C4, C5]
+
+Second workload family kept from round 1 (a procedural stand-in mesh, "blob" = bumpy icosphere, 5120 triangles;
+geometry uses only + - * / sqrt and integer hashing, so the OBJ text is identical on every machine):
+
+  s_bunny()  blob (5120) + floor box (12) + emissive sphere (320) = 5452 tris
+  s_1m()     195 blobs on a 15x13 grid + 4 emissive spheres + floor = 999,692 tris
 """
+import os
 import numpy as np
 
 from . import api
@@ -92,6 +100,27 @@ def blob_obj(subdiv=4, seed=7):
     return _CACHE[key]
 
 
+def bunny_obj():
+    """The Stanford bunny asset as OBJ text ("%.9g" round-trips fp32)."""
+    key = ("bunny",)
+    if key not in _CACHE:
+        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "bunny.npz"))
+        lines = ["v %.9g %.9g %.9g" % (p[0], p[1], p[2]) for p in z["verts"]]
+        lines += ["f %d %d %d" % (a + 1, b + 1, c + 1) for a, b, c in z["faces"]]
+        _CACHE[key] = "\n".join(lines) + "\n"
+    return _CACHE[key]
+
+
+def _unit_ymin(text):
+    """Lowest y of a mesh after readObj's unit-box normalisation (identity transform): instances are set on the floor with it."""
+    key = ("ymin", hash(text))
+    if key not in _CACHE:
+        tl = TriangleList()
+        tl.read_obj_text(text, Material(), transform_matrix(), False)
+        _CACHE[key] = float(tl.encode_triangles()[:, :9].reshape(-1, 3)[:, 1].min())
+    return _CACHE[key]
+
+
 def sphere_obj(subdiv=2):
     """320-triangle sphere (same count as the reference's sphere.obj)."""
     key = ("sphere", subdiv)
@@ -141,21 +170,27 @@ def s_bunny(builder=api.BVH_SAH_FAST):
     return tris, nodes, eye, cam
 
 
-def grid_meshes(nx, nz, n_lights=4, pitch=1.2):
-    """nx*nz blob instances on a grid (y-rotation and scale from wang_hash, material preset id%8),
-    `n_lights` emissive spheres above it and a floor box, as readObj calls: [(obj text, Material, trans, smooth)]"""
+def grid_meshes(nx, nz, n_lights=4, pitch=1.2, mesh="blob", count=None):
+    """Instances of `mesh` ("blob" | "bunny") in the first `count` (default all) row-major slots of an nx x nz grid
+    (y-rotation 360*u0 and scale 0.8+0.4*u1 from successive wang_hash outputs of seed (id*9781+1)|1, material preset
+    id%8), `n_lights` emissive spheres above it and a floor box, as readObj calls: [(obj text, Material, trans, smooth)]"""
     out = []
-    text = blob_obj()
+    text = blob_obj() if mesh == "blob" else bunny_obj()
+    ymin = None if mesh == "blob" else _unit_ymin(text)
+    count = nx * nz if count is None else count
     inst = 0
     for iz in range(nz):
         for ix in range(nx):
+            if inst >= count:
+                break
             u = _unit_randoms(inst * 9781 + 1, 2)
             rot = 360.0 * u[0]
             sc = 0.8 + 0.4 * u[1]
             x = (ix - (nx - 1) / 2.0) * pitch
             z = (iz - (nz - 1) / 2.0) * pitch
             m = MATERIAL_PRESETS[inst % 8]
-            out.append((text, m, transform_matrix((0, rot, 0), (x, -1.4 + 0.6 * sc, z), (sc, sc, sc)), True))
+            y = (-1.4 + 0.6 * sc) if ymin is None else (-1.395 - sc * ymin)  # feet on the floor (top face at y = -1.395)
+            out.append((text, m, transform_matrix((0, rot, 0), (x, y, z), (sc, sc, sc)), True))
             inst += 1
     light = Material(baseColor=(1, 1, 1), emissive=(20, 20, 20))
     sph = sphere_obj()
@@ -170,10 +205,10 @@ def grid_meshes(nx, nz, n_lights=4, pitch=1.2):
     return out
 
 
-def s_grid(nx, nz, n_lights=4, builder=api.BVH_SAH_FAST, pitch=1.2):
+def s_grid(nx, nz, n_lights=4, builder=api.BVH_SAH_FAST, pitch=1.2, mesh="blob", count=None):
     """grid_meshes() built with the default leaf size.  Returns (tris, nodes, eye, cam)."""
     tl = TriangleList()
-    for text, m, trans, smooth in grid_meshes(nx, nz, n_lights, pitch):
+    for text, m, trans, smooth in grid_meshes(nx, nz, n_lights, pitch, mesh, count):
         tl.read_obj_text(text, m, trans, smooth)
     tris, nodes = tl.build_bvh(8, builder)
     r = 0.62 * max(nx * pitch, nz * pitch) + 3.0
@@ -184,6 +219,31 @@ def s_grid(nx, nz, n_lights=4, builder=api.BVH_SAH_FAST, pitch=1.2):
 def s_1m(builder=api.BVH_SAH_FAST):
     """195 blobs (15 x 13) + 4 spheres + floor = 195*5120 + 1280 + 12 = 999,692 triangles."""
     return s_grid(15, 13, 4, builder)
+
+
+def s_1m_bunny(builder=api.BVH_SAH_FAST):
+    """S-1M of SURVEY.md 8(d): 201 Stanford bunnies (15 x 14 grid, first 201 slots) + 4 spheres + floor = 999,860 triangles,
+    camera orbit rotatAngle 30, upAngle 25."""
+    return s_grid(15, 14, 4, builder, mesh="bunny", count=201)
+
+
+def p3_bunny_meshes():
+    """P3's scene block (P3/main.cpp:690-701) with the real bunny."""
+    return [
+        (bunny_obj(), Material(baseColor=(1, 1, 1)), transform_matrix((0, 0, 0), (0.3, -1.6, 0.0), (1.5, 1.5, 1.5)), True),
+        (box_obj(), Material(baseColor=(0.725, 0.71, 0.68)), transform_matrix((0, 0, 0), (0, -1.4, 0), (18.83, 0.01, 18.83)), False),
+        (sphere_obj(), Material(baseColor=(1, 1, 1), emissive=(30, 20, 10)), transform_matrix((0, 0, 0), (0.0, 0.9, 0.0), (1, 1, 1)), False),
+    ]
+
+
+def s_p3_bunny(builder=api.BVH_SAH_FAST):
+    """Stanford bunny 4968 + floor 12 + emissive sphere 320 = 5300 triangles, eye (0,0,4) (P3/main.cpp:148-150)."""
+    tl = TriangleList()
+    for text, m, trans, smooth in p3_bunny_meshes():
+        tl.read_obj_text(text, m, trans, smooth)
+    tris, nodes = tl.build_bvh(8, builder)
+    eye, cam = api.camera_orbit(0.0, 0.0, 4.0)
+    return tris, nodes, eye, cam
 
 
 def synth_hdr(width=512, height=256, seed=3, n_lamps=16):

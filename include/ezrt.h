@@ -92,7 +92,9 @@ typedef struct ezrt_render_params {
      * writes them compactly (tile-major) unless part_count == 1. */
     int32_t part_rank, part_count;
     int32_t frames_per_batch; /* wavefront: display() calls traced concurrently (0 = auto)   */
-    int32_t profile;          /* 1: bracket every kernel with CUDA events (ezrt_get_kernel_times) */
+    int32_t profile;          /* 1: bracket every kernel with CUDA events (ezrt_get_kernel_times);
+                                 2: count the records the accel traversal fetches (ezrt_counters.node_visits / tri_tests;
+                                    a slower instantiation of the same kernels -- never inside a timed region) */
     int32_t reserved[3];
 } ezrt_render_params;
 
@@ -103,6 +105,9 @@ typedef struct ezrt_counters {
     uint64_t kernel_launches;
     double device_ms;       /* CUDA-event time of the last render on its stream              */
     uint64_t deferred_rays; /* accel policy: rays re-traced by the exact reference-order pass */
+    uint64_t node_visits;   /* profile = 2: acceleration-tree node records fetched ...       */
+    uint64_t tri_tests;     /*              ... and triangle records fetched by the accel kernels */
+    uint32_t node_record_bytes, tri_record_bytes; /* sizes of those records in HBM          */
 } ezrt_counters;
 
 typedef struct ezrt_scene ezrt_scene; /* device-resident scene (replaces the two TBOs + 2 textures) */

@@ -808,14 +808,19 @@ Scene makeScene(const float* tris, int nTriangles, const float* nodes, int nNode
 extern "C" {
 
 // counters_out[0..8] = rays_primary, rays_bounce, rays_shadow, N_node, N_tri, H, hdr_lookups, samples, max_stack
-int oracle_render(const float* tris, int nTriangles, const float* nodes, int nNodes, const float* hdr,
-                  const float* hdrCache, int hdrW, int hdrH, int hdrLinear, const ezrt_render_params* p,
-                  float* framebuffer, uint64_t* counters_out, int n_threads) {
+// Window form: only the pixels [x0,x1) x [y0,y1) of the width x height grid are rendered, into a framebuffer of
+// (y1-y0) x (x1-x0) pixels (row 0 = row y0).  Pixel (px,py) gets exactly the value the full render gives it: seed,
+// Sobol index and Cranley-Patterson shift depend only on (px, py, frame) (P5/fsh:315-318, :379-382).  This lets the
+// parity tests check the BASELINE configs on their OWN pixel grid (1920x1080, 1024x1024) at a cost of seconds.
+int oracle_render_window(const float* tris, int nTriangles, const float* nodes, int nNodes, const float* hdr,
+                         const float* hdrCache, int hdrW, int hdrH, int hdrLinear, const ezrt_render_params* p,
+                         int x0, int y0, int x1, int y1, float* framebuffer, uint64_t* counters_out, int n_threads) {
     if (!tris || !nodes || !p || !framebuffer || nTriangles <= 0 || nNodes < 2) return -1;
+    if (x0 < 0 || y0 < 0 || x1 > p->width || y1 > p->height || x1 <= x0 || y1 <= y0) return -1;
     if (p->mode == EZRT_MODE_DISNEY_IS_MIS_P5 && (!hdr || !hdrCache)) return -1;
     Scene sc = makeScene(tris, nTriangles, nodes, nNodes, hdr, hdrCache, hdrW, hdrH, hdrLinear, p->env_color, p->mode,
                          p->traverse);
-    const int W = p->width, H = p->height, C = (p->out_channels == 4) ? 4 : 3;
+    const int C = (p->out_channels == 4) ? 4 : 3;
     Counters total;
     memset(&total, 0, sizeof(total));
 #ifdef _OPENMP
@@ -826,9 +831,9 @@ int oracle_render(const float* tris, int nTriangles, const float* nodes, int nNo
         Counters cn;
         memset(&cn, 0, sizeof(cn));
 #pragma omp for schedule(dynamic, 1)
-        for (int py = 0; py < H; py++) {
-            for (int pxl = 0; pxl < W; pxl++) {
-                float* dst = framebuffer + ((size_t)py * W + pxl) * C;
+        for (int py = y0; py < y1; py++) {
+            for (int pxl = x0; pxl < x1; pxl++) {
+                float* dst = framebuffer + ((size_t)(py - y0) * (x1 - x0) + (pxl - x0)) * C;
                 vec3 acc = ez_v3(dst[0], dst[1], dst[2]);
                 if (p->first_frame == 0) acc = ez_v3(0, 0, 0);
                 for (int s = 0; s < p->spp; s++) {
@@ -854,10 +859,18 @@ int oracle_render(const float* tris, int nTriangles, const float* nodes, int nNo
     if (counters_out) {
         counters_out[0] = total.rays[0]; counters_out[1] = total.rays[1]; counters_out[2] = total.rays[2];
         counters_out[3] = total.nodes; counters_out[4] = total.tris; counters_out[5] = total.hits;
-        counters_out[6] = total.hdr_lookups; counters_out[7] = (uint64_t)W * H * (uint64_t)p->spp;
+        counters_out[6] = total.hdr_lookups; counters_out[7] = (uint64_t)(x1 - x0) * (y1 - y0) * (uint64_t)p->spp;
         counters_out[8] = total.max_stack;
     }
     return 0;
+}
+
+int oracle_render(const float* tris, int nTriangles, const float* nodes, int nNodes, const float* hdr,
+                  const float* hdrCache, int hdrW, int hdrH, int hdrLinear, const ezrt_render_params* p,
+                  float* framebuffer, uint64_t* counters_out, int n_threads) {
+    if (!p) return -1;
+    return oracle_render_window(tris, nTriangles, nodes, nNodes, hdr, hdrCache, hdrW, hdrH, hdrLinear, p, 0, 0, p->width, p->height,
+                                framebuffer, counters_out, n_threads);
 }
 
 // hitBVH for n rays; brute = 1 runs hitArray over all triangles instead (P2/main.cpp:585's cross-check).

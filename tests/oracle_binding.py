@@ -17,6 +17,9 @@ _ip = C.POINTER(C.c_int32)
 _u64p = C.POINTER(C.c_uint64)
 _o.oracle_render.restype = C.c_int
 _o.oracle_render.argtypes = [_fp, C.c_int, _fp, C.c_int, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(RenderParams), _fp, _u64p, C.c_int]
+_o.oracle_render_window.restype = C.c_int
+_o.oracle_render_window.argtypes = [_fp, C.c_int, _fp, C.c_int, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(RenderParams), C.c_int, C.c_int, C.c_int, C.c_int,
+                                    _fp, _u64p, C.c_int]
 _o.oracle_trace_rays.restype = C.c_int
 _o.oracle_trace_rays.argtypes = [_fp, C.c_int, _fp, C.c_int, C.c_int, _fp, _fp, C.c_int, C.c_int, C.c_int, _ip, _fp, _ip, _ip, _fp, _fp, _u64p]
 _o.oracle_eval_brdf.restype = C.c_int
@@ -43,18 +46,20 @@ def _f32(a, shape=None):
     return a if shape is None else a.reshape(shape)
 
 
-def render(tris, nodes, cfg, hdr=None, hdr_cache=None, hdr_linear=True, framebuffer=None, threads=0):
-    """ezrt_ref_render: `cfg.spp` display() calls on the CPU.  Returns (image [H,W,C], counters dict)."""
+def render(tris, nodes, cfg, hdr=None, hdr_cache=None, hdr_linear=True, framebuffer=None, threads=0, window=None):
+    """ezrt_ref_render: `cfg.spp` display() calls on the CPU.  Returns (image [H,W,C], counters dict).
+    window = (x0, y0, x1, y1): only that pixel rectangle of the cfg.width x cfg.height grid, image [y1-y0, x1-x0, C]."""
     tris = _f32(tris, (-1, 36)); nodes = _f32(nodes, (-1, 12))
     hw = hh = 0
     if hdr is not None:
         hdr = _f32(hdr); hdr_cache = None if hdr_cache is None else _f32(hdr_cache)
         hh, hw = hdr.shape[0], hdr.shape[1]
-    fb = np.zeros((cfg.height, cfg.width, cfg.out_channels), dtype=np.float32) if framebuffer is None else framebuffer
+    x0, y0, x1, y1 = (0, 0, cfg.width, cfg.height) if window is None else window
+    fb = np.zeros((y1 - y0, x1 - x0, cfg.out_channels), dtype=np.float32) if framebuffer is None else framebuffer
     cnt = np.zeros(9, dtype=np.uint64)
     p = cfg.to_struct()
-    rc = _o.oracle_render(_f(tris), tris.shape[0], _f(nodes), nodes.shape[0], _f(hdr), _f(hdr_cache), hw, hh, int(bool(hdr_linear)),
-                          C.byref(p), _f(fb), cnt.ctypes.data_as(_u64p), int(threads))
+    rc = _o.oracle_render_window(_f(tris), tris.shape[0], _f(nodes), nodes.shape[0], _f(hdr), _f(hdr_cache), hw, hh, int(bool(hdr_linear)),
+                                 C.byref(p), int(x0), int(y0), int(x1), int(y1), _f(fb), cnt.ctypes.data_as(_u64p), int(threads))
     if rc != 0:
         raise RuntimeError("oracle_render failed (%d)" % rc)
     c = {k: int(v) for k, v in zip(COUNTER_NAMES, cnt)}

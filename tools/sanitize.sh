@@ -1,0 +1,19 @@
+#!/bin/bash
+# compute-sanitizer over the wavefront queues: memcheck, racecheck, initcheck, synccheck
+# on one small render per mode x policy x pipeline (tools/sanitize_case.py).  GPU box:  bash tools/sanitize.sh [WxH]
+# Output: gpurun_out/sanitizer_<tool>.log (+ a one-line verdict each in gpurun_out/sanitizer_summary.txt)
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+SZ=${1:-96x54}
+CS=$(command -v compute-sanitizer || echo /usr/local/cuda/bin/compute-sanitizer)
+: > gpurun_out/sanitizer_summary.txt
+for tool in memcheck racecheck initcheck synccheck; do
+    log=gpurun_out/sanitizer_${tool}.log
+    extra=""
+    [ "$tool" = memcheck ] && extra="--leak-check no"
+    EZRT_AUTO_BUILD=0 timeout 900 "$CS" --tool $tool $extra --print-limit 20 python tools/sanitize_case.py "$SZ" > "$log" 2>&1
+    rc=$?
+    echo "$tool rc=$rc: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|sanitize_case:' "$log" | tr '\n' ' ')" >> gpurun_out/sanitizer_summary.txt
+done
+cat gpurun_out/sanitizer_summary.txt
