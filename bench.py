@@ -4,22 +4,28 @@
   python bench.py --gpus N --steps K --warmup W          (N > 1: launched by torch.distributed.run)
   python bench.py --impl reference ...                   (the reference shader source / CPU oracle on the host cores, same config)
 
-Workload (BASELINE.json): N = 1 is configs[2] "C3" -- the ~1M-triangle synthetic scene
-(ezrt_b200.scenes.s_1m: 999,692 triangles), 1920x1080, Disney BRDF + Sobol (mode disney_sobol_p5),
-2 bounces; the north_star target (>= 1 Gray/s) is quoted on this scene.  One step = one pass of the
-hot path over one batch: `--spp-per-step` consecutive display() calls (default 16; the default 16
-steps make up C3's 256 spp), accumulating into the same framebuffer with frameCounter advancing.
-N > 1 is weak scaling: every GPU owns 1920x1080 pixels' worth of 16x16 tiles of an image that
-grows with N (N=4 is C5's 3840x2160), and every step ends with the single NCCL framebuffer gather.
+Workloads (BASELINE.json configs; scenes of SURVEY.md 8d, ezrt_b200/scenes.py):
+  N = 1  : configs[2] "C3" -- S-1M (201 Stanford bunnies + 4 spheres + floor = 999,860 triangles), 1920x1080, Disney BRDF +
+           Sobol (mode disney_sobol_p5), 2 bounces; the north_star target (>= 1 Gray/s) is quoted on this scene.  After the
+           headline the same invocation measures configs[1] "C2" (bunny 5,300 triangles, 1024x1024, diffuse) and
+           configs[3] "C4" (C3 + HDR importance sampling + MIS) and appends them under "workloads".
+  N > 1  : configs[4] "C5" -- the SAME scene and integrator on ONE fixed 3840x2160 image split by 16x16 tiles over the N
+           GPUs (strong scaling; `--workload c4` selects the IS/MIS integrator), one NCCL framebuffer gather per render.
+           --scaling weak keeps round 1's growing image (1920x1080 pixels per GPU).
+One step = one pass of the hot path over one batch: `--spp-per-step` consecutive display() calls (default 16; the default
+16 steps make up C3's 256 spp), accumulating into the same framebuffer with frameCounter advancing.
 
-value  : total rays of all ranks / max-over-ranks CUDA-event time of the K timed steps, scene and
-         framebuffer resident in HBM (ezrt_render_device on the current stream).
-e2e    : the same steps through the host-buffer C ABI (ezrt_render): every step uploads lastFrame
-         from pinned host memory and reads the new framebuffer back.
+value     total rays of all ranks / max-over-ranks CUDA-event time of the K timed steps, scene and framebuffer resident in
+          HBM (ezrt_render_device on the current stream; N > 1: plus the single gather, inside the timed region).
+e2e       the same steps through host buffers: every step uploads lastFrame from pinned host memory and reads the new
+          framebuffer back (N = 1: ezrt_render; N > 1: per-rank parts every step, the gathered image once per render).
+parity    frame 0 of the workload (1 spp, the full image of all ranks) compared with the CPU reference render of the same
+          frame: L-inf and the number of differing floats (0 expected: the arithmetic is bit-specified).
 roofline / cpu_baseline: see DESIGN.md "Measurement".
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -32,18 +38,20 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per k_extend_accel launch on the C3 workload (16-frame batch), mean of the three launch
-# kinds (camera / bounce-1 / bounce-2), from the committed ncu capture profiles/ncu_extend_r1_summary.md
-NCU_DRAM_BYTES_PER_EXTEND_LAUNCH = 1841e6
-
 METRIC = "Mrays/s (primary+secondary)"
 UNIT = "Mrays/s"
+ENV_COLOR = (0.35, 0.45, 0.6)
 WORKLOADS = {
-    # name: (scene builder name, width, height, mode, max_bounce)
-    "c3": ("s_1m", 1920, 1080, 2, 2),   # configs[2]: 1M tris, 1080p, Disney + Sobol (mode disney_sobol_p5)
-    "c2": ("s_bunny", 1024, 1024, 0, 2),  # configs[1]: bunny-class 5k tris, 1024^2, diffuse-only (mode diffuse_p3)
-    "c4": ("s_1m", 1920, 1080, 3, 2),   # configs[3]: C3 + HDR env-map importance sampling + MIS (mode disney_is_mis_p5)
+    # name: (scene builder, width, height, mode, max_bounce, BASELINE config it stands for)
+    "c3": ("s_1m_bunny", 1920, 1080, 2, 2, "configs[2]: 1M-tri merged Stanford scene, 1920x1080, Disney BRDF + Sobol"),
+    "c2": ("s_p3_bunny", 1024, 1024, 0, 2, "configs[1]: bunny 5k tris, 1024x1024, diffuse-only BRDF"),
+    "c4": ("s_1m_bunny", 1920, 1080, 3, 2, "configs[3]: C3 scene + HDR env-map importance sampling + MIS"),
+    # round-1 stand-in scenes (procedural 'blob' mesh), kept as a second family
+    "c3_blob": ("s_1m", 1920, 1080, 2, 2, "round-1 stand-in for configs[2] (procedural mesh)"),
+    "c2_blob": ("s_bunny", 1024, 1024, 0, 2, "round-1 stand-in for configs[1] (procedural mesh)"),
+    "c4_blob": ("s_1m", 1920, 1080, 3, 2, "round-1 stand-in for configs[3] (procedural mesh)"),
 }
+C5_IMAGE = (3840, 2160)   # configs[4]
 
 
 def parse_args():
@@ -52,34 +60,54 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ezrt", choices=["ezrt", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"])
+    ap.add_argument("--image", default=None, help="WxH override of the whole image")
     ap.add_argument("--spp-per-step", type=int, default=16)
     ap.add_argument("--frames-per-batch", type=int, default=0)
     ap.add_argument("--traverse", default="accel", choices=["accel", "pruned", "reference"])
     ap.add_argument("--pipeline", default="wavefront", choices=["wavefront", "megakernel"])
+    ap.add_argument("--extra-workloads", default=None, help="comma list measured after the headline (default at N=1: c2,c4; '' = none)")
+    ap.add_argument("--extra-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", default="1920x1080x1", help="oracle sample WxHxSPP used for cpu_baseline and B_ray")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--cpu-reps", type=int, default=3, help="repetitions of the CPU sample (the fastest is reported, all are listed)")
+    ap.add_argument("--cpu-sample", default=None, help="WxHxSPP of the CPU baseline sample (default: frame 0 of the whole image, 1 spp)")
     return ap.parse_args()
 
 
-def weak_image(width, height, n):
-    """Image of N GPUs: pixels per GPU fixed (1: WxH, 2: 2WxH, 4: 2Wx2H, 8: 4Wx2H)."""
-    a = b = 1
-    k = n
-    while k > 1:
-        if a <= b:
-            a *= 2
-        else:
-            b *= 2
-        k //= 2
-    if a * b != n:
-        a, b = n, 1
-    return width * a, height * b
+# ----------------------------------------------------------------------------------------------------------------------
+# host resources
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_threads():
+    """Threads the CPU legs may use: the scheduler affinity, capped by the cgroup CPU quota.  os.cpu_count() reports the
+    host's cores even inside a container limited to a few, and torch.distributed.run sets OMP_NUM_THREADS=1 -- the CPU
+    legs therefore always pass an explicit thread count to the renderers."""
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = os.cpu_count() or 1
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except Exception:
+            continue
+    n = aff if quota is None else max(1, min(aff, int(math.ceil(quota))))
+    return n, {"affinity": aff, "cgroup_cpus": quota, "os_cpu_count": os.cpu_count(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")}
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 50 ms during the timed region (a default run times ~0.4 s)."""
+    """nvidia-smi clocks/throttle reasons sampled every 50 ms during the timed region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -124,103 +152,164 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_workload(name):
-    from ezrt_b200 import scenes
-    builder, w, h, mode, bounces = WORKLOADS[name]
+# ----------------------------------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------------------------------
+_SCENE_CACHE = {}
+
+
+def find_reference_hdr():
+    """The reference's own 2k environment map (P5/main.cpp:897) when the reference tree or an installed copy is readable."""
+    rel = os.path.join("part 5 -- Importance Sampling & Low Discrepancy Sequence", "source code", "HDR", "chinese_garden_2k.hdr")
+    for base in ("/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        p = os.path.join(base, rel)
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def build_workload(name, device_cache=False):
+    from ezrt_b200 import api, scenes
+    builder, w, h, mode, bounces, what = WORKLOADS[name]
     t0 = time.time()
-    tris, nodes, eye, cam = getattr(scenes, builder)()
+    if builder not in _SCENE_CACHE:
+        _SCENE_CACHE[builder] = getattr(scenes, builder)()
+    tris, nodes, eye, cam = _SCENE_CACHE[builder]
     hdr = cache = None
-    if mode == 3:  # procedural 2k environment map (the reference's chinese_garden_2k.hdr is not on the GPU box)
-        from ezrt_b200 import api
-        hdr = scenes.synth_hdr(2048, 1024)
-        cache = api.hdr_cache(hdr)
-    return dict(tris=tris, nodes=nodes, eye=eye, cam=cam, width=w, height=h, mode=mode, max_bounce=bounces, scene=builder,
-                hdr=hdr, cache=cache, build_s=time.time() - t0)
+    env = "constant colour %s" % (ENV_COLOR,)
+    if mode == 3:
+        path = find_reference_hdr()
+        if path is not None:
+            hdr = api.hdr_load(path)
+            env = "chinese_garden_2k.hdr (the reference's own map, P5/main.cpp:897)"
+        else:
+            hdr = scenes.synth_hdr(2048, 1024)
+            env = "procedural 2048x1024 map (scenes.synth_hdr; the reference's chinese_garden_2k.hdr is not on this box)"
+        # calculateHdrCache: on the GPU when there is one (bit-identical to the host restatement, tests/test_post.py)
+        cache = api.hdr_cache_device(hdr)[0] if device_cache else api.hdr_cache(hdr)
+    return dict(name=name, what=what, tris=tris, nodes=nodes, eye=eye, cam=cam, width=w, height=h, mode=mode, max_bounce=bounces, scene=builder,
+                hdr=hdr, cache=cache, env=env, build_s=time.time() - t0)
 
 
-def oracle_sample(wl, sample, traverse, threads=0):
-    """Time the CPU oracle on a bounded sample of the workload; returns (Mrays/s, counters, seconds)."""
+def workload_config(args, wl, W, H, world, scaling):
+    """The `config` object: identical in the ezrt arm and the reference arm of one invocation."""
+    return {"workload": wl["name"], "baseline_config": wl["what"], "scene": wl["scene"], "triangles": int(wl["tris"].shape[0]),
+            "bvh_nodes": int(wl["nodes"].shape[0]), "image": [W, H], "spp_per_step": args.spp_per_step, "mode": wl["mode"],
+            "max_bounce": wl["max_bounce"], "environment": wl["env"], "first_frame": 0, "parallelism": "tiles%d" % world, "scaling": scaling,
+            "l2": "inputs larger than L2: scene > 120 MB + wavefront state > 600 MB per step vs 126 MB L2"}
+
+
+def image_for(args, wl, world):
+    """(W, H, scaling label) of the whole image rendered by `world` GPUs."""
+    if args.image:
+        w, h = (int(x) for x in args.image.lower().split("x"))
+        return w, h, ("strong" if args.scaling != "weak" else "weak")
+    if world == 1:
+        return wl["width"], wl["height"], "strong"
+    if args.scaling == "weak":   # round 1: pixels per GPU fixed (2: 2WxH, 4: 2Wx2H, 8: 4Wx2H)
+        a = b = 1
+        k = world
+        while k > 1:
+            if a <= b:
+                a *= 2
+            else:
+                b *= 2
+            k //= 2
+        if a * b != world:
+            a, b = world, 1
+        return wl["width"] * a, wl["height"] * b, "weak"
+    return C5_IMAGE[0], C5_IMAGE[1], "strong"   # configs[4]: one fixed 3840x2160 image
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_render(wl, W, H, spp, threads, want_counters=False):
+    """Frame range [0, spp) of the workload on the host cores.  Uses the reference's own shader source compiled for the CPU
+    (oracle/_ref/libezrt_refshader.so, kind "reference") when that library travelled here, else the oracle port.
+    Returns dict(image, seconds, kind, counters or None)."""
     from ezrt_b200 import api
-    from tests import oracle_binding as oracle  # the CPU baseline leg: the one place bench.py may execute oracle/
-    w, h, spp = [int(x) for x in sample.lower().split("x")]
-    cfg = api.RenderConfig(width=w, height=h, spp=spp, max_bounce=wl["max_bounce"], mode=wl["mode"], eye=tuple(wl["eye"]),
-                           camera_rotate=tuple(wl["cam"]), env_color=(0.35, 0.45, 0.6), traverse=traverse)
-    t0 = time.perf_counter()
-    img, c = oracle.render(wl["tris"], wl["nodes"], cfg, hdr=wl.get("hdr"), hdr_cache=wl.get("cache"), threads=threads)
-    dt = time.perf_counter() - t0
-    c["image"] = img
-    return c["rays"] / dt / 1e6, c, dt
-
-
-def reference_shader_sample(wl, sample, check_against=None):
-    """Time the REFERENCE'S OWN SHADER SOURCE (oracle/_ref/libezrt_refshader.so: P3/P4/P5 fshader.fsh transpiled to C++
-    in the authoring container, oracle/ref_shader/) on the same bounded sample, all host threads.  Returns seconds, or
-    None when the library is not there.  A scene without an environment map gets a 1x1 map of the constant colour
-    (GL_NEAREST), which is what env_color means to the shader."""
-    import numpy as np
-    from ezrt_b200 import api
-    from tests import refshader_binding as refshader  # CPU baseline leg only, like oracle_binding
-    if not refshader.available():
-        return None
-    w, h, spp = [int(x) for x in sample.lower().split("x")]
-    cfg = api.RenderConfig(width=w, height=h, spp=spp, max_bounce=wl["max_bounce"], mode=wl["mode"], eye=tuple(wl["eye"]),
-                           camera_rotate=tuple(wl["cam"]), env_color=(0.35, 0.45, 0.6), traverse=1)
+    from tests import oracle_binding as oracle
+    from tests import refshader_binding as refshader
+    cfg = api.RenderConfig(width=W, height=H, spp=spp, max_bounce=wl["max_bounce"], mode=wl["mode"], eye=tuple(wl["eye"]),
+                           camera_rotate=tuple(wl["cam"]), env_color=ENV_COLOR, traverse=api.TRAVERSE_REFERENCE)
+    counters = None
+    if want_counters or not refshader.available():
+        t0 = time.perf_counter()
+        img, counters = oracle.render(wl["tris"], wl["nodes"], cfg, hdr=wl.get("hdr"), hdr_cache=wl.get("cache"), threads=threads)
+        dt = time.perf_counter() - t0
+        if not refshader.available():
+            return dict(image=img, seconds=dt, kind="port", counters=counters)
     hdr, cache, linear = wl.get("hdr"), wl.get("cache"), True
-    if hdr is None:
-        hdr, cache, linear = np.array([[[0.35, 0.45, 0.6]]], np.float32), None, False
+    if hdr is None:  # a scene without an environment map gets a 1x1 map of the constant colour (GL_NEAREST): what env_color means to the shader
+        hdr, cache, linear = np.array([[list(ENV_COLOR)]], np.float32), None, False
     t0 = time.perf_counter()
-    img = refshader.render(wl["tris"], wl["nodes"], cfg, hdr, cache, hdr_linear=linear)
+    img = refshader.render(wl["tris"], wl["nodes"], cfg, hdr, cache, hdr_linear=linear, threads=threads)
     dt = time.perf_counter() - t0
-    if check_against is not None:  # the port and the reference shader must agree bit for bit
-        assert img.tobytes() == check_against.tobytes(), "oracle port and transpiled reference shader disagree"
-    return dt
+    return dict(image=img, seconds=dt, kind="reference", counters=counters)
 
 
-def b_ray(c):
-    """Algorithmic bytes per ray on the reference layout (SURVEY.md 8d): 48 N_node + 72 N_tri + 72 H + 24."""
-    return (48.0 * c["n_node"] + 72.0 * c["n_tri"] + 72.0 * c["hits"]) / c["rays"] + 24.0
+def cpu_baseline_leg(args, wl, W, H, threads, thread_info):
+    """cpu_baseline: a bounded sample of the workload (default frame 0 of the whole image) timed `--cpu-reps` times with an
+    explicit thread count.  Also returns the frame for the parity check and the oracle's ray counters."""
+    if args.cpu_sample:
+        sw, sh, sspp = (int(x) for x in args.cpu_sample.lower().split("x"))
+    else:
+        sw, sh, sspp = W, H, 1
+    first = cpu_render(wl, sw, sh, sspp, threads, want_counters=True)
+    secs = [first["seconds"]]
+    for _ in range(max(0, args.cpu_reps - 1)):
+        secs.append(cpu_render(wl, sw, sh, sspp, threads)["seconds"])
+    c = first["counters"]
+    best = min(secs)
+    what = "reference shader source (fshader.fsh of the mode transpiled to C++, oracle/_ref)" if first["kind"] == "reference" else "oracle port (oracle/ezrt_oracle.cpp)"
+    base = {"value": c["rays"] / best / 1e6, "unit": UNIT, "cores": threads, "threads_used": threads, "kind": first["kind"],
+            "sample": "%s renders frames [0,%d) of the %dx%d image of this workload, literal hitBVH traversal; best of %d runs (%s s)" %
+                      (what, sspp, sw, sh, len(secs), ", ".join("%.2f" % s for s in secs)),
+            "rays_in_sample": c["rays"], "host": thread_info}
+    return base, first, (sw, sh, sspp)
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own implementation of the path on the host cores, all threads: the transpiled
-    reference shaders (oracle/_ref, kind "reference") when that library travelled here, else the oracle port."""
+    """--impl reference: the reference's own implementation of the path on the host cores (rank 0 only)."""
     if rank != 0:
         return
     wl = build_workload(args.workload)
-    cores = os.cpu_count() or 1
-    sample = args.cpu_sample
-    _, c, _ = oracle_sample(wl, sample, 1)  # ray count of the sample (the shader library does not count; same paths, same image)
-    kind = "reference" if reference_shader_sample(wl, "64x36x1") is not None else "port"
-    t_start = time.perf_counter()
+    W, H, scaling = image_for(args, wl, world)
+    threads, tinfo = cpu_threads()
+    if args.cpu_sample:
+        sw, sh, sspp = (int(x) for x in args.cpu_sample.lower().split("x"))
+    else:
+        sw, sh, sspp = W, H, 1
+    first = cpu_render(wl, sw, sh, sspp, threads, want_counters=True)   # ray count of the sample + which implementation is available
+    rays = first["counters"]["rays"]
+    secs = []
     for i in range(args.warmup + args.steps):
-        if i == args.warmup:
-            t_start = time.perf_counter()
-        if kind == "reference":
-            reference_shader_sample(wl, sample, check_against=c["image"] if i == 0 else None)
-        else:
-            oracle_sample(wl, sample, 1)
-    total_s = time.perf_counter() - t_start
-    value = c["rays"] * args.steps / total_s / 1e6
-    what = ("reference shader source (P3|P4|P5 fshader.fsh of the mode, transpiled to C++, oracle/_ref)" if kind == "reference" else "oracle port")
+        r = cpu_render(wl, sw, sh, sspp, threads)
+        if i >= args.warmup:
+            secs.append(r["seconds"])
+    total_s = sum(secs)
+    value = rays * len(secs) / total_s / 1e6
+    what = "reference shader source (P3|P4|P5 fshader.fsh of the mode, transpiled to C++, oracle/_ref)" if first["kind"] == "reference" else "oracle port"
+    sample = "%s renders frames [0,%d) of the %dx%d image per step (literal hitBVH traversal), %d threads" % (what, sspp, sw, sh, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "scene": wl["scene"], "triangles": int(wl["tris"].shape[0]), "mode": wl["mode"],
-                   "max_bounce": wl["max_bounce"], "step": what + " renders sample " + sample + " (literal hitBVH traversal)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample + " (WxHxspp) of the workload per step"},
+        "ms_per_step": 1e3 * total_s / max(1, len(secs)), "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, wl, W, H, world, scaling),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "threads_used": threads, "kind": first["kind"], "sample": sample, "host": tinfo},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
 _REAL_STDOUT = None
 
 
 def quiet_stdout():
-    """Everything but the one JSON line goes to stderr: libraries (NCCL prints its version banner on stdout, the
-    reference shaders' host code chats) must not share the stream the driver parses."""
+    """Everything but the one JSON line goes to stderr: libraries (NCCL's version banner, the reference shaders' host
+    code) must not share the stream the driver parses."""
     global _REAL_STDOUT
     if _REAL_STDOUT is None:
         sys.stdout.flush()
@@ -234,20 +323,269 @@ def emit(line):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
+def load_json(path):
+    try:
+        return json.load(open(path))
+    except Exception:
+        return None
+
+
+def gather_peak(record_bytes):
+    """Measured ceiling for the traversal kernels' access pattern (tools/gather_bench.cu on this pool's B200, committed as
+    profiles/gather_peak_r2.json): records/s of `record_bytes`-byte records read by divergent lanes with 256-bit loads from an
+    L2-resident table."""
+    data = load_json(os.path.join(ROOT, "profiles", "gather_peak_r2.json"))
+    if not data:
+        return None
+    best = None
+    for r in data.get("results", []):
+        if r.get("record_bytes") == record_bytes and "ld256" in r.get("table", "") and r.get("table", "").startswith("global_16MB"):
+            best = r["grecords_per_s"] * 1e9
+    return best
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# one measured configuration on the GPUs
+# ----------------------------------------------------------------------------------------------------------------------
+class Runner:
+    def __init__(self, args, wl, rank, world, local_rank, W, H):
+        import torch
+        from ezrt_b200 import api
+        from ezrt_b200 import dist as ezdist
+        self.torch, self.api = torch, api
+        self.args, self.wl, self.rank, self.world, self.W, self.H = args, wl, rank, world, W, H
+        t0 = time.perf_counter()
+        self.scene = api.Scene(wl["tris"], wl["nodes"], wl.get("hdr"), wl.get("cache"), device=local_rank)
+        self.upload_ms = 1e3 * (time.perf_counter() - t0)
+        self.C = 3
+        self.n_local = api.partition_pixels(W, H, rank, world)
+        self.traverse = {"accel": api.TRAVERSE_ACCEL, "pruned": api.TRAVERSE_PRUNED, "reference": api.TRAVERSE_REFERENCE}[args.traverse]
+        self.pipeline = api.PIPELINE_WAVEFRONT if args.pipeline == "wavefront" else api.PIPELINE_MEGAKERNEL
+        self.stream = torch.cuda.current_stream()
+        self.d_fb = torch.zeros(max(1, self.n_local) * self.C, dtype=torch.float32, device="cuda")
+        self.gatherer = ezdist.FramebufferGather(W, H, self.C, rank, world, self.d_fb.device) if world > 1 else None
+
+    def cfg(self, first_frame, spp, profile=0, accumulate=False):
+        wl = self.wl
+        return self.api.RenderConfig(width=self.W, height=self.H, spp=spp, first_frame=first_frame, max_bounce=wl["max_bounce"], mode=wl["mode"],
+                                     eye=tuple(wl["eye"]), camera_rotate=tuple(wl["cam"]), env_color=ENV_COLOR, traverse=self.traverse,
+                                     pipeline=self.pipeline, part_rank=self.rank, part_count=self.world,
+                                     frames_per_batch=self.args.frames_per_batch, profile=profile, accumulate=accumulate)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def step(self, s, profile=0, accumulate=False):
+        spp = self.args.spp_per_step
+        self.scene.render_device(self.cfg(s * spp, spp, profile, accumulate), self.d_fb, self.stream)
+
+    def gather(self):
+        """The single collective of a render: compact per-rank parts -> the row-major image on rank 0 (device tensor)."""
+        if self.world == 1:
+            return self.d_fb.reshape(self.H, self.W, self.C)
+        return self.gatherer(self.d_fb)
+
+    def frame0(self):
+        """Frame 0 of the workload, 1 spp, as the whole image on rank 0 (host array) -- for the parity check."""
+        self.scene.render_device(self.cfg(0, 1), self.d_fb, self.stream)
+        full = self.gather()
+        self.torch.cuda.synchronize()
+        return None if full is None else full.detach().cpu().numpy().reshape(self.H, self.W, self.C)
+
+    def allreduce(self, vals, op):
+        import torch.distributed as dist
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    def measure(self, steps, warmup, do_e2e=True, sample_clocks=False):
+        torch, args = self.torch, self.args
+        # ---------------- value: device-resident inputs -----------------
+        for s in range(warmup):
+            self.step(s)
+        if self.world > 1:
+            self.gather()
+        self.barrier()
+        sampler = ClockSampler(torch.cuda.current_device()) if (sample_clocks and self.rank == 0) else None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(self.stream)
+        for s in range(steps):
+            self.step(warmup + s, profile=1, accumulate=(s > 0))   # counters / kernel spans are read once, after the loop
+        self.gather()                                              # N > 1: the render's single NCCL gather
+        ev1.record(self.stream)
+        self.barrier()
+        clocks = sampler.stop() if sampler else None
+        ms_local = ev0.elapsed_time(ev1)
+        c = self.scene.counters()
+        kt = self.scene.kernel_times()
+        (ms,) = self.allreduce([ms_local], "max")
+        rays, launches = self.allreduce([float(c.rays), float(c.kernel_launches)], "sum")
+        rank_rays = self.allreduce([float(c.rays) if r == self.rank else 0.0 for r in range(self.world)], "sum")
+        out = dict(value=rays / (ms * 1e-3) / 1e6, ms=ms, rays=rays, launches=launches, clocks=clocks, upload_ms=self.upload_ms,
+                   kernel_ms={k: v[0] for k, v in kt.items()}, kernel_launches={k: v[1] for k, v in kt.items()},
+                   deferred=float(c.deferred_rays), rank0_rays=float(c.rays), rank_rays=rank_rays, steps=steps,
+                   samples=self.allreduce([float(c.samples)], "sum")[0])
+        # ---------------- e2e: host buffers -----------------
+        if do_e2e:
+            host_fb = torch.zeros(max(1, self.n_local) * self.C, dtype=torch.float32).pin_memory()
+            host_np = host_fb.numpy()
+            full_host = torch.zeros(self.W * self.H * self.C, dtype=torch.float32).pin_memory() if (self.world > 1 and self.rank == 0) else None
+            spp = args.spp_per_step
+
+            def e2e_step(s, acc):
+                if self.world == 1:
+                    self.scene.render(self.cfg(s * spp, spp, 0, acc), framebuffer=host_np)  # H2D lastFrame (s > 0), kernels, D2H, sync
+                    return
+                self.d_fb.copy_(host_fb, non_blocking=True)                                   # H2D this rank's lastFrame part
+                self.scene.render_device(self.cfg(s * spp, spp, 0, acc), self.d_fb, self.stream)
+                host_fb.copy_(self.d_fb, non_blocking=True)                                   # D2H this rank's part
+                torch.cuda.synchronize()
+
+            for s in range(warmup):
+                e2e_step(s, False)
+            self.barrier()
+            t0 = time.perf_counter()
+            for s in range(steps):
+                e2e_step(warmup + s, s > 0)
+            if self.world > 1:   # once per render: the NCCL gather and the assembled image to the host on rank 0
+                full = self.gather()
+                if full is not None:
+                    full_host.copy_(full.reshape(-1), non_blocking=True)
+                torch.cuda.synchronize()
+            self.barrier()
+            e_ms_local = 1e3 * (time.perf_counter() - t0)
+            (e_ms,) = self.allreduce([e_ms_local], "max")
+            (e_rays,) = self.allreduce([float(self.scene.counters().rays)], "sum")
+            part_bytes = self.n_local * self.C * 4
+            out["e2e"] = {"value": e_rays / (e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": part_bytes, "d2h_bytes_per_step": part_bytes,
+                          "d2h_bytes_once_per_render": (self.W * self.H * self.C * 4 if self.world > 1 else 0), "ms_per_step": e_ms / max(1, steps),
+                          "what": "ezrt_render with pinned host framebuffers" if self.world == 1 else
+                                  "per step: H2D lastFrame part, kernels, D2H part on every rank; once per render: NCCL gather + D2H of the whole image on rank 0"}
+        return out
+
+    def traversal_counts(self):
+        """One step with the counting instantiation (params.profile = 2), outside every timed region: records the accel kernels
+        fetch on their own layout."""
+        spp = self.args.spp_per_step
+        self.scene.render_device(self.cfg(self.args.warmup * spp, spp, profile=2), self.d_fb, self.stream)
+        self.torch.cuda.synchronize()
+        c = self.scene.counters()
+        return dict(node_visits=int(c.node_visits), tri_tests=int(c.tri_tests), node_bytes=int(c.node_record_bytes), tri_bytes=int(c.tri_record_bytes),
+                    rays=int(c.rays), primary=int(c.primary_rays), bounce=int(c.bounce_rays), shadow=int(c.shadow_rays))
+
+    def close(self):
+        self.scene.close()
+
+
+def parity_of(gpu_img, cpu_img, what):
+    if gpu_img is None or cpu_img is None:
+        return None
+    a, b = np.ascontiguousarray(gpu_img, np.float32), np.ascontiguousarray(cpu_img, np.float32)
+    same_nan = np.isnan(a) == np.isnan(b)
+    diff = np.abs(np.nan_to_num(a) - np.nan_to_num(b))
+    differing = int((a.view(np.uint32) != b.view(np.uint32)).sum())
+    return {"config": what, "linf": float(diff.max()), "differing": differing, "floats": int(a.size), "nan_positions_equal": bool(same_nan.all()),
+            "tolerance": 1e-4}
+
+
+def roofline_of(res, counts, wl_means, hbm_peak, peak_kind, kernel_name):
+    """Roofline of the extend stage (accel kernels + their exact fallback passes, > 80 % of a step) on the kernel's OWN layout:
+    achieved = bytes of node / triangle / ray records the traversal fetched per second; peak = the measured gather ceiling for
+    that mix of record sizes (tools/gather_bench.cu).  HBM-side and reference-layout demand figures ride along."""
+    ext_ms, ext_n = res["kernel_ms"]["extend"] + res["kernel_ms"]["shadow"], res["kernel_launches"]["extend"] + res["kernel_launches"]["shadow"]
+    if not counts or ext_ms <= 0 or counts["node_visits"] == 0:
+        return None
+    steps = res["steps"]
+    node_b, tri_b = counts["node_bytes"], counts["tri_bytes"]
+    rays_step = counts["rays"]
+    queue_rays = counts["bounce"] + counts["shadow"]
+    # per step (rank 0): node records + triangle records + 32-byte ray records read (queue rays) + 8-byte hit records written
+    bytes_step = counts["node_visits"] * node_b + counts["tri_tests"] * tri_b + queue_rays * 32 + rays_step * 8
+    t_step = ext_ms * 1e-3 / steps
+    achieved = bytes_step / t_step / 1e9
+    pn, pt = gather_peak(node_b), gather_peak(tri_b)
+    out = {"bound": "hbm", "bound_detail": "memory system: L2 -> L1 gather of node / triangle records by divergent lanes (no dense contraction: tensor cores unused)",
+           "kernel": kernel_name, "achieved": achieved, "unit": "GB/s",
+           "algorithmic_bytes_per_launch": bytes_step * steps / max(1, ext_n), "launches": ext_n, "ms_per_launch": ext_ms / max(1, ext_n),
+           "extend_share_of_step": ext_ms / res["ms"],
+           "per_ray": {"node_records": counts["node_visits"] / rays_step, "triangle_records": counts["tri_tests"] / rays_step,
+                       "node_record_bytes": node_b, "triangle_record_bytes": tri_b, "bytes": bytes_step / rays_step}}
+    if pn and pt:
+        t_floor = counts["node_visits"] / pn + counts["tri_tests"] / pt   # seconds per step at the measured gather ceiling
+        peak = bytes_step / t_floor / 1e9 if t_floor > 0 else None
+        out.update({"peak": peak, "frac": achieved / peak if peak else None,
+                    "peak_source": "measured gather ceiling (profiles/gather_peak_r2.json: %d-byte records %.1f G/s, %d-byte records %.1f G/s, 256-bit loads, "
+                                   "L2-resident table, this pool's B200), mixed by record counts" % (node_b, pn / 1e9, tri_b, pt / 1e9)})
+    else:
+        out.update({"peak": hbm_peak, "frac": achieved / hbm_peak, "peak_source": peak_kind + " (no gather_peak_r2.json)"})
+    # HBM side: DRAM bytes of the extend kernels from the committed ncu capture of this command (tools/ncu_summaries.py dram)
+    dram = load_json(os.path.join(ROOT, "profiles", "ncu_dram_r2.json"))
+    key = kernel_name
+    traffic = None
+    if dram and key in dram.get(res.get("workload", ""), {}):
+        traffic = dram[res["workload"]][key]["dram_bytes_per_launch"]
+    out["traffic"] = traffic
+    out["traffic_source"] = "profiles/ncu_dram_r2.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu capture of this command)" if traffic else None
+    out["hbm"] = {"peak": hbm_peak, "peak_source": peak_kind, "achieved_gbs": (traffic / (ext_ms * 1e-3 / max(1, ext_n)) / 1e9) if traffic else None}
+    if out["hbm"]["achieved_gbs"]:
+        out["hbm"]["frac"] = out["hbm"]["achieved_gbs"] / hbm_peak
+    if wl_means:   # SURVEY 8(d)'s demand figure on the REFERENCE layout and policy (48 N_node + 72 N_tri + 72 H + 24 per ray), for continuity
+        demand = res["rank0_rays"] * wl_means["bytes_per_ray_reference"] / (ext_ms * 1e-3) / 1e9
+        out["demand"] = {"gbs": demand, "frac_of_hbm_peak": demand / hbm_peak, "bytes_per_ray_reference_layout": wl_means["bytes_per_ray_reference"],
+                         "ray_means": wl_means, "note": "demand bytes of the reference's layout and un-pruned traversal with no cross-ray reuse; "
+                                                        "the kernels walk their own 8-wide tree, so this exceeds every physical peak by design"}
+    return out
+
+
+def b_ray(c):
+    """Algorithmic bytes per ray on the reference layout (SURVEY.md 8d): 48 N_node + 72 N_tri + 72 H + 24."""
+    return (48.0 * c["n_node"] + 72.0 * c["n_tri"] + 72.0 * c["hits"]) / c["rays"] + 24.0
+
+
+def measure_workload(args, name, rank, world, local_rank, steps, warmup, headline):
+    """Build, measure, check one workload.  Returns (result dict for the JSON line, Runner-independent extras)."""
+    wl = build_workload(name, device_cache=True)
+    W, H, scaling = image_for(args, wl, world)
+    runner = Runner(args, wl, rank, world, local_rank, W, H)
+    res = runner.measure(steps, warmup, do_e2e=not args.no_e2e, sample_clocks=headline)
+    res["workload"] = name
+    counts = runner.traversal_counts() if args.traverse == "accel" and args.pipeline == "wavefront" else None
+    gpu0 = None if args.no_parity else runner.frame0()
+    runner.close()
+    out = {"config": workload_config(args, wl, W, H, world, scaling), "res": res, "counts": counts, "scaling": scaling, "wl": wl, "W": W, "H": H}
+    if rank != 0:
+        return out
+    cpu_base = parity = means = None
+    if not args.no_cpu_baseline:
+        threads, tinfo = cpu_threads()
+        cpu_base, first, (sw, sh, sspp) = cpu_baseline_leg(args, wl, W, H, threads, tinfo)
+        c = first["counters"]
+        means = {"n_node": c["n_node"] / c["rays"], "n_tri": c["n_tri"] / c["rays"], "hit_frac": c["hits"] / c["rays"], "bytes_per_ray_reference": b_ray(c)}
+        if gpu0 is not None and (sw, sh, sspp) == (W, H, 1):
+            parity = parity_of(gpu0, first["image"], "%s: frame 0 (1 spp) of the whole %dx%d image on %d GPU(s) vs the CPU %s render of the same frame" %
+                               (name, W, H, world, "reference-shader" if first["kind"] == "reference" else "oracle"))
+    out.update(cpu_baseline=cpu_base, parity=parity, means=means)
+    return out
+
+
 def main():
     args = parse_args()
     quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload is None:
+        args.workload = "c3"   # every N measures the same scene and integrator; `--workload c4` gives configs[4] with the IS/MIS integrator
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
 
     import torch
     import torch.distributed as dist
-    from ezrt_b200 import api
-    from ezrt_b200 import dist as ezdist
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
@@ -255,165 +593,55 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    wl = build_workload(args.workload)
-    W, H = weak_image(wl["width"], wl["height"], world)
-    t0 = time.perf_counter()
-    scene = api.Scene(wl["tris"], wl["nodes"], wl.get("hdr"), wl.get("cache"), device=local_rank)
-    upload_ms = 1e3 * (time.perf_counter() - t0)
-    C = 3
-    n_local = api.partition_pixels(W, H, rank, world)
-    traverse = {"accel": api.TRAVERSE_ACCEL, "pruned": api.TRAVERSE_PRUNED, "reference": api.TRAVERSE_REFERENCE}[args.traverse]
-    pipeline = api.PIPELINE_WAVEFRONT if args.pipeline == "wavefront" else api.PIPELINE_MEGAKERNEL
-
-    def cfg_for(step, profile=0):
-        return api.RenderConfig(width=W, height=H, spp=args.spp_per_step, first_frame=step * args.spp_per_step, max_bounce=wl["max_bounce"],
-                                mode=wl["mode"], eye=tuple(wl["eye"]), camera_rotate=tuple(wl["cam"]), env_color=(0.35, 0.45, 0.6),
-                                traverse=traverse, pipeline=pipeline, part_rank=rank, part_count=world,
-                                frames_per_batch=args.frames_per_batch, profile=profile)
-
-    stream = torch.cuda.current_stream()
-    d_fb = torch.zeros(max(1, n_local) * C, dtype=torch.float32, device="cuda")
-
-    gatherer = ezdist.FramebufferGather(W, H, C, rank, world, d_fb.device) if world > 1 else None
-
-    def device_step(step, profile=0):
-        scene.render_device(cfg_for(step, profile), d_fb, stream)
-        if world > 1:
-            return gatherer(d_fb)  # the single NCCL collective of the step
-        return None
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- value: device-resident inputs -----------------
-    for s in range(args.warmup):
-        device_step(s)
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    rays = launches = 0
-    ktimes = {"extend": [0.0, 0], "shade": [0.0, 0], "shadow": [0.0, 0], "other": [0.0, 0]}
-    ev0.record(stream)
-    for s in range(args.steps):
-        device_step(args.warmup + s, profile=1)
-        # counters are read after the loop would need per-step storage; reading them synchronises this step only
-        c = scene.counters()
-        rays += c.rays
-        launches += c.kernel_launches
-        for k, (ms, n) in scene.kernel_times().items():
-            ktimes[k][0] += ms
-            ktimes[k][1] += n
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.stop() if sampler else None
-    ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms, float(rays), float(launches)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, rays, launches = float(tmax[0]), float(tsum[1]), float(tsum[2])
-    value = rays / (ms * 1e-3) / 1e6
-
-    # ---------------- e2e: host buffers through ezrt_render -----------------
-    e2e = None
-    if not args.no_e2e:
-        host_fb = torch.zeros(max(1, n_local) * C, dtype=torch.float32).pin_memory()
-        host_np = host_fb.numpy()
-        full_host = torch.zeros(W * H * C, dtype=torch.float32).pin_memory() if (world > 1 and rank == 0) else None
-        e_rays = 0
-
-        def e2e_step(step):
-            if world == 1:
-                scene.render(cfg_for(step), framebuffer=host_np)  # H2D lastFrame (step > 0), kernels, D2H, sync
-                return scene.counters().rays
-            d_fb.copy_(host_fb, non_blocking=True)                  # H2D lastFrame part
-            full = device_step(step)                                # kernels + the single NCCL gather
-            host_fb.copy_(d_fb, non_blocking=True)                  # D2H this rank's part
-            if full is not None:
-                full_host.copy_(full.reshape(-1), non_blocking=True)  # D2H the assembled image on rank 0
-            torch.cuda.synchronize()
-            return scene.counters().rays
-
-        for s in range(args.warmup):
-            e2e_step(s)
-        barrier()
-        t0 = time.perf_counter()
-        for s in range(args.steps):
-            e_rays += e2e_step(args.warmup + s)
-        barrier()
-        e_ms = 1e3 * (time.perf_counter() - t0)
-        te = torch.tensor([e_ms, float(e_rays)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            tm = te.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            tsu = te.clone(); dist.all_reduce(tsu, op=dist.ReduceOp.SUM)
-            e_ms, e_rays = float(tm[0]), float(tsu[1])
-        part_bytes = n_local * C * 4
-        e2e = {"value": e_rays / (e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": part_bytes,
-               "d2h_bytes_per_step": part_bytes + (W * H * C * 4 if world > 1 else 0), "ms_per_step": e_ms / max(1, args.steps)}
+    head = measure_workload(args, args.workload, rank, world, local_rank, args.steps, args.warmup, headline=True)
+    extras = {}
+    names = args.extra_workloads
+    if names is None:
+        names = "c2,c4" if (world == 1 and args.workload == "c3") else ""
+    for nm in [x for x in names.split(",") if x]:
+        extras[nm] = measure_workload(args, nm, rank, world, local_rank, args.extra_steps, args.warmup, headline=False)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---------------- roofline + cpu baseline (rank 0) -----------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json")) or {}
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    cpu_baseline = None
-    bray_ref = bray_pruned = None
-    means = {}
-    if not args.no_cpu_baseline:
-        rate, c_ref, dt = oracle_sample(wl, args.cpu_sample, 1)
-        bray_ref = b_ray(c_ref)
-        _, c_pr, _ = oracle_sample(wl, args.cpu_sample, 0)
-        bray_pruned = b_ray(c_pr)
-        means = {"n_node": c_ref["n_node"] / c_ref["rays"], "n_tri": c_ref["n_tri"] / c_ref["rays"], "hit_frac": c_ref["hits"] / c_ref["rays"],
-                 "n_node_pruned": c_pr["n_node"] / c_pr["rays"], "n_tri_pruned": c_pr["n_tri"] / c_pr["rays"]}
-        cpu_baseline = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                        "sample": "oracle render of %s (WxHxspp) of the workload, reference traversal, %.1f s" % (args.cpu_sample, dt)}
-        dt_ref = reference_shader_sample(wl, args.cpu_sample, check_against=c_ref["image"])
-        if dt_ref is not None:  # the reference's own shader source compiled for the CPU travelled here: report that one
-            cpu_baseline = {"value": c_ref["rays"] / dt_ref / 1e6, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference",
-                            "sample": "reference shader source (fshader.fsh transpiled to C++, oracle/_ref) renders %s (WxHxspp) of the workload, "
-                                      "%.1f s; image bit-identical to the oracle port's, which runs it at %.2f %s" % (args.cpu_sample, dt_ref, rate, UNIT)}
-    ext_ms, ext_n = ktimes["extend"]
-    roofline = None
-    if bray_ref and ext_ms > 0:
-        rays_rank0 = rays / world  # rank 0's own launches were timed; rays are evenly spread by the tile interleave
-        achieved = rays_rank0 * bray_ref / (ext_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_extend_accel" if args.traverse == "accel" else "k_extend", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": NCU_DRAM_BYTES_PER_EXTEND_LAUNCH, "traffic_unit": "bytes/launch (dram read+write, ncu --set full, profiles/ncu_extend_r1_summary.md)",
-                    "algorithmic_bytes_per_launch": rays_rank0 * bray_ref / max(1, ext_n), "peak_source": peak_kind, "bytes_per_ray": bray_ref, "bytes_per_ray_pruned_policy": bray_pruned,
-                    "traffic_gbs": NCU_DRAM_BYTES_PER_EXTEND_LAUNCH / (ext_ms * 1e-3 / max(1, ext_n)) / 1e9,
-                    "traffic_frac_of_peak": NCU_DRAM_BYTES_PER_EXTEND_LAUNCH / (ext_ms * 1e-3 / max(1, ext_n)) / 1e9 / hbm_peak,
-                    "ray_means": means, "extend_ms_per_launch": ext_ms / max(1, ext_n), "extend_launches": ext_n,
-                    "extend_share_of_step": ext_ms / ms,
-                    "note": "achieved/frac = ALGORITHMIC demand bytes of the reference layout and traversal policy (SURVEY 8d: 48 N_node + 72 N_tri + 72 H + 24 per ray, oracle counters) with no cross-ray reuse; the kernel walks its own acceleration tree out of L2/L1, so frac >> 1 is expected. traffic_* = measured DRAM bytes (ncu): the kernel is bound by the L1 data pipe and issue slots, not by HBM (measured_limiter).",
-                    "measured_limiter": {"source": "profiles/ncu_extend_r1_summary.md (ncu --set full, three launches of one batch)",
-                                         "l1tex_data_pipe_lsu_wavefronts_pct": [71.2, 82.5, 84.7], "issue_active_pct": [72.0, 63.4, 59.8],
-                                         "dram_throughput_pct": [3.5, 3.8, 4.7], "launches": ["camera rays", "bounce 1", "bounce 2"]}}
+    peak_kind = "measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    kname = {"accel": "k_extend_w8", "pruned": "k_extend<PRUNE>", "reference": "k_extend"}[args.traverse]
+
+    def pack(m):
+        res = m["res"]
+        d = {"value": res["value"], "unit": UNIT, "ms_per_step": res["ms"] / max(1, res["steps"]), "steps": res["steps"], "rays_per_step": res["rays"] / max(1, res["steps"]),
+             "e2e": res.get("e2e"), "gpu_launches": int(res["launches"]), "kernel_ms": res["kernel_ms"], "deferred_ray_fraction": res["deferred"] / max(1.0, res["rank0_rays"]),
+             "parity": m.get("parity"), "cpu_baseline": m.get("cpu_baseline"),
+             "roofline": roofline_of(res, m["counts"], m.get("means"), hbm_peak, peak_kind, kname),
+             "setup": {"scene_build_s": round(m["wl"]["build_s"], 2), "scene_upload_ms": round(res["upload_ms"], 1)}}
+        if world > 1:
+            rr = res["rank_rays"]
+            d["rank_rays"] = {"per_rank": rr, "max_over_mean": max(rr) / (sum(rr) / len(rr)) if sum(rr) > 0 else None}
+        return d
+
+    h = pack(head)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload + (" (BASELINE configs[2]: 1M-tri scene, 1920x1080, Disney+Sobol)" if args.workload == "c3" else ""),
-                   "scene": wl["scene"], "triangles": int(wl["tris"].shape[0]), "bvh_nodes": int(wl["nodes"].shape[0]),
-                   "image": [W, H], "pixels_per_gpu": n_local, "spp_per_step": args.spp_per_step, "mode": wl["mode"], "max_bounce": wl["max_bounce"],
-                   "traverse": args.traverse, "pipeline": args.pipeline, "parallelism": "tiles%d" % world,
-                   "l2": "inputs larger than L2: scene 124 MB + wavefront state > 600 MB per step vs 126 MB L2",
-                   "scene_build_s": round(wl["build_s"], 2), "scene_upload_ms": round(upload_ms, 1)},
-        "rays_per_step": rays / max(1, args.steps), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "kernel_ms": {k: v[0] for k, v in ktimes.items()}, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "metric": METRIC, "value": h["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": head["scaling"], "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": head["config"],
+        "rays_per_step": h["rays_per_step"], "e2e": h["e2e"], "gpu_launches": h["gpu_launches"], "clocks": head["res"]["clocks"],
+        "kernel_ms": h["kernel_ms"], "parity": h["parity"], "roofline": h["roofline"], "cpu_baseline": h["cpu_baseline"],
+        "deferred_ray_fraction": h["deferred_ray_fraction"], "setup": h["setup"],
+        "run": {"traverse": args.traverse, "pipeline": args.pipeline,
+                "gather": "none (1 GPU)" if world == 1 else "one NCCL gather of the compact per-rank framebuffers per render, after the K timed steps, inside the timed region"},
     }
+    if world > 1:
+        line["rank_rays"] = h["rank_rays"]
+    if extras:
+        line["workloads"] = {}
+        for nm, m in extras.items():
+            d = pack(m)
+            d["config"] = m["config"]
+            line["workloads"][nm] = d
     emit(line)
     if world > 1:
         dist.destroy_process_group()

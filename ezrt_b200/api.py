@@ -205,6 +205,7 @@ class RenderConfig:
     part_count: int = 1
     frames_per_batch: int = 0
     profile: int = 0
+    accumulate: bool = False   # EZRT_PARAM_ACCUMULATE: counters / kernel times continue from the previous render
 
     def to_struct(self):
         p = RenderParams()
@@ -216,6 +217,7 @@ class RenderConfig:
         p.traverse, p.pipeline, p.out_channels = int(self.traverse), int(self.pipeline), int(self.out_channels)
         p.part_rank, p.part_count, p.frames_per_batch = int(self.part_rank), int(self.part_count), int(self.frames_per_batch)
         p.profile = int(self.profile)
+        p.reserved[0] = 1 if self.accumulate else 0
         return p
 
 

@@ -93,6 +93,7 @@ struct ezrt_scene {
     int sort_rays = 0;  // env EZRT_SORT_RAYS=1 enables the bounce-ray sort (measured: no gain with per-lane refill)
     int tiles_key[4] = {-1, -1, -1, -1};
     std::vector<TileDev> tiles;
+    size_t n_pixels = 0;       // pixels of the owned tiles
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool have_timing = false;
@@ -169,6 +170,8 @@ int prepare_tiles(ezrt_scene* s, const ezrt_render_params* p, cudaStream_t st) {
     if (!s->tiles.empty()) CU_CHECK(cudaMemcpyAsync(s->tiles_buf.p, s->tiles.data(), sizeof(TileDev) * s->tiles.size(), cudaMemcpyHostToDevice, st));
     CU_CHECK(cudaStreamSynchronize(st));  // s->tiles is pageable host memory
     memcpy(s->tiles_key, key, sizeof(key));
+    s->n_pixels = 0;
+    for (const TileDev& t : s->tiles) s->n_pixels += (size_t)t.w * t.h;
     return EZRT_OK;
 }
 
@@ -423,7 +426,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
                 float rec[32];
                 int refs[4];
                 for (int k = 0; k < 4; k++) {
-                    float AA[3] = {3.0e38f, 3.0e38f, 3.0e38f}, BB[3] = {-3.0e38f, -3.0e38f, -3.0e38f};  // absent: an inverted box, never hit
+                    float AA[3] = {3.0e38f, 3.0e38f, 3.0e38f}, BB[3] = {3.0e38f, 3.0e38f, 3.0e38f};  // absent: a far-away point box (min/max slab test)
                     refs[k] = (int)EZRT_LEAF_FLAG;  // EZRT_REF_DONE, never followed
                     if (k < cnt) {
                         const EzrtAccelNode& c = an[ch[k]];
@@ -522,6 +525,8 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.w8_stack_entries = std::max(1, std::min(w8_depth, EZRT_W8_SMEM_STACK));
     d.w8_origin_limit = W8_ORIGIN_LIMIT_REL * max_abs;
     d.w8_decode_bits = W8_DECODE_BITS;
+    d.w8_tri_weight = 2;
+    if (const char* e = getenv("EZRT_TRI_W")) d.w8_tri_weight = std::max(1, std::min(64, atoi(e)));
     if (!acc_wide.empty()) d.w8_nodes = nullptr;   // EZRT_ACCEL=4: the round-1 kernel
     d.acc_tri_geo = (const float4*)((const char*)sc->acc_nodes.p + acc_nodes_bytes);
     d.acc_tri_ref = (const uint32_t*)sc->acc_tri_ref.p;
@@ -600,19 +605,25 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     rc = s->totals_buf.ensure(sizeof(unsigned long long) * 8);
     if (rc) return rc;
     unsigned long long* totals = (unsigned long long*)s->totals_buf.p;
-    CU_CHECK(cudaEventRecord(s->ev_start, st));
-    CU_CHECK(cudaMemsetAsync(totals, 0, sizeof(unsigned long long) * 8, st));
-    s->launches = 0;
-    s->have_timing = true;
+    // EZRT_PARAM_ACCUMULATE: counters, kernel spans and the device-time bracket continue from the previous render
+    // (a benchmark reads them once after K renders instead of synchronising after every one)
+    const bool accumulate = (p->reserved[0] & EZRT_PARAM_ACCUMULATE) != 0 && s->have_timing;
+    if (!accumulate) {
+        CU_CHECK(cudaEventRecord(s->ev_start, st));
+        CU_CHECK(cudaMemsetAsync(totals, 0, sizeof(unsigned long long) * 8, st));
+        s->launches = 0;
+        s->spans.clear();
+        s->ev_used = 0;
+    }
+    s->have_timing = false;   // set again once ev_stop is recorded (an early error return must not leave a dangling bracket)
     s->profiling = (p->profile == 1);
-    s->spans.clear();
-    s->ev_used = 0;
     RenderDev rd = make_render_dev(s, p);
     const TileDev* d_tiles = (const TileDev*)s->tiles_buf.p;
     const bool prune = s->regular_tree && (p->traverse != EZRT_TRAVERSE_REFERENCE);
     const bool accel = s->regular_tree && s->have_accel && (p->traverse == EZRT_TRAVERSE_ACCEL);
     if (rd.n_tiles == 0 || p->spp == 0) {
         CU_CHECK(cudaEventRecord(s->ev_stop, st));
+        s->have_timing = true;
         return EZRT_OK;
     }
 
@@ -623,21 +634,35 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
         s->launches++;
         CU_CHECK(cudaGetLastError());
         CU_CHECK(cudaEventRecord(s->ev_stop, st));
+        s->have_timing = true;
         return EZRT_OK;
     }
 
     const size_t per_frame = (size_t)rd.n_tiles * EZRT_TILE_PIXELS;
+    const bool is_mode = (p->mode == EZRT_MODE_DISNEY_IS_MIS_P5);
     int F = p->frames_per_batch;
     if (F <= 0) F = (int)std::max<size_t>(1, ((size_t)32 << 20) / per_frame);  // ~32 M sample slots per batch (~7.5 GB of state):
                                                                               // long queues amortise the persistent kernels' ramp-up and tail
     F = std::min(F, p->spp);
+    {   // bound the batch by the memory that is actually there (scratch already held by this scene counts as available)
+        const size_t per_slot = 2 * (sizeof(float4) * 4 + sizeof(uint2) + sizeof(float2)) + 2 * sizeof(float4) + sizeof(uint32_t) +
+                                (is_mode ? 3 * sizeof(float4) : 0) + (s->sort_rays ? 2 * sizeof(uint32_t) : 0);
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t held = s->queue_buf[0].bytes + s->queue_buf[1].bytes + s->shadow_buf.bytes + s->lo_buf.bytes + s->le_buf.bytes +
+                                s->defer_buf.bytes + s->sort_buf.bytes;
+            const size_t avail = (size_t)((double)(free_b + held) * 0.9);
+            const size_t f_max = avail / per_slot / per_frame;
+            if (f_max < 1) return ezrt_set_error(EZRT_ERR_NOMEM, "render: %zu MB free, one frame of wavefront state needs %zu MB", free_b >> 20, (per_slot * per_frame) >> 20);
+            F = (int)std::min<size_t>((size_t)F, f_max);
+        }
+    }
     const size_t capacity = per_frame * (size_t)F;
     if (capacity >= ((size_t)1 << 31)) return ezrt_set_error(EZRT_ERR_INVALID, "render: batch too large");
     PathQueue q[2];
     ShadowQueue sq{};
     if ((rc = carve_queue(s->queue_buf[0], capacity, q[0]))) return rc;
     if ((rc = carve_queue(s->queue_buf[1], capacity, q[1]))) return rc;
-    const bool is_mode = (p->mode == EZRT_MODE_DISNEY_IS_MIS_P5);
     if ((rc = carve_shadow(s->shadow_buf, is_mode ? capacity : 1, sq))) return rc;
     if ((rc = s->lo_buf.ensure(sizeof(float4) * capacity))) return rc;
     if ((rc = s->le_buf.ensure(sizeof(float4) * capacity))) return rc;
@@ -653,10 +678,13 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     uint32_t* defer_list = (uint32_t*)s->defer_buf.p;
     float4* Lo = (float4*)s->lo_buf.p;
     float4* Le = (float4*)s->le_buf.p;
-    if ((rc = s->sort_buf.ensure(sizeof(uint32_t) * (2 * capacity + EZRT_SORT_BINS + 64)))) return rc;
-    uint32_t* sort_keys = (uint32_t*)s->sort_buf.p;
-    uint32_t* sort_perm = sort_keys + capacity;
-    uint32_t* sort_bins = sort_perm + capacity;
+    uint32_t *sort_keys = nullptr, *sort_perm = nullptr, *sort_bins = nullptr;
+    if (s->sort_rays) {   // the optional bounce-ray sort (exact policies only)
+        if ((rc = s->sort_buf.ensure(sizeof(uint32_t) * (2 * capacity + EZRT_SORT_BINS + 64)))) return rc;
+        sort_keys = (uint32_t*)s->sort_buf.p;
+        sort_perm = sort_keys + capacity;
+        sort_bins = sort_perm + capacity;
+    }
 
     unsigned long long* const count_ptr = (p->profile == 2) ? totals + 5 : nullptr;  // node visits, triangle tests of the W8 kernels
     const bool l2_window = accel && s->l2_persist_bytes > 0 && s->hot_bytes > 0;
@@ -676,10 +704,14 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
         const uint32_t n_slots = (uint32_t)(per_frame * (size_t)nf);
         const uint32_t batch_first = p->first_frame + (uint32_t)done;
         CU_CHECK(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * n_counters, st));
-        int sp = s->span_begin(3, st);
-        launch_generate(rd, d_tiles, n_slots, batch_first, q[0], &q_count[0], s->n_sms, st);
-        s->span_end(sp, st);
-        s->launches++;
+        const bool fused_camera = accel && s->dev.w8_nodes != nullptr;   // camera rays are generated inside the first extend kernel
+        int sp = -1;
+        if (!fused_camera) {
+            sp = s->span_begin(3, st);
+            launch_generate(rd, d_tiles, n_slots, batch_first, q[0], &q_count[0], s->n_sms, st);
+            s->span_end(sp, st);
+            s->launches++;
+        }
         for (int b = 0; b <= p->max_bounce; b++) {
             PathQueue& qin = q[b & 1];
             PathQueue& qout = q[(b + 1) & 1];
@@ -692,7 +724,10 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
                 perm = sort_perm;
             }
             sp = s->span_begin(0, st);
-            if (accel) {
+            if (accel && fused_camera && b == 0) {
+                launch_extend_camera(s->dev, rd, d_tiles, batch_first, n_slots, qin, &w_ext[b], defer_list, &d_ext[b], &dw_ext[b], s->n_sms, count_ptr, st);
+                s->launches++;
+            } else if (accel) {
                 launch_extend_accel(s->dev, qin, &q_count[b], &w_ext[b], defer_list, &d_ext[b], &dw_ext[b], n_slots, s->n_sms, count_ptr, st);
                 s->launches++;
             } else {
@@ -701,7 +736,7 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
             s->span_end(sp, st);
             sp = s->span_begin(1, st);
             launch_shade(s->dev, rd, d_tiles, b, batch_first, qin, &q_count[b], qout, &q_count[b + 1], sq, &s_count[b], Lo, Le,
-                         n_slots, s->n_sms, st);
+                         n_slots, (fused_camera && b == 0) ? n_slots : 0u, s->n_sms, st);
             s->span_end(sp, st);
             s->launches += 2;
             if (is_mode && b < p->max_bounce) {
@@ -718,7 +753,7 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
         }
         sp = s->span_begin(3, st);
         launch_blend(rd, d_tiles, nf, batch_first, Lo, Le, d_fb, st);
-        launch_tally(q_count, s_count, d_ext, d_sh, p->max_bounce + 1, totals, st);
+        launch_tally(q_count, s_count, d_ext, d_sh, p->max_bounce + 1, totals, fused_camera ? (uint32_t)(s->n_pixels * (size_t)nf) : 0u, st);
         s->span_end(sp, st);
         s->launches += 2;
     }
@@ -731,6 +766,7 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     }
     CU_CHECK(cudaGetLastError());
     CU_CHECK(cudaEventRecord(s->ev_stop, st));
+    s->have_timing = true;
     return EZRT_OK;
 }
 

@@ -742,7 +742,7 @@ template <bool ANYHIT, bool COUNT, class RayIO>
 __device__ __forceinline__ void extend_w8(const SceneDev& sc, uint32_t n, uint32_t* work, RayIO io, const unsigned char* s_perm, uint2* stack_sm,
                                           W8Counts counts) {
     const bool tri_na = sc.tri_l1_bypass != 0;
-    const int refill_thresh = sc.refill_thresh, inner_thresh = sc.inner_thresh, leaf_thresh = sc.leaf_thresh;
+    const int refill_thresh = sc.refill_thresh, leaf_thresh = sc.w8_tri_weight;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -778,7 +778,7 @@ __device__ __forceinline__ void extend_w8(const SceneDev& sc, uint32_t n, uint32
                 HitRec h;
                 h.t = best;
                 h.tri = best_tri;
-                io.store((uint32_t)ray, h, tie, o, inv);
+                io.store((uint32_t)ray, h, tie, o, d, inv);
                 ray = -1;
                 node = -1;
                 return;
@@ -825,7 +825,7 @@ __device__ __forceinline__ void extend_w8(const SceneDev& sc, uint32_t n, uint32
                         best_tri = -1;
                         tie = false;
                     } else {  // outside the decode error bound: the exact kernel traces it
-                        io.defer(idx);
+                        io.defer(idx, o, d);
                     }
                 }
             }
@@ -838,16 +838,21 @@ __device__ __forceinline__ void extend_w8(const SceneDev& sc, uint32_t n, uint32
             if (exhausted) break;
             continue;
         }
+        // ---------------- traverse: every iteration the warp runs ONE of two steps, chosen by a vote ----------------
+        //   node step     : every lane holding a node visits it (three 256-bit loads, eight slab tests; ~200 instructions)
+        //   triangle step : every lane with pending triangles tests one (two 256-bit loads; ~100 instructions)
+        // A lane with pending triangles cannot take a node step (its next node depends on them), so the warp takes the
+        // triangle step as soon as  tri_weight * (lanes with triangles) >= (lanes with a node)  -- the step that serves
+        // more lanes per instruction (tri_weight ~ cost ratio of the two steps, env EZRT_TRI_W).
+        const int tri_weight = leaf_thresh;
         unsigned busy;
         do {
-            // ---------------- node phase: lanes holding a node visit it, one node per iteration, while enough of them do ----------------
-            const unsigned m_busy = __ballot_sync(FULL, ray >= 0);
-            while (true) {
-                const bool at_node = node >= 0;
-                const unsigned m_node = __ballot_sync(FULL, at_node);
-                if (m_node == 0u) break;
-                const unsigned m_wait = m_busy & ~m_node;   // lanes waiting with triangles to test
-                if (m_wait != 0u && (__popc(m_node) < inner_thresh || __popc(m_wait) >= leaf_thresh)) break;
+            const bool at_node = node >= 0;
+            const bool has_tri = t_mask != 0u;
+            const unsigned m_node = __ballot_sync(FULL, at_node);
+            const unsigned m_tri = __ballot_sync(FULL, has_tri);
+            if ((m_node | m_tri) == 0u) { busy = 0u; break; }
+            if (m_node != 0u && tri_weight * __popc(m_tri) < __popc(m_node)) {
                 if (at_node) {
                     const uint4* nd = nodes + (size_t)node * 6;
                     uint4 h0, h1, l0, l1, u0, u1;
@@ -903,29 +908,22 @@ __device__ __forceinline__ void extend_w8(const SceneDev& sc, uint32_t n, uint32
                     node = -1;
                     if (t_mask == 0u) select_next();
                 }
-            }
-            // ---------------- triangle phase: every lane with pending triangles tests one per iteration ----------------
-            while (true) {
-                const bool has = t_mask != 0u;
-                const unsigned m_tri = __ballot_sync(FULL, has);
-                if (m_tri == 0u) break;
-                if (has) {
-                    const int k = __ffs(t_mask) - 1;
-                    t_mask &= t_mask - 1u;
-                    const int tri = (int)t_base + k;
-                    if (COUNT) n_tests++;
-                    float t;
-                    const int r = tri_test_t<true>(sc.acc_tri_geo + (size_t)tri * 4, o, d, best, t, tri_na);
-                    if (r == 2) {
-                        tie = true;              // a second triangle at exactly the best distance: visit order would decide
-                    } else if (r == 1) {
-                        best = t;
-                        best_tri = tri;
-                        tie = false;
-                        if (ANYHIT) { t_mask = 0u; g_bits = 0u; sp = 0; }   // any accepted hit ends a shadow ray
-                    }
-                    if (t_mask == 0u) select_next();
+            } else if (has_tri) {
+                const int k = __ffs(t_mask) - 1;
+                t_mask &= t_mask - 1u;
+                const int tri = (int)t_base + k;
+                if (COUNT) n_tests++;
+                float t;
+                const int r = tri_test_t<true>(sc.acc_tri_geo + (size_t)tri * 4, o, d, best, t, tri_na);
+                if (r == 2) {
+                    tie = true;              // a second triangle at exactly the best distance: visit order would decide
+                } else if (r == 1) {
+                    best = t;
+                    best_tri = tri;
+                    tie = false;
+                    if (ANYHIT) { t_mask = 0u; g_bits = 0u; sp = 0; }   // any accepted hit ends a shadow ray
                 }
+                if (t_mask == 0u) select_next();
             }
             busy = __ballot_sync(FULL, ray >= 0);
         } while (busy != 0u && (exhausted || __popc(busy) >= refill_thresh));

@@ -22,7 +22,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define EZRT_MAX_STACK 64        // >= validated tree depth + 1 (the shader's bound is 256, P5/fsh:260)
+#define EZRT_MAX_STACK 256       // >= validated tree depth + 1: the shader's own bound, int stack[256] (P5/fsh:260)
 #define EZRT_LEAF_FLAG 0x80000000u
 #define EZRT_LEAF_MAX_N 127
 #define EZRT_TOP_NODES_MAX 1023   // 10 full levels; 80 B each in shared memory (bank-conflict padding)
@@ -53,6 +53,7 @@ struct SceneDev {
     const uint4* w8_nodes;         // the tree as 8-wide nodes with 8-bit quantised child boxes (96 B records, w8_node.h); null = none
     int w8_near_bit[3];            // significance of axis a in the slot index (octant order)
     int w8_stack_entries;          // per-lane stack entries kept in shared memory (>= depth of the 8-wide tree, or the smem cap)
+    int w8_tri_weight;             // step vote of the W8 kernels: triangle step iff w8_tri_weight * lanes_with_triangles >= lanes_with_a_node (env EZRT_TRI_W)
     uint32_t w8_decode_bits;       // W8_DECODE_BITS (passed as data: see w8_plane in device_functions.cuh)
     float w8_origin_limit;         // rays starting further out than this (any |coordinate|) go to the exact kernel (decode error bound)
     const float4* acc_wide_nodes;  // the same tree collapsed to 4-wide nodes with exact boxes (128 B records): round-1 kernel, env EZRT_ACCEL=4

@@ -222,7 +222,7 @@ int read_obj_stream(std::istream& fin, std::vector<Tri>& triangles, const float 
             }
             if (fv.size() < 3) return EZRT_ERR_IO;
             for (int idx : fv)
-                if (idx < 1 || (size_t)idx > vertices.size()) return EZRT_ERR_IO;
+                if (idx < 1) return EZRT_ERR_IO;   // upper bound: after the whole file is read (a face may precede its vertices)
             for (size_t k = 2; k < fv.size(); k++) {
                 indices.push_back((unsigned)(fv[0] - 1));
                 indices.push_back((unsigned)(fv[k - 1] - 1));
@@ -230,6 +230,9 @@ int read_obj_stream(std::istream& fin, std::vector<Tri>& triangles, const float 
             }
         }
     }
+
+    for (unsigned idx : indices)   // the reference resolves indices after reading the whole file (P5/main.cpp:344-362)
+        if ((size_t)idx >= vertices.size()) return EZRT_ERR_IO;
 
     float lenx = maxx - minx, leny = maxy - miny, lenz = maxz - minz;
     float maxaxis = ez_max(lenx, ez_max(leny, lenz));
@@ -403,6 +406,8 @@ struct FastCtx {
     Key* keys;
     int leaf_n;
     float inf;  // cost sentinel / box seed: EZ_INF (114514, the reference's quirk) or FLT_MAX (accel tree)
+    int median_depth = 0;  // > 0 (acceleration tree only): below this depth split at the median, whatever the SAH says -- equal costs
+                           // (coincident triangles) make the sweep peel one triangle per level, i.e. an O(n)-deep chain
 };
 bool kcmpx(const Key& a, const Key& b) { return a.cx < b.cx; }
 bool kcmpy(const Key& a, const Key& b) { return a.cy < b.cy; }
@@ -466,6 +471,7 @@ void build_sah_fast(const FastCtx& cx, int l, int r, std::vector<Node>& out, int
     if (Axis == 0) std::sort(keys + l, keys + r + 1, kcmpx);
     if (Axis == 1) std::sort(keys + l, keys + r + 1, kcmpy);
     if (Axis == 2) std::sort(keys + l, keys + r + 1, kcmpz);
+    if (cx.median_depth > 0 && depth >= cx.median_depth) Split = (l + r) / 2;
 
     std::vector<Node> leftNodes, rightNodes;
     bool par = (depth < 6) && (cnt > 4096);
@@ -523,6 +529,7 @@ int ezrt_build_accel(const float* tris, int n_tris, int leaf_n, std::vector<Ezrt
     }
     FastCtx cx;
     cx.bmin = &bmin; cx.bmax = &bmax; cx.keys = keys.data(); cx.leaf_n = leaf_n; cx.inf = 3.0e38f;
+    cx.median_depth = 32;   // depth <= 32 + log2(n): the traversal stacks always suffice, the recursion stays shallow
     std::vector<Node> sub;
     build_sah_fast(cx, 0, n_tris - 1, sub, 0);
     nodes_out.resize(sub.size());
@@ -663,7 +670,10 @@ int ezrt_trilist_encode_nodes(const ezrt_trilist* list, float* out) {
 namespace {
 typedef unsigned char RGBE[4];
 
-bool old_decrunch(RGBE* scanline, int len, FILE* file) {  // hdrloader.cpp:161-191
+// Hardened against what the reference's decoder trusts the file for (hdrloader.cpp:161-191): a run marker (1,1,1,n) needs
+// a previous pixel IN THIS SCANLINE to repeat (the reference reads scanline[-1], i.e. before the buffer, for a marker at
+// x = 0), and the run length n << rshift must stay defined (rshift = 32 after four consecutive markers is UB in C).
+bool old_decrunch(RGBE* scanline, int len, FILE* file, const RGBE* line_start) {
     int rshift = 0;
     while (len > 0) {
         scanline[0][0] = (unsigned char)fgetc(file);
@@ -672,6 +682,7 @@ bool old_decrunch(RGBE* scanline, int len, FILE* file) {  // hdrloader.cpp:161-1
         scanline[0][3] = (unsigned char)fgetc(file);
         if (feof(file)) return false;
         if (scanline[0][0] == 1 && scanline[0][1] == 1 && scanline[0][2] == 1) {
+            if (scanline == line_start || rshift > 24) return false;   // malformed: nothing to repeat / run length overflow
             for (int i = scanline[0][3] << rshift; i > 0 && len > 0; i--) {
                 memcpy(&scanline[0][0], &scanline[-1][0], 4);
                 scanline++;
@@ -688,11 +699,11 @@ bool old_decrunch(RGBE* scanline, int len, FILE* file) {  // hdrloader.cpp:161-1
 }
 
 bool decrunch(RGBE* scanline, int len, FILE* file) {  // hdrloader.cpp:118-159
-    if (len < 8 || len > 0x7fff) return old_decrunch(scanline, len, file);
+    if (len < 8 || len > 0x7fff) return old_decrunch(scanline, len, file, scanline);
     int i = fgetc(file);
     if (i != 2) {
         fseek(file, -1, SEEK_CUR);
-        return old_decrunch(scanline, len, file);
+        return old_decrunch(scanline, len, file, scanline);
     }
     scanline[0][1] = (unsigned char)fgetc(file);
     scanline[0][2] = (unsigned char)fgetc(file);
@@ -700,7 +711,7 @@ bool decrunch(RGBE* scanline, int len, FILE* file) {  // hdrloader.cpp:118-159
     if (scanline[0][1] != 2 || (scanline[0][2] & 128)) {
         scanline[0][0] = 2;
         scanline[0][3] = (unsigned char)i;
-        return old_decrunch(scanline + 1, len - 1, file);
+        return old_decrunch(scanline + 1, len - 1, file, scanline);
     }
     for (i = 0; i < 4; i++) {
         for (int j = 0; j < len;) {
@@ -762,8 +773,9 @@ int ezrt_hdr_load(const char* path, int* width, int* height, float* cols) {
     RGBE* scanline = reinterpret_cast<RGBE*>(buf.data());
     memset(cols, 0, sizeof(float) * (size_t)w * h * 3);
     float* out = cols;
+    bool truncated = false;
     for (int y = h - 1; y >= 0; y--) {
-        if (!decrunch(scanline, w, file)) break;
+        if (!decrunch(scanline, w, file)) { truncated = true; break; }  // the reference stops here too and keeps what it has (rows of 0)
         for (int x = 0; x < w; x++) {  // workOnRGBE, hdrloader.cpp:106-116
             int expo = (int)scanline[x][3] - 128;
             out[0] = convert_component(expo, scanline[x][0]);
@@ -773,7 +785,7 @@ int ezrt_hdr_load(const char* path, int* width, int* height, float* cols) {
         }
     }
     fclose(file);
-    return EZRT_OK;
+    return truncated ? 1 : EZRT_OK;   // 1: the pixel data ended early or was malformed; the remaining rows are zero (include/ezrt.h)
 }
 
 // ---- calculateHdrCache, P5/main.cpp:592-689 ------------------------------------------------

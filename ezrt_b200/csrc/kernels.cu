@@ -372,15 +372,67 @@ struct W8ExtendIO {
         d = ez_v3(d4.x, d4.y, d4.z);
         return true;
     }
-    __device__ __forceinline__ void defer(uint32_t i) const { defer_list[atomicAdd(defer_count, 1u)] = i; }
-    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool tie, vec3 o, vec3 inv) const {
+    __device__ __forceinline__ void defer(uint32_t i, vec3, vec3) const { defer_list[atomicAdd(defer_count, 1u)] = i; }
+    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool tie, vec3 o, vec3 d, vec3 inv) const {
         if (h.tri >= 0 && (tie || !reference_reaches_leaf_inv(acc_tri_leaf, leaf_box, h.tri, o, inv))) {
-            defer(i);
+            defer(i, o, d);
             return;
         }
         __stcs(q.hit + i, make_float2(h.t, __int_as_float(h.tri)));  // accel-order triangle index
     }
 };
+
+// Camera pass with the ray generation fused in (main(), P5/fsh:920-925): ray `i` IS sample slot i, generated in the
+// lane that traces it -- no k_generate pass, no 40-byte queue record written and read back per camera ray.  Slots of
+// clipped edge tiles that lie outside the image are skipped.  Only a deferred ray is written to the queue, for the
+// exact kernel that re-traces it.
+struct W8CameraIO {
+    RenderDev rd;
+    const TileDev* tiles;
+    uint32_t batch_first_frame;
+    PathQueue q;
+    const int* acc_tri_leaf;
+    const float4* leaf_box;
+    uint32_t* defer_list;
+    uint32_t* defer_count;
+    __device__ __forceinline__ bool load(uint32_t i, vec3& o, vec3& d) const {
+        uint32_t px, py, fib, seed;
+        if (!slot_pixel(rd, tiles, i, px, py, fib)) return false;
+        primary_ray(rd, px, py, batch_first_frame + fib, seed, o, d);
+        return true;
+    }
+    __device__ __forceinline__ void defer(uint32_t i, vec3 o, vec3 d) const {
+        q.ray_o[i] = make_float4(o.x, o.y, o.z, 0.0f);
+        q.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+        defer_list[atomicAdd(defer_count, 1u)] = i;
+    }
+    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool tie, vec3 o, vec3 d, vec3 inv) const {
+        if (h.tri >= 0 && (tie || !reference_reaches_leaf_inv(acc_tri_leaf, leaf_box, h.tri, o, inv))) {
+            defer(i, o, d);
+            return;
+        }
+        __stcs(q.hit + i, make_float2(h.t, __int_as_float(h.tri)));
+    }
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend_w8_camera(SceneDev sc, RenderDev rd, const TileDev* __restrict__ tiles,
+                                                                   uint32_t batch_first_frame, uint32_t n_slots, PathQueue q, uint32_t* work,
+                                                                   uint32_t* defer_list, uint32_t* defer_count, W8Counts counts) {
+    unsigned char* s_perm;
+    uint2* stack_sm;
+    w8_smem_setup(s_perm, stack_sm);
+    W8CameraIO io;
+    io.rd = rd;
+    io.tiles = tiles;
+    io.batch_first_frame = batch_first_frame;
+    io.q = q;
+    io.acc_tri_leaf = sc.acc_tri_leaf;
+    io.leaf_box = sc.leaf_box;
+    io.defer_list = defer_list;
+    io.defer_count = defer_count;
+    extend_w8<false, COUNT>(sc, n_slots, work, io, s_perm, stack_sm, counts);
+}
 
 template <bool COUNT>
 __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend_w8(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count, uint32_t* work,
@@ -404,14 +456,14 @@ struct W8ShadowIO {
     uint32_t* defer_list;
     uint32_t* defer_count;
     __device__ __forceinline__ bool load(uint32_t i, vec3& o, vec3& d) const { return base.load(i, o, d); }
-    __device__ __forceinline__ void defer(uint32_t i) const { defer_list[atomicAdd(defer_count, 1u)] = i; }
-    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3 o, vec3 inv) const {
+    __device__ __forceinline__ void defer(uint32_t i, vec3, vec3) const { defer_list[atomicAdd(defer_count, 1u)] = i; }
+    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3 o, vec3 d, vec3 inv) const {
         if (h.tri < 0) {  // nothing accepted anywhere: the shader finds nothing either
             base.add(i);
             return;
         }
         // occluded if the shader reaches the occluder's leaf; otherwise the exact kernel decides
-        if (!reference_reaches_leaf_inv(acc_tri_leaf, leaf_box, h.tri, o, inv)) defer(i);
+        if (!reference_reaches_leaf_inv(acc_tri_leaf, leaf_box, h.tri, o, inv)) defer(i, o, d);
     }
 };
 
@@ -439,9 +491,11 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
 __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev sc, RenderDev rd, const TileDev* __restrict__ tiles, int bounce,
                                                uint32_t batch_first_frame, PathQueue qin, const uint32_t* __restrict__ in_count,
                                                PathQueue qout, uint32_t* out_count, ShadowQueue sq, uint32_t* s_count,
-                                               float4* __restrict__ Lo, float4* __restrict__ Le) {
+                                               float4* __restrict__ Lo, float4* __restrict__ Le, uint32_t n_fused) {
+    // n_fused != 0 (bounce 0 of the W8 policy): entry i is sample slot i, its camera ray was generated inside
+    // k_extend_w8_camera and is generated again here instead of being read from a queue; only q.hit[i] is read
     __shared__ uint32_t s_scan[34];
-    const uint32_t n = *in_count;
+    const uint32_t n = n_fused ? n_fused : *in_count;
     const uint32_t n_round = ((n + blockDim.x - 1u) / blockDim.x) * blockDim.x;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
@@ -450,14 +504,23 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
         ShadowRay sh;
         sh.valid = false;
         uint32_t slot = 0;
-        if (i < n) {
-            float4 o4 = __ldcs(qin.ray_o + i), d4 = __ldcs(qin.ray_d + i);
+        uint32_t px = 0, py = 0, fib = 0;
+        bool present = i < n;
+        if (present && n_fused) present = slot_pixel(rd, tiles, i, px, py, fib);   // slots of clipped tiles outside the image
+        if (present) {
             const float2 hit = __ldcs(qin.hit + i);
-            uint2 meta = __ldcs(qin.meta + i);
-            slot = meta.y;
-            p.o = ez_v3(o4.x, o4.y, o4.z);
-            p.d = ez_v3(d4.x, d4.y, d4.z);
-            p.seed = meta.x;
+            if (n_fused) {
+                slot = i;
+                primary_ray(rd, px, py, batch_first_frame + fib, p.seed, p.o, p.d);
+            } else {
+                float4 o4 = __ldcs(qin.ray_o + i), d4 = __ldcs(qin.ray_d + i);
+                uint2 meta = __ldcs(qin.meta + i);
+                slot = meta.y;
+                p.o = ez_v3(o4.x, o4.y, o4.z);
+                p.d = ez_v3(d4.x, d4.y, d4.z);
+                p.seed = meta.x;
+                slot_pixel(rd, tiles, slot, px, py, fib);
+            }
             vec3 lo = splat3(0.0f), le = splat3(0.0f);
             bool pmiss = false;
             if (bounce > 0) {
@@ -474,8 +537,6 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
                 p.cosine_i = 0.0f;
                 p.pdf = 1.0f;
             }
-            uint32_t px, py, fib;
-            slot_pixel(rd, tiles, slot, px, py, fib);
             alive = shade_step(sc, rd, bounce, p, hit.x, __float_as_int(hit.y), px, py, batch_first_frame + fib, lo, le, pmiss, sh);
             Lo[slot] = make_float4(lo.x, lo.y, lo.z, pmiss ? 1.0f : 0.0f);
             if (bounce == 0) Le[slot] = make_float4(le.x, le.y, le.z, 0.0f);
@@ -531,15 +592,16 @@ __global__ void __launch_bounds__(256) k_blend(RenderDev rd, const TileDev* __re
 
 // totals[0..2] += primary, bounce, shadow rays of this batch; totals[3] += samples; totals[4] += deferred rays
 __global__ void k_tally(const uint32_t* __restrict__ q_counts, const uint32_t* __restrict__ s_counts, const uint32_t* __restrict__ d_ext,
-                        const uint32_t* __restrict__ d_sh, int n_stages, unsigned long long* totals) {
+                        const uint32_t* __restrict__ d_sh, int n_stages, unsigned long long* totals, uint32_t n_primary) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     unsigned long long bounce = 0, shadow = 0, deferred = 0;
     for (int b = 1; b < n_stages; b++) bounce += q_counts[b];
     for (int b = 0; b < n_stages; b++) { shadow += s_counts[b]; deferred += d_ext[b] + d_sh[b]; }
-    totals[0] += q_counts[0];
+    const unsigned long long primary = n_primary ? n_primary : q_counts[0];  // fused camera pass: no queue 0, the host knows the count
+    totals[0] += primary;
     totals[1] += bounce;
     totals[2] += shadow;
-    totals[3] += q_counts[0];
+    totals[3] += primary;
     totals[4] += deferred;
 }
 
@@ -774,6 +836,18 @@ void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_
     if (prune) k_shadow<true><<<blocks, threads, smem_for(k_shadow<true>, sc.top_nodes), st>>>(sc, sq, s_count, work, Lo, perm);
     else k_shadow<false><<<blocks, threads, smem_for(k_shadow<false>, sc.top_nodes), st>>>(sc, sq, s_count, work, Lo, perm);
 }
+// camera pass of the W8 policy: rays generated in the kernel (slot i = ray i), then the exact pass over the deferred ones
+void launch_extend_camera(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, uint32_t batch_first_frame, uint32_t n_slots, PathQueue q,
+                          uint32_t* work, uint32_t* defer_list, uint32_t* defer_count, uint32_t* defer_work, int n_sms, unsigned long long* counts,
+                          cudaStream_t st) {
+    const int threads = extend_threads(), blocks = persistent_blocks(n_slots, n_sms);
+    W8Counts c;
+    c.node_visits = counts;
+    c.tri_tests = counts ? counts + 1 : nullptr;
+    if (counts) k_extend_w8_camera<true><<<blocks, threads, w8_smem_for(k_extend_w8_camera<true>, sc), st>>>(sc, rd, tiles, batch_first_frame, n_slots, q, work, defer_list, defer_count, c);
+    else k_extend_w8_camera<false><<<blocks, threads, w8_smem_for(k_extend_w8_camera<false>, sc), st>>>(sc, rd, tiles, batch_first_frame, n_slots, q, work, defer_list, defer_count, c);
+    launch_extend(sc, true, false, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_slots, 65536u), n_sms, st);
+}
 void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo, uint32_t* defer_list,
                          uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, unsigned long long* counts, cudaStream_t st) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
@@ -790,10 +864,10 @@ void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_c
 }
 void launch_shade(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, int bounce, uint32_t batch_first_frame,
                   PathQueue qin, const uint32_t* in_count, PathQueue qout, uint32_t* out_count, ShadowQueue sq,
-                  uint32_t* s_count, float4* Lo, float4* Le, uint32_t n_max, int n_sms, cudaStream_t st) {
+                  uint32_t* s_count, float4* Lo, float4* Le, uint32_t n_max, uint32_t n_fused, int n_sms, cudaStream_t st) {
     int blocks = std::min(div_up(n_max, 128), n_sms * 4 * EZRT_SHADE_MIN_BLOCKS);
     if (blocks < 1) blocks = 1;
-    k_shade<<<blocks, 128, 0, st>>>(sc, rd, tiles, bounce, batch_first_frame, qin, in_count, qout, out_count, sq, s_count, Lo, Le);
+    k_shade<<<blocks, 128, 0, st>>>(sc, rd, tiles, bounce, batch_first_frame, qin, in_count, qout, out_count, sq, s_count, Lo, Le, n_fused);
 }
 void launch_blend(const RenderDev& rd, const TileDev* tiles, int nf, uint32_t batch_first_frame, const float4* Lo,
                   const float4* Le, float* fb, cudaStream_t st) {
@@ -801,8 +875,8 @@ void launch_blend(const RenderDev& rd, const TileDev* tiles, int nf, uint32_t ba
     k_blend<<<div_up(per_frame, 256), 256, 0, st>>>(rd, tiles, nf, batch_first_frame, Lo, Le, fb);
 }
 void launch_tally(const uint32_t* q_counts, const uint32_t* s_counts, const uint32_t* d_ext, const uint32_t* d_sh, int n_stages,
-                  unsigned long long* totals, cudaStream_t st) {
-    k_tally<<<1, 32, 0, st>>>(q_counts, s_counts, d_ext, d_sh, n_stages, totals);
+                  unsigned long long* totals, uint32_t n_primary, cudaStream_t st) {
+    k_tally<<<1, 32, 0, st>>>(q_counts, s_counts, d_ext, d_sh, n_stages, totals, n_primary);
 }
 void launch_megakernel(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, bool prune, int spp, float* fb,
                        unsigned long long* totals, cudaStream_t st) {

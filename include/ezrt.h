@@ -95,8 +95,12 @@ typedef struct ezrt_render_params {
     int32_t profile;          /* 1: bracket every kernel with CUDA events (ezrt_get_kernel_times);
                                  2: count the records the accel traversal fetches (ezrt_counters.node_visits / tri_tests;
                                     a slower instantiation of the same kernels -- never inside a timed region) */
-    int32_t reserved[3];
+    int32_t reserved[3];      /* [0]: flags, EZRT_PARAM_*; [1], [2]: 0 */
 } ezrt_render_params;
+
+/* ezrt_render_params.reserved[0]: keep counting -- ezrt_get_counters / ezrt_get_kernel_times then report the sums over all
+   renders since the last one issued without this flag (a benchmark loop reads them once, without a sync per render) */
+#define EZRT_PARAM_ACCUMULATE 1
 
 typedef struct ezrt_counters {
     uint64_t rays;          /* hitBVH invocations: primary + bounce + shadow     */
@@ -137,7 +141,11 @@ int ezrt_scene_destroy(ezrt_scene* scene);
 int ezrt_render(ezrt_scene* scene, const ezrt_render_params* params, float* framebuffer);
 
 /* Same, but `d_framebuffer` is DEVICE memory on the scene's GPU and the work is enqueued on
- * `cuda_stream` (a cudaStream_t, NULL = default stream) without host synchronisation. */
+ * `cuda_stream` (a cudaStream_t, NULL = default stream).  Steady state: no host synchronisation.  The FIRST
+ * call for a given (image size, partition, batch size) allocates the scene's scratch buffers (cudaMalloc synchronises
+ * the device) and uploads the tile list (one stream synchronisation).  The scratch belongs to the scene: at most ONE
+ * render of a scene may be in flight at a time -- enqueue renders of the same scene on one stream, or order them with
+ * events; different scenes (one per GPU) are independent. */
 int ezrt_render_device(ezrt_scene* scene, const ezrt_render_params* params, float* d_framebuffer,
                        void* cuda_stream);
 
@@ -246,7 +254,9 @@ int ezrt_trilist_encode_nodes(const ezrt_trilist* list, float* nodes_out);
 int ezrt_scene_file_load(const char* path, ezrt_trilist* list, float camera[3], char* hdr_path, size_t hdr_path_cap);
 
 /* HDRLoader::load (P5/lib/hdrloader.cpp:29-97): Radiance .hdr -> float RGB rows.  Call with
- * cols = NULL to query width/height. */
+ * cols = NULL to query width/height.  Returns 0, or 1 when the pixel data ended early or was malformed (a run marker
+ * with nothing to repeat, a run length beyond 32 bits): like the reference the rows decoded so far are kept and the
+ * rest is zero, but unlike it nothing outside the scanline buffer is read; < 0 on errors. */
 int ezrt_hdr_load(const char* path, int* width, int* height, float* cols);
 /* calculateHdrCache (P5/main.cpp:592-689): (sample_x, sample_y, pdf) lookup texture. */
 int ezrt_hdr_cache(const float* hdr, int width, int height, float* cache_out);

@@ -65,10 +65,25 @@ def test_gather_framebuffer_gloo(tmp_path, world, W, H):
     np.testing.assert_array_equal(got, _pixel_value(W, H, C))
 
 
-def test_weak_image_keeps_pixels_per_gpu():
+def test_bench_image_per_gpu_count():
+    """bench.py: N = 1 renders the C3 image, N > 1 one fixed 3840x2160 image (BASELINE configs[4], strong scaling);
+    --scaling weak keeps the pixels per GPU fixed."""
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    wl = dict(width=1920, height=1080)
+    strong = argparse.Namespace(image=None, scaling="auto")
+    weak = argparse.Namespace(image=None, scaling="weak")
+    assert bench.image_for(strong, wl, 1) == (1920, 1080, "strong")
+    for n in (2, 4, 8):
+        assert bench.image_for(strong, wl, n) == (3840, 2160, "strong")
+        w, h, label = bench.image_for(weak, wl, n)
+        assert w * h == 1920 * 1080 * n and label == "weak"
+    assert bench.image_for(argparse.Namespace(image="640x360", scaling="auto"), wl, 4)[:2] == (640, 360)
+
+
+def test_cpu_thread_count_is_explicit_and_bounded():
     sys.path.insert(0, ROOT)
     import bench
-    for n in (1, 2, 4, 8):
-        w, h = bench.weak_image(1920, 1080, n)
-        assert w * h == 1920 * 1080 * n
-    assert bench.weak_image(1920, 1080, 4) == (3840, 2160)  # BASELINE configs[4] resolution
+    n, info = bench.cpu_threads()
+    assert 1 <= n <= (os.cpu_count() or 1) and info["affinity"] >= n
