@@ -524,10 +524,12 @@ def roofline_of(res, counts, wl_means, hbm_peak, peak_kind, kernel_name):
         out.update({"peak": hbm_peak, "frac": achieved / hbm_peak, "peak_source": peak_kind + " (no gather_peak_r2.json)"})
     # HBM side: DRAM bytes of the extend kernels from the committed ncu capture of this command (tools/ncu_summaries.py dram)
     dram = load_json(os.path.join(ROOT, "profiles", "ncu_dram_r2.json"))
-    key = kernel_name
     traffic = None
-    if dram and key in dram.get(res.get("workload", ""), {}):
-        traffic = dram[res["workload"]][key]["dram_bytes_per_launch"]
+    cls = (dram or {}).get(res.get("workload", ""), {})
+    if "extend" in cls:   # mean over the accel launches of one step (extend + shadow passes)
+        tot = sum(cls[k]["dram_bytes_per_launch"] * cls[k]["launches"] for k in ("extend", "shadow") if k in cls)
+        cnt = sum(cls[k]["launches"] for k in ("extend", "shadow") if k in cls)
+        traffic = tot / max(1, cnt)
     out["traffic"] = traffic
     out["traffic_source"] = "profiles/ncu_dram_r2.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu capture of this command)" if traffic else None
     out["hbm"] = {"peak": hbm_peak, "peak_source": peak_kind, "achieved_gbs": (traffic / (ext_ms * 1e-3 / max(1, ext_n)) / 1e9) if traffic else None}
@@ -609,7 +611,7 @@ def main():
     peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json")) or {}
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    kname = {"accel": "k_extend_w8", "pruned": "k_extend<PRUNE>", "reference": "k_extend"}[args.traverse]
+    kname = {"accel": "k_extend_accel (+ k_shadow_accel)", "pruned": "k_extend<PRUNE>", "reference": "k_extend"}[args.traverse]
 
     def pack(m):
         res = m["res"]

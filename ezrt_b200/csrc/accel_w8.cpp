@@ -30,8 +30,93 @@ void ezrt_w8_axis_bits(const float bmin[3], const float bmax[3], int axis_bit[3]
     for (int k = 0; k < 3; k++) axis_bit[idx[k]] = k;
 }
 
-// Cost model of the collapse (surface-area heuristic, after Ylitie et al. 2017 section 3.1): visiting an 8-wide node costs
-// W8_COST_NODE, testing one triangle W8_COST_TRI (ratio of the kernel's instruction counts for the two).
+// ------------------------------------------------------------------------------------------
+// Optimal collapse of the binary tree to `width`-wide nodes by dynamic programming over the binary tree (surface-area
+// heuristic, after Ylitie et al. 2017 section 3.1; children have larger indices than their parent):
+//   C(n,1) = min(cost of n as ONE leaf (<= max_leaf triangles, consecutive), area(n) * cost_node + best split of n into <= width roots)
+//   C(n,i) = min(C(n,i-1), min_k C(left,k) + C(right,i-k))          i = 2..width-1: n's sub-tree represented by <= i roots
+// Visiting a wide node costs cost_node, testing one triangle cost_tri (ratio of the kernels' instruction counts).
+// ------------------------------------------------------------------------------------------
+int EzrtCollapse::build(const std::vector<EzrtAccelNode>& an_, int width_, int max_leaf, double cost_node, double cost_tri) {
+    an = &an_;
+    width = width_;
+    const int NB = (int)an_.size();
+    first.assign(NB, 0);
+    count.assign(NB, 0);
+    as_leaf.assign(NB, 0);
+    C.assign((size_t)NB * 8, 0.0f);
+    if (width < 2 || width > 8) return -1;
+    for (int i = NB - 1; i >= 0; i--) {
+        const EzrtAccelNode& nd = an_[i];
+        const double area = (double)box_area(nd);
+        float* c = &C[(size_t)i * 8];
+        if (nd.n > 0) {
+            if (nd.n > max_leaf) return -3;
+            first[i] = nd.index;
+            count[i] = nd.n;
+            as_leaf[i] = 1;
+            for (int k = 1; k <= 7; k++) c[k] = (float)(area * nd.n * cost_tri);
+            continue;
+        }
+        const float *cl = &C[(size_t)nd.left * 8], *cr = &C[(size_t)nd.right * 8];
+        first[i] = std::min(first[nd.left], first[nd.right]);
+        count[i] = count[nd.left] + count[nd.right];
+        float dist[9];
+        for (int j = 2; j <= width; j++) {
+            float best = 3.0e38f;
+            for (int k = 1; k < j; k++)
+                if (k <= width - 1 && j - k <= width - 1) best = std::min(best, cl[k] + cr[j - k]);
+            dist[j] = best;
+        }
+        const float c_internal = (float)(area * cost_node) + dist[width];
+        const float c_leaf = (count[i] <= max_leaf && first[nd.left] + count[nd.left] == first[nd.right]) ? (float)(area * count[i] * cost_tri) : 3.0e38f;
+        as_leaf[i] = c_leaf <= c_internal;
+        c[1] = std::min(c_leaf, c_internal);
+        for (int j = 2; j <= width - 1; j++) c[j] = std::min(c[j - 1], dist[j]);
+        for (int j = width; j <= 7; j++) c[j] = c[width - 1];
+    }
+    return 0;
+}
+
+// roots of the best representation of sub-tree n0 by <= k0 roots (left to right)
+int EzrtCollapse::collect(int n0, int k0, int* roots) const {
+    const std::vector<EzrtAccelNode>& a = *an;
+    struct Pick { int n, k; };
+    int cnt = 0;
+    Pick stack[32];
+    int sp = 0;
+    stack[sp++] = {n0, k0};
+    while (sp > 0) {
+        Pick p = stack[--sp];
+        const float* c = &C[(size_t)p.n * 8];
+        while (p.k > 1 && c[p.k] == c[p.k - 1]) p.k--;
+        if (p.k == 1 || a[p.n].n > 0) { roots[cnt++] = p.n; continue; }
+        const EzrtAccelNode& nd = a[p.n];
+        const float *cl = &C[(size_t)nd.left * 8], *cr = &C[(size_t)nd.right * 8];
+        int bk = 1;
+        float best = 3.0e38f;
+        for (int k = 1; k < p.k; k++)
+            if (cl[k] + cr[p.k - k] < best) { best = cl[k] + cr[p.k - k]; bk = k; }
+        stack[sp++] = {nd.right, p.k - bk};   // right first on the stack: the left roots come out first
+        stack[sp++] = {nd.left, bk};
+    }
+    return cnt;
+}
+
+// children (binary nodes; as_leaf[] says which become leaves) of the wide node made from inner binary node b
+int EzrtCollapse::children(int b, int* ch) const {
+    const std::vector<EzrtAccelNode>& a = *an;
+    const EzrtAccelNode& nd = a[b];
+    const float *cl = &C[(size_t)nd.left * 8], *cr = &C[(size_t)nd.right * 8];
+    int bk = 1;
+    float best = 3.0e38f;
+    for (int k = 1; k <= width - 1; k++)
+        if (cl[k] + cr[width - k] < best) { best = cl[k] + cr[width - k]; bk = k; }
+    int cnt = collect(nd.left, bk, ch);
+    cnt += collect(nd.right, width - bk, ch + cnt);
+    return cnt;
+}
+
 #define W8_COST_NODE 1.0
 #define W8_COST_TRI 0.4
 
@@ -46,65 +131,12 @@ int ezrt_build_w8(const std::vector<EzrtAccelNode>& an, const std::vector<uint32
     if (an.empty()) return -1;
     const int NB = (int)an.size();
     const double min_step = (double)max_abs_coord * (double)W8_MIN_STEP_REL;
-
-    // ---- optimal collapse by dynamic programming over the binary tree (children have larger indices than their parent):
-    //   C(n,1) = min(cost of n as ONE leaf slot (<= W8_MAX_LEAF_TRIS triangles), area(n) * W8_COST_NODE + best split of n into <= 8 roots)
-    //   C(n,i) = min(C(n,i-1), min_k C(left,k) + C(right,i-k))          i = 2..7: n's sub-tree represented by <= i roots
-    std::vector<int> first(NB), count(NB);
-    std::vector<float> C((size_t)NB * 8, 0.0f);   // C[n*8 + i], i = 1..7
-    std::vector<char> as_leaf(NB, 0);
-    for (int i = NB - 1; i >= 0; i--) {
-        const EzrtAccelNode& nd = an[i];
-        const double area = (double)box_area(nd);
-        float* c = &C[(size_t)i * 8];
-        if (nd.n > 0) {
-            if (nd.n > W8_MAX_LEAF_TRIS) return -3;
-            first[i] = nd.index;
-            count[i] = nd.n;
-            as_leaf[i] = 1;
-            for (int k = 1; k <= 7; k++) c[k] = (float)(area * nd.n * W8_COST_TRI);
-            continue;
-        }
-        const float *cl = &C[(size_t)nd.left * 8], *cr = &C[(size_t)nd.right * 8];
-        first[i] = std::min(first[nd.left], first[nd.right]);
-        count[i] = count[nd.left] + count[nd.right];
-        float dist[9];
-        for (int j = 2; j <= 8; j++) {
-            float best = 3.0e38f;
-            for (int k = 1; k < j; k++)
-                if (k <= 7 && j - k <= 7) best = std::min(best, cl[k] + cr[j - k]);
-            dist[j] = best;
-        }
-        const float c_internal = (float)(area * W8_COST_NODE) + dist[8];
-        const float c_leaf = (count[i] <= W8_MAX_LEAF_TRIS && first[nd.left] + count[nd.left] == first[nd.right])
-                                 ? (float)(area * count[i] * W8_COST_TRI) : 3.0e38f;
-        as_leaf[i] = c_leaf <= c_internal;
-        c[1] = std::min(c_leaf, c_internal);
-        for (int j = 2; j <= 7; j++) c[j] = std::min(c[j - 1], dist[j]);
-    }
-    // roots of the best representation of sub-tree n by <= k roots
-    struct Pick { int n, k; };
-    auto collect = [&](int n0, int k0, int* roots) -> int {
-        int cnt = 0;
-        Pick stack[32];
-        int sp = 0;
-        stack[sp++] = {n0, k0};
-        while (sp > 0) {
-            Pick p = stack[--sp];
-            const float* c = &C[(size_t)p.n * 8];
-            while (p.k > 1 && c[p.k] == c[p.k - 1]) p.k--;
-            if (p.k == 1 || an[p.n].n > 0) { roots[cnt++] = p.n; continue; }
-            const EzrtAccelNode& nd = an[p.n];
-            const float *cl = &C[(size_t)nd.left * 8], *cr = &C[(size_t)nd.right * 8];
-            int bk = 1;
-            float best = 3.0e38f;
-            for (int k = 1; k < p.k; k++)
-                if (cl[k] + cr[p.k - k] < best) { best = cl[k] + cr[p.k - k]; bk = k; }
-            stack[sp++] = {nd.right, p.k - bk};   // right first on the stack: the left roots come out first
-            stack[sp++] = {nd.left, bk};
-        }
-        return cnt;
-    };
+    EzrtCollapse col;
+    const int crc = col.build(an, 8, W8_MAX_LEAF_TRIS, W8_COST_NODE, W8_COST_TRI);
+    if (crc) return crc;
+    const std::vector<int>& first = col.first;
+    const std::vector<int>& count = col.count;
+    const std::vector<char>& as_leaf = col.as_leaf;
 
     struct Item { int bnode, level; };
     std::vector<Item> queue;   // wide node i is built from queue[i] (breadth-first: a node's inner children are consecutive)
@@ -120,14 +152,7 @@ int ezrt_build_w8(const std::vector<EzrtAccelNode>& an, const std::vector<uint32
         if (an[b].n > 0 || (wi == 0 && as_leaf[b])) {  // the whole tree is one leaf slot
             ch[cnt++] = b;
         } else {
-            const EzrtAccelNode& nd = an[b];
-            const float *cl = &C[(size_t)nd.left * 8], *cr = &C[(size_t)nd.right * 8];
-            int bk = 1;
-            float best = 3.0e38f;
-            for (int k = 1; k <= 7; k++)
-                if (cl[k] + cr[8 - k] < best) { best = cl[k] + cr[8 - k]; bk = k; }
-            cnt = collect(nd.left, bk, ch);
-            cnt += collect(nd.right, 8 - bk, ch + cnt);
+            cnt = col.children(b, ch);
         }
         // ---- octant-ordered slots: greedy assignment of (child, slot) pairs by dot(child centre - node centre, slot corner)
         double nlo[3] = {3.0e38, 3.0e38, 3.0e38}, nhi[3] = {-3.0e38, -3.0e38, -3.0e38};  // union of the padded child boxes (exact in double)

@@ -381,70 +381,94 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         // boxes inflated by 2*delta: a hit hitTriangle accepts lies within delta of its triangle's box, so
         // the inflated boxes of the whole ancestor chain are entered no later than the hit distance
         const float pad = 2.0f * prune_delta;
+        // Which form of the tree the accel kernels walk (env EZRT_ACCEL, read at scene creation):
+        //   4 (default): 4-wide nodes with exact fp32 boxes, children sorted by entry distance (k_extend_accel): measured
+        //                faster on B200 (3272 vs 3005 Mrays/s on C3, profiles/sweep_w8_r2.txt)
+        //   8          : 8-wide nodes with 8-bit quantised boxes in octant order (k_extend_w8): 45 % fewer L1 wavefronts per
+        //                ray, 36 % more instructions
+        int accel_form = 4;
+        if (const char* we = getenv("EZRT_ACCEL")) accel_form = (atoi(we) == 8) ? 8 : 4;
+        if (an[0].n > 0) accel_form = 8;   // a single-leaf tree: the W8 builder handles it
         EzrtW8Tree w8;
         ezrt_w8_axis_bits(bmin, bmax, w8_near_bit);
-        const int wrc = ezrt_build_w8(an, order_bin, pad, max_abs, w8_near_bit, w8);
-        if (wrc != 0 || w8.depth > EZRT_W8_SMEM_STACK + W8_LOCAL_STACK) {
-            have_accel = false;
+        if (accel_form == 8) {
+            const int wrc = ezrt_build_w8(an, order_bin, pad, max_abs, w8_near_bit, w8);
+            if (wrc != 0 || w8.depth > EZRT_W8_SMEM_STACK + W8_LOCAL_STACK) {
+                have_accel = false;
+            } else {
+                acc_order = w8.tri_order;
+                w8_words.swap(w8.nodes);
+                w8_depth = w8.depth;
+            }
+        } else {
+            // 4-wide collapse: SAH-optimal choice of each node's children (EzrtCollapse; env EZRT_W4_COLLAPSE=greedy: round 1's
+            // "replace the largest inner child" rule); leaves = sub-trees of <= 4 consecutive triangles
+            const char* ce = getenv("EZRT_W4_COLLAPSE");
+            const bool greedy = ce && !strcmp(ce, "greedy");
+            EzrtCollapse col;
+            if (col.build(an, 4, W8_MAX_LEAF_TRIS, 1.0, 0.3) != 0) {
+                have_accel = false;
+            } else {
+                acc_order = order_bin;
+                auto area = [&](int c) {
+                    float x = an[c].BB[0] - an[c].AA[0], y = an[c].BB[1] - an[c].AA[1], z = an[c].BB[2] - an[c].AA[2];
+                    return x * y + x * z + y * z;
+                };
+                int wide_depth = 0;
+                std::function<int(int, int)> build_wide = [&](int b, int depth) -> int {
+                    wide_depth = std::max(wide_depth, depth);
+                    const int id = (int)(acc_wide.size() / 8);
+                    acc_wide.resize(acc_wide.size() + 8, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+                    int ch[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+                    int cnt = 0;
+                    if (greedy) {
+                        ch[0] = an[b].left; ch[1] = an[b].right;
+                        cnt = 2;
+                        while (cnt < 4) {
+                            int best = -1;
+                            float ba = -1.0f;
+                            for (int k = 0; k < cnt; k++)
+                                if (an[ch[k]].n <= 0 && area(ch[k]) > ba) { ba = area(ch[k]); best = k; }
+                            if (best < 0) break;
+                            const int c = ch[best];
+                            for (int k = cnt; k > best + 1; k--) ch[k] = ch[k - 1];
+                            ch[best] = an[c].left;
+                            ch[best + 1] = an[c].right;
+                            cnt++;
+                        }
+                    } else {
+                        cnt = col.children(b, ch);
+                    }
+                    float rec[32];
+                    int refs[4];
+                    for (int k = 0; k < 4; k++) {
+                        float AA[3] = {3.0e38f, 3.0e38f, 3.0e38f}, BB[3] = {3.0e38f, 3.0e38f, 3.0e38f};  // absent: a far-away point box (min/max slab test)
+                        refs[k] = (int)EZRT_LEAF_FLAG;  // EZRT_REF_DONE, never followed
+                        if (k < cnt) {
+                            const EzrtAccelNode& c = an[ch[k]];
+                            for (int a = 0; a < 3; a++) { AA[a] = c.AA[a] - pad; BB[a] = c.BB[a] + pad; }
+                            const bool leaf = greedy ? (c.n > 0) : (col.as_leaf[ch[k]] != 0);
+                            refs[k] = leaf ? (int)(EZRT_LEAF_FLAG | ((uint32_t)col.first[ch[k]] << 7) | (uint32_t)col.count[ch[k]]) : build_wide(ch[k], depth + 1);
+                        }
+                        rec[4 * k + 0] = AA[0]; rec[4 * k + 1] = AA[1]; rec[4 * k + 2] = BB[0]; rec[4 * k + 3] = BB[1];
+                        rec[16 + 2 * k] = AA[2]; rec[16 + 2 * k + 1] = BB[2];
+                    }
+                    memcpy(&rec[24], refs, 16);
+                    for (int k = 24 + 4; k < 32; k++) rec[k] = 0.0f;
+                    memcpy(&acc_wide[(size_t)id * 8], rec, sizeof(rec));
+                    return id;
+                };
+                acc_wide_root = build_wide(0, 1);
+                acc_depth = wide_depth;
+                if (3 * wide_depth + 2 > EZRT_ACCEL_STACK) { acc_wide.clear(); have_accel = false; }  // too deep for the traversal stack
+            }
+        }
+        if (!have_accel) {
             acc_order.resize(n_triangles);
             for (int i = 0; i < n_triangles; i++) acc_order[i] = (uint32_t)i;
-        } else {
-            acc_order = w8.tri_order;
-            w8_words.swap(w8.nodes);
-            w8_depth = w8.depth;
         }
         for (int i = 0; i < n_triangles; i++)
             for (int k = 0; k < 4; k++) acc_geo[(size_t)i * 4 + k] = geo[(size_t)acc_order[i] * 4 + k];
-
-        // ---- the round-1 form of the same tree (env EZRT_ACCEL=4, kept for A/B measurements): 4-wide nodes with exact
-        // boxes; a node's children are its binary children with the largest inner ones replaced by their own children
-        const char* we = getenv("EZRT_ACCEL");
-        if (have_accel && we && atoi(we) == 4 && an[0].n <= 0) {
-            auto area = [&](int c) {
-                float x = an[c].BB[0] - an[c].AA[0], y = an[c].BB[1] - an[c].AA[1], z = an[c].BB[2] - an[c].AA[2];
-                return x * y + x * z + y * z;
-            };
-            int wide_depth = 0;
-            std::function<int(int, int)> build_wide = [&](int b, int depth) -> int {
-                wide_depth = std::max(wide_depth, depth);
-                const int id = (int)(acc_wide.size() / 8);
-                acc_wide.resize(acc_wide.size() + 8, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
-                int ch[4] = {an[b].left, an[b].right, -1, -1};
-                int cnt = 2;
-                while (cnt < 4) {
-                    int best = -1;
-                    float ba = -1.0f;
-                    for (int k = 0; k < cnt; k++)
-                        if (an[ch[k]].n <= 0 && area(ch[k]) > ba) { ba = area(ch[k]); best = k; }
-                    if (best < 0) break;
-                    const int c = ch[best];
-                    for (int k = cnt; k > best + 1; k--) ch[k] = ch[k - 1];
-                    ch[best] = an[c].left;
-                    ch[best + 1] = an[c].right;
-                    cnt++;
-                }
-                float rec[32];
-                int refs[4];
-                for (int k = 0; k < 4; k++) {
-                    float AA[3] = {3.0e38f, 3.0e38f, 3.0e38f}, BB[3] = {3.0e38f, 3.0e38f, 3.0e38f};  // absent: a far-away point box (min/max slab test)
-                    refs[k] = (int)EZRT_LEAF_FLAG;  // EZRT_REF_DONE, never followed
-                    if (k < cnt) {
-                        const EzrtAccelNode& c = an[ch[k]];
-                        for (int a = 0; a < 3; a++) { AA[a] = c.AA[a] - pad; BB[a] = c.BB[a] + pad; }
-                        refs[k] = (c.n > 0) ? (int)(EZRT_LEAF_FLAG | ((uint32_t)w8.leaf_first[ch[k]] << 7) | (uint32_t)c.n) : build_wide(ch[k], depth + 1);
-                    }
-                    rec[4 * k + 0] = AA[0]; rec[4 * k + 1] = AA[1]; rec[4 * k + 2] = BB[0]; rec[4 * k + 3] = BB[1];
-                    rec[16 + 2 * k] = AA[2]; rec[16 + 2 * k + 1] = BB[2];
-                }
-                memcpy(&rec[24], refs, 16);
-                for (int k = 24 + 4; k < 32; k++) rec[k] = 0.0f;
-                memcpy(&acc_wide[(size_t)id * 8], rec, sizeof(rec));
-                return id;
-            };
-            acc_wide_root = build_wide(0, 1);
-            acc_depth = wide_depth;
-            if (3 * wide_depth + 2 > EZRT_MAX_STACK) acc_wide.clear();  // too deep for its stack: the W8 kernel serves
-        }
     }
     // shading data and the reference-leaf map in the acceleration tree's order, and the inverse permutation
     std::vector<float4> acc_shade((size_t)n_triangles * 3);
@@ -527,7 +551,6 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.w8_decode_bits = W8_DECODE_BITS;
     d.w8_tri_weight = 2;
     if (const char* e = getenv("EZRT_TRI_W")) d.w8_tri_weight = std::max(1, std::min(64, atoi(e)));
-    if (!acc_wide.empty()) d.w8_nodes = nullptr;   // EZRT_ACCEL=4: the round-1 kernel
     d.acc_tri_geo = (const float4*)((const char*)sc->acc_nodes.p + acc_nodes_bytes);
     d.acc_tri_ref = (const uint32_t*)sc->acc_tri_ref.p;
     d.acc_wide_nodes = acc_wide.empty() ? nullptr : (const float4*)sc->acc_wide.p;
@@ -704,7 +727,7 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
         const uint32_t n_slots = (uint32_t)(per_frame * (size_t)nf);
         const uint32_t batch_first = p->first_frame + (uint32_t)done;
         CU_CHECK(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * n_counters, st));
-        const bool fused_camera = accel && s->dev.w8_nodes != nullptr;   // camera rays are generated inside the first extend kernel
+        const bool fused_camera = accel;   // accel policy: camera rays are generated inside the first extend kernel
         int sp = -1;
         if (!fused_camera) {
             sp = s->span_begin(3, st);

@@ -438,11 +438,19 @@ __device__ __forceinline__ bool reference_reaches_leaf_inv(const int* __restrict
 // ACCEL: `tree` is the device's own acceleration tree, not the reference tree: the closest hit it
 // finds is the global minimum over all triangles; ties (two triangles at exactly the same t) and rays
 // with non-finite 1/d are handed to io.defer() and re-traced by the exact reference-order kernel.
-template <bool PRUNE, bool ANYHIT, bool ACCEL, bool WIDE, int LL, class RayIO>
+struct W8Counts {   // COUNT instantiations only (bench.py roofline: records fetched on the kernel's own layout)
+    unsigned long long* node_visits;
+    unsigned long long* tri_tests;
+};
+
+template <bool PRUNE, bool ANYHIT, bool ACCEL, bool WIDE, int LL, bool COUNT, class RayIO>
 __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const TreeView tree, uint32_t n, uint32_t* work, RayIO io,
-                                                  const float4* smem_top) {
+                                                  const float4* smem_top, W8Counts counts = W8Counts{nullptr, nullptr}) {
+    unsigned long long n_visits = 0, n_tests = 0;
     const int top_nodes = tree.top_nodes;
     const bool tri_na = sc.tri_l1_bypass != 0;
+    __shared__ unsigned char s_owner_all[(EZRT_EXTEND_MAX_THREADS / 32) * 8];   // leaf phase: rank -> owner lane, 8 bytes per warp
+    unsigned char* const s_owner = s_owner_all + (threadIdx.x >> 5) * 8;
     bool tie = false;          // ACCEL: another triangle was accepted at exactly the best distance
     const int refill_thresh = sc.refill_thresh;  // go back to refill when fewer lanes than this are busy
     const int inner_thresh = sc.inner_thresh;    // leave the inner-node phase when fewer lanes than this walk
@@ -453,7 +461,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
     // stack of (child reference, slab entry distance bits).  Entries below EZRT_SMEM_STACK live in shared
     // memory at [entry][thread] (a lane always hits its own banks: 2 wavefronts per warp access however the
     // lanes' stack pointers differ), deeper ones in local memory.
-    int2 stack_local[EZRT_MAX_STACK];
+    int2 stack_local[ACCEL ? EZRT_ACCEL_STACK : EZRT_MAX_STACK];
 #if EZRT_SMEM_STACK > 0
     int2* const stack_sm = reinterpret_cast<int2*>(const_cast<float4*>(smem_top) + (size_t)tree.top_nodes * EZRT_TOP_STRIDE) + threadIdx.x;
     const int stack_stride = blockDim.x;
@@ -490,8 +498,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
             }
             if (!exhausted && ray < 0) {
                 uint32_t idx = chunk_pos + (uint32_t)__popc(need & lt_mask);
-                if (idx < chunk_end) {
-                    io.load(idx, o, d);
+                if (idx < chunk_end && io.load(idx, o, d)) {
                     inv = ez_v3(EZ_DIV(1.0f, d.x), EZ_DIV(1.0f, d.y), EZ_DIV(1.0f, d.z));
                     float ax = ez_abs(inv.x), ay = ez_abs(inv.y), az = ez_abs(inv.z);
                     slack = sc.prune_delta * ez_max(ax, ez_max(ay, az));
@@ -504,9 +511,9 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                         best_tri = -1;
                         tie = false;
                     } else if (ACCEL) {  // exact kernel handles the literal ternary min/max path
-                        io.defer(idx);
+                        io.defer(idx, o, d);
                     } else {  // a zero / NaN direction component: literal ternary min/max path (rare)
-                        io.store(idx, trace_impl<PRUNE, ANYHIT, false>(sc, o, d, inv, slack), false, o, rs);
+                        io.store(idx, trace_impl<PRUNE, ANYHIT, false>(sc, o, d, inv, slack), false, o, d, inv);
                     }
                 }
             }
@@ -540,6 +547,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                     if (at_inner) {  // 4-wide acceleration-tree node: nearest child next, the others pushed far-to-near
                         const float limit = best + (best * 0.000244140625f + slack);
                         const WideVisit w = wide_visit(tree.nodes + (size_t)ref * 8, rs, limit);
+                        if (COUNT) n_visits++;
 #if EZRT_WIDE_SORT
                         WideVisit v = w;
                         cswap(v.k0, v.r0, v.k1, v.r1);
@@ -623,18 +631,19 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
             bool stop = false;
             const int q = lane / LL, k = lane % LL;
             while (m_leaf != 0u) {
-                // the G lowest waiting lanes own this pass (warp-uniform arithmetic)
-                unsigned taken = 0u;
-                int owner = -1;
+                // the G lowest waiting lanes own this pass: lane with rank g (g-th set bit of m_leaf) serves group g.  The
+                // rank -> lane map goes through a few bytes of shared memory (one STS / LDS per pass; the unrolled
+                // find-first-set loop it replaces was 16 % of the kernel's instructions, profiles/ncu_extend_r1_summary.md)
+                unsigned rest = m_leaf;
 #pragma unroll
-                for (int g = 0; g < G; g++) {
-                    if (m_leaf != 0u) {
-                        const int j = __ffs(m_leaf) - 1;
-                        m_leaf &= m_leaf - 1u;
-                        taken |= 1u << j;
-                        if (q == g) owner = j;
-                    }
-                }
+                for (int g = 0; g < G; g++) rest &= rest - 1u;          // m_leaf without its G lowest bits (0 & -1 stays 0)
+                const unsigned taken = m_leaf ^ rest;
+                const int my_rank = __popc(m_leaf & lt_mask);
+                __syncwarp();
+                if ((taken >> lane) & 1u) s_owner[my_rank] = (unsigned char)lane;
+                __syncwarp();
+                const int owner = (q < __popc(taken)) ? (int)s_owner[q] : -1;
+                m_leaf = rest;
                 const int src = (owner < 0) ? lane : owner;
                 vec3 ro, rdir;
                 ro.x = __shfl_sync(FULL, o.x, src); ro.y = __shfl_sync(FULL, o.y, src); ro.z = __shfl_sync(FULL, o.z, src);
@@ -645,6 +654,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                 unsigned tb = 0xffffffffu;  // t bits of this lane's triangle, or "no hit"
                 if (owner >= 0 && k < rcnt) {
                     float t;
+                    if (COUNT) n_tests++;
                     if (tri_test_t<ACCEL>(tree.tri_geo + (size_t)(rfirst + k) * 4, ro, rdir, rbest, t, tri_na) != 0) tb = __float_as_uint(t);
                 }
                 unsigned mn = tb;
@@ -685,11 +695,18 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                 HitRec h;
                 h.t = best;
                 h.tri = best_tri;
-                io.store((uint32_t)ray, h, tie, o, rs);
+                float ix, iy, iz, iz2;   // 1/d lives in the slab constants (no extra registers across the loop)
+                pk2_split(rs.inv_xy, ix, iy);
+                pk2_split(rs.inv_zz, iz, iz2);
+                io.store((uint32_t)ray, h, tie, o, d, ez_v3(ix, iy, iz));
                 ray = -1;
             }
             busy = __ballot_sync(FULL, ray >= 0);
         } while (busy != 0u && (exhausted || __popc(busy) >= refill_thresh));
+    }
+    if (COUNT) {
+        atomicAdd(counts.node_visits, n_visits);
+        atomicAdd(counts.tri_tests, n_tests);
     }
 }
 
@@ -730,11 +747,6 @@ __device__ __forceinline__ bool w8_slot_hit(uint32_t nx, uint32_t ny, uint32_t n
     const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, limit));
     return tmin <= tmax;
 }
-
-struct W8Counts {   // COUNT instantiations only (bench.py roofline: records fetched on the kernel's own layout)
-    unsigned long long* node_visits;
-    unsigned long long* tri_tests;
-};
 
 // s_perm: 8 x 256 bytes in shared memory, s_perm[m * 256 + x] = the bits of x moved from position s to position s ^ m
 // stack : uint2 [entries][blockDim.x] in shared memory
@@ -1217,7 +1229,7 @@ __device__ __forceinline__ void to_spherical(vec3 v, float& ou, float& ov) {
     ov = 1.0f - w;
 }
 // hdrColor P5/fsh:693-697; sampleHdr P3/fsh:151-156 (clamped to 10) / P4/fsh:366-371
-__device__ __forceinline__ vec3 hdr_color(const SceneDev& sc, const RenderDev& rd, vec3 L) {
+__device__ __forceinline__ vec3 hdr_color(const SceneDev& sc, const RenderDev& rd, vec3 L, int mode) {
     vec3 color;
     if (!sc.hdr) {
         color = ez_v3(rd.env[0], rd.env[1], rd.env[2]);
@@ -1226,7 +1238,7 @@ __device__ __forceinline__ vec3 hdr_color(const SceneDev& sc, const RenderDev& r
         to_spherical(ez_normalize(L), u, v);
         color = tex2d(sc.hdr, sc.hdr_w, sc.hdr_h, u, v, sc.hdr_linear);
     }
-    if (rd.mode == EZRT_MODE_DIFFUSE_P3) color = ez_vmin(color, splat3(10.0f));
+    if (mode == EZRT_MODE_DIFFUSE_P3) color = ez_vmin(color, splat3(10.0f));
     return color;
 }
 // SampleHdr, P5/fsh:667-679
@@ -1291,25 +1303,29 @@ __device__ __forceinline__ vec3 contrib3(vec3 a, vec3 b, vec3 c, float s, float 
 // Account for the result (t,tri) of tracing p's ray, which was generated at bounce-1 (bounce==0:
 // the primary ray), then -- if the path continues -- sample the next direction and fill p with the
 // next ray.  Returns false when the path ends.  Lo/Le/primary_miss are the sample's accumulators.
+// MODE >= 0: the integrator is a compile-time constant (k_shade<MODE>: each instantiation carries only its own
+// integrator -- the four-in-one kernel was 7288 instructions = 116 KB and instruction-fetch bound in the IS/MIS mode,
+// profiles/ncu_shade_c4_r2_summary.md); MODE < 0: rd.mode at run time (megakernel).
+template <int MODE>
 __device__ __forceinline__ bool shade_step(const SceneDev& sc, const RenderDev& rd, int bounce, PathRegs& p, float hit_t,
                                            int hit_tri, uint32_t px, uint32_t py, uint32_t frame, vec3& Lo, vec3& Le,
                                            bool& primary_miss, ShadowRay& sh) {
     sh.valid = false;
-    const int mode = rd.mode;
+    const int mode = (MODE < 0) ? rd.mode : MODE;
     const bool is_mode = (mode == EZRT_MODE_DISNEY_IS_MIS_P5);
     if (bounce == 0) {
         Lo = splat3(0.0f);
         Le = splat3(0.0f);
         primary_miss = false;
         if (hit_tri < 0) {  // P5/fsh:931-933
-            Lo = hdr_color(sc, rd, p.d);
+            Lo = hdr_color(sc, rd, p.d, mode);
             primary_miss = true;
             return false;
         }
     } else {
         if (is_mode && p.pdf <= 0.0f) return false;  // P5/fsh:865
         if (hit_tri < 0) {  // miss: sky contribution, then break
-            vec3 sky = hdr_color(sc, rd, p.d);
+            vec3 sky = hdr_color(sc, rd, p.d, mode);
             if (is_mode) {  // P5/fsh:868-878
                 float pdf_light = hdr_pdf(sc, p.d);
                 float mis_weight = mis_mix_weight(p.pdf, pdf_light);
@@ -1336,31 +1352,43 @@ __device__ __forceinline__ bool shade_step(const SceneDev& sc, const RenderDev& 
     vec3 N = hit.N;
     vec3 L;
     if (is_mode) {
-        // environment importance sample + shadow ray, P5/fsh:820-842
+        // environment importance sample + shadow ray (P5/fsh:820-842), then the BRDF sample (:845-865).  The three
+        // random numbers are drawn in the shader's order (two for SampleHdr :822, one for the lobe choice :849); the BRDF
+        // value and pdf of the two directions are evaluated by ONE copy of the code (a two-trip loop that is not unrolled)
         float r1 = rand01(p.seed);
         float r2 = rand01(p.seed);
-        vec3 Lh = sample_hdr(sc, r1, r2);
-        float NdotLh = ez_dot(N, Lh);
-        if (NdotLh > 0.0f) {
-            vec3 color = hdr_color(sc, rd, Lh);
-            float pdf_light = hdr_pdf(sc, Lh);
-            vec3 f_r = brdf_evaluate<false>(V, N, Lh, mat);
-            float pdf_brdf = brdf_pdf(V, N, Lh, mat);
-            float mis_weight = mis_mix_weight(pdf_light, pdf_brdf);
-            sh.valid = true;
-            sh.o = hit.P;
-            sh.d = Lh;
-            sh.contrib = ez_divs(ez_scale(ez_mul(ez_mul(ez_scale(p.history, mis_weight), color), f_r), NdotLh), pdf_light);
-        }
         float xi_1 = sobol_gray((uint32_t)bounce * 2u, frame + 1u);
         float xi_2 = sobol_gray((uint32_t)bounce * 2u + 1u, frame + 1u);
         cp_rotate(xi_1, xi_2, px, py);
         float xi_3 = rand01(p.seed);
+        const vec3 Lh = sample_hdr(sc, r1, r2);
+        const float NdotLh = ez_dot(N, Lh);
         L = sample_brdf(xi_1, xi_2, xi_3, V, N, mat);
-        float NdotL = ez_dot(N, L);
+        const float NdotL = ez_dot(N, L);
+        vec3 fr_h = splat3(0.0f), fr_l = splat3(0.0f);
+        float pdf_h = 0.0f, pdf_l = 0.0f;
+#pragma unroll 1
+        for (int k = 0; k < 2; k++) {
+            const bool want = (k == 0) ? (NdotLh > 0.0f) : (NdotL > 0.0f);
+            if (want) {
+                const vec3 dir = (k == 0) ? Lh : L;
+                const vec3 f = brdf_evaluate<false>(V, N, dir, mat);
+                const float q = brdf_pdf(V, N, dir, mat);
+                if (k == 0) { fr_h = f; pdf_h = q; } else { fr_l = f; pdf_l = q; }
+            }
+        }
+        if (NdotLh > 0.0f) {
+            vec3 color = hdr_color(sc, rd, Lh, mode);
+            float pdf_light = hdr_pdf(sc, Lh);
+            float mis_weight = mis_mix_weight(pdf_light, pdf_h);
+            sh.valid = true;
+            sh.o = hit.P;
+            sh.d = Lh;
+            sh.contrib = ez_divs(ez_scale(ez_mul(ez_mul(ez_scale(p.history, mis_weight), color), fr_h), NdotLh), pdf_light);
+        }
         if (NdotL <= 0.0f) return false;  // :854
-        p.f_r = brdf_evaluate<false>(V, N, L, mat);
-        p.pdf = brdf_pdf(V, N, L, mat);   // <= 0: traced, then break (:860-865)
+        p.f_r = fr_l;
+        p.pdf = pdf_l;   // <= 0: traced, then break (:860-865)
         p.cosine_i = NdotL;
     } else {
         vec3 Lh;

@@ -27,6 +27,7 @@
 #define EZRT_LEAF_MAX_N 127
 #define EZRT_TOP_NODES_MAX 1023   // 10 full levels; 80 B each in shared memory (bank-conflict padding)
 #define EZRT_ACC_TOP_NODES_MAX 255 // acceleration tree: 8 levels are enough (its upper levels are real SAH splits)
+#define EZRT_ACCEL_STACK 64       // stack entries of the 4-wide accel kernel (<= 3 pushes per level): trees deeper than 20 levels are not built
 #define EZRT_W8_SMEM_STACK 16      // per-lane W8 stack entries held in shared memory (8 B each x 1024 threads = 128 KB at most)
 #define EZRT_TOP_STRIDE 5         // float4 per shared-memory record
 #define EZRT_TILE 16             // == EZRT_PART_TILE
@@ -56,7 +57,7 @@ struct SceneDev {
     int w8_tri_weight;             // step vote of the W8 kernels: triangle step iff w8_tri_weight * lanes_with_triangles >= lanes_with_a_node (env EZRT_TRI_W)
     uint32_t w8_decode_bits;       // W8_DECODE_BITS (passed as data: see w8_plane in device_functions.cuh)
     float w8_origin_limit;         // rays starting further out than this (any |coordinate|) go to the exact kernel (decode error bound)
-    const float4* acc_wide_nodes;  // the same tree collapsed to 4-wide nodes with exact boxes (128 B records): round-1 kernel, env EZRT_ACCEL=4
+    const float4* acc_wide_nodes;  // 4-wide nodes with exact boxes (128 B records): the default accel form (env EZRT_ACCEL=8 selects W8 instead)
     int acc_wide_root_ref;
     // reference leaf of every reference triangle + the leaves' boxes (AA, BB as float4 pairs)
     const int* tri_leaf;

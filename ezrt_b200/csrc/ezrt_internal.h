@@ -30,6 +30,19 @@ struct EzrtAccelNode {
 // host_scene.cpp: sentinel-free SAH tree over the triangles of a Triangle_encoded array
 int ezrt_build_accel(const float* tris, int n_tris, int leaf_n, std::vector<EzrtAccelNode>& nodes, std::vector<uint32_t>& order);
 
+// accel_w8.cpp: SAH-optimal collapse of the binary tree to `width`-wide nodes (dynamic programming; shared by the 4-wide
+// exact-box form and the 8-wide quantised form)
+struct EzrtCollapse {
+    const std::vector<EzrtAccelNode>* an = nullptr;
+    int width = 0;
+    std::vector<int> first, count;   // per binary node: first triangle / triangle count of its sub-tree (in the binary tree's order)
+    std::vector<char> as_leaf;       // per binary node: as a child of a wide node it is ONE leaf (all its triangles)
+    std::vector<float> C;            // C[n * 8 + i]: cost of representing n's sub-tree by <= i roots
+    int build(const std::vector<EzrtAccelNode>& an, int width, int max_leaf, double cost_node, double cost_tri);
+    int collect(int n0, int k0, int* roots) const;
+    int children(int b, int* ch) const;   // b: an inner binary node that is not as_leaf; returns the child count (<= width)
+};
+
 // accel_w8.cpp: the same tree collapsed to 8-wide nodes with 8-bit quantised child boxes (w8_node.h)
 struct EzrtW8Tree {
     std::vector<uint32_t> nodes;       // W8_NODE_WORDS words per node; node 0 = root; breadth-first numbering

@@ -212,13 +212,13 @@ struct ExtendIO {
         d = ez_v3(d4.x, d4.y, d4.z);
         return true;
     }
-    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3, const RaySlab&) const {
+    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3, vec3, vec3) const {
         const uint32_t j = perm ? perm[i] : i;
         int tri = h.tri;
         if (to_accel && tri >= 0) tri = (int)__ldg(to_accel + tri);
         __stcs(q.hit + j, make_float2(h.t, __int_as_float(tri)));
     }
-    __device__ __forceinline__ void defer(uint32_t) const {}
+    __device__ __forceinline__ void defer(uint32_t, vec3, vec3) const {}
 };
 
 template <bool PRUNE, bool ANYHIT>
@@ -230,47 +230,15 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     io.to_accel = to_accel ? sc.ref_to_acc : nullptr;
     const TreeView tree = reference_tree(sc);
     stage_top_nodes(tree);
-    extend_persistent<PRUNE, ANYHIT, false, false, 8>(sc, tree, *q_count, work, io, g_smem_top);
+    extend_persistent<PRUNE, ANYHIT, false, false, 8, false>(sc, tree, *q_count, work, io, g_smem_top);
 }
 
 // ---- accel kernels: the device's own SAH tree finds the global closest hit G; the result is kept when
 // the shader's traversal provably reaches G's leaf and nothing ties with G, otherwise the ray index is
 // appended to `defer_list` for the exact kernel (DESIGN.md "accel").
-struct AccelIO {
-    PathQueue q;
-    const int* acc_tri_leaf;
-    const float4* leaf_box;
-    uint32_t* defer_list;
-    uint32_t* defer_count;
-    __device__ __forceinline__ bool load(uint32_t i, vec3& o, vec3& d) const {
-        float4 o4 = __ldcs(q.ray_o + i), d4 = __ldcs(q.ray_d + i);
-        o = ez_v3(o4.x, o4.y, o4.z);
-        d = ez_v3(d4.x, d4.y, d4.z);
-        return true;
-    }
-    __device__ __forceinline__ void defer(uint32_t i) const { defer_list[atomicAdd(defer_count, 1u)] = i; }
-    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool tie, vec3 o, const RaySlab& rs) const {
-        if (h.tri >= 0 && (tie || !reference_reaches_leaf(acc_tri_leaf, leaf_box, h.tri, o, rs))) {
-            defer(i);
-            return;
-        }
-        __stcs(q.hit + i, make_float2(h.t, __int_as_float(h.tri)));  // accel-order triangle index
-    }
-};
-
 // LL = lanes per leaf in the cooperative leaf phase: 4 when the acceleration tree was built with leaves <= 4
-template <bool ANYHIT, bool WIDE, int LL>
-__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend_accel(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
-                                                                      uint32_t* work, uint32_t* defer_list, uint32_t* defer_count) {
-    AccelIO io;
-    io.q = q;
-    io.acc_tri_leaf = sc.acc_tri_leaf;
-    io.leaf_box = sc.leaf_box;
-    io.defer_list = defer_list;
-    io.defer_count = defer_count;
-    const TreeView tree = accel_tree(sc);  // 4-wide records, read straight from global memory / L1
-    extend_persistent<true, ANYHIT, true, WIDE, LL>(sc, tree, *q_count, work, io, g_smem_top);
-}
+// (the IO structs of the accel kernels -- queue rays, fused camera rays, shadow rays -- are shared by the 4-wide and the W8
+// kernel: AccelExtendIO, AccelCameraIO, AccelShadowIO below)
 
 // ---- shadow rays: any hit; an unoccluded ray adds its precomputed contribution (P5/fsh:829-841).
 // One path per sample slot -> no two lanes touch the same Lo entry.
@@ -292,10 +260,10 @@ struct ShadowIO {
         lo.x += c.x; lo.y += c.y; lo.z += c.z;
         Lo[slot] = lo;
     }
-    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3, const RaySlab&) const {
+    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3, vec3, vec3) const {
         if (h.tri < 0) add(perm ? perm[i] : i);
     }
-    __device__ __forceinline__ void defer(uint32_t) const {}
+    __device__ __forceinline__ void defer(uint32_t, vec3, vec3) const {}
 };
 
 template <bool PRUNE>
@@ -307,45 +275,13 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     io.perm = perm;
     const TreeView tree = reference_tree(sc);
     stage_top_nodes(tree);
-    extend_persistent<PRUNE, true, false, false, 8>(sc, tree, *s_count, work, io, g_smem_top);
+    extend_persistent<PRUNE, true, false, false, 8, false>(sc, tree, *s_count, work, io, g_smem_top);
 }
 
-struct ShadowAccelIO {
-    ShadowIO base;
-    const int* acc_tri_leaf;
-    const float4* leaf_box;
-    uint32_t* defer_list;
-    uint32_t* defer_count;
-    __device__ __forceinline__ bool load(uint32_t i, vec3& o, vec3& d) const { return base.load(i, o, d); }
-    __device__ __forceinline__ void defer(uint32_t i) const { defer_list[atomicAdd(defer_count, 1u)] = i; }
-    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3 o, const RaySlab& rs) const {
-        if (h.tri < 0) {  // nothing accepted anywhere: the shader finds nothing either
-            base.add(i);
-            return;
-        }
-        // occluded if the shader reaches the occluder's leaf; otherwise let the exact kernel decide
-        if (!reference_reaches_leaf(acc_tri_leaf, leaf_box, h.tri, o, rs)) defer(i);
-    }
-};
-
-template <bool WIDE, int LL>
-__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_shadow_accel(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count,
-                                                                      uint32_t* work, float4* __restrict__ Lo, uint32_t* defer_list,
-                                                                      uint32_t* defer_count) {
-    ShadowAccelIO io;
-    io.base.sq = sq;
-    io.base.Lo = Lo;
-    io.base.perm = nullptr;
-    io.acc_tri_leaf = sc.acc_tri_leaf;
-    io.leaf_box = sc.leaf_box;
-    io.defer_list = defer_list;
-    io.defer_count = defer_count;
-    const TreeView tree = accel_tree(sc);
-    extend_persistent<true, true, true, WIDE, LL>(sc, tree, *s_count, work, io, g_smem_top);
-}
-
-// ---- W8 kernels (default accel policy): extend_w8 on the 8-wide quantised tree, per-lane stacks and the octant
-// permutation table in shared memory.  Same deferral rule as k_extend_accel.
+// ---- accel kernels: the device's own tree (4-wide exact boxes: extend_persistent<ACCEL, WIDE>; or W8: extend_w8 on the
+// 8-wide quantised tree with per-lane stacks and the octant permutation table in shared memory) finds the global closest hit
+// G; the result is kept when the shader's traversal provably reaches G's leaf and nothing ties with G, otherwise the ray
+// index is appended to `defer_list` for the exact kernel (DESIGN.md "accel").
 __device__ __forceinline__ void w8_smem_setup(unsigned char*& s_perm, uint2*& stack_sm) {
     unsigned char* base = reinterpret_cast<unsigned char*>(g_smem_top);
     s_perm = base;
@@ -360,7 +296,7 @@ __device__ __forceinline__ void w8_smem_setup(unsigned char*& s_perm, uint2*& st
     __syncthreads();
 }
 
-struct W8ExtendIO {
+struct AccelExtendIO {
     PathQueue q;
     const int* acc_tri_leaf;
     const float4* leaf_box;
@@ -386,7 +322,7 @@ struct W8ExtendIO {
 // lane that traces it -- no k_generate pass, no 40-byte queue record written and read back per camera ray.  Slots of
 // clipped edge tiles that lie outside the image are skipped.  Only a deferred ray is written to the queue, for the
 // exact kernel that re-traces it.
-struct W8CameraIO {
+struct AccelCameraIO {
     RenderDev rd;
     const TileDev* tiles;
     uint32_t batch_first_frame;
@@ -422,7 +358,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     unsigned char* s_perm;
     uint2* stack_sm;
     w8_smem_setup(s_perm, stack_sm);
-    W8CameraIO io;
+    AccelCameraIO io;
     io.rd = rd;
     io.tiles = tiles;
     io.batch_first_frame = batch_first_frame;
@@ -440,7 +376,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     unsigned char* s_perm;
     uint2* stack_sm;
     w8_smem_setup(s_perm, stack_sm);
-    W8ExtendIO io;
+    AccelExtendIO io;
     io.q = q;
     io.acc_tri_leaf = sc.acc_tri_leaf;
     io.leaf_box = sc.leaf_box;
@@ -449,7 +385,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     extend_w8<false, COUNT>(sc, *q_count, work, io, s_perm, stack_sm, counts);
 }
 
-struct W8ShadowIO {
+struct AccelShadowIO {
     ShadowIO base;
     const int* acc_tri_leaf;
     const float4* leaf_box;
@@ -473,7 +409,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     unsigned char* s_perm;
     uint2* stack_sm;
     w8_smem_setup(s_perm, stack_sm);
-    W8ShadowIO io;
+    AccelShadowIO io;
     io.base.sq = sq;
     io.base.Lo = Lo;
     io.base.perm = nullptr;
@@ -484,10 +420,56 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     extend_w8<true, COUNT>(sc, *s_count, work, io, s_perm, stack_sm, counts);
 }
 
+// ---- the same three passes on the 4-wide exact-box tree (default form, env EZRT_ACCEL): extend_persistent<ACCEL, WIDE>
+template <bool COUNT>
+__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend_accel(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count, uint32_t* work,
+                                                                      uint32_t* defer_list, uint32_t* defer_count, W8Counts counts) {
+    AccelExtendIO io;
+    io.q = q;
+    io.acc_tri_leaf = sc.acc_tri_leaf;
+    io.leaf_box = sc.leaf_box;
+    io.defer_list = defer_list;
+    io.defer_count = defer_count;
+    extend_persistent<true, false, true, true, 4, COUNT>(sc, accel_tree(sc), *q_count, work, io, g_smem_top, counts);
+}
+template <bool COUNT>
+__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend_accel_camera(SceneDev sc, RenderDev rd, const TileDev* __restrict__ tiles,
+                                                                      uint32_t batch_first_frame, uint32_t n_slots, PathQueue q, uint32_t* work,
+                                                                      uint32_t* defer_list, uint32_t* defer_count, W8Counts counts) {
+    AccelCameraIO io;
+    io.rd = rd;
+    io.tiles = tiles;
+    io.batch_first_frame = batch_first_frame;
+    io.q = q;
+    io.acc_tri_leaf = sc.acc_tri_leaf;
+    io.leaf_box = sc.leaf_box;
+    io.defer_list = defer_list;
+    io.defer_count = defer_count;
+    extend_persistent<true, false, true, true, 4, COUNT>(sc, accel_tree(sc), n_slots, work, io, g_smem_top, counts);
+}
+template <bool COUNT>
+__global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_shadow_accel(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count, uint32_t* work,
+                                                                      float4* __restrict__ Lo, uint32_t* defer_list, uint32_t* defer_count, W8Counts counts) {
+    AccelShadowIO io;
+    io.base.sq = sq;
+    io.base.Lo = Lo;
+    io.base.perm = nullptr;
+    io.acc_tri_leaf = sc.acc_tri_leaf;
+    io.leaf_box = sc.leaf_box;
+    io.defer_list = defer_list;
+    io.defer_count = defer_count;
+    extend_persistent<true, true, true, true, 4, COUNT>(sc, accel_tree(sc), *s_count, work, io, g_smem_top, counts);
+}
+
 // ------------------------------------------------------------------------------------------
+#ifndef EZRT_SHADE_REGROUP
+#define EZRT_SHADE_REGROUP 1      // k_shade: reorder each 128-path chunk by miss | material id (0: queue order, for A/B runs)
+#endif
+#define EZRT_SHADE_KEYS 18        // material id mod 16, "left the scene", "beyond the queue end"
 #ifndef EZRT_SHADE_MIN_BLOCKS
 #define EZRT_SHADE_MIN_BLOCKS 8   // 64 registers: k_shade is latency-bound, 32 resident warps beat 20 despite small spills
 #endif
+template <int MODE>
 __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev sc, RenderDev rd, const TileDev* __restrict__ tiles, int bounce,
                                                uint32_t batch_first_frame, PathQueue qin, const uint32_t* __restrict__ in_count,
                                                PathQueue qout, uint32_t* out_count, ShadowQueue sq, uint32_t* s_count,
@@ -498,7 +480,42 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
     const uint32_t n = n_fused ? n_fused : *in_count;
     const uint32_t n_round = ((n + blockDim.x - 1u) / blockDim.x) * blockDim.x;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+#if EZRT_SHADE_REGROUP
+    // Regrouping between bounces (north_star: "compact active rays and sort by material-id"): the 128 paths a block takes per
+    // iteration are reordered in shared memory by key = miss | material id, so that a warp shades paths that run the same code
+    // on the same material record: bounce paths that left the scene (one environment lookup) no longer idle through the BRDF of
+    // their neighbours (ncu: 16 of 32 lanes active on bounce 1 before, profiles/).  The result does not depend on the order.
+    __shared__ unsigned short s_cnt[4][EZRT_SHADE_KEYS];
+    __shared__ unsigned char s_order[128];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#endif
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n_round; i0 += stride) {
+        uint32_t i = i0;
+#if EZRT_SHADE_REGROUP
+        if (bounce > 0) {   // camera paths are coherent as they are
+            uint32_t key = EZRT_SHADE_KEYS - 1;                      // beyond the queue end: last
+            if (i0 < n) {
+                const int tri = __float_as_int(__ldcs(qin.hit + i0).y);
+                key = EZRT_SHADE_KEYS - 2;                           // left the scene
+                if (tri >= 0) {
+                    const float4* sh4 = (rd.accel_space ? sc.acc_tri_shade : sc.tri_shade) + (size_t)tri * 3;
+                    key = (uint32_t)__float_as_int(ldg4(sh4).w) % (EZRT_SHADE_KEYS - 2);
+                }
+            }
+            const unsigned same = __match_any_sync(0xffffffffu, key);
+            const uint32_t rank = (uint32_t)__popc(same & ((1u << lane) - 1u));
+            if (threadIdx.x < 4 * EZRT_SHADE_KEYS) (&s_cnt[0][0])[threadIdx.x] = 0;
+            __syncthreads();
+            if (rank == 0) s_cnt[wid][key] = (unsigned short)__popc(same);
+            __syncthreads();
+            uint32_t before = 0;                                      // paths with a smaller key, or the same key in an earlier warp
+            for (uint32_t k = 0; k < key; k++) before += s_cnt[0][k] + s_cnt[1][k] + s_cnt[2][k] + s_cnt[3][k];
+            for (int w = 0; w < wid; w++) before += s_cnt[w][key];
+            s_order[before + rank] = (unsigned char)threadIdx.x;
+            __syncthreads();
+            i = i0 - threadIdx.x + s_order[threadIdx.x];
+        }
+#endif
         bool alive = false;
         PathRegs p;
         ShadowRay sh;
@@ -537,7 +554,7 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
                 p.cosine_i = 0.0f;
                 p.pdf = 1.0f;
             }
-            alive = shade_step(sc, rd, bounce, p, hit.x, __float_as_int(hit.y), px, py, batch_first_frame + fib, lo, le, pmiss, sh);
+            alive = shade_step<MODE>(sc, rd, bounce, p, hit.x, __float_as_int(hit.y), px, py, batch_first_frame + fib, lo, le, pmiss, sh);
             Lo[slot] = make_float4(lo.x, lo.y, lo.z, pmiss ? 1.0f : 0.0f);
             if (bounce == 0) Le[slot] = make_float4(le.x, le.y, le.z, 0.0f);
         }
@@ -549,7 +566,7 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
             __stcs(qout.fr + pos, make_float4(p.f_r.x, p.f_r.y, p.f_r.z, p.pdf));
             __stcs(qout.meta + pos, make_uint2(p.seed, slot));
         }
-        if (rd.mode == EZRT_MODE_DISNEY_IS_MIS_P5) {
+        if (MODE == EZRT_MODE_DISNEY_IS_MIS_P5) {
             uint32_t spos = block_append(sh.valid, s_count, s_scan);
             if (sh.valid) {
                 __stcs(sq.ray_o + spos, make_float4(sh.o.x, sh.o.y, sh.o.z, __uint_as_float(slot)));
@@ -636,7 +653,7 @@ __global__ void __launch_bounds__(128) k_megakernel(SceneDev sc, RenderDev rd, c
             HitRec h = trace_ray<PRUNE, false>(sc, p.o, p.d);
             if (bounce == 0) n_primary++; else n_bounce++;
             ShadowRay sh;
-            bool alive = shade_step(sc, rd, bounce, p, h.t, h.tri, px, py, frame, lo, le, pmiss, sh);
+            bool alive = shade_step<-1>(sc, rd, bounce, p, h.t, h.tri, px, py, frame, lo, le, pmiss, sh);
             if (sh.valid) {
                 HitRec hs = trace_ray<PRUNE, true>(sc, sh.o, sh.d);
                 n_shadow++;
@@ -817,7 +834,11 @@ void launch_extend_accel(const SceneDev& sc, PathQueue q, const uint32_t* q_coun
         if (counts) k_extend_w8<true><<<blocks, threads, w8_smem_for(k_extend_w8<true>, sc), st>>>(sc, q, q_count, work, defer_list, defer_count, c);
         else k_extend_w8<false><<<blocks, threads, w8_smem_for(k_extend_w8<false>, sc), st>>>(sc, q, q_count, work, defer_list, defer_count, c);
     } else {
-        k_extend_accel<false, true, 4><<<blocks, threads, smem_for(k_extend_accel<false, true, 4>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count);
+        W8Counts c;
+        c.node_visits = counts;
+        c.tri_tests = counts ? counts + 1 : nullptr;
+        if (counts) k_extend_accel<true><<<blocks, threads, smem_for(k_extend_accel<true>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count, c);
+        else k_extend_accel<false><<<blocks, threads, smem_for(k_extend_accel<false>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count, c);
     }
     launch_extend(sc, true, false, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_max, 65536u), n_sms, st);
 }
@@ -844,8 +865,13 @@ void launch_extend_camera(const SceneDev& sc, const RenderDev& rd, const TileDev
     W8Counts c;
     c.node_visits = counts;
     c.tri_tests = counts ? counts + 1 : nullptr;
-    if (counts) k_extend_w8_camera<true><<<blocks, threads, w8_smem_for(k_extend_w8_camera<true>, sc), st>>>(sc, rd, tiles, batch_first_frame, n_slots, q, work, defer_list, defer_count, c);
-    else k_extend_w8_camera<false><<<blocks, threads, w8_smem_for(k_extend_w8_camera<false>, sc), st>>>(sc, rd, tiles, batch_first_frame, n_slots, q, work, defer_list, defer_count, c);
+    if (sc.w8_nodes) {
+        if (counts) k_extend_w8_camera<true><<<blocks, threads, w8_smem_for(k_extend_w8_camera<true>, sc), st>>>(sc, rd, tiles, batch_first_frame, n_slots, q, work, defer_list, defer_count, c);
+        else k_extend_w8_camera<false><<<blocks, threads, w8_smem_for(k_extend_w8_camera<false>, sc), st>>>(sc, rd, tiles, batch_first_frame, n_slots, q, work, defer_list, defer_count, c);
+    } else {
+        if (counts) k_extend_accel_camera<true><<<blocks, threads, smem_for(k_extend_accel_camera<true>, 0), st>>>(sc, rd, tiles, batch_first_frame, n_slots, q, work, defer_list, defer_count, c);
+        else k_extend_accel_camera<false><<<blocks, threads, smem_for(k_extend_accel_camera<false>, 0), st>>>(sc, rd, tiles, batch_first_frame, n_slots, q, work, defer_list, defer_count, c);
+    }
     launch_extend(sc, true, false, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_slots, 65536u), n_sms, st);
 }
 void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo, uint32_t* defer_list,
@@ -858,7 +884,11 @@ void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_c
         if (counts) k_shadow_w8<true><<<blocks, threads, w8_smem_for(k_shadow_w8<true>, sc), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count, c);
         else k_shadow_w8<false><<<blocks, threads, w8_smem_for(k_shadow_w8<false>, sc), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count, c);
     } else {
-        k_shadow_accel<true, 4><<<blocks, threads, smem_for(k_shadow_accel<true, 4>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count);
+        W8Counts c;
+        c.node_visits = counts;
+        c.tri_tests = counts ? counts + 1 : nullptr;
+        if (counts) k_shadow_accel<true><<<blocks, threads, smem_for(k_shadow_accel<true>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count, c);
+        else k_shadow_accel<false><<<blocks, threads, smem_for(k_shadow_accel<false>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count, c);
     }
     launch_shadow(sc, true, sq, defer_count, defer_work, Lo, defer_list, std::min<uint32_t>(n_max, 65536u), n_sms, st);
 }
@@ -867,7 +897,14 @@ void launch_shade(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles,
                   uint32_t* s_count, float4* Lo, float4* Le, uint32_t n_max, uint32_t n_fused, int n_sms, cudaStream_t st) {
     int blocks = std::min(div_up(n_max, 128), n_sms * 4 * EZRT_SHADE_MIN_BLOCKS);
     if (blocks < 1) blocks = 1;
-    k_shade<<<blocks, 128, 0, st>>>(sc, rd, tiles, bounce, batch_first_frame, qin, in_count, qout, out_count, sq, s_count, Lo, Le, n_fused);
+#define EZRT_LAUNCH_SHADE(M) k_shade<M><<<blocks, 128, 0, st>>>(sc, rd, tiles, bounce, batch_first_frame, qin, in_count, qout, out_count, sq, s_count, Lo, Le, n_fused)
+    switch (rd.mode) {
+        case EZRT_MODE_DIFFUSE_P3: EZRT_LAUNCH_SHADE(EZRT_MODE_DIFFUSE_P3); break;
+        case EZRT_MODE_DISNEY_ANISO_P4: EZRT_LAUNCH_SHADE(EZRT_MODE_DISNEY_ANISO_P4); break;
+        case EZRT_MODE_DISNEY_SOBOL_P5: EZRT_LAUNCH_SHADE(EZRT_MODE_DISNEY_SOBOL_P5); break;
+        default: EZRT_LAUNCH_SHADE(EZRT_MODE_DISNEY_IS_MIS_P5); break;
+    }
+#undef EZRT_LAUNCH_SHADE
 }
 void launch_blend(const RenderDev& rd, const TileDev* tiles, int nf, uint32_t batch_first_frame, const float4* Lo,
                   const float4* Le, float* fb, cudaStream_t st) {
