@@ -383,6 +383,9 @@ __device__ __forceinline__ HitRec trace_ray(const SceneDev& sc, vec3 o, vec3 d) 
 // of trace_impl / the shader's hitBVH.
 //   io.load(i, o, d) fetches ray i; io.store(i, hit) receives its result.
 // ------------------------------------------------------------------------------------------
+#ifndef EZRT_IS_DEDUPE
+#define EZRT_IS_DEDUPE 0    // IS/MIS integrator: 1 = evaluate the BRDF of the light and the BRDF sample in one non-unrolled loop
+#endif
 #ifndef EZRT_SMEM_STACK
 #define EZRT_SMEM_STACK 0   // stack entries kept in shared memory (experiment; 0 = all in local memory)
 #endif
@@ -1367,6 +1370,7 @@ __device__ __forceinline__ bool shade_step(const SceneDev& sc, const RenderDev& 
         const float NdotL = ez_dot(N, L);
         vec3 fr_h = splat3(0.0f), fr_l = splat3(0.0f);
         float pdf_h = 0.0f, pdf_l = 0.0f;
+#if EZRT_IS_DEDUPE   // one copy of the BRDF code for both directions (a two-trip loop that is not unrolled): smaller kernel
 #pragma unroll 1
         for (int k = 0; k < 2; k++) {
             const bool want = (k == 0) ? (NdotLh > 0.0f) : (NdotL > 0.0f);
@@ -1377,6 +1381,10 @@ __device__ __forceinline__ bool shade_step(const SceneDev& sc, const RenderDev& 
                 if (k == 0) { fr_h = f; pdf_h = q; } else { fr_l = f; pdf_l = q; }
             }
         }
+#else
+        if (NdotLh > 0.0f) { fr_h = brdf_evaluate<false>(V, N, Lh, mat); pdf_h = brdf_pdf(V, N, Lh, mat); }
+        if (NdotL > 0.0f) { fr_l = brdf_evaluate<false>(V, N, L, mat); pdf_l = brdf_pdf(V, N, L, mat); }
+#endif
         if (NdotLh > 0.0f) {
             vec3 color = hdr_color(sc, rd, Lh, mode);
             float pdf_light = hdr_pdf(sc, Lh);

@@ -463,7 +463,10 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
 
 // ------------------------------------------------------------------------------------------
 #ifndef EZRT_SHADE_REGROUP
-#define EZRT_SHADE_REGROUP 1      // k_shade: reorder each 128-path chunk by miss | material id (0: queue order, for A/B runs)
+#define EZRT_SHADE_REGROUP 0      // k_shade: reorder each 128-path chunk -- 1: surface hits before paths that left the scene; 2: hits also
+                                  // by material id; 0: queue order.  Measured on B200 (profiles/sweep_shade_r2.txt): shade ms per step
+                                  // C3 2.73 / 2.86 / 3.03, C4 9.45 / 9.95 / 10.10 for 0 / 1 / 2 -- the warps get fuller (ncu) but the
+                                  // kernel waits on its scattered record reads, not on issue slots, and the sort adds three barriers: off.
 #endif
 #define EZRT_SHADE_KEYS 18        // material id mod 16, "left the scene", "beyond the queue end"
 #ifndef EZRT_SHADE_MIN_BLOCKS
@@ -498,8 +501,11 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
                 const int tri = __float_as_int(__ldcs(qin.hit + i0).y);
                 key = EZRT_SHADE_KEYS - 2;                           // left the scene
                 if (tri >= 0) {
+                    key = 0;
+#if EZRT_SHADE_REGROUP >= 2   // ... and by material id (one more dependent load before the sort)
                     const float4* sh4 = (rd.accel_space ? sc.acc_tri_shade : sc.tri_shade) + (size_t)tri * 3;
                     key = (uint32_t)__float_as_int(ldg4(sh4).w) % (EZRT_SHADE_KEYS - 2);
+#endif
                 }
             }
             const unsigned same = __match_any_sync(0xffffffffu, key);
