@@ -437,13 +437,8 @@ class Runner:
             spp = args.spp_per_step
 
             def e2e_step(s, acc):
-                if self.world == 1:
-                    self.scene.render(self.cfg(s * spp, spp, 0, acc), framebuffer=host_np)  # H2D lastFrame (s > 0), kernels, D2H, sync
-                    return
-                self.d_fb.copy_(host_fb, non_blocking=True)                                   # H2D this rank's lastFrame part
-                self.scene.render_device(self.cfg(s * spp, spp, 0, acc), self.d_fb, self.stream)
-                host_fb.copy_(self.d_fb, non_blocking=True)                                   # D2H this rank's part
-                torch.cuda.synchronize()
+                # ezrt_render: H2D of this rank's lastFrame part (s > 0; it runs beside the tracing kernels), kernels, D2H of the part, sync
+                self.scene.render(self.cfg(s * spp, spp, 0, acc), framebuffer=host_np)
 
             for s in range(warmup):
                 e2e_step(s, False)
@@ -451,7 +446,8 @@ class Runner:
             t0 = time.perf_counter()
             for s in range(steps):
                 e2e_step(warmup + s, s > 0)
-            if self.world > 1:   # once per render: the NCCL gather and the assembled image to the host on rank 0
+            if self.world > 1:   # once per render: the parts go back to the devices, NCCL gather, the assembled image to the host on rank 0
+                self.d_fb.copy_(host_fb, non_blocking=True)
                 full = self.gather()
                 if full is not None:
                     full_host.copy_(full.reshape(-1), non_blocking=True)
@@ -464,7 +460,8 @@ class Runner:
             out["e2e"] = {"value": e_rays / (e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": part_bytes, "d2h_bytes_per_step": part_bytes,
                           "d2h_bytes_once_per_render": (self.W * self.H * self.C * 4 if self.world > 1 else 0), "ms_per_step": e_ms / max(1, steps),
                           "what": "ezrt_render with pinned host framebuffers" if self.world == 1 else
-                                  "per step: H2D lastFrame part, kernels, D2H part on every rank; once per render: NCCL gather + D2H of the whole image on rank 0"}
+                                  "per step: ezrt_render of this rank's part with pinned host buffers (H2D lastFrame part, kernels, D2H part) on every rank; "
+                                  "once per render: H2D of the parts, NCCL gather, D2H of the whole image on rank 0"}
         return out
 
     def traversal_counts(self):

@@ -78,7 +78,7 @@ struct ezrt_scene {
     int n_sms = 148;
     SceneDev dev{};
     DeviceBuffer nodes, tri_geo, tri_shade, materials, hdr, hdr_cache;
-    DeviceBuffer acc_nodes, acc_tri_geo, acc_tri_ref, tri_leaf, leaf_box, defer_buf, acc_tri_shade, acc_tri_leaf, ref_to_acc, acc_wide;
+    DeviceBuffer acc_hot, acc_tri_ref, tri_leaf, leaf_box, defer_buf, acc_tri_leaf, ref_to_acc, acc_wide;   // acc_hot = W8 nodes | geometry | shading records of the accel order
     int acc_depth = 0;
     int n_materials = 0;
     int tree_depth = 0;
@@ -94,7 +94,8 @@ struct ezrt_scene {
     int tiles_key[4] = {-1, -1, -1, -1};
     std::vector<TileDev> tiles;
     size_t n_pixels = 0;       // pixels of the owned tiles
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t fb_event = nullptr, fb_wait = nullptr;   // ezrt_render: the H2D of lastFrame runs beside the tracing kernels
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool have_timing = false;
     unsigned long long launches = 0;
@@ -507,9 +508,9 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     const size_t acc_nodes_bytes = ((std::max<size_t>(w8_words.size(), 4) * sizeof(uint32_t) + 255) / 256) * 256;
     const size_t acc_geo_bytes = ((acc_geo.size() * sizeof(float4) + 255) / 256) * 256;
     const size_t acc_shade_bytes = ((acc_shade.size() * sizeof(float4) + 255) / 256) * 256;
-    if (!rc) rc = sc->acc_nodes.ensure(acc_nodes_bytes + acc_geo_bytes + acc_shade_bytes);
+    if (!rc) rc = sc->acc_hot.ensure(acc_nodes_bytes + acc_geo_bytes + acc_shade_bytes);
     if (!rc) {
-        char* base = (char*)sc->acc_nodes.p;
+        char* base = (char*)sc->acc_hot.p;
         cudaError_t e = w8_words.empty() ? cudaSuccess : cudaMemcpy(base, w8_words.data(), w8_words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(base + acc_nodes_bytes, acc_geo.data(), acc_geo.size() * sizeof(float4), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(base + acc_nodes_bytes + acc_geo_bytes, acc_shade.data(), acc_shade.size() * sizeof(float4), cudaMemcpyHostToDevice);
@@ -544,20 +545,20 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.hdr_cache = hdr_cache ? (const float*)sc->hdr_cache.p : nullptr;
     d.hdr_w = hdr_w; d.hdr_h = hdr_h; d.hdr_linear = hdr_filter_linear ? 1 : 0;
     d.root_ref = child_ref(1);
-    d.w8_nodes = w8_words.empty() ? nullptr : (const uint4*)sc->acc_nodes.p;
+    d.w8_nodes = w8_words.empty() ? nullptr : (const uint4*)sc->acc_hot.p;
     for (int k = 0; k < 3; k++) d.w8_near_bit[k] = w8_near_bit[k];
     d.w8_stack_entries = std::max(1, std::min(w8_depth, EZRT_W8_SMEM_STACK));
     d.w8_origin_limit = W8_ORIGIN_LIMIT_REL * max_abs;
     d.w8_decode_bits = W8_DECODE_BITS;
     d.w8_tri_weight = 2;
     if (const char* e = getenv("EZRT_TRI_W")) d.w8_tri_weight = std::max(1, std::min(64, atoi(e)));
-    d.acc_tri_geo = (const float4*)((const char*)sc->acc_nodes.p + acc_nodes_bytes);
+    d.acc_tri_geo = (const float4*)((const char*)sc->acc_hot.p + acc_nodes_bytes);
     d.acc_tri_ref = (const uint32_t*)sc->acc_tri_ref.p;
     d.acc_wide_nodes = acc_wide.empty() ? nullptr : (const float4*)sc->acc_wide.p;
     d.acc_wide_root_ref = acc_wide_root;
     d.tri_l1_bypass = ((size_t)n_triangles * 64 > ((size_t)4 << 20)) ? 1 : 0;  // > 4 MB of triangle records: stream them past L1
     if (const char* e = getenv("EZRT_TRI_L1_BYPASS")) d.tri_l1_bypass = atoi(e) != 0;
-    d.acc_tri_shade = (const float4*)((const char*)sc->acc_nodes.p + acc_nodes_bytes + acc_geo_bytes);
+    d.acc_tri_shade = (const float4*)((const char*)sc->acc_hot.p + acc_nodes_bytes + acc_geo_bytes);
     d.acc_tri_leaf = (const int*)sc->acc_tri_leaf.p;
     d.ref_to_acc = (const uint32_t*)sc->ref_to_acc.p;
     d.tri_leaf = (const int*)sc->tri_leaf.p;
@@ -602,11 +603,13 @@ int ezrt_scene_destroy(ezrt_scene* s) {
     cudaSetDevice(s->device);
     s->nodes.release(); s->tri_geo.release(); s->tri_shade.release(); s->materials.release();
     s->hdr.release(); s->hdr_cache.release(); s->tiles_buf.release();
-    s->acc_nodes.release(); s->acc_tri_geo.release(); s->acc_tri_ref.release(); s->tri_leaf.release(); s->leaf_box.release(); s->defer_buf.release();
-    s->acc_tri_shade.release(); s->acc_tri_leaf.release(); s->ref_to_acc.release(); s->acc_wide.release();
+    s->acc_hot.release(); s->acc_tri_ref.release(); s->tri_leaf.release(); s->leaf_box.release(); s->defer_buf.release();
+    s->acc_tri_leaf.release(); s->ref_to_acc.release(); s->acc_wide.release();
     s->queue_buf[0].release(); s->queue_buf[1].release(); s->shadow_buf.release();
     s->lo_buf.release(); s->le_buf.release(); s->counters_buf.release(); s->totals_buf.release(); s->fb_buf.release(); s->sort_buf.release();
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    if (s->fb_event) cudaEventDestroy(s->fb_event);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
     if (s->ev_stop) cudaEventDestroy(s->ev_stop);
     for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
@@ -651,6 +654,10 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     }
 
     if (p->pipeline == EZRT_PIPELINE_MEGAKERNEL) {
+        if (s->fb_wait) {
+            CU_CHECK(cudaStreamWaitEvent(st, s->fb_wait, 0));
+            s->fb_wait = nullptr;
+        }
         int sp = s->span_begin(0, st);
         launch_megakernel(s->dev, rd, d_tiles, prune, p->spp, d_fb, totals, st);
         s->span_end(sp, st);
@@ -775,6 +782,10 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
             }
         }
         sp = s->span_begin(3, st);
+        if (s->fb_wait) {   // ezrt_render: lastFrame arrives on the copy stream
+            CU_CHECK(cudaStreamWaitEvent(st, s->fb_wait, 0));
+            s->fb_wait = nullptr;
+        }
         launch_blend(rd, d_tiles, nf, batch_first, Lo, Le, d_fb, st);
         launch_tally(q_count, s_count, d_ext, d_sh, p->max_bounce + 1, totals, fused_camera ? (uint32_t)(s->n_pixels * (size_t)nf) : 0u, st);
         s->span_end(sp, st);
@@ -803,8 +814,20 @@ int ezrt_render(ezrt_scene* s, const ezrt_render_params* p, float* framebuffer) 
     rc = s->fb_buf.ensure(std::max<size_t>(bytes, 16));
     if (rc) return rc;
     cudaStream_t st = s->own_stream;
-    if (p->first_frame > 0) CU_CHECK(cudaMemcpyAsync(s->fb_buf.p, framebuffer, bytes, cudaMemcpyHostToDevice, st));
+    // lastFrame is only needed by the first k_blend: its upload runs on a second stream, under the tracing kernels
+    s->fb_wait = nullptr;
+    if (p->first_frame > 0) {
+        if (!s->copy_stream && cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return ezrt_set_error(EZRT_ERR_CUDA, "render: stream");
+        if (!s->fb_event && cudaEventCreateWithFlags(&s->fb_event, cudaEventDisableTiming) != cudaSuccess) return ezrt_set_error(EZRT_ERR_CUDA, "render: event");
+        CU_CHECK(cudaMemcpyAsync(s->fb_buf.p, framebuffer, bytes, cudaMemcpyHostToDevice, s->copy_stream));
+        CU_CHECK(cudaEventRecord(s->fb_event, s->copy_stream));
+        s->fb_wait = s->fb_event;
+    }
     rc = ezrt_render_device(s, p, (float*)s->fb_buf.p, st);
+    if (s->fb_wait) {  // the render returned before its first blend (error, empty part): do not leave the copy behind
+        cudaStreamWaitEvent(st, s->fb_wait, 0);
+        s->fb_wait = nullptr;
+    }
     if (rc) return rc;
     CU_CHECK(cudaMemcpyAsync(framebuffer, s->fb_buf.p, bytes, cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaStreamSynchronize(st));

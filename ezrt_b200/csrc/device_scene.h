@@ -16,6 +16,9 @@
 //   triangle shading (48 B): (n1, matId) (n2, 0) (n3, 0)  -- fetched only for the final hit
 //   material table (80 B each): the 18-float material block de-duplicated (materials
 //       are stored per triangle in the reference), padded to 5 x float4.
+//   acceleration tree of the default traversal policy: the device's own sentinel-free SAH tree over the
+//       same triangles, as 4-wide nodes with exact boxes (128 B: four child boxes + four references, default) or as 8-wide
+//       nodes with 8-bit quantised boxes (96 B, w8_node.h; env EZRT_ACCEL=8), plus geometry / shading records in its order.
 #ifndef EZRT_DEVICE_SCENE_H
 #define EZRT_DEVICE_SCENE_H
 
@@ -26,7 +29,6 @@
 #define EZRT_LEAF_FLAG 0x80000000u
 #define EZRT_LEAF_MAX_N 127
 #define EZRT_TOP_NODES_MAX 1023   // 10 full levels; 80 B each in shared memory (bank-conflict padding)
-#define EZRT_ACC_TOP_NODES_MAX 255 // acceleration tree: 8 levels are enough (its upper levels are real SAH splits)
 #define EZRT_ACCEL_STACK 64       // stack entries of the 4-wide accel kernel (<= 3 pushes per level): trees deeper than 20 levels are not built
 #define EZRT_W8_SMEM_STACK 16      // per-lane W8 stack entries held in shared memory (8 B each x 1024 threads = 128 KB at most)
 #define EZRT_TOP_STRIDE 5         // float4 per shared-memory record

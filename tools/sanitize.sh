@@ -8,12 +8,14 @@ mkdir -p gpurun_out
 SZ=${1:-96x54}
 CS=$(command -v compute-sanitizer || echo /usr/local/cuda/bin/compute-sanitizer)
 : > gpurun_out/sanitizer_summary.txt
+for form in 4 8; do          # both forms of the acceleration tree (EZRT_ACCEL): 4-wide exact boxes (default), W8
 for tool in memcheck racecheck initcheck synccheck; do
-    log=gpurun_out/sanitizer_${tool}.log
+    log=gpurun_out/sanitizer_${tool}_accel${form}.log
     extra=""
     [ "$tool" = memcheck ] && extra="--leak-check no"
-    EZRT_AUTO_BUILD=0 timeout 900 "$CS" --tool $tool $extra --print-limit 20 python tools/sanitize_case.py "$SZ" > "$log" 2>&1
+    EZRT_ACCEL=$form EZRT_AUTO_BUILD=0 timeout 900 "$CS" --tool $tool $extra --print-limit 20 python tools/sanitize_case.py "$SZ" > "$log" 2>&1
     rc=$?
-    echo "$tool rc=$rc: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|sanitize_case:' "$log" | tr '\n' ' ')" >> gpurun_out/sanitizer_summary.txt
+    echo "EZRT_ACCEL=$form $tool rc=$rc: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|sanitize_case:' "$log" | tr '\n' ' ')" >> gpurun_out/sanitizer_summary.txt
+done
 done
 cat gpurun_out/sanitizer_summary.txt
