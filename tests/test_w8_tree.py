@@ -17,6 +17,7 @@ def _run_model(tmp_path, tris, rays, brute):
     r = subprocess.run([exe, tf, str(tris.shape[0]), rf] + (["brute"] if brute else []), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout
     assert "differing from" in r.stdout and ": 0 of" in r.stdout, r.stdout
+    assert "violations 0" in r.stdout, r.stdout        # the 4-wide collapse covers every triangle exactly once, leaves <= 4
     return r.stdout
 
 

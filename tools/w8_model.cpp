@@ -75,6 +75,34 @@ int main(int argc, char** argv) {
     if (rc) { fprintf(stderr, "ezrt_build_w8 failed: %d\n", rc); return 1; }
     printf("binary nodes %zu, 8-wide nodes %d (%.1f MB), depth %d, mean fill %.2f, axis bits x%d y%d z%d\n", an.size(), w8.n_nodes,
            w8.n_nodes * 96.0 / 1e6, w8.depth, (double)w8.n_children / w8.n_nodes, axis_bit[0], axis_bit[1], axis_bit[2]);
+    {   // the 4-wide collapse the default kernel uses (same dynamic programme, width 4): every triangle in exactly one leaf of <= 4
+        EzrtCollapse c4;
+        if (c4.build(an, 4, W8_MAX_LEAF_TRIS, 1.0, 0.3) != 0) { fprintf(stderr, "4-wide collapse failed\n"); return 1; }
+        std::vector<char> seen(n, 0);
+        long nodes4 = 0, kids = 0, bad = 0;
+        std::vector<int> todo;
+        if (an[0].n <= 0 && !c4.as_leaf[0]) todo.push_back(0);
+        while (!todo.empty()) {
+            const int b = todo.back();
+            todo.pop_back();
+            int ch[8];
+            const int cnt = c4.children(b, ch);
+            nodes4++;
+            kids += cnt;
+            if (cnt < 2 || cnt > 4) bad++;
+            for (int k = 0; k < cnt; k++) {
+                if (c4.as_leaf[ch[k]]) {
+                    if (c4.count[ch[k]] < 1 || c4.count[ch[k]] > W8_MAX_LEAF_TRIS) bad++;
+                    for (int t = 0; t < c4.count[ch[k]]; t++) { if (seen[c4.first[ch[k]] + t]++) bad++; }
+                } else {
+                    todo.push_back(ch[k]);
+                }
+            }
+        }
+        if (nodes4 > 0) for (int i = 0; i < n; i++) if (seen[i] != 1) bad++;
+        printf("4-wide collapse: %ld nodes, mean fill %.2f, violations %ld\n", nodes4, nodes4 ? (double)kids / nodes4 : 0.0, bad);
+        if (bad) return 4;
+    }
     std::vector<TriRec> rec(n);
     for (int i = 0; i < n; i++) {
         const float* s = &tris[(size_t)w8.tri_order[i] * 36];
