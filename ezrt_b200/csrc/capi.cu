@@ -176,6 +176,16 @@ int prepare_tiles(ezrt_scene* s, const ezrt_render_params* p, cudaStream_t st) {
     return EZRT_OK;
 }
 
+struct ScatterEntry { TileDev* d_tiles; int n; };
+std::map<std::array<int, 5>, ScatterEntry>& scatter_cache() {
+    static std::map<std::array<int, 5>, ScatterEntry> cache;
+    return cache;
+}
+std::mutex& scatter_mutex() {
+    static std::mutex mu;
+    return mu;
+}
+
 RenderDev make_render_dev(const ezrt_scene* s, const ezrt_render_params* p) {
     RenderDev rd;
     rd.width = p->width; rd.height = p->height;
@@ -587,6 +597,8 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         }
     }
     d.refill_thresh = 24;
+    d.refill_thresh_camera = 0;
+    if (const char* e = getenv("EZRT_REFILL_CAM")) d.refill_thresh_camera = std::max(0, std::min(32, atoi(e)));
     d.inner_thresh = 16;
     d.leaf_thresh = 12;
     d.work_chunk = 32;
@@ -816,7 +828,10 @@ int ezrt_render(ezrt_scene* s, const ezrt_render_params* p, float* framebuffer) 
     cudaStream_t st = s->own_stream;
     // lastFrame is only needed by the first k_blend: its upload runs on a second stream, under the tracing kernels
     s->fb_wait = nullptr;
-    if (p->first_frame > 0) {
+    static const bool overlap_upload = []() { const char* e = getenv("EZRT_RENDER_OVERLAP"); return !(e && atoi(e) == 0); }();
+    if (p->first_frame > 0 && !overlap_upload) {
+        CU_CHECK(cudaMemcpyAsync(s->fb_buf.p, framebuffer, bytes, cudaMemcpyHostToDevice, st));
+    } else if (p->first_frame > 0) {
         if (!s->copy_stream && cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return ezrt_set_error(EZRT_ERR_CUDA, "render: stream");
         if (!s->fb_event && cudaEventCreateWithFlags(&s->fb_event, cudaEventDisableTiming) != cudaSuccess) return ezrt_set_error(EZRT_ERR_CUDA, "render: event");
         CU_CHECK(cudaMemcpyAsync(s->fb_buf.p, framebuffer, bytes, cudaMemcpyHostToDevice, s->copy_stream));
@@ -886,21 +901,20 @@ int ezrt_partition_scatter(const float* d_compact, float* d_full, int width, int
                            void* cuda_stream) {
     if (!d_compact || !d_full || channels < 1) return ezrt_set_error(EZRT_ERR_INVALID, "partition_scatter: bad argument");
     if (width <= 0 || height <= 0 || count < 1 || rank < 0 || rank >= count) return ezrt_set_error(EZRT_ERR_INVALID, "partition_scatter: bad partition");
-    // device tile lists are cached per (device, image, part): the gather runs every step
-    struct Entry { TileDev* d_tiles; int n; };
-    static std::map<std::array<int, 5>, Entry> cache;
-    static std::mutex mu;
+    // device tile lists are cached per (device, image, part): the gather runs once per render
+    auto& cache = scatter_cache();
+    std::mutex& mu = scatter_mutex();
     int device = 0;
     CU_CHECK(cudaGetDevice(&device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    Entry ent;
+    ScatterEntry ent;
     {
         std::lock_guard<std::mutex> lock(mu);
         std::array<int, 5> key = {device, width, height, rank, count};
         auto it = cache.find(key);
         if (it == cache.end()) {
             std::vector<TileDev> tiles = partition_tiles(width, height, rank, count);
-            Entry e{nullptr, (int)tiles.size()};
+            ScatterEntry e{nullptr, (int)tiles.size()};
             if (!tiles.empty()) {
                 CU_CHECK(cudaMalloc(&e.d_tiles, sizeof(TileDev) * tiles.size()));
                 CU_CHECK(cudaMemcpy(e.d_tiles, tiles.data(), sizeof(TileDev) * tiles.size(), cudaMemcpyHostToDevice));
@@ -912,6 +926,27 @@ int ezrt_partition_scatter(const float* d_compact, float* d_full, int width, int
     if (ent.n == 0) return EZRT_OK;
     launch_partition_scatter(d_compact, d_full, ent.d_tiles, ent.n, width, channels, st);
     CU_CHECK(cudaGetLastError());
+    return EZRT_OK;
+}
+
+int ezrt_partition_cache_clear(int device) {
+    std::lock_guard<std::mutex> lock(scatter_mutex());
+    auto& cache = scatter_cache();
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (auto it = cache.begin(); it != cache.end();) {
+        if (device < 0 || it->first[0] == device) {
+            if (it->second.d_tiles) {
+                cudaSetDevice(it->first[0]);
+                cudaFree(it->second.d_tiles);
+            }
+            it = cache.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    cudaSetDevice(prev);
+    cudaGetLastError();
     return EZRT_OK;
 }
 

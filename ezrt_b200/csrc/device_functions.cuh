@@ -448,14 +448,14 @@ struct W8Counts {   // COUNT instantiations only (bench.py roofline: records fet
 
 template <bool PRUNE, bool ANYHIT, bool ACCEL, bool WIDE, int LL, bool COUNT, class RayIO>
 __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const TreeView tree, uint32_t n, uint32_t* work, RayIO io,
-                                                  const float4* smem_top, W8Counts counts = W8Counts{nullptr, nullptr}) {
+                                                  const float4* smem_top, W8Counts counts = W8Counts{nullptr, nullptr}, int refill_override = 0) {
     unsigned long long n_visits = 0, n_tests = 0;
     const int top_nodes = tree.top_nodes;
     const bool tri_na = sc.tri_l1_bypass != 0;
     __shared__ unsigned char s_owner_all[(EZRT_EXTEND_MAX_THREADS / 32) * 8];   // leaf phase: rank -> owner lane, 8 bytes per warp
     unsigned char* const s_owner = s_owner_all + (threadIdx.x >> 5) * 8;
     bool tie = false;          // ACCEL: another triangle was accepted at exactly the best distance
-    const int refill_thresh = sc.refill_thresh;  // go back to refill when fewer lanes than this are busy
+    const int refill_thresh = refill_override ? refill_override : sc.refill_thresh;  // go back to refill when fewer lanes than this are busy
     const int inner_thresh = sc.inner_thresh;    // leave the inner-node phase when fewer lanes than this walk
     const int leaf_thresh = sc.leaf_thresh;      // ... or when at least this many lanes wait at a leaf
     const unsigned FULL = 0xffffffffu;

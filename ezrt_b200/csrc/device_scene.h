@@ -70,6 +70,7 @@ struct SceneDev {
     int top_nodes;            // records [0, top_nodes) = the top tree levels, staged in shared memory
     float prune_delta;        // 2^-16 * max |vertex coordinate|
     int refill_thresh;        // persistent traversal tunables (env EZRT_REFILL_T / EZRT_INNER_T)
+    int refill_thresh_camera; // the same for the camera pass, whose rays are coherent (env EZRT_REFILL_CAM; 0 = refill_thresh)
     int inner_thresh;
     int leaf_thresh;
     int work_chunk;           // rays a warp takes from the work counter at a time (env EZRT_CHUNK)

@@ -160,9 +160,12 @@ int ezrt_get_kernel_times(ezrt_scene* scene, double* ms, uint64_t* launches);
 /* Number of pixels part `rank` of `count` owns for a width x height image. */
 int64_t ezrt_partition_pixels(int width, int height, int rank, int count);
 /* Device kernel: scatter the compact tile-major buffer of part `rank` into a full
- * width x height framebuffer (both device pointers, same channel count). */
+ * width x height framebuffer (both device pointers, same channel count).  The device tile lists are cached per
+ * (device, image size, rank, count) -- the gather runs once per render -- and live until ezrt_partition_cache_clear(). */
 int ezrt_partition_scatter(const float* d_compact, float* d_full, int width, int height, int channels,
                            int rank, int count, void* cuda_stream);
+/* Frees the tile lists ezrt_partition_scatter cached on the calling thread's current device (all devices: device < 0). */
+int ezrt_partition_cache_clear(int device);
 /* Host version of the same scatter (used by the CPU/gloo path and by tests). */
 int ezrt_partition_scatter_host(const float* compact, float* full, int width, int height, int channels,
                                 int rank, int count);
