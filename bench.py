@@ -412,14 +412,17 @@ class Runner:
         self.barrier()
         sampler = ClockSampler(torch.cuda.current_device()) if (sample_clocks and self.rank == 0) else None
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         ev0.record(self.stream)
         for s in range(steps):
             self.step(warmup + s, profile=1, accumulate=(s > 0))   # counters / kernel spans are read once, after the loop
+            marks[s].record(self.stream)                           # per-step times for the stability record (no sync)
         self.gather()                                              # N > 1: the render's single NCCL gather
         ev1.record(self.stream)
         self.barrier()
         clocks = sampler.stop() if sampler else None
         ms_local = ev0.elapsed_time(ev1)
+        per_step = [(ev0 if s == 0 else marks[s - 1]).elapsed_time(marks[s]) for s in range(steps)]
         c = self.scene.counters()
         kt = self.scene.kernel_times()
         (ms,) = self.allreduce([ms_local], "max")
@@ -428,6 +431,7 @@ class Runner:
         out = dict(value=rays / (ms * 1e-3) / 1e6, ms=ms, rays=rays, launches=launches, clocks=clocks, upload_ms=self.upload_ms,
                    kernel_ms={k: v[0] for k, v in kt.items()}, kernel_launches={k: v[1] for k, v in kt.items()},
                    deferred=float(c.deferred_rays), rank0_rays=float(c.rays), rank_rays=rank_rays, steps=steps,
+                   step_ms={"min": min(per_step), "median": statistics.median(per_step), "max": max(per_step)},
                    samples=self.allreduce([float(c.samples)], "sum")[0])
         # ---------------- e2e: host buffers -----------------
         if do_e2e:
@@ -613,7 +617,7 @@ def main():
     def pack(m):
         res = m["res"]
         d = {"value": res["value"], "unit": UNIT, "ms_per_step": res["ms"] / max(1, res["steps"]), "steps": res["steps"], "rays_per_step": res["rays"] / max(1, res["steps"]),
-             "e2e": res.get("e2e"), "gpu_launches": int(res["launches"]), "kernel_ms": res["kernel_ms"], "deferred_ray_fraction": res["deferred"] / max(1.0, res["rank0_rays"]),
+             "e2e": res.get("e2e"), "gpu_launches": int(res["launches"]), "kernel_ms": res["kernel_ms"], "step_ms_rank0": res["step_ms"], "deferred_ray_fraction": res["deferred"] / max(1.0, res["rank0_rays"]),
              "parity": m.get("parity"), "cpu_baseline": m.get("cpu_baseline"),
              "roofline": roofline_of(res, m["counts"], m.get("means"), hbm_peak, peak_kind, kname),
              "setup": {"scene_build_s": round(m["wl"]["build_s"], 2), "scene_upload_ms": round(res["upload_ms"], 1)}}
@@ -628,7 +632,7 @@ def main():
         "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": head["scaling"], "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": head["config"],
         "rays_per_step": h["rays_per_step"], "e2e": h["e2e"], "gpu_launches": h["gpu_launches"], "clocks": head["res"]["clocks"],
-        "kernel_ms": h["kernel_ms"], "parity": h["parity"], "roofline": h["roofline"], "cpu_baseline": h["cpu_baseline"],
+        "kernel_ms": h["kernel_ms"], "step_ms_rank0": h["step_ms_rank0"], "parity": h["parity"], "roofline": h["roofline"], "cpu_baseline": h["cpu_baseline"],
         "deferred_ray_fraction": h["deferred_ray_fraction"], "setup": h["setup"],
         "run": {"traverse": args.traverse, "pipeline": args.pipeline,
                 "gather": "none (1 GPU)" if world == 1 else "one NCCL gather of the compact per-rank framebuffers per render, after the K timed steps, inside the timed region"},

@@ -3,6 +3,7 @@
 // test entry points.  Host-side scene building lives in host_scene.cpp.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -94,6 +95,7 @@ struct ezrt_scene {
     int tiles_key[4] = {-1, -1, -1, -1};
     std::vector<TileDev> tiles;
     size_t n_pixels = 0;       // pixels of the owned tiles
+    size_t fmax = 0, fmax_key[2] = {0, 0};   // frames per batch that fit the free memory, for (slots per frame, bytes per slot)
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
     cudaEvent_t fb_event = nullptr, fb_wait = nullptr;   // ezrt_render: the H2D of lastFrame runs beside the tracing kernels
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -126,7 +128,7 @@ struct ezrt_scene {
 namespace {
 
 int carve_queue(DeviceBuffer& buf, size_t capacity, PathQueue& q) {
-    size_t per = sizeof(float4) * 4 + sizeof(uint2) + sizeof(float2);
+    size_t per = sizeof(float4) * 4 + sizeof(float2);
     int rc = buf.ensure(per * capacity + 256);
     if (rc) return rc;
     char* p = (char*)buf.p;
@@ -134,7 +136,6 @@ int carve_queue(DeviceBuffer& buf, size_t capacity, PathQueue& q) {
     q.ray_d = (float4*)p; p += sizeof(float4) * capacity;
     q.hist = (float4*)p;  p += sizeof(float4) * capacity;
     q.fr = (float4*)p;    p += sizeof(float4) * capacity;
-    q.meta = (uint2*)p;   p += sizeof(uint2) * capacity;
     q.hit = (float2*)p;
     return EZRT_OK;
 }
@@ -218,6 +219,15 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     CU_CHECK(cudaGetDeviceCount(&n_dev));
     if (device < 0 || device >= n_dev) return ezrt_set_error(EZRT_ERR_CUDA, "scene_create: no CUDA device %d (have %d)", device, n_dev);
     CU_CHECK(cudaSetDevice(device));
+    // env EZRT_VERBOSE=1: wall-clock of the stages on stderr (all host work except the uploads)
+    const bool verbose = getenv("EZRT_VERBOSE") && atoi(getenv("EZRT_VERBOSE")) != 0;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!verbose) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ezrt_scene_create] %-44s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
 
     // ---- decode + validate the tree (getBVHNode, P5/fsh:138-155) ----
     struct HNode { int left, right, n, index; };
@@ -333,6 +343,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         for (int k = 0; k < hn[i].n; k++) tri_leaf[hn[i].index + k] = slot;
     }
 
+    lap("reference tree: decode, validate, repack");
     // ---- triangles: geometry records, shading records, de-duplicated material table ----
     std::vector<float4> geo((size_t)n_triangles * 4), shade((size_t)n_triangles * 3);
     std::map<std::string, int> mat_ids;
@@ -375,6 +386,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         shade[(size_t)i * 3 + 2] = make_float4(s[15], s[16], s[17], 0.0f);
     }
 
+    lap("triangles: geometry / shading records, materials");
     // ---- acceleration tree: sentinel-free SAH over the same triangles (DESIGN.md "accel"), collapsed to 8-wide
     // quantised nodes (accel_w8.cpp, w8_node.h).  A tree too deep for the traversal stacks (degenerate input) is
     // dropped: the scene then renders with the PRUNED policy on the caller's tree, as for an irregular tree.
@@ -389,6 +401,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         std::vector<EzrtAccelNode> an;
         std::vector<uint32_t> order_bin;
         ezrt_build_accel(tris, n_triangles, W8_MAX_LEAF_TRIS, an, order_bin);
+        lap("acceleration tree: binary SAH build");
         // boxes inflated by 2*delta: a hit hitTriangle accepts lies within delta of its triangle's box, so
         // the inflated boxes of the whole ancestor chain are entered no later than the hit distance
         const float pad = 2.0f * prune_delta;
@@ -481,6 +494,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         for (int i = 0; i < n_triangles; i++)
             for (int k = 0; k < 4; k++) acc_geo[(size_t)i * 4 + k] = geo[(size_t)acc_order[i] * 4 + k];
     }
+    lap("acceleration tree: collapse, pack, reorder geometry");
     // shading data and the reference-leaf map in the acceleration tree's order, and the inverse permutation
     std::vector<float4> acc_shade((size_t)n_triangles * 3);
     std::vector<int> acc_leaf(n_triangles);
@@ -492,6 +506,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         ref_to_acc[r] = (uint32_t)i;
     }
 
+    lap("shading records in the tree's order");
     ezrt_scene* sc = new (std::nothrow) ezrt_scene();
     if (!sc) return ezrt_set_error(EZRT_ERR_NOMEM, "scene_create: out of host memory");
     sc->device = device;
@@ -542,6 +557,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         ezrt_scene_destroy(sc);
         return rc;
     }
+    lap("uploads");
     sc->n_materials = (int)mat_ids.size();
     sc->regular_tree = regular_tree;
     sc->have_accel = have_accel;
@@ -600,8 +616,8 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.refill_thresh_camera = 0;
     if (const char* e = getenv("EZRT_REFILL_CAM")) d.refill_thresh_camera = std::max(0, std::min(32, atoi(e)));
     d.inner_thresh = 16;
-    d.leaf_thresh = 12;
-    d.work_chunk = 32;
+    d.leaf_thresh = 16;   // round 2 (cheaper leaf passes, S-1M): 16 / chunk 64 measured +3 % over 12 / 32 (profiles/sweep_thresh_r2.txt)
+    d.work_chunk = 64;
     if (const char* e = getenv("EZRT_CHUNK")) d.work_chunk = std::max(32, std::min(65536, atoi(e)));
     if (const char* e = getenv("EZRT_LEAF_T")) d.leaf_thresh = std::max(1, std::min(33, atoi(e)));
     if (const char* e = getenv("EZRT_REFILL_T")) d.refill_thresh = std::max(1, std::min(32, atoi(e)));
@@ -686,18 +702,24 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     if (F <= 0) F = (int)std::max<size_t>(1, ((size_t)32 << 20) / per_frame);  // ~32 M sample slots per batch (~7.5 GB of state):
                                                                               // long queues amortise the persistent kernels' ramp-up and tail
     F = std::min(F, p->spp);
-    {   // bound the batch by the memory that is actually there (scratch already held by this scene counts as available)
-        const size_t per_slot = 2 * (sizeof(float4) * 4 + sizeof(uint2) + sizeof(float2)) + 2 * sizeof(float4) + sizeof(uint32_t) +
+    {   // bound the batch by the memory that is actually there (scratch already held by this scene counts as available);
+        // asked once per (slots per frame, integrator): cudaMemGetInfo is a driver round trip, the render path is launch-only
+        const size_t per_slot = 2 * (sizeof(float4) * 4 + sizeof(float2)) + 2 * sizeof(float4) + sizeof(uint32_t) +
                                 (is_mode ? 3 * sizeof(float4) : 0) + (s->sort_rays ? 2 * sizeof(uint32_t) : 0);
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            const size_t held = s->queue_buf[0].bytes + s->queue_buf[1].bytes + s->shadow_buf.bytes + s->lo_buf.bytes + s->le_buf.bytes +
-                                s->defer_buf.bytes + s->sort_buf.bytes;
-            const size_t avail = (size_t)((double)(free_b + held) * 0.9);
-            const size_t f_max = avail / per_slot / per_frame;
-            if (f_max < 1) return ezrt_set_error(EZRT_ERR_NOMEM, "render: %zu MB free, one frame of wavefront state needs %zu MB", free_b >> 20, (per_slot * per_frame) >> 20);
-            F = (int)std::min<size_t>((size_t)F, f_max);
+        if (s->fmax_key[0] != per_frame || s->fmax_key[1] != per_slot) {
+            size_t free_b = 0, total_b = 0;
+            s->fmax = (size_t)1 << 30;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                const size_t held = s->queue_buf[0].bytes + s->queue_buf[1].bytes + s->shadow_buf.bytes + s->lo_buf.bytes + s->le_buf.bytes +
+                                    s->defer_buf.bytes + s->sort_buf.bytes;
+                const size_t avail = (size_t)((double)(free_b + held) * 0.9);
+                s->fmax = avail / per_slot / per_frame;
+                if (s->fmax < 1) return ezrt_set_error(EZRT_ERR_NOMEM, "render: %zu MB free, one frame of wavefront state needs %zu MB", free_b >> 20, (per_slot * per_frame) >> 20);
+            }
+            s->fmax_key[0] = per_frame;
+            s->fmax_key[1] = per_slot;
         }
+        F = (int)std::min<size_t>((size_t)F, s->fmax);
     }
     const size_t capacity = per_frame * (size_t)F;
     if (capacity >= ((size_t)1 << 31)) return ezrt_set_error(EZRT_ERR_INVALID, "render: batch too large");

@@ -383,6 +383,9 @@ __device__ __forceinline__ HitRec trace_ray(const SceneDev& sc, vec3 o, vec3 d) 
 // of trace_impl / the shader's hitBVH.
 //   io.load(i, o, d) fetches ray i; io.store(i, hit) receives its result.
 // ------------------------------------------------------------------------------------------
+#ifndef EZRT_LEAF_SERIAL
+#define EZRT_LEAF_SERIAL 0  // 1: lane-serial leaf tests in the accel kernels instead of the cooperative quads (A/B, profiles/sweep_leaf_r2.txt)
+#endif
 #ifndef EZRT_IS_DEDUPE
 #define EZRT_IS_DEDUPE 0    // IS/MIS integrator: 1 = evaluate the BRDF of the light and the BRDF sample in one non-unrolled loop
 #endif
@@ -633,6 +636,23 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
             const bool long_leaves = __ballot_sync(FULL, leaf_cnt > LL) != 0u;
             bool stop = false;
             const int q = lane / LL, k = lane % LL;
+#if EZRT_LEAF_SERIAL   // experiment: every lane tests the triangles of its own leaf one after the other (accel kernels, leaves <= 4)
+            if (ACCEL) {
+                m_leaf = 0u;
+                int cnt = leaf_cnt, first = leaf_first;
+                while (__ballot_sync(FULL, cnt > 0 && !stop) != 0u) {
+                    if (cnt > 0 && !stop) {
+                        float t;
+                        if (COUNT) n_tests++;
+                        const int r = tri_test_t<true>(tree.tri_geo + (size_t)first * 4, o, d, best, t, tri_na);
+                        if (r == 2) tie = true;
+                        else if (r == 1) { best = t; best_tri = first; if (ANYHIT) stop = true; }
+                        first++;
+                        cnt--;
+                    }
+                }
+            }
+#endif
             while (m_leaf != 0u) {
                 // the G lowest waiting lanes own this pass: lane with rank g (g-th set bit of m_leaf) serves group g.  The
                 // rank -> lane map goes through a few bytes of shared memory (one STS / LDS per pass; the unrolled

@@ -98,14 +98,13 @@ struct TileDev {
     int pixel_offset;         // offset of the tile's first pixel in the compact buffer
 };
 
-// SoA path state of the wavefront pipeline (one set per queue; two queues ping-pong).
+// SoA path state of the wavefront pipeline (one set per queue; two queues ping-pong): 64 B per path + 8 B hit record.
 struct PathQueue {
-    float4* ray_o;    // (origin.xyz, -)
-    float4* ray_d;    // (direction.xyz, -)
+    float4* ray_o;    // (origin.xyz, rng seed as bits)
+    float4* ray_d;    // (direction.xyz, sample slot as bits)
     float2* hit;      // written by extend: (hit distance, triangle index as int bits; -1 = miss)
     float4* hist;     // (history.xyz, cosine_i)
     float4* fr;       // (f_r.xyz, pdf)   pdf <= 0 marks "break after trace" (P5/fsh:865)
-    uint2* meta;      // (rng seed, sample slot)
 };
 
 struct ShadowQueue {

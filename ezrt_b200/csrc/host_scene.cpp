@@ -515,32 +515,137 @@ struct ezrt_trilist {
 // SAH as buildBVHwithSAH but WITHOUT the reference's INF = 114514 cost sentinel, so the top levels
 // are real SAH splits instead of median splits on axis 0.  nodes[0] is the root; child links are
 // indices into `nodes` (0 = none); order[i] = index (in `tris`) of the i-th triangle of the tree.
+// The sweep of buildBVHwithSAH re-sorts the node's triangles four times at every node (P5/main.cpp:493-575): O(n log^2 n),
+// 1.4 s of the 1.7 s ezrt_scene_create took at 1 M triangles.  The acceleration tree does not have to reproduce the
+// reference's permutation, so this builder sorts ONCE per axis and keeps the three orders through every split by stable
+// partition (Wald 2007 "sort once"): the same cost function, the same exhaustive sweep over every split position of every
+// axis, O(n log n).  Sub-trees are built on separate threads as in build_sah_fast.
+namespace {
+struct PresortCtx {
+    const ez_vec3* bmin;
+    const ez_vec3* bmax;
+    uint32_t* idx[3];      // triangle ids of the whole array, three times: sorted by centroid x / y / z within every node's range
+    uint32_t* tmp;         // partition scratch, n entries
+    unsigned char* side;   // per triangle id: 1 = goes to the right child
+    int leaf_n;
+    int median_depth;
+};
+
+void build_accel_presorted(const PresortCtx& cx, int l, int r, std::vector<EzrtAccelNode>& out, int depth) {
+    const size_t base = out.size();
+    out.push_back(EzrtAccelNode());
+    {
+        ez_vec3 AA = ez_v3(3.0e38f, 3.0e38f, 3.0e38f), BB = ez_v3(-3.0e38f, -3.0e38f, -3.0e38f);
+        const uint32_t* ix = cx.idx[0];
+        for (int i = l; i <= r; i++) {
+            AA = ez_vmin(AA, cx.bmin[ix[i]]);
+            BB = ez_vmax(BB, cx.bmax[ix[i]]);
+        }
+        EzrtAccelNode& nd = out[base];
+        nd.left = nd.right = nd.n = nd.index = 0;
+        nd.AA[0] = AA.x; nd.AA[1] = AA.y; nd.AA[2] = AA.z;
+        nd.BB[0] = BB.x; nd.BB[1] = BB.y; nd.BB[2] = BB.z;
+    }
+    const int cnt = r - l + 1;
+    if (cnt <= cx.leaf_n) {
+        out[base].n = cnt;
+        out[base].index = l;
+        return;
+    }
+    float Cost = 3.0e38f;
+    int Axis = 0, Split = (l + r) / 2;
+    {
+        std::vector<float> rightArea(cnt);
+        for (int axis = 0; axis < 3; axis++) {
+            const uint32_t* ix = cx.idx[axis];
+            ez_vec3 rmax = ez_v3(-3.0e38f, -3.0e38f, -3.0e38f), rmin = ez_v3(3.0e38f, 3.0e38f, 3.0e38f);
+            for (int i = r; i > l; i--) {
+                rmax = ez_vmax(rmax, cx.bmax[ix[i]]);
+                rmin = ez_vmin(rmin, cx.bmin[ix[i]]);
+                rightArea[i - l] = half_area2(rmin, rmax);
+            }
+            ez_vec3 lmax = ez_v3(-3.0e38f, -3.0e38f, -3.0e38f), lmin = ez_v3(3.0e38f, 3.0e38f, 3.0e38f);
+            for (int i = l; i <= r - 1; i++) {
+                lmax = ez_vmax(lmax, cx.bmax[ix[i]]);
+                lmin = ez_vmin(lmin, cx.bmin[ix[i]]);
+                const float total = half_area2(lmin, lmax) * (float)(i - l + 1) + rightArea[i + 1 - l] * (float)(r - i);
+                if (total < Cost) { Cost = total; Axis = axis; Split = i; }
+            }
+        }
+    }
+    if (cx.median_depth > 0 && depth >= cx.median_depth) Split = (l + r) / 2;   // coincident triangles: no O(n)-deep chains
+    // children keep the three orders: mark the sides along the split axis, stable-partition the other two
+    for (int i = l; i <= r; i++) cx.side[cx.idx[Axis][i]] = (i > Split) ? 1 : 0;
+    for (int a = 0; a < 3; a++) {
+        if (a == Axis) continue;
+        uint32_t* ix = cx.idx[a];
+        int nl = l, nr = 0;
+        for (int i = l; i <= r; i++) {
+            const uint32_t t = ix[i];
+            if (cx.side[t]) cx.tmp[l + nr++] = t; else ix[nl++] = t;
+        }
+        memcpy(ix + nl, cx.tmp + l, sizeof(uint32_t) * (size_t)nr);
+    }
+    std::vector<EzrtAccelNode> leftNodes, rightNodes;
+    const bool par = (depth < 6) && (cnt > 4096);
+    if (par) {
+        auto fut = std::async(std::launch::async, [&]() { build_accel_presorted(cx, l, Split, leftNodes, depth + 1); });
+        build_accel_presorted(cx, Split + 1, r, rightNodes, depth + 1);
+        fut.get();
+    } else {
+        build_accel_presorted(cx, l, Split, leftNodes, depth + 1);
+        build_accel_presorted(cx, Split + 1, r, rightNodes, depth + 1);
+    }
+    const int lo = 1, ro = 1 + (int)leftNodes.size();   // splice: [this][left block][right block], links relative to this block
+    out[base].left = lo;
+    out[base].right = ro;
+    out.reserve(out.size() + leftNodes.size() + rightNodes.size());
+    for (auto nd : leftNodes) {
+        if (nd.n <= 0) { nd.left += lo; nd.right += lo; }
+        out.push_back(nd);
+    }
+    for (auto nd : rightNodes) {
+        if (nd.n <= 0) { nd.left += ro; nd.right += ro; }
+        out.push_back(nd);
+    }
+}
+}  // namespace
+
 int ezrt_build_accel(const float* tris, int n_tris, int leaf_n, std::vector<EzrtAccelNode>& nodes_out, std::vector<uint32_t>& order) {
-    std::vector<Key> keys(n_tris);
-    std::vector<ez_vec3> bmin(n_tris), bmax(n_tris);
+    std::vector<ez_vec3> bmin(n_tris), bmax(n_tris), cen(n_tris);
     for (int i = 0; i < n_tris; i++) {
         const float* t = tris + (size_t)i * EZRT_TRIANGLE_FLOATS;
         Tri tr;
         tr.p1 = ez_v3(t[0], t[1], t[2]); tr.p2 = ez_v3(t[3], t[4], t[5]); tr.p3 = ez_v3(t[6], t[7], t[8]);
-        ez_vec3 c = centroid(tr);
-        keys[i].cx = c.x; keys[i].cy = c.y; keys[i].cz = c.z; keys[i].id = (unsigned)i;
+        cen[i] = centroid(tr);
         bmin[i] = tri_min(tr);
         bmax[i] = tri_max(tr);
     }
-    FastCtx cx;
-    cx.bmin = &bmin; cx.bmax = &bmax; cx.keys = keys.data(); cx.leaf_n = leaf_n; cx.inf = 3.0e38f;
-    cx.median_depth = 32;   // depth <= 32 + log2(n): the traversal stacks always suffice, the recursion stays shallow
-    std::vector<Node> sub;
-    build_sah_fast(cx, 0, n_tris - 1, sub, 0);
-    nodes_out.resize(sub.size());
-    for (size_t i = 0; i < sub.size(); i++) {
-        EzrtAccelNode& d = nodes_out[i];
-        d.left = sub[i].left; d.right = sub[i].right; d.n = sub[i].n; d.index = sub[i].index;
-        d.AA[0] = sub[i].AA.x; d.AA[1] = sub[i].AA.y; d.AA[2] = sub[i].AA.z;
-        d.BB[0] = sub[i].BB.x; d.BB[1] = sub[i].BB.y; d.BB[2] = sub[i].BB.z;
+    std::vector<uint32_t> idx[3], tmp(n_tris);
+    std::vector<unsigned char> side(n_tris, 0);
+    {
+        std::future<void> f[3];
+        for (int a = 0; a < 3; a++) {
+            idx[a].resize(n_tris);
+            for (int i = 0; i < n_tris; i++) idx[a][i] = (uint32_t)i;
+            f[a] = std::async(std::launch::async, [&, a]() {
+                const ez_vec3* c = cen.data();
+                if (a == 0) std::stable_sort(idx[0].begin(), idx[0].end(), [c](uint32_t p, uint32_t q) { return c[p].x < c[q].x; });
+                if (a == 1) std::stable_sort(idx[1].begin(), idx[1].end(), [c](uint32_t p, uint32_t q) { return c[p].y < c[q].y; });
+                if (a == 2) std::stable_sort(idx[2].begin(), idx[2].end(), [c](uint32_t p, uint32_t q) { return c[p].z < c[q].z; });
+            });
+        }
+        for (int a = 0; a < 3; a++) f[a].get();
     }
-    order.resize(n_tris);
-    for (int i = 0; i < n_tris; i++) order[i] = keys[i].id;
+    PresortCtx cx;
+    cx.bmin = bmin.data(); cx.bmax = bmax.data();
+    cx.idx[0] = idx[0].data(); cx.idx[1] = idx[1].data(); cx.idx[2] = idx[2].data();
+    cx.tmp = tmp.data(); cx.side = side.data();
+    cx.leaf_n = leaf_n;
+    cx.median_depth = 32;   // depth <= 32 + log2(n): the traversal stacks always suffice, the recursion stays shallow
+    nodes_out.clear();
+    build_accel_presorted(cx, 0, n_tris - 1, nodes_out, 0);
+    order = idx[0];
     return (int)nodes_out.size();
 }
 

@@ -14,6 +14,8 @@
 #include "kernels.h"
 
 #include <cstdlib>
+#include <map>
+#include <mutex>
 
 #include "device_functions.cuh"
 
@@ -81,9 +83,8 @@ __global__ void __launch_bounds__(256) k_generate(RenderDev rd, const TileDev* _
         uint32_t seed;
         vec3 o, d;
         primary_ray(rd, px, py, batch_first_frame + fib, seed, o, d);
-        __stcs(q.ray_o + pos, make_float4(o.x, o.y, o.z, 0.0f));
-        __stcs(q.ray_d + pos, make_float4(d.x, d.y, d.z, 0.0f));
-        __stcs(q.meta + pos, make_uint2(seed, slot));
+        __stcs(q.ray_o + pos, make_float4(o.x, o.y, o.z, __uint_as_float(seed)));
+        __stcs(q.ray_d + pos, make_float4(d.x, d.y, d.z, __uint_as_float(slot)));
     }
 }
 
@@ -536,12 +537,11 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
                 slot = i;
                 primary_ray(rd, px, py, batch_first_frame + fib, p.seed, p.o, p.d);
             } else {
-                float4 o4 = __ldcs(qin.ray_o + i), d4 = __ldcs(qin.ray_d + i);
-                uint2 meta = __ldcs(qin.meta + i);
-                slot = meta.y;
+                float4 o4 = __ldcs(qin.ray_o + i), d4 = __ldcs(qin.ray_d + i);   // .w: rng seed / sample slot
+                slot = __float_as_uint(d4.w);
                 p.o = ez_v3(o4.x, o4.y, o4.z);
                 p.d = ez_v3(d4.x, d4.y, d4.z);
-                p.seed = meta.x;
+                p.seed = __float_as_uint(o4.w);
                 slot_pixel(rd, tiles, slot, px, py, fib);
             }
             vec3 lo = splat3(0.0f), le = splat3(0.0f);
@@ -566,11 +566,10 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
         }
         uint32_t pos = block_append(alive, out_count, s_scan);
         if (alive) {
-            __stcs(qout.ray_o + pos, make_float4(p.o.x, p.o.y, p.o.z, 0.0f));
-            __stcs(qout.ray_d + pos, make_float4(p.d.x, p.d.y, p.d.z, 0.0f));
+            __stcs(qout.ray_o + pos, make_float4(p.o.x, p.o.y, p.o.z, __uint_as_float(p.seed)));
+            __stcs(qout.ray_d + pos, make_float4(p.d.x, p.d.y, p.d.z, __uint_as_float(slot)));
             __stcs(qout.hist + pos, make_float4(p.history.x, p.history.y, p.history.z, p.cosine_i));
             __stcs(qout.fr + pos, make_float4(p.f_r.x, p.f_r.y, p.f_r.z, p.pdf));
-            __stcs(qout.meta + pos, make_uint2(p.seed, slot));
         }
         if (MODE == EZRT_MODE_DISNEY_IS_MIS_P5) {
             uint32_t spos = block_append(sh.valid, s_count, s_scan);
@@ -801,10 +800,20 @@ void launch_generate(const RenderDev& rd, const TileDev* tiles, uint32_t n_slots
     int blocks = std::min(div_up(n_slots, 256), n_sms * 8);
     k_generate<<<blocks, 256, 0, st>>>(rd, tiles, n_slots, batch_first_frame, q, q_count);
 }
+// cudaFuncSetAttribute once per (kernel, size): the launchers run for every bounce of every batch
+static void set_dynamic_smem(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<const void*, size_t> done;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = done.find(kernel);
+    if (it != done.end() && it->second == bytes) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    done[kernel] = bytes;
+}
 template <class K>
 static size_t smem_for(K kernel, int top_nodes) {
     size_t bytes = (size_t)top_nodes * EZRT_TOP_STRIDE * sizeof(float4) + (size_t)EZRT_SMEM_STACK * sizeof(int2) * extend_threads();
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bytes, 1024));
+    set_dynamic_smem((const void*)kernel, std::max<size_t>(bytes, 1024));
     return bytes;
 }
 static int persistent_blocks(uint32_t n_max, int n_sms) {
@@ -825,7 +834,7 @@ void launch_extend(const SceneDev& sc, bool prune, bool anyhit, PathQueue q, con
 template <class K>
 static size_t w8_smem_for(K kernel, const SceneDev& sc) {
     size_t bytes = 2048 + (size_t)sc.w8_stack_entries * sizeof(uint2) * extend_threads();
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    set_dynamic_smem((const void*)kernel, bytes);
     return bytes;
 }
 // accel policy: acceleration-tree pass (W8, or the round-1 4-wide kernel when the scene carries no W8 tree), then the
