@@ -91,6 +91,7 @@ struct ezrt_scene {
     size_t max_window_bytes = 0;  // persisting L2 set-aside granted by the device (0 = feature off)
     bool regular_tree = true;  // false: only the literal REFERENCE traversal is valid for the caller's tree
     bool have_accel = true;    // false: no acceleration tree (irregular caller tree, or a degenerate one too deep for the stacks): ACCEL runs as PRUNED
+    int camera_pixel_major = 1;  // camera pass: a warp traces the samples of one pixel (env EZRT_CAMERA_ORDER=frame: an 8x4 block of one frame)
     int sort_rays = 0;  // env EZRT_SORT_RAYS=1 enables the bounce-ray sort (measured: no gain with per-lane refill)
     int tiles_key[4] = {-1, -1, -1, -1};
     std::vector<TileDev> tiles;
@@ -603,6 +604,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         d.cell_scale[k] = (ext > 0.0f) ? 32.0f / ext : 0.0f;
     }
     if (const char* e = getenv("EZRT_SORT_RAYS")) sc->sort_rays = atoi(e);
+    if (const char* e = getenv("EZRT_CAMERA_ORDER")) sc->camera_pixel_major = strcmp(e, "frame") != 0;
     {   // optional L2 persistence for the randomly-accessed tree data (env EZRT_L2_PERSIST=1)
         // measured on C3: -8 % (the set-aside shrinks the L2 left for the streaming queue traffic) -> off by default
         const char* e = getenv("EZRT_L2_PERSIST");
@@ -616,8 +618,10 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.refill_thresh_camera = 0;
     if (const char* e = getenv("EZRT_REFILL_CAM")) d.refill_thresh_camera = std::max(0, std::min(32, atoi(e)));
     d.inner_thresh = 16;
-    d.leaf_thresh = 16;   // round 2 (cheaper leaf passes, S-1M): 16 / chunk 64 measured +3 % over 12 / 32 (profiles/sweep_thresh_r2.txt)
-    d.work_chunk = 64;
+    d.leaf_thresh = 16;   // round 2 (cheaper leaf passes, S-1M): 16 measured +3 % over 12 (profiles/sweep_thresh_r2.txt); chunks: sweep_camera_r2.txt
+    d.work_chunk = 32;
+    d.work_chunk_camera = 64;
+    if (const char* e = getenv("EZRT_CHUNK_CAM")) d.work_chunk_camera = std::max(32, std::min(65536, atoi(e)));
     if (const char* e = getenv("EZRT_CHUNK")) d.work_chunk = std::max(32, std::min(65536, atoi(e)));
     if (const char* e = getenv("EZRT_LEAF_T")) d.leaf_thresh = std::max(1, std::min(33, atoi(e)));
     if (const char* e = getenv("EZRT_REFILL_T")) d.refill_thresh = std::max(1, std::min(32, atoi(e)));
@@ -780,7 +784,7 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
             PathQueue& qin = q[b & 1];
             PathQueue& qout = q[(b + 1) & 1];
             const uint32_t* perm = nullptr;
-            if (b > 0 && s->sort_rays && !accel) {  // optional experiment (exact policies only)
+            if (b > 0 && s->sort_rays) {  // optional experiment
                 sp = s->span_begin(3, st);
                 launch_ray_sort(s->dev, qin, &q_count[b], sort_keys, sort_bins, sort_perm, n_slots, s->n_sms, st);
                 s->span_end(sp, st);
@@ -789,10 +793,11 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
             }
             sp = s->span_begin(0, st);
             if (accel && fused_camera && b == 0) {
-                launch_extend_camera(s->dev, rd, d_tiles, batch_first, n_slots, qin, &w_ext[b], defer_list, &d_ext[b], &dw_ext[b], s->n_sms, count_ptr, st);
+                launch_extend_camera(s->dev, rd, d_tiles, batch_first, n_slots, s->camera_pixel_major ? (uint32_t)nf : 0u, qin, &w_ext[b], defer_list, &d_ext[b], &dw_ext[b],
+                                     s->n_sms, count_ptr, st);
                 s->launches++;
             } else if (accel) {
-                launch_extend_accel(s->dev, qin, &q_count[b], &w_ext[b], defer_list, &d_ext[b], &dw_ext[b], n_slots, s->n_sms, count_ptr, st);
+                launch_extend_accel(s->dev, qin, &q_count[b], &w_ext[b], defer_list, &d_ext[b], &dw_ext[b], n_slots, s->n_sms, count_ptr, perm, st);
                 s->launches++;
             } else {
                 launch_extend(s->dev, prune, false, qin, &q_count[b], &w_ext[b], perm, 0, n_slots, s->n_sms, st);
@@ -1036,7 +1041,7 @@ int ezrt_trace_rays(ezrt_scene* s, int n, const float* origins, const float* dir
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_cnt, counters, sizeof(counters), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         if (traverse == EZRT_TRAVERSE_ACCEL)
-            launch_extend_accel(s->dev, q, d_cnt, d_cnt + 1, d_defer, d_cnt + 2, d_cnt + 3, (uint32_t)n, s->n_sms, nullptr, st);
+            launch_extend_accel(s->dev, q, d_cnt, d_cnt + 1, d_defer, d_cnt + 2, d_cnt + 3, (uint32_t)n, s->n_sms, nullptr, nullptr, st);
         else
             launch_extend(s->dev, traverse != EZRT_TRAVERSE_REFERENCE, any_hit != 0, q, d_cnt, d_cnt + 1, nullptr, 0, (uint32_t)n, s->n_sms, st);
         launch_trace_finish(s->dev, n, q, p3_normal_fudge, traverse == EZRT_TRAVERSE_ACCEL, d_hit, d_dist, d_tri, d_inside, d_point, d_normal, st);

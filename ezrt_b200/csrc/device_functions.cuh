@@ -451,7 +451,8 @@ struct W8Counts {   // COUNT instantiations only (bench.py roofline: records fet
 
 template <bool PRUNE, bool ANYHIT, bool ACCEL, bool WIDE, int LL, bool COUNT, class RayIO>
 __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const TreeView tree, uint32_t n, uint32_t* work, RayIO io,
-                                                  const float4* smem_top, W8Counts counts = W8Counts{nullptr, nullptr}, int refill_override = 0) {
+                                                  const float4* smem_top, W8Counts counts = W8Counts{nullptr, nullptr}, int refill_override = 0,
+                                                  int chunk_override = 0) {
     unsigned long long n_visits = 0, n_tests = 0;
     const int top_nodes = tree.top_nodes;
     const bool tri_na = sc.tri_l1_bypass != 0;
@@ -486,7 +487,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
     int best_tri = -1;
     bool exhausted = false;    // warp-uniform: the work counter has run past n
     uint32_t chunk_pos = 0, chunk_end = 0;  // warp-uniform: this warp's current range of ray indices
-    const uint32_t chunk = (uint32_t)sc.work_chunk;
+    const uint32_t chunk = (uint32_t)(chunk_override ? chunk_override : sc.work_chunk);
 
     while (true) {
         // ---------------- refill idle lanes ----------------

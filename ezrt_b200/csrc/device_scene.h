@@ -74,6 +74,7 @@ struct SceneDev {
     int inner_thresh;
     int leaf_thresh;
     int work_chunk;           // rays a warp takes from the work counter at a time (env EZRT_CHUNK)
+    int work_chunk_camera;    // the same for the camera pass (pixel-major order: 64 = the 16 samples of 4 pixels; env EZRT_CHUNK_CAM)
     float bmin[3];            // scene bounding box (ray-sort cells)
     float cell_scale[3];      // 32 / extent per axis
 };

@@ -229,9 +229,12 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     io.q = q;
     io.perm = perm;
     io.to_accel = to_accel ? sc.ref_to_acc : nullptr;
+    const uint32_t n = *q_count;
+    if (blockIdx.x * blockDim.x >= n) return;   // nothing for this block (the pass over an accel kernel's deferred rays is usually empty):
+                                                // do not stage 80 KB of tree for it
     const TreeView tree = reference_tree(sc);
     stage_top_nodes(tree);
-    extend_persistent<PRUNE, ANYHIT, false, false, 8, false>(sc, tree, *q_count, work, io, g_smem_top);
+    extend_persistent<PRUNE, ANYHIT, false, false, 8, false>(sc, tree, n, work, io, g_smem_top);
 }
 
 // ---- accel kernels: the device's own SAH tree finds the global closest hit G; the result is kept when
@@ -274,9 +277,11 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     io.sq = sq;
     io.Lo = Lo;
     io.perm = perm;
+    const uint32_t n = *s_count;
+    if (blockIdx.x * blockDim.x >= n) return;
     const TreeView tree = reference_tree(sc);
     stage_top_nodes(tree);
-    extend_persistent<PRUNE, true, false, false, 8, false>(sc, tree, *s_count, work, io, g_smem_top);
+    extend_persistent<PRUNE, true, false, false, 8, false>(sc, tree, n, work, io, g_smem_top);
 }
 
 // ---- accel kernels: the device's own tree (4-wide exact boxes: extend_persistent<ACCEL, WIDE>; or W8: extend_w8 on the
@@ -303,19 +308,21 @@ struct AccelExtendIO {
     const float4* leaf_box;
     uint32_t* defer_list;
     uint32_t* defer_count;
+    const uint32_t* perm;      // non-null (env EZRT_SORT_RAYS=1, experiment): trace the queue entries in this order
     __device__ __forceinline__ bool load(uint32_t i, vec3& o, vec3& d) const {
-        float4 o4 = __ldcs(q.ray_o + i), d4 = __ldcs(q.ray_d + i);
+        const uint32_t j = perm ? perm[i] : i;
+        float4 o4 = __ldcs(q.ray_o + j), d4 = __ldcs(q.ray_d + j);
         o = ez_v3(o4.x, o4.y, o4.z);
         d = ez_v3(d4.x, d4.y, d4.z);
         return true;
     }
-    __device__ __forceinline__ void defer(uint32_t i, vec3, vec3) const { defer_list[atomicAdd(defer_count, 1u)] = i; }
+    __device__ __forceinline__ void defer(uint32_t i, vec3, vec3) const { defer_list[atomicAdd(defer_count, 1u)] = perm ? perm[i] : i; }
     __device__ __forceinline__ void store(uint32_t i, HitRec h, bool tie, vec3 o, vec3 d, vec3 inv) const {
         if (h.tri >= 0 && (tie || !reference_reaches_leaf_inv(acc_tri_leaf, leaf_box, h.tri, o, inv))) {
             defer(i, o, d);
             return;
         }
-        __stcs(q.hit + i, make_float2(h.t, __int_as_float(h.tri)));  // accel-order triangle index
+        __stcs(q.hit + (perm ? perm[i] : i), make_float2(h.t, __int_as_float(h.tri)));  // accel-order triangle index
     }
 };
 
@@ -327,34 +334,46 @@ struct AccelCameraIO {
     RenderDev rd;
     const TileDev* tiles;
     uint32_t batch_first_frame;
+    uint32_t n_frames;       // frames of this batch; 0: trace the slots in slot order (frame-major)
+    uint32_t per_frame;      // sample slots per frame
     PathQueue q;
     const int* acc_tri_leaf;
     const float4* leaf_box;
     uint32_t* defer_list;
     uint32_t* defer_count;
+    // Work index -> sample slot.  Pixel-major order: consecutive work items are the n_frames samples of ONE pixel -- camera rays
+    // that differ only by their sub-pixel jitter (P5/fsh:923) -- so the 32 rays of a warp walk the same nodes and hit the same
+    // triangles almost always (frame-major order gives a warp an 8x4 pixel block of one frame, which splits at every silhouette).
+    __device__ __forceinline__ uint32_t slot_of(uint32_t i) const {
+        if (n_frames == 0u) return i;
+        const uint32_t p = i / n_frames;
+        return (i - p * n_frames) * per_frame + p;
+    }
     __device__ __forceinline__ bool load(uint32_t i, vec3& o, vec3& d) const {
         uint32_t px, py, fib, seed;
-        if (!slot_pixel(rd, tiles, i, px, py, fib)) return false;
+        if (!slot_pixel(rd, tiles, slot_of(i), px, py, fib)) return false;
         primary_ray(rd, px, py, batch_first_frame + fib, seed, o, d);
         return true;
     }
-    __device__ __forceinline__ void defer(uint32_t i, vec3 o, vec3 d) const {
-        q.ray_o[i] = make_float4(o.x, o.y, o.z, 0.0f);
-        q.ray_d[i] = make_float4(d.x, d.y, d.z, 0.0f);
-        defer_list[atomicAdd(defer_count, 1u)] = i;
+    __device__ __forceinline__ void defer_slot(uint32_t slot, vec3 o, vec3 d) const {
+        q.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
+        q.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
+        defer_list[atomicAdd(defer_count, 1u)] = slot;
     }
+    __device__ __forceinline__ void defer(uint32_t i, vec3 o, vec3 d) const { defer_slot(slot_of(i), o, d); }
     __device__ __forceinline__ void store(uint32_t i, HitRec h, bool tie, vec3 o, vec3 d, vec3 inv) const {
+        const uint32_t slot = slot_of(i);
         if (h.tri >= 0 && (tie || !reference_reaches_leaf_inv(acc_tri_leaf, leaf_box, h.tri, o, inv))) {
-            defer(i, o, d);
+            defer_slot(slot, o, d);
             return;
         }
-        __stcs(q.hit + i, make_float2(h.t, __int_as_float(h.tri)));
+        __stcs(q.hit + slot, make_float2(h.t, __int_as_float(h.tri)));
     }
 };
 
 template <bool COUNT>
 __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend_w8_camera(SceneDev sc, RenderDev rd, const TileDev* __restrict__ tiles,
-                                                                   uint32_t batch_first_frame, uint32_t n_slots, PathQueue q, uint32_t* work,
+                                                                   uint32_t batch_first_frame, uint32_t n_slots, uint32_t n_frames, PathQueue q, uint32_t* work,
                                                                    uint32_t* defer_list, uint32_t* defer_count, W8Counts counts) {
     unsigned char* s_perm;
     uint2* stack_sm;
@@ -363,6 +382,8 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     io.rd = rd;
     io.tiles = tiles;
     io.batch_first_frame = batch_first_frame;
+    io.n_frames = n_frames;
+    io.per_frame = (uint32_t)rd.n_tiles * EZRT_TILE_PIXELS;
     io.q = q;
     io.acc_tri_leaf = sc.acc_tri_leaf;
     io.leaf_box = sc.leaf_box;
@@ -373,7 +394,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
 
 template <bool COUNT>
 __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend_w8(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count, uint32_t* work,
-                                                                   uint32_t* defer_list, uint32_t* defer_count, W8Counts counts) {
+                                                                   uint32_t* defer_list, uint32_t* defer_count, W8Counts counts, const uint32_t* __restrict__ perm) {
     unsigned char* s_perm;
     uint2* stack_sm;
     w8_smem_setup(s_perm, stack_sm);
@@ -383,6 +404,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     io.leaf_box = sc.leaf_box;
     io.defer_list = defer_list;
     io.defer_count = defer_count;
+    io.perm = perm;
     extend_w8<false, COUNT>(sc, *q_count, work, io, s_perm, stack_sm, counts);
 }
 
@@ -424,29 +446,32 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
 // ---- the same three passes on the 4-wide exact-box tree (default form, env EZRT_ACCEL): extend_persistent<ACCEL, WIDE>
 template <bool COUNT>
 __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend_accel(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count, uint32_t* work,
-                                                                      uint32_t* defer_list, uint32_t* defer_count, W8Counts counts) {
+                                                                      uint32_t* defer_list, uint32_t* defer_count, W8Counts counts, const uint32_t* __restrict__ perm) {
     AccelExtendIO io;
     io.q = q;
     io.acc_tri_leaf = sc.acc_tri_leaf;
     io.leaf_box = sc.leaf_box;
     io.defer_list = defer_list;
     io.defer_count = defer_count;
+    io.perm = perm;
     extend_persistent<true, false, true, true, 4, COUNT>(sc, accel_tree(sc), *q_count, work, io, g_smem_top, counts);
 }
 template <bool COUNT>
 __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend_accel_camera(SceneDev sc, RenderDev rd, const TileDev* __restrict__ tiles,
-                                                                      uint32_t batch_first_frame, uint32_t n_slots, PathQueue q, uint32_t* work,
+                                                                      uint32_t batch_first_frame, uint32_t n_slots, uint32_t n_frames, PathQueue q, uint32_t* work,
                                                                       uint32_t* defer_list, uint32_t* defer_count, W8Counts counts) {
     AccelCameraIO io;
     io.rd = rd;
     io.tiles = tiles;
     io.batch_first_frame = batch_first_frame;
+    io.n_frames = n_frames;
+    io.per_frame = (uint32_t)rd.n_tiles * EZRT_TILE_PIXELS;
     io.q = q;
     io.acc_tri_leaf = sc.acc_tri_leaf;
     io.leaf_box = sc.leaf_box;
     io.defer_list = defer_list;
     io.defer_count = defer_count;
-    extend_persistent<true, false, true, true, 4, COUNT>(sc, accel_tree(sc), n_slots, work, io, g_smem_top, counts, sc.refill_thresh_camera);
+    extend_persistent<true, false, true, true, 4, COUNT>(sc, accel_tree(sc), n_slots, work, io, g_smem_top, counts, sc.refill_thresh_camera, sc.work_chunk_camera);
 }
 template <bool COUNT>
 __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_shadow_accel(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count, uint32_t* work,
@@ -840,20 +865,21 @@ static size_t w8_smem_for(K kernel, const SceneDev& sc) {
 // accel policy: acceleration-tree pass (W8, or the round-1 4-wide kernel when the scene carries no W8 tree), then the
 // exact pass over whatever it deferred.  counts != null selects the counting instantiation (params.profile = 2).
 void launch_extend_accel(const SceneDev& sc, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t* defer_list,
-                         uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, unsigned long long* counts, cudaStream_t st) {
+                         uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, unsigned long long* counts, const uint32_t* perm,
+                         cudaStream_t st) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
     if (sc.w8_nodes) {
         W8Counts c;
         c.node_visits = counts;
         c.tri_tests = counts ? counts + 1 : nullptr;
-        if (counts) k_extend_w8<true><<<blocks, threads, w8_smem_for(k_extend_w8<true>, sc), st>>>(sc, q, q_count, work, defer_list, defer_count, c);
-        else k_extend_w8<false><<<blocks, threads, w8_smem_for(k_extend_w8<false>, sc), st>>>(sc, q, q_count, work, defer_list, defer_count, c);
+        if (counts) k_extend_w8<true><<<blocks, threads, w8_smem_for(k_extend_w8<true>, sc), st>>>(sc, q, q_count, work, defer_list, defer_count, c, perm);
+        else k_extend_w8<false><<<blocks, threads, w8_smem_for(k_extend_w8<false>, sc), st>>>(sc, q, q_count, work, defer_list, defer_count, c, perm);
     } else {
         W8Counts c;
         c.node_visits = counts;
         c.tri_tests = counts ? counts + 1 : nullptr;
-        if (counts) k_extend_accel<true><<<blocks, threads, smem_for(k_extend_accel<true>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count, c);
-        else k_extend_accel<false><<<blocks, threads, smem_for(k_extend_accel<false>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count, c);
+        if (counts) k_extend_accel<true><<<blocks, threads, smem_for(k_extend_accel<true>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count, c, perm);
+        else k_extend_accel<false><<<blocks, threads, smem_for(k_extend_accel<false>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count, c, perm);
     }
     launch_extend(sc, true, false, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_max, 65536u), n_sms, st);
 }
@@ -873,7 +899,7 @@ void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_
     else k_shadow<false><<<blocks, threads, smem_for(k_shadow<false>, sc.top_nodes), st>>>(sc, sq, s_count, work, Lo, perm);
 }
 // camera pass of the W8 policy: rays generated in the kernel (slot i = ray i), then the exact pass over the deferred ones
-void launch_extend_camera(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, uint32_t batch_first_frame, uint32_t n_slots, PathQueue q,
+void launch_extend_camera(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, uint32_t batch_first_frame, uint32_t n_slots, uint32_t n_frames, PathQueue q,
                           uint32_t* work, uint32_t* defer_list, uint32_t* defer_count, uint32_t* defer_work, int n_sms, unsigned long long* counts,
                           cudaStream_t st) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_slots, n_sms);
@@ -881,11 +907,11 @@ void launch_extend_camera(const SceneDev& sc, const RenderDev& rd, const TileDev
     c.node_visits = counts;
     c.tri_tests = counts ? counts + 1 : nullptr;
     if (sc.w8_nodes) {
-        if (counts) k_extend_w8_camera<true><<<blocks, threads, w8_smem_for(k_extend_w8_camera<true>, sc), st>>>(sc, rd, tiles, batch_first_frame, n_slots, q, work, defer_list, defer_count, c);
-        else k_extend_w8_camera<false><<<blocks, threads, w8_smem_for(k_extend_w8_camera<false>, sc), st>>>(sc, rd, tiles, batch_first_frame, n_slots, q, work, defer_list, defer_count, c);
+        if (counts) k_extend_w8_camera<true><<<blocks, threads, w8_smem_for(k_extend_w8_camera<true>, sc), st>>>(sc, rd, tiles, batch_first_frame, n_slots, n_frames, q, work, defer_list, defer_count, c);
+        else k_extend_w8_camera<false><<<blocks, threads, w8_smem_for(k_extend_w8_camera<false>, sc), st>>>(sc, rd, tiles, batch_first_frame, n_slots, n_frames, q, work, defer_list, defer_count, c);
     } else {
-        if (counts) k_extend_accel_camera<true><<<blocks, threads, smem_for(k_extend_accel_camera<true>, 0), st>>>(sc, rd, tiles, batch_first_frame, n_slots, q, work, defer_list, defer_count, c);
-        else k_extend_accel_camera<false><<<blocks, threads, smem_for(k_extend_accel_camera<false>, 0), st>>>(sc, rd, tiles, batch_first_frame, n_slots, q, work, defer_list, defer_count, c);
+        if (counts) k_extend_accel_camera<true><<<blocks, threads, smem_for(k_extend_accel_camera<true>, 0), st>>>(sc, rd, tiles, batch_first_frame, n_slots, n_frames, q, work, defer_list, defer_count, c);
+        else k_extend_accel_camera<false><<<blocks, threads, smem_for(k_extend_accel_camera<false>, 0), st>>>(sc, rd, tiles, batch_first_frame, n_slots, n_frames, q, work, defer_list, defer_count, c);
     }
     launch_extend(sc, true, false, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_slots, 65536u), n_sms, st);
 }
