@@ -79,7 +79,7 @@ struct ezrt_scene {
     int n_sms = 148;
     SceneDev dev{};
     DeviceBuffer nodes, tri_geo, tri_shade, materials, hdr, hdr_cache;
-    DeviceBuffer acc_hot, acc_tri_ref, tri_leaf, leaf_box, defer_buf, acc_tri_leaf, ref_to_acc, acc_wide;   // acc_hot = W8 nodes | geometry | shading records of the accel order
+    DeviceBuffer acc_hot, acc_tri_ref, tri_leaf, leaf_box, defer_buf, acc_tri_leaf, ref_to_acc, acc_wide, acc_wide_q16;   // acc_hot = W8 nodes | geometry | shading records of the accel order
     int acc_depth = 0;
     int n_materials = 0;
     int tree_depth = 0;
@@ -393,7 +393,8 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     // dropped: the scene then renders with the PRUNED policy on the caller's tree, as for an irregular tree.
     const float prune_delta = max_abs * 1.52587890625e-05f;  // 2^-16 * scene extent
     std::vector<float4> acc_geo((size_t)n_triangles * 4), acc_wide;
-    std::vector<uint32_t> w8_words;
+    std::vector<uint32_t> w8_words, acc_wide_q;
+    bool q16_ok = true;
     int acc_wide_root = 0;
     std::vector<uint32_t> acc_order;
     int acc_depth = 0, w8_depth = 0, w8_near_bit[3] = {0, 1, 2};
@@ -440,6 +441,9 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
                     return x * y + x * z + y * z;
                 };
                 int wide_depth = 0;
+                const char* qe = getenv("EZRT_ACCEL_Q16");
+                const bool want_q16 = !(qe && atoi(qe) == 0);
+                const double q16_min_step = (double)max_abs * (double)W8_MIN_STEP_REL;
                 std::function<int(int, int)> build_wide = [&](int b, int depth) -> int {
                     wide_depth = std::max(wide_depth, depth);
                     const int id = (int)(acc_wide.size() / 8);
@@ -481,11 +485,46 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
                     memcpy(&rec[24], refs, 16);
                     for (int k = 24 + 4; k < 32; k++) rec[k] = 0.0f;
                     memcpy(&acc_wide[(size_t)id * 8], rec, sizeof(rec));
+                    if (want_q16) {   // the same node with 16-bit planes (device_functions.cuh "Q16"): 96 bytes
+                        uint32_t w[24];
+                        memset(w, 0, sizeof(w));
+                        for (int a = 0; a < 3; a++) {
+                            double nlo = 3.0e38, nhi = -3.0e38;
+                            for (int k = 0; k < cnt; k++) {
+                                nlo = std::min(nlo, (double)an[ch[k]].AA[a] - (double)pad);
+                                nhi = std::max(nhi, (double)an[ch[k]].BB[a] + (double)pad);
+                            }
+                            int e;
+                            frexp(std::max((nhi - nlo) / 65000.0, 1.0e-300), &e);
+                            double sc = ldexp(1.0, e);
+                            while (sc < q16_min_step) sc *= 2.0;
+                            float org = (float)(nlo - 2.0 * sc);
+                            while ((double)org > nlo - 2.0 * sc) org = nextafterf(org, -3.0e38f);
+                            const float scf = (float)sc;
+                            memcpy(&w[a], &org, 4);
+                            memcpy(&w[3 + a], &scf, 4);
+                            for (int k = 0; k < 4; k++) {
+                                uint32_t ql = 65535u, qh = 65535u;   // absent: a point at the far corner of the grid, outside every real child
+                                if (k < cnt) {
+                                    const double lo = (double)an[ch[k]].AA[a] - (double)pad, hi = (double)an[ch[k]].BB[a] + (double)pad;
+                                    const double l = floor((lo - (double)org) / sc - 1.25), h = ceil((hi - (double)org) / sc + 1.25);
+                                    if (l < 0.0 || h > 65534.0 || l > h) q16_ok = false;
+                                    ql = (uint32_t)std::max(0.0, l);
+                                    qh = (uint32_t)std::min(65535.0, h);
+                                }
+                                w[6 + 3 * k + a] = ql | (qh << 16);
+                            }
+                        }
+                        for (int k = 0; k < 4; k++) w[18 + k] = (k < cnt) ? (uint32_t)refs[k] : (EZRT_LEAF_FLAG | (1u << 7));  // absent: an empty leaf, should the point ever be hit
+                        if (acc_wide_q.size() < ((size_t)id + 1) * 24) acc_wide_q.resize(((size_t)id + 1) * 24, 0u);
+                        memcpy(&acc_wide_q[(size_t)id * 24], w, sizeof(w));
+                    }
                     return id;
                 };
                 acc_wide_root = build_wide(0, 1);
                 acc_depth = wide_depth;
                 if (3 * wide_depth + 2 > EZRT_ACCEL_STACK) { acc_wide.clear(); have_accel = false; }  // too deep for the traversal stack
+                if (!want_q16 || !q16_ok || !have_accel) acc_wide_q.clear();
             }
         }
         if (!have_accel) {
@@ -546,6 +585,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     }
     if (!rc) rc = upload(sc->acc_tri_ref, acc_order.data(), acc_order.size() * sizeof(uint32_t));
     if (!rc && !acc_wide.empty()) rc = upload(sc->acc_wide, acc_wide.data(), acc_wide.size() * sizeof(float4));
+    if (!rc && !acc_wide_q.empty()) rc = upload(sc->acc_wide_q16, acc_wide_q.data(), acc_wide_q.size() * sizeof(uint32_t));
     if (!rc) rc = upload(sc->tri_leaf, tri_leaf.data(), tri_leaf.size() * sizeof(int));
     if (!rc) rc = upload(sc->leaf_box, leaf_box.data(), leaf_box.size() * sizeof(float4));
     if (!rc) rc = upload(sc->acc_tri_leaf, acc_leaf.data(), acc_leaf.size() * sizeof(int));
@@ -583,6 +623,8 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.acc_tri_ref = (const uint32_t*)sc->acc_tri_ref.p;
     d.acc_wide_nodes = acc_wide.empty() ? nullptr : (const float4*)sc->acc_wide.p;
     d.acc_wide_root_ref = acc_wide_root;
+    d.acc_wide_q16 = acc_wide_q.empty() ? nullptr : (const uint4*)sc->acc_wide_q16.p;
+    d.q16_decode_bits = 0x4B000000u;
     d.tri_l1_bypass = ((size_t)n_triangles * 64 > ((size_t)4 << 20)) ? 1 : 0;  // > 4 MB of triangle records: stream them past L1
     if (const char* e = getenv("EZRT_TRI_L1_BYPASS")) d.tri_l1_bypass = atoi(e) != 0;
     d.acc_tri_shade = (const float4*)((const char*)sc->acc_hot.p + acc_nodes_bytes + acc_geo_bytes);
@@ -636,7 +678,7 @@ int ezrt_scene_destroy(ezrt_scene* s) {
     s->nodes.release(); s->tri_geo.release(); s->tri_shade.release(); s->materials.release();
     s->hdr.release(); s->hdr_cache.release(); s->tiles_buf.release();
     s->acc_hot.release(); s->acc_tri_ref.release(); s->tri_leaf.release(); s->leaf_box.release(); s->defer_buf.release();
-    s->acc_tri_leaf.release(); s->ref_to_acc.release(); s->acc_wide.release();
+    s->acc_tri_leaf.release(); s->ref_to_acc.release(); s->acc_wide.release(); s->acc_wide_q16.release();
     s->queue_buf[0].release(); s->queue_buf[1].release(); s->shadow_buf.release();
     s->lo_buf.release(); s->le_buf.release(); s->counters_buf.release(); s->totals_buf.release(); s->fb_buf.release(); s->sort_buf.release();
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -887,7 +929,7 @@ int ezrt_get_counters(ezrt_scene* s, ezrt_counters* out) {
     out->deferred_rays = t[4];
     out->node_visits = t[5];
     out->tri_tests = t[6];
-    out->node_record_bytes = s->dev.w8_nodes ? W8_NODE_BYTES : (s->dev.acc_wide_nodes ? 128 : 64);
+    out->node_record_bytes = s->dev.w8_nodes ? W8_NODE_BYTES : (s->dev.acc_wide_q16 ? 96 : (s->dev.acc_wide_nodes ? 128 : 64));   // Q16: the camera pass reads the 128-byte form
     out->tri_record_bytes = 64;
     float ms = 0.0f;
     CU_CHECK(cudaEventElapsedTime(&ms, s->ev_start, s->ev_stop));

@@ -248,6 +248,53 @@ __device__ __forceinline__ WideVisit wide_visit(const float4* __restrict__ nd, c
     v.r0 = refs.x; v.r1 = refs.y; v.r2 = refs.z; v.r3 = refs.w;
     return v;
 }
+// ---- the same node with 16-bit quantised planes (96 B = three 256-bit loads instead of 3.5; DESIGN.md section 4, "Q16"):
+//   w0..2 origin.xyz   w3..5 scale.xyz (powers of two)   w6 + 3 c + a : child c, axis a, (lo | hi << 16)   w18..21 references
+// plane = origin + q * scale, stored floor(x - 1.25) / ceil(x + 1.25) steps: supersets of the exact boxes under the decode
+//   t = fma(as_float(0x4B000000 | q), scale * inv_d, fma(-2^23, scale * inv_d, (origin - o) * inv_d))
+// (error bound as in w8_node.h with the A term rounded at magnitude 2^23 * B: half a step; the builder keeps scale >=
+// W8_MIN_STEP_REL * max|coordinate|).  The bounce / shadow launches are bound by the L1 gather rate, and a 96-byte record is
+// gathered at 97 G/s against 52 G/s for the 128-byte one (profiles/gather_peak_r2.json); the decode costs ~24 instructions.
+__device__ __forceinline__ void q16_axis(uint32_t w, uint32_t bias, float B, float A, float& lo, float& hi) {
+    uint32_t fh;
+    asm("prmt.b32 %0, %1, %2, 0x7532;" : "=r"(fh) : "r"(w), "r"(bias));           // (w >> 16) | 0x4B000000
+    lo = __fmaf_rn(__uint_as_float((w & 0xffffu) | bias), B, A);
+    hi = __fmaf_rn(__uint_as_float(fh), B, A);
+}
+__device__ __forceinline__ float q16_child(uint32_t wx, uint32_t wy, uint32_t wz, uint32_t bias, float Bx, float By, float Bz, float Ax, float Ay, float Az,
+                                           float limit) {
+    float lx, hx, ly, hy, lz, hz;
+    q16_axis(wx, bias, Bx, Ax, lx, hx);
+    q16_axis(wy, bias, By, Ay, ly, hy);
+    q16_axis(wz, bias, Bz, Az, lz, hz);
+    const float t0 = fmaxf(fminf(hx, lx), fminf(hy, ly)), t1 = fminf(fmaxf(hx, lx), fmaxf(hy, ly));
+    return wide_key(t0, t1, lz, hz, limit);
+}
+__device__ __forceinline__ WideVisit wide_visit_q16(const uint4* __restrict__ nd, vec3 o, const RaySlab& rs, float limit, uint32_t bias) {
+    ulonglong2 a, b;
+    ldg256_b64(nd, a, b);
+    const uint32_t w0 = (uint32_t)a.x, w1 = (uint32_t)(a.x >> 32), w2 = (uint32_t)a.y, w3 = (uint32_t)(a.y >> 32);
+    const uint32_t w4 = (uint32_t)b.x, w5 = (uint32_t)(b.x >> 32), w6 = (uint32_t)b.y, w7 = (uint32_t)(b.y >> 32);
+    ldg256_b64(nd + 2, a, b);
+    const uint32_t w8 = (uint32_t)a.x, w9 = (uint32_t)(a.x >> 32), w10 = (uint32_t)a.y, w11 = (uint32_t)(a.y >> 32);
+    const uint32_t w12 = (uint32_t)b.x, w13 = (uint32_t)(b.x >> 32), w14 = (uint32_t)b.y, w15 = (uint32_t)(b.y >> 32);
+    ldg256_b64(nd + 4, a, b);
+    const uint32_t w16 = (uint32_t)a.x, w17 = (uint32_t)(a.x >> 32);
+    float ix, iy, iz, iz2;
+    pk2_split(rs.inv_xy, ix, iy);
+    pk2_split(rs.inv_zz, iz, iz2);
+    const float Bx = __uint_as_float(w3) * ix, By = __uint_as_float(w4) * iy, Bz = __uint_as_float(w5) * iz;
+    const float Ax = __fmaf_rn(-8388608.0f, Bx, (__uint_as_float(w0) - o.x) * ix);
+    const float Ay = __fmaf_rn(-8388608.0f, By, (__uint_as_float(w1) - o.y) * iy);
+    const float Az = __fmaf_rn(-8388608.0f, Bz, (__uint_as_float(w2) - o.z) * iz);
+    WideVisit v;
+    v.k0 = q16_child(w6, w7, w8, bias, Bx, By, Bz, Ax, Ay, Az, limit);
+    v.k1 = q16_child(w9, w10, w11, bias, Bx, By, Bz, Ax, Ay, Az, limit);
+    v.k2 = q16_child(w12, w13, w14, bias, Bx, By, Bz, Ax, Ay, Az, limit);
+    v.k3 = q16_child(w15, w16, w17, bias, Bx, By, Bz, Ax, Ay, Az, limit);
+    v.r0 = (int)a.y; v.r1 = (int)(a.y >> 32); v.r2 = (int)b.x; v.r3 = (int)(b.x >> 32);
+    return v;
+}
 __device__ __forceinline__ void cswap(float& ka, int& ra, float& kb, int& rb) {  // ascending by key
     const bool sw = kb < ka;
     const float tk = sw ? kb : ka, uk = sw ? ka : kb;
@@ -449,7 +496,7 @@ struct W8Counts {   // COUNT instantiations only (bench.py roofline: records fet
     unsigned long long* tri_tests;
 };
 
-template <bool PRUNE, bool ANYHIT, bool ACCEL, bool WIDE, int LL, bool COUNT, class RayIO>
+template <bool PRUNE, bool ANYHIT, bool ACCEL, bool WIDE, int LL, bool COUNT, bool Q16, class RayIO>
 __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const TreeView tree, uint32_t n, uint32_t* work, RayIO io,
                                                   const float4* smem_top, W8Counts counts = W8Counts{nullptr, nullptr}, int refill_override = 0,
                                                   int chunk_override = 0) {
@@ -509,7 +556,12 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                     inv = ez_v3(EZ_DIV(1.0f, d.x), EZ_DIV(1.0f, d.y), EZ_DIV(1.0f, d.z));
                     float ax = ez_abs(inv.x), ay = ez_abs(inv.y), az = ez_abs(inv.z);
                     slack = sc.prune_delta * ez_max(ax, ez_max(ay, az));
-                    if ((ax < 3.0e38f) && (ay < 3.0e38f) && (az < 3.0e38f)) {
+                    bool traceable = (ax < 3.0e38f) && (ay < 3.0e38f) && (az < 3.0e38f);
+                    if (Q16) {   // the quantised planes are conservative only within the decode error bound (w8_node.h): the rest goes to the exact kernel
+                        const float ao = fmaxf(ez_abs(o.x), fmaxf(ez_abs(o.y), ez_abs(o.z)));
+                        traceable = traceable && (fmaxf(ax, fmaxf(ay, az)) <= W8_INV_LIMIT) && (fminf(ax, fminf(ay, az)) >= W8_INV_MIN) && (ao <= sc.w8_origin_limit);
+                    }
+                    if (traceable) {
                         rs = make_ray_slab(o, inv);
                         ray = (int)idx;
                         ref = tree.root_ref;
@@ -553,7 +605,8 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                 if (WIDE) {
                     if (at_inner) {  // 4-wide acceleration-tree node: nearest child next, the others pushed far-to-near
                         const float limit = best + (best * 0.000244140625f + slack);
-                        const WideVisit w = wide_visit(tree.nodes + (size_t)ref * 8, rs, limit);
+                        const WideVisit w = Q16 ? wide_visit_q16(sc.acc_wide_q16 + (size_t)ref * 6, o, rs, limit, sc.q16_decode_bits)
+                                                : wide_visit(tree.nodes + (size_t)ref * 8, rs, limit);
                         if (COUNT) n_visits++;
 #if EZRT_WIDE_SORT
                         WideVisit v = w;

@@ -61,6 +61,8 @@ struct SceneDev {
     float w8_origin_limit;         // rays starting further out than this (any |coordinate|) go to the exact kernel (decode error bound)
     const float4* acc_wide_nodes;  // 4-wide nodes with exact boxes (128 B records): the default accel form (env EZRT_ACCEL=8 selects W8 instead)
     int acc_wide_root_ref;
+    const uint4* acc_wide_q16;     // the same 4-wide nodes with 16-bit quantised planes (96 B records, same numbering): bounce / shadow launches
+    uint32_t q16_decode_bits;      // 0x4B000000, passed as data so that it stays in a register (see w8_plane)
     // reference leaf of every reference triangle + the leaves' boxes (AA, BB as float4 pairs)
     const int* tri_leaf;
     const float4* leaf_box;

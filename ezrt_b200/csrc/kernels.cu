@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
                                                 // do not stage 80 KB of tree for it
     const TreeView tree = reference_tree(sc);
     stage_top_nodes(tree);
-    extend_persistent<PRUNE, ANYHIT, false, false, 8, false>(sc, tree, n, work, io, g_smem_top);
+    extend_persistent<PRUNE, ANYHIT, false, false, 8, false, false>(sc, tree, n, work, io, g_smem_top);
 }
 
 // ---- accel kernels: the device's own SAH tree finds the global closest hit G; the result is kept when
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     if (blockIdx.x * blockDim.x >= n) return;
     const TreeView tree = reference_tree(sc);
     stage_top_nodes(tree);
-    extend_persistent<PRUNE, true, false, false, 8, false>(sc, tree, n, work, io, g_smem_top);
+    extend_persistent<PRUNE, true, false, false, 8, false, false>(sc, tree, n, work, io, g_smem_top);
 }
 
 // ---- accel kernels: the device's own tree (4-wide exact boxes: extend_persistent<ACCEL, WIDE>; or W8: extend_w8 on the
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
 }
 
 // ---- the same three passes on the 4-wide exact-box tree (default form, env EZRT_ACCEL): extend_persistent<ACCEL, WIDE>
-template <bool COUNT>
+template <bool COUNT, bool Q16>
 __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend_accel(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count, uint32_t* work,
                                                                       uint32_t* defer_list, uint32_t* defer_count, W8Counts counts, const uint32_t* __restrict__ perm) {
     AccelExtendIO io;
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     io.defer_list = defer_list;
     io.defer_count = defer_count;
     io.perm = perm;
-    extend_persistent<true, false, true, true, 4, COUNT>(sc, accel_tree(sc), *q_count, work, io, g_smem_top, counts);
+    extend_persistent<true, false, true, true, 4, COUNT, Q16>(sc, accel_tree(sc), *q_count, work, io, g_smem_top, counts);
 }
 template <bool COUNT>
 __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend_accel_camera(SceneDev sc, RenderDev rd, const TileDev* __restrict__ tiles,
@@ -471,9 +471,9 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     io.leaf_box = sc.leaf_box;
     io.defer_list = defer_list;
     io.defer_count = defer_count;
-    extend_persistent<true, false, true, true, 4, COUNT>(sc, accel_tree(sc), n_slots, work, io, g_smem_top, counts, sc.refill_thresh_camera, sc.work_chunk_camera);
+    extend_persistent<true, false, true, true, 4, COUNT, false>(sc, accel_tree(sc), n_slots, work, io, g_smem_top, counts, sc.refill_thresh_camera, sc.work_chunk_camera);
 }
-template <bool COUNT>
+template <bool COUNT, bool Q16>
 __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_shadow_accel(SceneDev sc, ShadowQueue sq, const uint32_t* __restrict__ s_count, uint32_t* work,
                                                                       float4* __restrict__ Lo, uint32_t* defer_list, uint32_t* defer_count, W8Counts counts) {
     AccelShadowIO io;
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
     io.leaf_box = sc.leaf_box;
     io.defer_list = defer_list;
     io.defer_count = defer_count;
-    extend_persistent<true, true, true, true, 4, COUNT>(sc, accel_tree(sc), *s_count, work, io, g_smem_top, counts);
+    extend_persistent<true, true, true, true, 4, COUNT, Q16>(sc, accel_tree(sc), *s_count, work, io, g_smem_top, counts);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -878,8 +878,14 @@ void launch_extend_accel(const SceneDev& sc, PathQueue q, const uint32_t* q_coun
         W8Counts c;
         c.node_visits = counts;
         c.tri_tests = counts ? counts + 1 : nullptr;
-        if (counts) k_extend_accel<true><<<blocks, threads, smem_for(k_extend_accel<true>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count, c, perm);
-        else k_extend_accel<false><<<blocks, threads, smem_for(k_extend_accel<false>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count, c, perm);
+        // incoherent rays: the 96-byte quantised form of the nodes when the scene carries it (env EZRT_ACCEL_Q16=0: exact nodes)
+        if (sc.acc_wide_q16) {
+            if (counts) k_extend_accel<true, true><<<blocks, threads, smem_for(k_extend_accel<true, true>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count, c, perm);
+            else k_extend_accel<false, true><<<blocks, threads, smem_for(k_extend_accel<false, true>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count, c, perm);
+        } else {
+            if (counts) k_extend_accel<true, false><<<blocks, threads, smem_for(k_extend_accel<true, false>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count, c, perm);
+            else k_extend_accel<false, false><<<blocks, threads, smem_for(k_extend_accel<false, false>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count, c, perm);
+        }
     }
     launch_extend(sc, true, false, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_max, 65536u), n_sms, st);
 }
@@ -928,8 +934,13 @@ void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_c
         W8Counts c;
         c.node_visits = counts;
         c.tri_tests = counts ? counts + 1 : nullptr;
-        if (counts) k_shadow_accel<true><<<blocks, threads, smem_for(k_shadow_accel<true>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count, c);
-        else k_shadow_accel<false><<<blocks, threads, smem_for(k_shadow_accel<false>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count, c);
+        if (sc.acc_wide_q16) {
+            if (counts) k_shadow_accel<true, true><<<blocks, threads, smem_for(k_shadow_accel<true, true>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count, c);
+            else k_shadow_accel<false, true><<<blocks, threads, smem_for(k_shadow_accel<false, true>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count, c);
+        } else {
+            if (counts) k_shadow_accel<true, false><<<blocks, threads, smem_for(k_shadow_accel<true, false>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count, c);
+            else k_shadow_accel<false, false><<<blocks, threads, smem_for(k_shadow_accel<false, false>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count, c);
+        }
     }
     launch_shadow(sc, true, sq, defer_count, defer_work, Lo, defer_list, std::min<uint32_t>(n_max, 65536u), n_sms, st);
 }
