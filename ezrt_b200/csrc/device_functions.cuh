@@ -255,22 +255,31 @@ __device__ __forceinline__ WideVisit wide_visit(const float4* __restrict__ nd, c
 // (error bound as in w8_node.h with the A term rounded at magnitude 2^23 * B: half a step; the builder keeps scale >=
 // W8_MIN_STEP_REL * max|coordinate|).  The bounce / shadow launches are bound by the L1 gather rate, and a 96-byte record is
 // gathered at 97 G/s against 52 G/s for the 128-byte one (profiles/gather_peak_r2.json); the decode costs ~24 instructions.
-__device__ __forceinline__ void q16_axis(uint32_t w, uint32_t bias, float B, float A, float& lo, float& hi) {
-    uint32_t fh;
-    asm("prmt.b32 %0, %1, %2, 0x7532;" : "=r"(fh) : "r"(w), "r"(bias));           // (w >> 16) | 0x4B000000
-    lo = __fmaf_rn(__uint_as_float((w & 0xffffu) | bias), B, A);
-    hi = __fmaf_rn(__uint_as_float(fh), B, A);
+// Near / far planes are picked by the PRMT selector: sel_a = 0x7510 takes the low half (the lo plane), 0x7532 the high half; the
+// ray keeps the NEAR selector per axis (lo iff d_a >= 0), the far one is near ^ 0x0022 -- no min/max per axis.
+__device__ __forceinline__ float q16_plane(uint32_t w, uint32_t bias, uint32_t sel, float B, float A) {
+    uint32_t f;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(w), "r"(bias), "r"(sel));
+    return __fmaf_rn(__uint_as_float(f), B, A);
 }
-__device__ __forceinline__ float q16_child(uint32_t wx, uint32_t wy, uint32_t wz, uint32_t bias, float Bx, float By, float Bz, float Ax, float Ay, float Az,
-                                           float limit) {
-    float lx, hx, ly, hy, lz, hz;
-    q16_axis(wx, bias, Bx, Ax, lx, hx);
-    q16_axis(wy, bias, By, Ay, ly, hy);
-    q16_axis(wz, bias, Bz, Az, lz, hz);
-    const float t0 = fmaxf(fminf(hx, lx), fminf(hy, ly)), t1 = fminf(fmaxf(hx, lx), fmaxf(hy, ly));
-    return wide_key(t0, t1, lz, hz, limit);
+struct Q16Ray {
+    uint32_t nx, ny, nz;   // near-plane selectors
+};
+__device__ __forceinline__ Q16Ray make_q16_ray(vec3 d) {
+    Q16Ray r;
+    r.nx = (d.x >= 0.0f) ? 0x7510u : 0x7532u;
+    r.ny = (d.y >= 0.0f) ? 0x7510u : 0x7532u;
+    r.nz = (d.z >= 0.0f) ? 0x7510u : 0x7532u;
+    return r;
 }
-__device__ __forceinline__ WideVisit wide_visit_q16(const uint4* __restrict__ nd, vec3 o, const RaySlab& rs, float limit, uint32_t bias) {
+__device__ __forceinline__ float q16_child(uint32_t wx, uint32_t wy, uint32_t wz, uint32_t bias, const Q16Ray& qr, uint32_t fx, uint32_t fy, uint32_t fz, float Bx,
+                                           float By, float Bz, float Ax, float Ay, float Az, float limit) {
+    const float t0 = fmaxf(fmaxf(q16_plane(wx, bias, qr.nx, Bx, Ax), q16_plane(wy, bias, qr.ny, By, Ay)), q16_plane(wz, bias, qr.nz, Bz, Az));
+    const float t1 = fminf(fminf(q16_plane(wx, bias, fx, Bx, Ax), q16_plane(wy, bias, fy, By, Ay)), q16_plane(wz, bias, fz, Bz, Az));
+    const bool ok = (t1 >= t0) && (t1 > 0.0f) && !(t0 > limit);
+    return ok ? t0 : 3.0e38f;
+}
+__device__ __forceinline__ WideVisit wide_visit_q16(const uint4* __restrict__ nd, vec3 o, const RaySlab& rs, float limit, uint32_t bias, const Q16Ray& qr) {
     ulonglong2 a, b;
     ldg256_b64(nd, a, b);
     const uint32_t w0 = (uint32_t)a.x, w1 = (uint32_t)(a.x >> 32), w2 = (uint32_t)a.y, w3 = (uint32_t)(a.y >> 32);
@@ -287,11 +296,12 @@ __device__ __forceinline__ WideVisit wide_visit_q16(const uint4* __restrict__ nd
     const float Ax = __fmaf_rn(-8388608.0f, Bx, (__uint_as_float(w0) - o.x) * ix);
     const float Ay = __fmaf_rn(-8388608.0f, By, (__uint_as_float(w1) - o.y) * iy);
     const float Az = __fmaf_rn(-8388608.0f, Bz, (__uint_as_float(w2) - o.z) * iz);
+    const uint32_t fx = qr.nx ^ 0x0022u, fy = qr.ny ^ 0x0022u, fz = qr.nz ^ 0x0022u;
     WideVisit v;
-    v.k0 = q16_child(w6, w7, w8, bias, Bx, By, Bz, Ax, Ay, Az, limit);
-    v.k1 = q16_child(w9, w10, w11, bias, Bx, By, Bz, Ax, Ay, Az, limit);
-    v.k2 = q16_child(w12, w13, w14, bias, Bx, By, Bz, Ax, Ay, Az, limit);
-    v.k3 = q16_child(w15, w16, w17, bias, Bx, By, Bz, Ax, Ay, Az, limit);
+    v.k0 = q16_child(w6, w7, w8, bias, qr, fx, fy, fz, Bx, By, Bz, Ax, Ay, Az, limit);
+    v.k1 = q16_child(w9, w10, w11, bias, qr, fx, fy, fz, Bx, By, Bz, Ax, Ay, Az, limit);
+    v.k2 = q16_child(w12, w13, w14, bias, qr, fx, fy, fz, Bx, By, Bz, Ax, Ay, Az, limit);
+    v.k3 = q16_child(w15, w16, w17, bias, qr, fx, fy, fz, Bx, By, Bz, Ax, Ay, Az, limit);
     v.r0 = (int)a.y; v.r1 = (int)(a.y >> 32); v.r2 = (int)b.x; v.r3 = (int)(b.x >> 32);
     return v;
 }
@@ -530,6 +540,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
     int ref = EZRT_REF_DONE;
     vec3 o = splat3(0.0f), d = splat3(0.0f), inv = splat3(0.0f);
     RaySlab rs = make_ray_slab(o, inv);
+    Q16Ray qr = make_q16_ray(d);
     float slack = 0.0f, best = EZ_INF;
     int best_tri = -1;
     bool exhausted = false;    // warp-uniform: the work counter has run past n
@@ -563,6 +574,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                     }
                     if (traceable) {
                         rs = make_ray_slab(o, inv);
+                        if (Q16) qr = make_q16_ray(d);
                         ray = (int)idx;
                         ref = tree.root_ref;
                         sp = 0;
@@ -605,7 +617,7 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                 if (WIDE) {
                     if (at_inner) {  // 4-wide acceleration-tree node: nearest child next, the others pushed far-to-near
                         const float limit = best + (best * 0.000244140625f + slack);
-                        const WideVisit w = Q16 ? wide_visit_q16(sc.acc_wide_q16 + (size_t)ref * 6, o, rs, limit, sc.q16_decode_bits)
+                        const WideVisit w = Q16 ? wide_visit_q16(sc.acc_wide_q16 + (size_t)ref * 6, o, rs, limit, sc.q16_decode_bits, qr)
                                                 : wide_visit(tree.nodes + (size_t)ref * 8, rs, limit);
                         if (COUNT) n_visits++;
 #if EZRT_WIDE_SORT
@@ -711,11 +723,9 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                 // the G lowest waiting lanes own this pass: lane with rank g (g-th set bit of m_leaf) serves group g.  The
                 // rank -> lane map goes through a few bytes of shared memory (one STS / LDS per pass; the unrolled
                 // find-first-set loop it replaces was 16 % of the kernel's instructions, profiles/ncu_extend_r1_summary.md)
-                unsigned rest = m_leaf;
-#pragma unroll
-                for (int g = 0; g < G; g++) rest &= rest - 1u;          // m_leaf without its G lowest bits (0 & -1 stays 0)
-                const unsigned taken = m_leaf ^ rest;
                 const int my_rank = __popc(m_leaf & lt_mask);
+                const unsigned taken = __ballot_sync(FULL, ((m_leaf >> lane) & 1u) != 0u && my_rank < G);   // the G lowest waiting lanes
+                const unsigned rest = m_leaf & ~taken;
                 __syncwarp();
                 if ((taken >> lane) & 1u) s_owner[my_rank] = (unsigned char)lane;
                 __syncwarp();

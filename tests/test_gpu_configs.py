@@ -150,3 +150,24 @@ def test_deep_caller_tree_and_degenerate_geometry(oracle):
         assert_same_bits(sc.render(cfg), ref, "coincident triangles")
     finally:
         sc.close()
+
+
+@pytest.mark.parametrize("env", [{}, {"EZRT_ACCEL_Q16": "0"}, {"EZRT_ACCEL": "8"}, {"EZRT_CAMERA_ORDER": "frame"}, {"EZRT_W4_COLLAPSE": "greedy"},
+                                 {"EZRT_SORT_RAYS": "1"}])
+def test_every_form_of_the_accel_policy_gives_the_oracle_image(oracle, grid_scene, small_hdr, env, monkeypatch):
+    """The acceleration tree's form (4-wide exact / 4-wide + 16-bit planes for the incoherent launches / W8), the collapse rule, the
+    order in which the camera pass takes its work and the optional ray sort are read from the environment at scene creation; none of
+    them may change a bit of the image or the ray counts."""
+    tris, nodes, eye, cam = grid_scene
+    hdr, cache = small_hdr
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    sc = api.Scene(tris, nodes, hdr, cache)
+    try:
+        for mode in (api.MODE_DISNEY_SOBOL_P5, api.MODE_DISNEY_IS_MIS_P5):
+            cfg = _cfg(eye, cam, width=200, height=120, spp=3, max_bounce=2, mode=mode)
+            ref, rc = oracle.render(tris, nodes, cfg, hdr=hdr, hdr_cache=cache)
+            assert_same_bits(sc.render(cfg), ref, "env %s mode %d" % (env, mode))
+            assert sc.counters().rays == rc["rays"]
+    finally:
+        sc.close()
