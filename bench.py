@@ -475,8 +475,8 @@ class Runner:
         self.scene.render_device(self.cfg(self.args.warmup * spp, spp, profile=2), self.d_fb, self.stream)
         self.torch.cuda.synchronize()
         c = self.scene.counters()
-        return dict(node_visits=int(c.node_visits), tri_tests=int(c.tri_tests), node_bytes=int(c.node_record_bytes), tri_bytes=int(c.tri_record_bytes),
-                    rays=int(c.rays), primary=int(c.primary_rays), bounce=int(c.bounce_rays), shadow=int(c.shadow_rays))
+        return dict(node_visits=int(c.node_visits), node_visits_96=int(c.node_visits_96), tri_tests=int(c.tri_tests), node_bytes=int(c.node_bytes),
+                    tri_bytes=int(c.tri_bytes), rays=int(c.rays), primary=int(c.primary_rays), bounce=int(c.bounce_rays), shadow=int(c.shadow_rays))
 
     def close(self):
         self.scene.close()
@@ -501,26 +501,26 @@ def roofline_of(res, counts, wl_means, hbm_peak, peak_kind, kernel_name):
     if not counts or ext_ms <= 0 or counts["node_visits"] == 0:
         return None
     steps = res["steps"]
-    node_b, tri_b = counts["node_bytes"], counts["tri_bytes"]
     rays_step = counts["rays"]
     queue_rays = counts["bounce"] + counts["shadow"]
+    n96, n128 = counts["node_visits_96"], counts["node_visits"] - counts["node_visits_96"]
     # per step (rank 0): node records + triangle records + 32-byte ray records read (queue rays) + 8-byte hit records written
-    bytes_step = counts["node_visits"] * node_b + counts["tri_tests"] * tri_b + queue_rays * 32 + rays_step * 8
+    bytes_step = counts["node_bytes"] + counts["tri_bytes"] + queue_rays * 32 + rays_step * 8
     t_step = ext_ms * 1e-3 / steps
     achieved = bytes_step / t_step / 1e9
-    pn, pt = gather_peak(node_b), gather_peak(tri_b)
+    p128, p96, p64 = gather_peak(128), gather_peak(96), gather_peak(64)
     out = {"bound": "hbm", "bound_detail": "memory system: L2 -> L1 gather of node / triangle records by divergent lanes (no dense contraction: tensor cores unused)",
            "kernel": kernel_name, "achieved": achieved, "unit": "GB/s",
            "algorithmic_bytes_per_launch": bytes_step * steps / max(1, ext_n), "launches": ext_n, "ms_per_launch": ext_ms / max(1, ext_n),
            "extend_share_of_step": ext_ms / res["ms"],
-           "per_ray": {"node_records": counts["node_visits"] / rays_step, "triangle_records": counts["tri_tests"] / rays_step,
-                       "node_record_bytes": node_b, "triangle_record_bytes": tri_b, "bytes": bytes_step / rays_step}}
-    if pn and pt:
-        t_floor = counts["node_visits"] / pn + counts["tri_tests"] / pt   # seconds per step at the measured gather ceiling
+           "per_ray": {"node_records_128B": n128 / rays_step, "node_records_96B": n96 / rays_step, "triangle_records_64B": counts["tri_tests"] / rays_step,
+                       "bytes": bytes_step / rays_step}}
+    if p128 and p96 and p64:
+        t_floor = n128 / p128 + n96 / p96 + counts["tri_tests"] / p64   # seconds per step at the measured gather ceilings
         peak = bytes_step / t_floor / 1e9 if t_floor > 0 else None
         out.update({"peak": peak, "frac": achieved / peak if peak else None,
-                    "peak_source": "measured gather ceiling (profiles/gather_peak_r2.json: %d-byte records %.1f G/s, %d-byte records %.1f G/s, 256-bit loads, "
-                                   "L2-resident table, this pool's B200), mixed by record counts" % (node_b, pn / 1e9, tri_b, pt / 1e9)})
+                    "peak_source": "measured gather ceiling (profiles/gather_peak_r2.json: 128-byte records %.1f G/s, 96-byte %.1f G/s, 64-byte %.1f G/s; 256-bit loads, "
+                                   "L2-resident table, this pool's B200), mixed by record counts" % (p128 / 1e9, p96 / 1e9, p64 / 1e9)})
     else:
         out.update({"peak": hbm_peak, "frac": achieved / hbm_peak, "peak_source": peak_kind + " (no gather_peak_r2.json)"})
     # HBM side: DRAM bytes of the extend kernels from the committed ncu capture of this command (tools/ncu_summaries.py dram)

@@ -30,8 +30,8 @@ class Counters(C.Structure):
     _fields_ = [
         ("rays", C.c_uint64), ("primary_rays", C.c_uint64), ("bounce_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
         ("samples", C.c_uint64), ("kernel_launches", C.c_uint64), ("device_ms", C.c_double),
-        ("deferred_rays", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64),
-        ("node_record_bytes", C.c_uint32), ("tri_record_bytes", C.c_uint32),
+        ("deferred_rays", C.c_uint64), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("node_visits_96", C.c_uint64),
+        ("node_bytes", C.c_uint64), ("tri_bytes", C.c_uint64),
     ]
 
 

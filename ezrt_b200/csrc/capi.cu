@@ -847,7 +847,7 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
             s->span_end(sp, st);
             sp = s->span_begin(1, st);
             launch_shade(s->dev, rd, d_tiles, b, batch_first, qin, &q_count[b], qout, &q_count[b + 1], sq, &s_count[b], Lo, Le,
-                         n_slots, (fused_camera && b == 0) ? n_slots : 0u, s->n_sms, st);
+                         n_slots, (fused_camera && b == 0) ? n_slots : 0u, (uint32_t)nf, s->n_sms, st);
             s->span_end(sp, st);
             s->launches += 2;
             if (is_mode && b < p->max_bounce) {
@@ -927,10 +927,11 @@ int ezrt_get_counters(ezrt_scene* s, ezrt_counters* out) {
     unsigned long long t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     CU_CHECK(cudaMemcpy(t, s->totals_buf.p, sizeof(t), cudaMemcpyDeviceToHost));
     out->deferred_rays = t[4];
-    out->node_visits = t[5];
+    out->node_visits = t[5] + t[7];          // t[5]: visits of 128-byte exact nodes, t[7]: of 96-byte nodes (Q16 form, W8)
     out->tri_tests = t[6];
-    out->node_record_bytes = s->dev.w8_nodes ? W8_NODE_BYTES : (s->dev.acc_wide_q16 ? 96 : (s->dev.acc_wide_nodes ? 128 : 64));   // Q16: the camera pass reads the 128-byte form
-    out->tri_record_bytes = 64;
+    out->node_bytes = t[5] * 128ull + t[7] * 96ull;
+    out->tri_bytes = t[6] * 64ull;
+    out->node_visits_96 = t[7];
     float ms = 0.0f;
     CU_CHECK(cudaEventElapsedTime(&ms, s->ev_start, s->ev_stop));
     out->primary_rays = t[0]; out->bounce_rays = t[1]; out->shadow_rays = t[2];

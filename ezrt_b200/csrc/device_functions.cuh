@@ -645,7 +645,21 @@ __device__ __forceinline__ void extend_persistent(const SceneDev& sc, const Tree
                         if (descend) {
                             ref = next;
 #if EZRT_NODE_PREFETCH
-                            if (next >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(tree.nodes + (size_t)next * 8));  // the whole 128-byte record
+                            if (next >= 0) {   // the next node record (Q16: 96 bytes, may straddle two lines) ...
+                                if (Q16) {
+                                    asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.acc_wide_q16 + (size_t)next * 6));
+                                    asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.acc_wide_q16 + (size_t)next * 6 + 4));
+                                } else {
+                                    asm volatile("prefetch.global.L1 [%0];" ::"l"(tree.nodes + (size_t)next * 8));
+                                }
+                            }
+#if EZRT_NODE_PREFETCH >= 2
+                            else if (next != EZRT_REF_DONE) {   // ... or the first triangles of the leaf this lane will wait at
+                                const uint32_t lb = (uint32_t)next & 0x7fffffffu;
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(tree.tri_geo + (size_t)(lb >> 7) * 4));
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(tree.tri_geo + (size_t)(lb >> 7) * 4 + 8));
+                            }
+#endif
 #endif
                         } else {  // pop
                             ref = EZRT_REF_DONE;
@@ -1393,9 +1407,14 @@ __device__ __forceinline__ vec3 contrib3(vec3 a, vec3 b, vec3 c, float s, float 
 // MODE >= 0: the integrator is a compile-time constant (k_shade<MODE>: each instantiation carries only its own
 // integrator -- the four-in-one kernel was 7288 instructions = 116 KB and instruction-fetch bound in the IS/MIS mode,
 // profiles/ncu_shade_c4_r2_summary.md); MODE < 0: rd.mode at run time (megakernel).
+// (sob_u, sob_v) = sobolVec2(frame + 1, bounce) (P5/fsh:372-376), the same for every pixel of a frame: the caller looks it
+// up (k_shade: a per-block table) or computes it (sobol_pair).
+__device__ __forceinline__ float2 sobol_pair(int bounce, uint32_t frame) {
+    return make_float2(sobol_gray((uint32_t)bounce * 2u, frame + 1u), sobol_gray((uint32_t)bounce * 2u + 1u, frame + 1u));
+}
 template <int MODE>
 __device__ __forceinline__ bool shade_step(const SceneDev& sc, const RenderDev& rd, int bounce, PathRegs& p, float hit_t,
-                                           int hit_tri, uint32_t px, uint32_t py, uint32_t frame, vec3& Lo, vec3& Le,
+                                           int hit_tri, uint32_t px, uint32_t py, float2 sob, vec3& Lo, vec3& Le,
                                            bool& primary_miss, ShadowRay& sh) {
     sh.valid = false;
     const int mode = (MODE < 0) ? rd.mode : MODE;
@@ -1444,8 +1463,7 @@ __device__ __forceinline__ bool shade_step(const SceneDev& sc, const RenderDev& 
         // value and pdf of the two directions are evaluated by ONE copy of the code (a two-trip loop that is not unrolled)
         float r1 = rand01(p.seed);
         float r2 = rand01(p.seed);
-        float xi_1 = sobol_gray((uint32_t)bounce * 2u, frame + 1u);
-        float xi_2 = sobol_gray((uint32_t)bounce * 2u + 1u, frame + 1u);
+        float xi_1 = sob.x, xi_2 = sob.y;
         cp_rotate(xi_1, xi_2, px, py);
         float xi_3 = rand01(p.seed);
         const vec3 Lh = sample_hdr(sc, r1, r2);
@@ -1485,8 +1503,7 @@ __device__ __forceinline__ bool shade_step(const SceneDev& sc, const RenderDev& 
     } else {
         vec3 Lh;
         if (mode == EZRT_MODE_DISNEY_SOBOL_P5) {  // P5/fsh:771-776
-            float u = sobol_gray((uint32_t)bounce * 2u, frame + 1u);
-            float v = sobol_gray((uint32_t)bounce * 2u + 1u, frame + 1u);
+            float u = sob.x, v = sob.y;
             cp_rotate(u, v, px, py);
             Lh = sample_hemisphere(u, v);
         } else {  // P3/fsh:110-115: z = rand(), then phi

@@ -110,8 +110,9 @@ typedef struct ezrt_counters {
     double device_ms;       /* CUDA-event time of the last render on its stream              */
     uint64_t deferred_rays; /* accel policy: rays re-traced by the exact reference-order pass */
     uint64_t node_visits;   /* profile = 2: acceleration-tree node records fetched ...       */
-    uint64_t tri_tests;     /*              ... and triangle records fetched by the accel kernels */
-    uint32_t node_record_bytes, tri_record_bytes; /* sizes of those records in HBM          */
+    uint64_t tri_tests;     /*              ... and triangle records (64 B) fetched by the accel kernels */
+    uint64_t node_visits_96;/*              of node_visits: 96-byte records (16-bit planes / W8); the rest are 128-byte records */
+    uint64_t node_bytes, tri_bytes; /*      bytes of those records                           */
 } ezrt_counters;
 
 typedef struct ezrt_scene ezrt_scene; /* device-resident scene (replaces the two TBOs + 2 textures) */

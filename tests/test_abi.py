@@ -29,8 +29,8 @@ def test_struct_layout_matches_header():
     from ezrt_b200 import _lib
     # ezrt_render_params: 6 int32 + 3+16+3 floats + 6 int32 + 4 reserved
     assert ctypes.sizeof(_lib.RenderParams) == 4 * (6 + 22 + 6 + 4)
-    # ezrt_counters: 6 uint64 + double + 3 uint64 + 2 uint32
-    assert ctypes.sizeof(_lib.Counters) == 8 * 11
+    # ezrt_counters: 6 uint64 + double + 6 uint64
+    assert ctypes.sizeof(_lib.Counters) == 8 * 13
     assert _lib.lib.ezrt_version() == 200
 
 

@@ -84,7 +84,8 @@ def test_counting_instantiation_and_accumulating_counters(s1m):
     cb = sc.counters()
     assert b.tobytes() == a.tobytes() and cb.rays == ca.rays
     assert cb.node_visits > 3 * cb.rays and cb.tri_tests > cb.rays          # several node and triangle records per ray
-    assert cb.node_record_bytes in (96, 128) and cb.tri_record_bytes == 64     # 4-wide exact boxes (default) or W8 (EZRT_ACCEL=8)
+    assert cb.tri_bytes == 64 * cb.tri_tests
+    assert cb.node_bytes == 96 * cb.node_visits_96 + 128 * (cb.node_visits - cb.node_visits_96)
     # EZRT_PARAM_ACCUMULATE: the second render's counters continue from the first
     acc = _cfg(s1m["eye"], s1m["cam"], width=320, height=180, spp=2, first_frame=2, max_bounce=2, mode=api.MODE_DISNEY_IS_MIS_P5, accumulate=True)
     fb = a.reshape(-1, 3).copy()
