@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
                                   // C3 2.73 / 2.86 / 3.03, C4 9.45 / 9.95 / 10.10 for 0 / 1 / 2 -- the warps get fuller (ncu) but the
                                   // kernel waits on its scattered record reads, not on issue slots, and the sort adds three barriers: off.
 #endif
+#define EZRT_SOBOL_TABLE 256      // frames per batch whose Sobol pairs a k_shade block keeps in shared memory
 #define EZRT_SHADE_KEYS 18        // material id mod 16, "left the scene", "beyond the queue end"
 #ifndef EZRT_SHADE_MIN_BLOCKS
 #define EZRT_SHADE_MIN_BLOCKS 8   // 64 registers: k_shade is latency-bound, 32 resident warps beat 20 despite small spills
@@ -502,7 +503,15 @@ template <int MODE>
 __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev sc, RenderDev rd, const TileDev* __restrict__ tiles, int bounce,
                                                uint32_t batch_first_frame, PathQueue qin, const uint32_t* __restrict__ in_count,
                                                PathQueue qout, uint32_t* out_count, ShadowQueue sq, uint32_t* s_count,
-                                               float4* __restrict__ Lo, float4* __restrict__ Le, uint32_t n_fused) {
+                                               float4* __restrict__ Lo, float4* __restrict__ Le, uint32_t n_fused, uint32_t n_frames) {
+    // The Sobol pair of (bounce, frame) is the same for every pixel of a frame (P5/fsh:361-376: up to 2 x 32 table XORs per path): each
+    // block computes the pairs of the batch's frames once into shared memory (batches of more than EZRT_SOBOL_TABLE frames compute per path).
+    __shared__ float2 s_sobol[EZRT_SOBOL_TABLE];
+    const bool sobol_table = (MODE == EZRT_MODE_DISNEY_SOBOL_P5 || MODE == EZRT_MODE_DISNEY_IS_MIS_P5) && n_frames <= EZRT_SOBOL_TABLE;
+    if (sobol_table) {
+        for (uint32_t f = threadIdx.x; f < n_frames; f += blockDim.x) s_sobol[f] = sobol_pair(bounce, batch_first_frame + f);
+        __syncthreads();
+    }
     // n_fused != 0 (bounce 0 of the W8 policy): entry i is sample slot i, its camera ray was generated inside
     // k_extend_w8_camera and is generated again here instead of being read from a queue; only q.hit[i] is read
     __shared__ uint32_t s_scan[34];
@@ -585,7 +594,8 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
                 p.cosine_i = 0.0f;
                 p.pdf = 1.0f;
             }
-            alive = shade_step<MODE>(sc, rd, bounce, p, hit.x, __float_as_int(hit.y), px, py, batch_first_frame + fib, lo, le, pmiss, sh);
+            const float2 sob = sobol_table ? s_sobol[fib] : sobol_pair(bounce, batch_first_frame + fib);
+            alive = shade_step<MODE>(sc, rd, bounce, p, hit.x, __float_as_int(hit.y), px, py, sob, lo, le, pmiss, sh);
             Lo[slot] = make_float4(lo.x, lo.y, lo.z, pmiss ? 1.0f : 0.0f);
             if (bounce == 0) Le[slot] = make_float4(le.x, le.y, le.z, 0.0f);
         }
@@ -683,7 +693,7 @@ __global__ void __launch_bounds__(128) k_megakernel(SceneDev sc, RenderDev rd, c
             HitRec h = trace_ray<PRUNE, false>(sc, p.o, p.d);
             if (bounce == 0) n_primary++; else n_bounce++;
             ShadowRay sh;
-            bool alive = shade_step<-1>(sc, rd, bounce, p, h.t, h.tri, px, py, frame, lo, le, pmiss, sh);
+            bool alive = shade_step<-1>(sc, rd, bounce, p, h.t, h.tri, px, py, sobol_pair(bounce, frame), lo, le, pmiss, sh);
             if (sh.valid) {
                 HitRec hs = trace_ray<PRUNE, true>(sc, sh.o, sh.d);
                 n_shadow++;
@@ -870,13 +880,13 @@ void launch_extend_accel(const SceneDev& sc, PathQueue q, const uint32_t* q_coun
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
     if (sc.w8_nodes) {
         W8Counts c;
-        c.node_visits = counts;
+        c.node_visits = counts ? counts + 2 : nullptr;   // 96-byte records
         c.tri_tests = counts ? counts + 1 : nullptr;
         if (counts) k_extend_w8<true><<<blocks, threads, w8_smem_for(k_extend_w8<true>, sc), st>>>(sc, q, q_count, work, defer_list, defer_count, c, perm);
         else k_extend_w8<false><<<blocks, threads, w8_smem_for(k_extend_w8<false>, sc), st>>>(sc, q, q_count, work, defer_list, defer_count, c, perm);
     } else {
         W8Counts c;
-        c.node_visits = counts;
+        c.node_visits = counts ? (sc.acc_wide_q16 ? counts + 2 : counts) : nullptr;   // counts[2]: 96-byte records, counts[0]: 128-byte records
         c.tri_tests = counts ? counts + 1 : nullptr;
         // incoherent rays: the 96-byte quantised form of the nodes when the scene carries it (env EZRT_ACCEL_Q16=0: exact nodes)
         if (sc.acc_wide_q16) {
@@ -910,7 +920,7 @@ void launch_extend_camera(const SceneDev& sc, const RenderDev& rd, const TileDev
                           cudaStream_t st) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_slots, n_sms);
     W8Counts c;
-    c.node_visits = counts;
+    c.node_visits = counts ? (sc.w8_nodes ? counts + 2 : counts) : nullptr;   // the 4-wide camera pass reads the 128-byte exact nodes
     c.tri_tests = counts ? counts + 1 : nullptr;
     if (sc.w8_nodes) {
         if (counts) k_extend_w8_camera<true><<<blocks, threads, w8_smem_for(k_extend_w8_camera<true>, sc), st>>>(sc, rd, tiles, batch_first_frame, n_slots, n_frames, q, work, defer_list, defer_count, c);
@@ -926,13 +936,13 @@ void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_c
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
     if (sc.w8_nodes) {
         W8Counts c;
-        c.node_visits = counts;
+        c.node_visits = counts ? counts + 2 : nullptr;
         c.tri_tests = counts ? counts + 1 : nullptr;
         if (counts) k_shadow_w8<true><<<blocks, threads, w8_smem_for(k_shadow_w8<true>, sc), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count, c);
         else k_shadow_w8<false><<<blocks, threads, w8_smem_for(k_shadow_w8<false>, sc), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count, c);
     } else {
         W8Counts c;
-        c.node_visits = counts;
+        c.node_visits = counts ? (sc.acc_wide_q16 ? counts + 2 : counts) : nullptr;
         c.tri_tests = counts ? counts + 1 : nullptr;
         if (sc.acc_wide_q16) {
             if (counts) k_shadow_accel<true, true><<<blocks, threads, smem_for(k_shadow_accel<true, true>, 0), st>>>(sc, sq, s_count, work, Lo, defer_list, defer_count, c);
@@ -946,10 +956,10 @@ void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_c
 }
 void launch_shade(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, int bounce, uint32_t batch_first_frame,
                   PathQueue qin, const uint32_t* in_count, PathQueue qout, uint32_t* out_count, ShadowQueue sq,
-                  uint32_t* s_count, float4* Lo, float4* Le, uint32_t n_max, uint32_t n_fused, int n_sms, cudaStream_t st) {
+                  uint32_t* s_count, float4* Lo, float4* Le, uint32_t n_max, uint32_t n_fused, uint32_t n_frames, int n_sms, cudaStream_t st) {
     int blocks = std::min(div_up(n_max, 128), n_sms * 4 * EZRT_SHADE_MIN_BLOCKS);
     if (blocks < 1) blocks = 1;
-#define EZRT_LAUNCH_SHADE(M) k_shade<M><<<blocks, 128, 0, st>>>(sc, rd, tiles, bounce, batch_first_frame, qin, in_count, qout, out_count, sq, s_count, Lo, Le, n_fused)
+#define EZRT_LAUNCH_SHADE(M) k_shade<M><<<blocks, 128, 0, st>>>(sc, rd, tiles, bounce, batch_first_frame, qin, in_count, qout, out_count, sq, s_count, Lo, Le, n_fused, n_frames)
     switch (rd.mode) {
         case EZRT_MODE_DIFFUSE_P3: EZRT_LAUNCH_SHADE(EZRT_MODE_DIFFUSE_P3); break;
         case EZRT_MODE_DISNEY_ANISO_P4: EZRT_LAUNCH_SHADE(EZRT_MODE_DISNEY_ANISO_P4); break;
