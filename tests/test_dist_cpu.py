@@ -87,3 +87,25 @@ def test_cpu_thread_count_is_explicit_and_bounded():
     import bench
     n, info = bench.cpu_threads()
     assert 1 <= n <= (os.cpu_count() or 1) and info["affinity"] >= n
+
+
+def test_bench_roofline_accounting():
+    """roofline_of: own-layout bytes / measured gather ceiling, with mixed node record sizes (no GPU: synthetic counters)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    res = {"kernel_ms": {"extend": 100.0, "shadow": 0.0, "shade": 10.0, "other": 1.0}, "kernel_launches": {"extend": 30, "shadow": 0, "shade": 30, "other": 10},
+           "steps": 10, "ms": 120.0, "rank0_rays": 6.0e8, "workload": "c3"}
+    counts = {"node_visits": 6.0e8, "node_visits_96": 4.0e8, "tri_tests": 4.0e8, "node_bytes": 2.0e8 * 128 + 4.0e8 * 96, "tri_bytes": 4.0e8 * 64,
+              "rays": 6.0e7, "primary": 3.0e7, "bounce": 3.0e7, "shadow": 0}
+    r = bench.roofline_of(res, counts, {"bytes_per_ray_reference": 11000.0}, 6574.8, "measured", "k_extend_accel")
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s"
+    bytes_step = counts["node_bytes"] + counts["tri_bytes"] + 3.0e7 * 32 + 6.0e7 * 8
+    assert abs(r["achieved"] - bytes_step / 0.010 / 1e9) < 1e-6 * r["achieved"]
+    if r.get("peak"):
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+        # the ceiling is the record-count-weighted mix of the three measured gather rates
+        p128, p96, p64 = bench.gather_peak(128), bench.gather_peak(96), bench.gather_peak(64)
+        t_floor = 2.0e8 / p128 + 4.0e8 / p96 + 4.0e8 / p64
+        assert abs(r["peak"] - bytes_step / t_floor / 1e9) < 1e-6 * r["peak"]
+    assert r["demand"]["frac_of_hbm_peak"] > 1.0    # the reference-layout demand figure exceeds the HBM peak by design
+    assert bench.roofline_of(res, None, None, 6574.8, "measured", "k") is None
