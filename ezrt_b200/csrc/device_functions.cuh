@@ -22,6 +22,25 @@ __device__ __forceinline__ vec3 f4xyz(float4 q) { return ez_v3(q.x, q.y, q.z); }
 __device__ __forceinline__ vec3 splat3(float s) { return ez_v3(s, s, s); }
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
+// The transcendental functions of ezrt_math.h are 35-100 instructions each and the integrators call them at up to twenty sites;
+// inlined everywhere they made k_shade<IS/MIS> 5104 instructions (80 KB), whose largest stall is instruction fetch
+// (`no_instruction` 5.5 per issue, profiles/ncu_c4_r2_summary.md).  EZRT_MATH_NOINLINE=1 routes the calls through one out-of-line
+// copy per function (same code, same bits); measured in profiles/sweep_noinline_r2.txt.
+#ifndef EZRT_MATH_NOINLINE
+#define EZRT_MATH_NOINLINE 0
+#endif
+#if EZRT_MATH_NOINLINE
+#define EZD_MATH __device__ __noinline__
+#else
+#define EZD_MATH __device__ __forceinline__
+#endif
+EZD_MATH float ezd_sin(float x) { return ez_sin(x); }
+EZD_MATH float ezd_cos(float x) { return ez_cos(x); }
+EZD_MATH float ezd_log(float x) { return ez_log(x); }
+EZD_MATH float ezd_pow(float x, float y) { return ez_pow(x, y); }
+EZD_MATH float ezd_atan2(float y, float x) { return ez_atan2(y, x); }
+EZD_MATH float ezd_asin(float x) { return ez_asin(x); }
+
 // ------------------------------------------------------------------------------------------
 // RNG + low-discrepancy samplers
 // ------------------------------------------------------------------------------------------
@@ -1127,7 +1146,7 @@ __device__ __forceinline__ float GTR1(float NdotH, float a) {
     if (a >= 1.0f) return EZ_DIV(1.0f, EZ_PI);
     float a2 = a * a;
     float t = 1.0f + (a2 - 1.0f) * NdotH * NdotH;
-    return EZ_DIV(a2 - 1.0f, EZ_PI * ez_log(a2) * t);
+    return EZ_DIV(a2 - 1.0f, EZ_PI * ezd_log(a2) * t);
 }
 __device__ __forceinline__ float GTR2(float NdotH, float a) {
     float a2 = a * a;
@@ -1253,11 +1272,11 @@ __device__ __forceinline__ vec3 sample_hemisphere(float xi_1, float xi_2) {
     float z = xi_1;
     float r = ez_max(0.0f, EZ_SQRT(1.0f - z * z));
     float phi = 2.0f * EZ_PI * xi_2;
-    return ez_v3(r * ez_cos(phi), r * ez_sin(phi), z);
+    return ez_v3(r * ezd_cos(phi), r * ezd_sin(phi), z);
 }
 __device__ __forceinline__ vec3 half_vector_to_L(float sin_theta_h, float cos_theta_h, float phi_h, vec3 V, vec3 N) {
-    float sin_phi_h = ez_sin(phi_h);
-    float cos_phi_h = ez_cos(phi_h);
+    float sin_phi_h = ezd_sin(phi_h);
+    float cos_phi_h = ezd_cos(phi_h);
     vec3 H = ez_v3(sin_theta_h * cos_phi_h, sin_theta_h * sin_phi_h, cos_theta_h);
     H = to_normal_hemisphere(H, N);
     return ez_reflect(ez_neg(V), H);
@@ -1276,8 +1295,8 @@ __device__ __forceinline__ vec3 sample_brdf(float xi_1, float xi_2, float xi_3, 
     if (rd <= p_diffuse) {  // SampleCosineHemisphere :579-590
         float r = EZ_SQRT(xi_1);
         float theta = xi_2 * 2.0f * EZ_PI;
-        float x = r * ez_cos(theta);
-        float y = r * ez_sin(theta);
+        float x = r * ezd_cos(theta);
+        float y = r * ezd_sin(theta);
         float z = EZ_SQRT(1.0f - x * x - y * y);
         return to_normal_hemisphere(ez_v3(x, y, z), N);
     } else if (p_diffuse < rd && rd <= p_diffuse + p_specular) {  // SampleGTR2 :593-610
@@ -1288,7 +1307,7 @@ __device__ __forceinline__ vec3 sample_brdf(float xi_1, float xi_2, float xi_3, 
     } else if (p_diffuse + p_specular < rd) {  // SampleGTR1 :613-630
         float phi_h = 2.0f * EZ_PI * xi_1;
         float a2 = alpha_GTR1 * alpha_GTR1;
-        float cos_theta_h = EZ_SQRT(EZ_DIV(1.0f - ez_pow(a2, 1.0f - xi_2), 1.0f - a2));
+        float cos_theta_h = EZ_SQRT(EZ_DIV(1.0f - ezd_pow(a2, 1.0f - xi_2), 1.0f - a2));
         float sin_theta_h = EZ_SQRT(ez_max(0.0f, 1.0f - cos_theta_h * cos_theta_h));
         return half_vector_to_L(sin_theta_h, cos_theta_h, phi_h, V, N);
     }
@@ -1321,7 +1340,7 @@ __device__ __forceinline__ vec3 tex2d(const float* img, int W, int H, float u, f
 }
 // toSphericalCoord, P5/fsh:684-690
 __device__ __forceinline__ void to_spherical(vec3 v, float& ou, float& ov) {
-    float u = ez_atan2(v.z, v.x), w = ez_asin(v.y);
+    float u = ezd_atan2(v.z, v.x), w = ezd_asin(v.y);
     u = EZ_DIV(u, 2.0f * EZ_PI);
     w = EZ_DIV(w, EZ_PI);
     u += 0.5f;
@@ -1348,8 +1367,8 @@ __device__ __forceinline__ vec3 sample_hdr(const SceneDev& sc, float xi_1, float
     float x = c.x, y = 1.0f - c.y;
     float phi = 2.0f * EZ_PI * (x - 0.5f);
     float theta = EZ_PI * (y - 0.5f);
-    float ct = ez_cos(theta);
-    return ez_v3(ct * ez_cos(phi), ez_sin(theta), ct * ez_sin(phi));
+    float ct = ezd_cos(theta);
+    return ez_v3(ct * ezd_cos(phi), ezd_sin(theta), ct * ezd_sin(phi));
 }
 // hdrPdf, P5/fsh:701-712
 __device__ __forceinline__ float hdr_pdf(const SceneDev& sc, vec3 L) {
@@ -1357,7 +1376,7 @@ __device__ __forceinline__ float hdr_pdf(const SceneDev& sc, vec3 L) {
     to_spherical(ez_normalize(L), u, v);
     float pdf = tex2d(sc.hdr_cache, sc.hdr_w, sc.hdr_h, u, v, sc.hdr_linear).z;
     float theta = EZ_PI * (0.5f - v);
-    float sin_theta = ez_max(ez_sin(theta), 1e-10f);
+    float sin_theta = ez_max(ezd_sin(theta), 1e-10f);
     int res = sc.hdr_w;
     float p_convert = EZ_DIV((float)(res * res / 2), 2.0f * EZ_PI * EZ_PI * sin_theta);
     return pdf * p_convert;
@@ -1510,7 +1529,7 @@ __device__ __forceinline__ bool shade_step(const SceneDev& sc, const RenderDev& 
             float z = rand01(p.seed);
             float r = ez_max(0.0f, EZ_SQRT(1.0f - z * z));
             float phi = 2.0f * EZ_PI * rand01(p.seed);
-            Lh = ez_v3(r * ez_cos(phi), r * ez_sin(phi), z);
+            Lh = ez_v3(r * ezd_cos(phi), r * ezd_sin(phi), z);
         }
         L = to_normal_hemisphere(Lh, N);
         p.pdf = EZ_DIV(1.0f, 2.0f * EZ_PI);
