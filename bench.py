@@ -540,7 +540,7 @@ def roofline_of(res, counts, wl_means, hbm_peak, peak_kind, kernel_name):
         demand = res["rank0_rays"] * wl_means["bytes_per_ray_reference"] / (ext_ms * 1e-3) / 1e9
         out["demand"] = {"gbs": demand, "frac_of_hbm_peak": demand / hbm_peak, "bytes_per_ray_reference_layout": wl_means["bytes_per_ray_reference"],
                          "ray_means": wl_means, "note": "demand bytes of the reference's layout and un-pruned traversal with no cross-ray reuse; "
-                                                        "the kernels walk their own 8-wide tree, so this exceeds every physical peak by design"}
+                                                        "the kernels walk their own 4-wide tree (or the 8-wide one under EZRT_ACCEL=8), so this exceeds every physical peak by design"}
     return out
 
 

@@ -137,6 +137,12 @@ class TriangleList:
 OBJ_HARDENED = 2
 
 
+def host_sort_is_reference():
+    """True if this host's std::sort reproduces libstdc++'s order of equal keys, i.e. build_bvh yields the reference's
+    triangle order (ezrt_host_sort_is_reference, include/ezrt.h)."""
+    return bool(lib.ezrt_host_sort_is_reference())
+
+
 def load_scene_file(path):
     """Scene description file -> (TriangleList, (rotatAngle, upAngle, r), hdr path or None); see include/ezrt.h."""
     tl = TriangleList()

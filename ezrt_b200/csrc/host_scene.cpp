@@ -698,7 +698,38 @@ int ezrt_trilist_append_encoded(ezrt_trilist* list, const float* tris, int n) {
     return EZRT_OK;
 }
 
+// The reference sorts triangles with std::sort and an order-only comparator (P5/main.cpp:395-455, :458-589): which of several
+// triangles with EQUAL centroid coordinates ends up where is a property of the C++ library's introsort, and the triangle order
+// decides the tree and (through leaf order and ties) the image.  The goldens of this repository and the reference's own uploads
+// (tests/test_ref_host.py) were produced with libstdc++.  This known-answer check sorts a fixed array with many equal keys and
+// compares the permutation with libstdc++'s; a host whose std::sort differs still builds a VALID tree, but not the reference's.
+static uint32_t sort_kat_hash() {
+    struct E { int key, id; };
+    std::vector<E> v(613);
+    uint32_t x = 2463534242u;
+    for (int i = 0; i < (int)v.size(); i++) {
+        x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+        v[i].key = (int)(x % 23u);
+        v[i].id = i;
+    }
+    std::sort(v.begin(), v.end(), [](const E& a, const E& b) { return a.key < b.key; });
+    uint32_t h = 2166136261u;
+    for (const E& e : v) h = (h ^ (uint32_t)e.id) * 16777619u;
+    return h;
+}
+#define EZRT_SORT_KAT_LIBSTDCXX 1126591013u
+
+int ezrt_host_sort_is_reference(void) { return sort_kat_hash() == EZRT_SORT_KAT_LIBSTDCXX ? 1 : 0; }
+
 int ezrt_trilist_build_bvh(ezrt_trilist* list, int leaf_n, int builder) {
+    {
+        static int warned = 0;
+        if (!warned && builder != EZRT_BVH_SAH_NO_SENTINEL && !ezrt_host_sort_is_reference()) {
+            warned = 1;
+            fprintf(stderr, "ezrt: this C++ library's std::sort orders equal keys differently from libstdc++: the BVH is valid but is not "
+                            "the reference's triangle order (ezrt_host_sort_is_reference() == 0)\n");
+        }
+    }
     if (!list || leaf_n < 1) return ezrt_set_error(EZRT_ERR_INVALID, "build_bvh: bad argument");
     if (list->tris.empty()) return ezrt_set_error(EZRT_ERR_INVALID, "build_bvh: empty triangle list");
     // nodes{testNode}: the recognisable dummy element 0 (P5/main.cpp:830-836)

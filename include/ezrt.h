@@ -247,6 +247,11 @@ typedef enum ezrt_bvh_builder {
  * node count (incl. dummy node 0) or a negative status. */
 int ezrt_trilist_build_bvh(ezrt_trilist* list, int leaf_n, int builder);
 int ezrt_trilist_node_count(const ezrt_trilist* list);
+/* 1 if this host's std::sort orders equal keys as libstdc++ does, i.e. the SAH_LITERAL / SAH_FAST / MEDIAN builders
+ * reproduce the triangle order of the reference built with libstdc++ (its buildBVH* sort with order-only comparators,
+ * P5/main.cpp:403-413, :560-568) and the goldens of this repository; 0 = the trees are valid but differ from the
+ * reference's wherever centroid coordinates tie (ezrt_trilist_build_bvh then warns once on stderr). */
+int ezrt_host_sort_is_reference(void);
 /* Encode as P5/main.cpp:843-871 into caller buffers (36 floats/triangle, 12 floats/node). */
 int ezrt_trilist_encode_triangles(const ezrt_trilist* list, float* tris_out);
 int ezrt_trilist_encode_nodes(const ezrt_trilist* list, float* nodes_out);

@@ -86,6 +86,12 @@ def test_fast_builder_equals_literal_builder():
         assert np.array_equal(t0, t1) and np.array_equal(n0, n1)
 
 
+def test_std_sort_known_answer():
+    """The reference's builders sort with order-only comparators (P5/main.cpp:403-413, :560-568): the order of equal keys is the
+    C++ library's.  The goldens were made with libstdc++; the library reports whether this host's std::sort is the same."""
+    assert api.host_sort_is_reference()
+
+
 def test_sah_sentinel_quirk_falls_back_to_median_on_axis0():
     """cost >= INF=114514 disables SAH: split = (l+r)/2 on axis 0 (P5/main.cpp:20, :493-495, :569)."""
     tl = api.TriangleList()
