@@ -11,6 +11,7 @@ from . import build as _build
 
 c_float_p = C.POINTER(C.c_float)
 c_int32_p = C.POINTER(C.c_int32)
+c_uint32_p = C.POINTER(C.c_uint32)
 
 
 class RenderParams(C.Structure):
@@ -50,6 +51,7 @@ SIGNATURES = {
     "ezrt_partition_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ezrt_partition_cache_clear": (C.c_int, [C.c_int]),
     "ezrt_host_sort_is_reference": (C.c_int, []),
+    "ezrt_accel_build": (C.c_int, [C.c_int, c_float_p, C.c_int, C.c_int, C.c_int, c_int32_p, c_float_p, C.c_int, c_uint32_p, C.POINTER(C.c_double)]),
     "ezrt_partition_scatter_host": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ezrt_trace_rays": (C.c_int, [C.c_void_p, C.c_int, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, c_int32_p, c_float_p,
                                   c_int32_p, c_int32_p, c_float_p, c_float_p]),

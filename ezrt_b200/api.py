@@ -300,6 +300,23 @@ class Scene:
         return dict(hit=hit, distance=dist, triangle=tri, inside=inside, point=point, normal=normal)
 
 
+def accel_build(tris, leaf_n=4, where="device", device=0):
+    """The binary SAH tree ezrt_scene_create derives its acceleration tree from (ezrt_accel_build, include/ezrt.h):
+    returns (links int32 [n,4], boxes float32 [n,6], order uint32 [n_triangles], ms).  where: "device" | "host"."""
+    tris = _f32(tris).reshape(-1, 36)
+    n = tris.shape[0]
+    cap = 2 * n
+    links = np.zeros((cap, 4), np.int32)
+    boxes = np.zeros((cap, 6), np.float32)
+    order = np.zeros(n, np.uint32)
+    ms = C.c_double(0.0)
+    rc = lib.ezrt_accel_build(device, _fp(tris), n, leaf_n, 1 if where == "host" else 0, links.ctypes.data_as(_lib.c_int32_p), _fp(boxes), cap,
+                              order.ctypes.data_as(_lib.c_uint32_p), C.byref(ms))
+    if rc < 0:
+        check(rc)
+    return links[:rc].copy(), boxes[:rc].copy(), order, ms.value
+
+
 def post_tonemap(d_in, d_out=None, limit=1.5, stream=None):
     """pass3 (P5/shaders/pass3.fsh:14-25) on a device framebuffer (torch CUDA tensor [..., 3|4]) -> [..., 3]."""
     import torch

@@ -402,8 +402,25 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     {
         std::vector<EzrtAccelNode> an;
         std::vector<uint32_t> order_bin;
-        ezrt_build_accel(tris, n_triangles, W8_MAX_LEAF_TRIS, an, order_bin);
-        lap("acceleration tree: binary SAH build");
+        // on the GPU (accel_build.cu; the same tree node for node); env EZRT_BUILD=host: the host builder (host_scene.cpp)
+        const char* be = getenv("EZRT_BUILD");
+        if (be && !strcmp(be, "host")) {
+            ezrt_build_accel(tris, n_triangles, W8_MAX_LEAF_TRIS, an, order_bin);
+            lap("acceleration tree: binary SAH build (host)");
+        } else {
+            DeviceBuffer raw;
+            int brc = raw.ensure((size_t)n_triangles * EZRT_TRIANGLE_FLOATS * sizeof(float));
+            if (brc) return brc;
+            if (cudaMemcpy(raw.p, tris, (size_t)n_triangles * EZRT_TRIANGLE_FLOATS * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+                raw.release();
+                return ezrt_set_error(EZRT_ERR_CUDA, "scene_create: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+            lap("acceleration tree: triangle upload");
+            brc = ezrt_build_accel_device((const float*)raw.p, n_triangles, W8_MAX_LEAF_TRIS, an, order_bin, nullptr);
+            raw.release();
+            if (brc < 0) return brc;
+            lap("acceleration tree: binary SAH build (device)");
+        }
         // boxes inflated by 2*delta: a hit hitTriangle accepts lies within delta of its triangle's box, so
         // the inflated boxes of the whole ancestor chain are entered no later than the hit distance
         const float pad = 2.0f * prune_delta;
@@ -1132,6 +1149,42 @@ int ezrt_eval_brdf(int device, int which, int n, const float* V, const float* N,
     buf.release();
     if (e != cudaSuccess) return ezrt_set_error(EZRT_ERR_CUDA, "eval_brdf: %s", cudaGetErrorString(e));
     return EZRT_OK;
+}
+
+int ezrt_accel_build(int device, const float* tris, int n_triangles, int leaf_n, int where, int32_t* links_out, float* boxes_out,
+                     int nodes_cap, uint32_t* order_out, double* ms) {
+    if (!tris || n_triangles <= 0 || leaf_n < 1) return ezrt_set_error(EZRT_ERR_INVALID, "accel_build: bad argument");
+    std::vector<EzrtAccelNode> an;
+    std::vector<uint32_t> order;
+    const auto t0 = std::chrono::steady_clock::now();
+    int n_nodes = 0;
+    if (where == 1) {
+        n_nodes = ezrt_build_accel(tris, n_triangles, leaf_n, an, order);
+    } else {
+        int n_dev = 0;
+        CU_CHECK(cudaGetDeviceCount(&n_dev));
+        if (device < 0 || device >= n_dev) return ezrt_set_error(EZRT_ERR_CUDA, "accel_build: no CUDA device %d (have %d)", device, n_dev);
+        CU_CHECK(cudaSetDevice(device));
+        DeviceBuffer raw;
+        int rc = raw.ensure((size_t)n_triangles * EZRT_TRIANGLE_FLOATS * sizeof(float));
+        if (rc) return rc;
+        if (cudaMemcpy(raw.p, tris, (size_t)n_triangles * EZRT_TRIANGLE_FLOATS * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            raw.release();
+            return ezrt_set_error(EZRT_ERR_CUDA, "accel_build: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        n_nodes = ezrt_build_accel_device((const float*)raw.p, n_triangles, leaf_n, an, order, nullptr);
+        raw.release();
+    }
+    if (n_nodes < 0) return n_nodes;
+    if (ms) *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if ((links_out || boxes_out) && nodes_cap < n_nodes) return ezrt_set_error(EZRT_ERR_INVALID, "accel_build: %d nodes, room for %d", n_nodes, nodes_cap);
+    for (int i = 0; i < n_nodes; i++) {
+        if (links_out) { links_out[4 * i] = an[i].left; links_out[4 * i + 1] = an[i].right; links_out[4 * i + 2] = an[i].n; links_out[4 * i + 3] = an[i].index; }
+        if (boxes_out)
+            for (int k = 0; k < 3; k++) { boxes_out[6 * i + k] = an[i].AA[k]; boxes_out[6 * i + 3 + k] = an[i].BB[k]; }
+    }
+    if (order_out) memcpy(order_out, order.data(), sizeof(uint32_t) * (size_t)n_triangles);
+    return n_nodes;
 }
 
 int ezrt_eval_math(int device, int which, int n, const float* a, const float* b, float* out) {

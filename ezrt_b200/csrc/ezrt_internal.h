@@ -30,6 +30,11 @@ struct EzrtAccelNode {
 // host_scene.cpp: sentinel-free SAH tree over the triangles of a Triangle_encoded array
 int ezrt_build_accel(const float* tris, int n_tris, int leaf_n, std::vector<EzrtAccelNode>& nodes, std::vector<uint32_t>& order);
 
+// accel_build.cu: the same tree, node for node, built on the GPU from the Triangle_encoded array in device memory (the
+// current device).  Returns the node count or a negative status; *levels = depth of the tree.
+int ezrt_build_accel_device(const float* d_tris, int n_tris, int leaf_n, std::vector<EzrtAccelNode>& nodes, std::vector<uint32_t>& order,
+                            int* levels);
+
 // accel_w8.cpp: SAH-optimal collapse of the binary tree to `width`-wide nodes (dynamic programming; shared by the 4-wide
 // exact-box form and the 8-wide quantised form)
 struct EzrtCollapse {

@@ -189,6 +189,16 @@ int ezrt_eval_brdf(int device, int which, int n, const float* V, const float* N,
  * definition): which = 0 sin, 1 cos, 2 log, 3 exp, 4 pow(a,b), 5 atan2(a,b), 6 asin. */
 int ezrt_eval_math(int device, int which, int n, const float* a, const float* b, float* out);
 
+/* The binary SAH tree ezrt_scene_create derives its acceleration tree from (NOT the reference's tree: the same
+ * exhaustive sweep as buildBVHwithSAH, P5/main.cpp:458-589, without the INF = 114514 cost sentinel, leaves of <= leaf_n
+ * triangles), built where = 0 on the GPU (csrc/accel_build.cu, what ezrt_scene_create uses) or where = 1 on the host
+ * (host_scene.cpp); both produce the same array.  links_out: 4 ints per node (left, right, n, index; node 0 = root),
+ * boxes_out: 6 floats per node (AA, BB), order_out: n_triangles triangle indices (the tree's triangle order); any may be
+ * NULL.  nodes_cap = capacity of links_out / boxes_out in nodes.  Returns the node count or a negative status;
+ * *ms = wall-clock of the build (device: upload of the triangles and read-back of the tree included). */
+int ezrt_accel_build(int device, const float* tris, int n_triangles, int leaf_n, int where, int32_t* links_out,
+                     float* boxes_out, int nodes_cap, uint32_t* order_out, double* ms);
+
 /* ----------------------------------------------------------------------------------------
  * Post pass (SURVEY.md 8f "next" row 3): what the user sees.
  * -------------------------------------------------------------------------------------- */

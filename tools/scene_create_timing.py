@@ -12,3 +12,9 @@ for name in (sys.argv[1:] or ["c3"]):
         sc = api.Scene(wl["tris"], wl["nodes"], wl.get("hdr"), wl.get("cache"), device=0)
         print(f"== {name} rep {rep}: {len(wl['tris'])} triangles, ezrt_scene_create {1e3 * (time.time() - t0):.1f} ms", file=sys.stderr, flush=True)
         del sc
+
+    import numpy as np
+    for where in ("device", "host"):
+        for rep in range(2):
+            links, boxes, order, ms = api.accel_build(wl["tris"], 4, where)
+            print(f"== {name} binary SAH tree on the {where}: {len(links)} nodes, {ms:.1f} ms (upload + build + read-back)", file=sys.stderr, flush=True)
