@@ -171,6 +171,20 @@ def build_w8_model(force=False):
     return W8_MODEL_BIN
 
 
+W4_CHECK_BIN = os.path.join(ROOT, "build", "w4_check")
+
+
+def build_w4_check(force=False):
+    """build/w4_check: CPU check of the 4-wide acceleration-tree builder (tools/w4_check.cpp): thread-count independence, structure."""
+    srcs = [os.path.join(ROOT, "tools", "w4_check.cpp")] + [os.path.join(CSRC, f) for f in ("host_scene.cpp", "accel_w8.cpp", "errors.cpp")]
+    if force or _newer(W4_CHECK_BIN, srcs + _headers()):
+        os.makedirs(os.path.dirname(W4_CHECK_BIN), exist_ok=True)
+        tmp = W4_CHECK_BIN + ".tmp%d" % os.getpid()
+        _run(["g++"] + [f for f in HOST_FLAGS if f != "-fPIC"] + ["-pthread", "-I", INCLUDE, "-I", CSRC] + srcs + ["-o", tmp])
+        os.replace(tmp, W4_CHECK_BIN)
+    return W4_CHECK_BIN
+
+
 def build_all(force=False, verbose=False):
     build_product(force=force, verbose=verbose)
     build_oracle(force=force)

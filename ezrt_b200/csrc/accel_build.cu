@@ -255,6 +255,7 @@ int ezrt_build_accel_device(const float* d_tris, int n, int leaf_n, std::vector<
                             int* levels_out) {
     if (!d_tris || n <= 0 || leaf_n < 1) return ezrt_set_error(EZRT_ERR_INVALID, "accel build: bad argument");
     int rc = EZRT_OK;
+    EzrtLap lap("ezrt_build_accel_device");
     const int threads = 256, blocks = (n + threads - 1) / threads;
     const int n_slots = 2 * n;
     typedef cub::CountingInputIterator<int> Count;
@@ -315,6 +316,7 @@ int ezrt_build_accel_device(const float* d_tris, int n, int leaf_n, std::vector<
             return ezrt_set_error(EZRT_ERR_NOMEM, "accel build: %.1f MB of device scratch", need / 1048576.0);
         }
     }
+    lap("scratch allocation");
     temp = ar.take<char>(temp_bytes);
     tri_box = ar.take<Box>(n);
     for (int a = 0; a < 3; a++) keys[a] = ar.take<float>(n);
@@ -339,6 +341,7 @@ int ezrt_build_accel_device(const float* d_tris, int n, int leaf_n, std::vector<
         CUB_OK(cub::DeviceRadixSort::SortPairs(temp, b, (const float*)keys[a], keys_out, (const uint32_t*)iota, d.idx[a], n));
     }
     k_init_root<<<blocks, threads>>>(d);
+    if (lap.on) { cudaDeviceSynchronize(); lap("boxes, three sorts"); }
     for (int level = 0;; level++) {
         levels = level + 1;
         for (int a = 0; a < 3; a++) {
@@ -365,6 +368,7 @@ int ezrt_build_accel_device(const float* d_tris, int n, int leaf_n, std::vector<
         if (inner_next == 0) break;
         if (level > 4096) { rc = ezrt_set_error(EZRT_ERR_BAD_TREE, "accel build: runaway depth"); goto done; }
     }
+    lap("levels");
     {
         size_t b = temp_bytes;
         CUB_OK(cub::DeviceScan::ExclusiveSum(temp, b, (const int*)d.used, dense, n_slots));
@@ -378,10 +382,12 @@ int ezrt_build_accel_device(const float* d_tris, int n, int leaf_n, std::vector<
         CUB_OK(cudaMemcpy(nodes_out.data(), out_nodes, (size_t)n_nodes * sizeof(EzrtAccelNode), cudaMemcpyDeviceToHost));
         CUB_OK(cudaMemcpy(order.data(), d.idx[0], (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         CUB_OK(cudaGetLastError());
+        lap("compaction, read-back");
     }
     if (levels_out) *levels_out = levels;
     rc = n_nodes;
 done:
     cudaFree(ar.base);
+    lap("free");
     return rc;
 }

@@ -13,6 +13,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "device_scene.h"
@@ -231,42 +232,54 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     };
 
     // ---- decode + validate the tree (getBVHNode, P5/fsh:138-155) ----
+    // Host work on the caller's tree only: runs on its own thread while this one feeds the GPU (triangle upload, records,
+    // acceleration-tree build).  Errors are carried back as (code, message): ezrt_set_error is per thread.
     struct HNode { int left, right, n, index; };
     std::vector<HNode> hn(n_nodes);
+    std::vector<int> inner_id(n_nodes, -1);
+    int n_inner = 0, max_depth = 0, n_top = 0, root_ref = 0;
+    bool regular_tree = true;
+    std::vector<float4> gnodes, leaf_box;
+    std::vector<int> tri_leaf(n_triangles, 0);
+    std::string ref_msg;
+    auto ref_fail = [&](int code, const char* fmt, int a = 0, int b = 0, int c = 0) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), fmt, a, b, c);
+        ref_msg = buf;
+        return code;
+    };
+    auto ref_stage = [&]() -> int {
     for (int i = 0; i < n_nodes; i++) {
         const float* s = nodes + (size_t)i * EZRT_BVHNODE_FLOATS;
         hn[i].left = (int)s[0]; hn[i].right = (int)s[1]; hn[i].n = (int)s[3]; hn[i].index = (int)s[4];
     }
-    std::vector<int> inner_id(n_nodes, -1);
     std::vector<char> seen(n_nodes, 0);
-    int n_inner = 0, max_depth = 0;
     {
         std::vector<std::pair<int, int>> stk;
         stk.push_back({1, 1});
         while (!stk.empty()) {
             auto [i, depth] = stk.back();
             stk.pop_back();
-            if (i < 1 || i >= n_nodes) return ezrt_set_error(EZRT_ERR_BAD_TREE, "scene_create: child index %d out of range", i);
-            if (seen[i]) return ezrt_set_error(EZRT_ERR_BAD_TREE, "scene_create: node %d reachable twice", i);
+            if (i < 1 || i >= n_nodes) return ref_fail(EZRT_ERR_BAD_TREE, "scene_create: child index %d out of range", i);
+            if (seen[i]) return ref_fail(EZRT_ERR_BAD_TREE, "scene_create: node %d reachable twice", i);
             seen[i] = 1;
             max_depth = std::max(max_depth, depth);
             const HNode& nd = hn[i];
             if (nd.n > 0) {
-                if (nd.n > EZRT_LEAF_MAX_N) return ezrt_set_error(EZRT_ERR_BAD_TREE, "scene_create: leaf %d holds %d > %d triangles", i, nd.n, EZRT_LEAF_MAX_N);
-                if (nd.index < 0 || nd.index + nd.n > n_triangles) return ezrt_set_error(EZRT_ERR_BAD_TREE, "scene_create: leaf %d range out of bounds", i);
+                if (nd.n > EZRT_LEAF_MAX_N) return ref_fail(EZRT_ERR_BAD_TREE, "scene_create: leaf %d holds %d > %d triangles", i, nd.n, EZRT_LEAF_MAX_N);
+                if (nd.index < 0 || nd.index + nd.n > n_triangles) return ref_fail(EZRT_ERR_BAD_TREE, "scene_create: leaf %d range out of bounds", i);
             } else {
                 // the shader would read the dummy node 0 for a missing child (P5/fsh:278-302); not supported
-                if (nd.left <= 0 || nd.right <= 0) return ezrt_set_error(EZRT_ERR_BAD_TREE, "scene_create: inner node %d lacks a child", i);
+                if (nd.left <= 0 || nd.right <= 0) return ref_fail(EZRT_ERR_BAD_TREE, "scene_create: inner node %d lacks a child", i);
                 stk.push_back({nd.right, depth + 1});
                 stk.push_back({nd.left, depth + 1});
             }
         }
     }
-    if (max_depth + 1 > EZRT_MAX_STACK) return ezrt_set_error(EZRT_ERR_BAD_TREE, "scene_create: tree depth %d exceeds %d", max_depth, EZRT_MAX_STACK - 1);
+    if (max_depth + 1 > EZRT_MAX_STACK) return ref_fail(EZRT_ERR_BAD_TREE, "scene_create: tree depth %d exceeds %d", max_depth, EZRT_MAX_STACK - 1);
     // The ACCEL and PRUNED policies rely on what buildBVH* guarantees: every triangle in exactly one leaf,
     // leaf boxes bounding their triangles, child boxes inside their parent's.  A caller-supplied tree that
     // breaks any of these is only ever walked literally (REFERENCE policy), whatever the params ask for.
-    bool regular_tree = true;
     {
         std::vector<unsigned char> cover(n_triangles, 0);
         for (int i = 1; i < n_nodes && regular_tree; i++) {
@@ -294,7 +307,6 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     // Record numbering: the top of the tree level by level (these records are staged in shared memory
     // by the traversal kernels: 61% of all inner-node visits hit depth <= 9 on the 1M-triangle scene),
     // whole levels while they fit EZRT_TOP_NODES_MAX; everything below in the builder's pre-order.
-    int n_top = 0;
     {
         std::vector<int> level, next;
         if (hn[1].n <= 0) level.push_back(1);
@@ -325,7 +337,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         g[2] = make_float4(LA[2], LB[2], RA[2], RB[2]);  // left AA.z BB.z  | right AA.z BB.z
         g[3] = make_float4(fl, fr, 0.0f, 0.0f);          // child references
     };
-    std::vector<float4> gnodes((size_t)std::max(1, n_inner) * 4);
+    gnodes.assign((size_t)std::max(1, n_inner) * 4, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
     for (int i = 1; i < n_nodes; i++) {
         if (inner_id[i] < 0) continue;
         const float* L = nodes + (size_t)hn[i].left * EZRT_BVHNODE_FLOATS;
@@ -333,8 +345,6 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         pack_node(&gnodes[(size_t)inner_id[i] * 4], L + 6, L + 9, R + 6, R + 9, child_ref(hn[i].left), child_ref(hn[i].right));
     }
     // reference leaf of every triangle + leaf boxes (accel policy: "does the shader reach this leaf?")
-    std::vector<int> tri_leaf(n_triangles, 0);
-    std::vector<float4> leaf_box;
     for (int i = 1; i < n_nodes; i++) {
         if (!seen[i] || hn[i].n <= 0) continue;
         const float* B = nodes + (size_t)i * EZRT_BVHNODE_FLOATS;
@@ -344,57 +354,69 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         for (int k = 0; k < hn[i].n; k++) tri_leaf[hn[i].index + k] = slot;
     }
 
-    lap("reference tree: decode, validate, repack");
-    // ---- triangles: geometry records, shading records, de-duplicated material table ----
-    std::vector<float4> geo((size_t)n_triangles * 4), shade((size_t)n_triangles * 3);
-    std::map<std::string, int> mat_ids;
-    std::vector<float4> mats;
-    float max_abs = 0.0f;
-    float bmin[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bmax[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    for (int i = 0; i < n_triangles; i++) {
-        const float* s = tris + (size_t)i * EZRT_TRIANGLE_FLOATS;
-        ez_vec3 p1 = ez_v3(s[0], s[1], s[2]), p2 = ez_v3(s[3], s[4], s[5]), p3 = ez_v3(s[6], s[7], s[8]);
-        for (int k = 0; k < 9; k++) {
-            max_abs = ez_max(max_abs, ez_abs(s[k]));
-            if (s[k] < bmin[k % 3]) bmin[k % 3] = s[k];
-            if (s[k] > bmax[k % 3]) bmax[k % 3] = s[k];
+    root_ref = child_ref(1);
+    return EZRT_OK;
+    };   // ref_stage
+    // ---- the scene object, the worker for the caller's tree, and the clean-up of every early return ----
+    ezrt_scene* sc = new (std::nothrow) ezrt_scene();
+    if (!sc) return ezrt_set_error(EZRT_ERR_NOMEM, "scene_create: out of host memory");
+    sc->device = device;
+    int ref_rc = EZRT_OK;
+    double ref_ms = 0.0;
+    struct Cleanup {   // declared after everything the worker touches: joined first, then those locals go
+        ezrt_scene* sc = nullptr;
+        std::thread worker;
+        DeviceBuffer raw;
+        ~Cleanup() {
+            if (worker.joinable()) worker.join();
+            raw.release();
+            if (sc) ezrt_scene_destroy(sc);
         }
-        ez_vec3 N = ez_normalize(ez_cross(ez_sub(p2, p1), ez_sub(p3, p1)));  // hitTriangle, P5/fsh:172
-        float d0 = ez_dot(N, p1);                                            // P5/fsh:184
-        geo[(size_t)i * 4 + 0] = make_float4(p1.x, p1.y, p1.z, N.x);
-        geo[(size_t)i * 4 + 1] = make_float4(p2.x, p2.y, p2.z, N.y);
-        geo[(size_t)i * 4 + 2] = make_float4(p3.x, p3.y, p3.z, N.z);
-        geo[(size_t)i * 4 + 3] = make_float4(d0, 0.0f, 0.0f, 0.0f);
-        std::string key((const char*)(s + 18), sizeof(float) * EZRT_MATERIAL_FLOATS);
-        auto it = mat_ids.find(key);
-        int id;
-        if (it == mat_ids.end()) {
-            id = (int)mat_ids.size();
-            mat_ids.emplace(key, id);
-            const float* m = s + 18;
-            mats.push_back(make_float4(m[0], m[1], m[2], m[3]));
-            mats.push_back(make_float4(m[4], m[5], m[6], m[7]));
-            mats.push_back(make_float4(m[8], m[9], m[10], m[11]));
-            mats.push_back(make_float4(m[12], m[13], m[14], m[15]));
-            mats.push_back(make_float4(m[16], m[17], 0.0f, 0.0f));
-        } else {
-            id = it->second;
-        }
-        float fid;
-        memcpy(&fid, &id, 4);
-        shade[(size_t)i * 3 + 0] = make_float4(s[9], s[10], s[11], fid);
-        shade[(size_t)i * 3 + 1] = make_float4(s[12], s[13], s[14], 0.0f);
-        shade[(size_t)i * 3 + 2] = make_float4(s[15], s[16], s[17], 0.0f);
+    } guard;
+    guard.sc = sc;
+    guard.worker = std::thread([&]() {
+        const auto t0 = std::chrono::steady_clock::now();
+        ref_rc = ref_stage();
+        ref_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    });
+    // ---- triangles: upload the caller's array once; geometry records, shading records, material runs and the scene
+    // bounds are made from it on the device (scene_prep.cu) ----
+    DeviceBuffer& raw = guard.raw;
+    {
+        int r = raw.ensure((size_t)n_triangles * EZRT_TRIANGLE_FLOATS * sizeof(float));
+        if (r) return r;
+        if (cudaMemcpy(raw.p, tris, (size_t)n_triangles * EZRT_TRIANGLE_FLOATS * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+            return ezrt_set_error(EZRT_ERR_CUDA, "scene_create: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-
-    lap("triangles: geometry / shading records, materials");
+    lap("triangles: upload");
+    EzrtPrepInfo prep;
+    {
+        int r = sc->tri_geo.ensure((size_t)n_triangles * 4 * sizeof(float4));
+        if (!r) r = sc->tri_shade.ensure((size_t)n_triangles * 3 * sizeof(float4));
+        if (!r) r = ezrt_prep_records((const float*)raw.p, n_triangles, sc->tri_geo.p, sc->tri_shade.p, prep);
+        if (r) return r;
+    }
+    std::vector<float4> mats;
+    for (int m = 0; m < prep.n_materials; m++) {
+        const float* v = &prep.materials[(size_t)m * EZRT_MATERIAL_FLOATS];
+        mats.push_back(make_float4(v[0], v[1], v[2], v[3]));
+        mats.push_back(make_float4(v[4], v[5], v[6], v[7]));
+        mats.push_back(make_float4(v[8], v[9], v[10], v[11]));
+        mats.push_back(make_float4(v[12], v[13], v[14], v[15]));
+        mats.push_back(make_float4(v[16], v[17], 0.0f, 0.0f));
+    }
+    const float max_abs = prep.max_abs;
+    float bmin[3], bmax[3];
+    for (int k = 0; k < 3; k++) { bmin[k] = prep.bmin[k]; bmax[k] = prep.bmax[k]; }
+    lap("triangles: geometry / shading records, materials (device)");
     // ---- acceleration tree: sentinel-free SAH over the same triangles (DESIGN.md "accel"), collapsed to 8-wide
     // quantised nodes (accel_w8.cpp, w8_node.h).  A tree too deep for the traversal stacks (degenerate input) is
     // dropped: the scene then renders with the PRUNED policy on the caller's tree, as for an irregular tree.
     const float prune_delta = max_abs * 1.52587890625e-05f;  // 2^-16 * scene extent
-    std::vector<float4> acc_geo((size_t)n_triangles * 4), acc_wide;
-    std::vector<uint32_t> w8_words, acc_wide_q;
-    bool q16_ok = true;
+    EzrtW4Tree w4;
+    EzrtRawArray<float>& acc_wide = w4.nodes;
+    EzrtRawArray<uint32_t>& acc_wide_q = w4.q16;
+    std::vector<uint32_t> w8_words;
     int acc_wide_root = 0;
     std::vector<uint32_t> acc_order;
     int acc_depth = 0, w8_depth = 0, w8_near_bit[3] = {0, 1, 2};
@@ -408,16 +430,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
             ezrt_build_accel(tris, n_triangles, W8_MAX_LEAF_TRIS, an, order_bin);
             lap("acceleration tree: binary SAH build (host)");
         } else {
-            DeviceBuffer raw;
-            int brc = raw.ensure((size_t)n_triangles * EZRT_TRIANGLE_FLOATS * sizeof(float));
-            if (brc) return brc;
-            if (cudaMemcpy(raw.p, tris, (size_t)n_triangles * EZRT_TRIANGLE_FLOATS * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
-                raw.release();
-                return ezrt_set_error(EZRT_ERR_CUDA, "scene_create: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-            }
-            lap("acceleration tree: triangle upload");
-            brc = ezrt_build_accel_device((const float*)raw.p, n_triangles, W8_MAX_LEAF_TRIS, an, order_bin, nullptr);
-            raw.release();
+            const int brc = ezrt_build_accel_device((const float*)raw.p, n_triangles, W8_MAX_LEAF_TRIS, an, order_bin, nullptr);
             if (brc < 0) return brc;
             lap("acceleration tree: binary SAH build (device)");
         }
@@ -445,128 +458,33 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
             }
         } else {
             // 4-wide collapse: SAH-optimal choice of each node's children (EzrtCollapse; env EZRT_W4_COLLAPSE=greedy: round 1's
-            // "replace the largest inner child" rule); leaves = sub-trees of <= 4 consecutive triangles
+            // "replace the largest inner child" rule); leaves = sub-trees of <= 4 consecutive triangles; packed by accel_w8.cpp
             const char* ce = getenv("EZRT_W4_COLLAPSE");
             const bool greedy = ce && !strcmp(ce, "greedy");
-            EzrtCollapse col;
-            if (col.build(an, 4, W8_MAX_LEAF_TRIS, 1.0, 0.3) != 0) {
+            const char* qe = getenv("EZRT_ACCEL_Q16");
+            const bool want_q16 = !(qe && atoi(qe) == 0);
+            if (ezrt_build_w4(an, pad, max_abs, greedy, want_q16, ezrt_host_threads(), w4) != 0) {
                 have_accel = false;
             } else {
                 acc_order = order_bin;
-                auto area = [&](int c) {
-                    float x = an[c].BB[0] - an[c].AA[0], y = an[c].BB[1] - an[c].AA[1], z = an[c].BB[2] - an[c].AA[2];
-                    return x * y + x * z + y * z;
-                };
-                int wide_depth = 0;
-                const char* qe = getenv("EZRT_ACCEL_Q16");
-                const bool want_q16 = !(qe && atoi(qe) == 0);
-                const double q16_min_step = (double)max_abs * (double)W8_MIN_STEP_REL;
-                std::function<int(int, int)> build_wide = [&](int b, int depth) -> int {
-                    wide_depth = std::max(wide_depth, depth);
-                    const int id = (int)(acc_wide.size() / 8);
-                    acc_wide.resize(acc_wide.size() + 8, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
-                    int ch[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
-                    int cnt = 0;
-                    if (greedy) {
-                        ch[0] = an[b].left; ch[1] = an[b].right;
-                        cnt = 2;
-                        while (cnt < 4) {
-                            int best = -1;
-                            float ba = -1.0f;
-                            for (int k = 0; k < cnt; k++)
-                                if (an[ch[k]].n <= 0 && area(ch[k]) > ba) { ba = area(ch[k]); best = k; }
-                            if (best < 0) break;
-                            const int c = ch[best];
-                            for (int k = cnt; k > best + 1; k--) ch[k] = ch[k - 1];
-                            ch[best] = an[c].left;
-                            ch[best + 1] = an[c].right;
-                            cnt++;
-                        }
-                    } else {
-                        cnt = col.children(b, ch);
-                    }
-                    float rec[32];
-                    int refs[4];
-                    for (int k = 0; k < 4; k++) {
-                        float AA[3] = {3.0e38f, 3.0e38f, 3.0e38f}, BB[3] = {3.0e38f, 3.0e38f, 3.0e38f};  // absent: a far-away point box (min/max slab test)
-                        refs[k] = (int)EZRT_LEAF_FLAG;  // EZRT_REF_DONE, never followed
-                        if (k < cnt) {
-                            const EzrtAccelNode& c = an[ch[k]];
-                            for (int a = 0; a < 3; a++) { AA[a] = c.AA[a] - pad; BB[a] = c.BB[a] + pad; }
-                            const bool leaf = greedy ? (c.n > 0) : (col.as_leaf[ch[k]] != 0);
-                            refs[k] = leaf ? (int)(EZRT_LEAF_FLAG | ((uint32_t)col.first[ch[k]] << 7) | (uint32_t)col.count[ch[k]]) : build_wide(ch[k], depth + 1);
-                        }
-                        rec[4 * k + 0] = AA[0]; rec[4 * k + 1] = AA[1]; rec[4 * k + 2] = BB[0]; rec[4 * k + 3] = BB[1];
-                        rec[16 + 2 * k] = AA[2]; rec[16 + 2 * k + 1] = BB[2];
-                    }
-                    memcpy(&rec[24], refs, 16);
-                    for (int k = 24 + 4; k < 32; k++) rec[k] = 0.0f;
-                    memcpy(&acc_wide[(size_t)id * 8], rec, sizeof(rec));
-                    if (want_q16) {   // the same node with 16-bit planes (device_functions.cuh "Q16"): 96 bytes
-                        uint32_t w[24];
-                        memset(w, 0, sizeof(w));
-                        for (int a = 0; a < 3; a++) {
-                            double nlo = 3.0e38, nhi = -3.0e38;
-                            for (int k = 0; k < cnt; k++) {
-                                nlo = std::min(nlo, (double)an[ch[k]].AA[a] - (double)pad);
-                                nhi = std::max(nhi, (double)an[ch[k]].BB[a] + (double)pad);
-                            }
-                            int e;
-                            frexp(std::max((nhi - nlo) / 65000.0, 1.0e-300), &e);
-                            double sc = ldexp(1.0, e);
-                            while (sc < q16_min_step) sc *= 2.0;
-                            float org = (float)(nlo - 2.0 * sc);
-                            while ((double)org > nlo - 2.0 * sc) org = nextafterf(org, -3.0e38f);
-                            const float scf = (float)sc;
-                            memcpy(&w[a], &org, 4);
-                            memcpy(&w[3 + a], &scf, 4);
-                            for (int k = 0; k < 4; k++) {
-                                uint32_t ql = 65535u, qh = 65535u;   // absent: a point at the far corner of the grid, outside every real child
-                                if (k < cnt) {
-                                    const double lo = (double)an[ch[k]].AA[a] - (double)pad, hi = (double)an[ch[k]].BB[a] + (double)pad;
-                                    const double l = floor((lo - (double)org) / sc - 1.25), h = ceil((hi - (double)org) / sc + 1.25);
-                                    if (l < 0.0 || h > 65534.0 || l > h) q16_ok = false;
-                                    ql = (uint32_t)std::max(0.0, l);
-                                    qh = (uint32_t)std::min(65535.0, h);
-                                }
-                                w[6 + 3 * k + a] = ql | (qh << 16);
-                            }
-                        }
-                        for (int k = 0; k < 4; k++) w[18 + k] = (k < cnt) ? (uint32_t)refs[k] : (EZRT_LEAF_FLAG | (1u << 7));  // absent: an empty leaf, should the point ever be hit
-                        if (acc_wide_q.size() < ((size_t)id + 1) * 24) acc_wide_q.resize(((size_t)id + 1) * 24, 0u);
-                        memcpy(&acc_wide_q[(size_t)id * 24], w, sizeof(w));
-                    }
-                    return id;
-                };
-                acc_wide_root = build_wide(0, 1);
-                acc_depth = wide_depth;
-                if (3 * wide_depth + 2 > EZRT_ACCEL_STACK) { acc_wide.clear(); have_accel = false; }  // too deep for the traversal stack
-                if (!want_q16 || !q16_ok || !have_accel) acc_wide_q.clear();
+                acc_wide_root = w4.root;
+                acc_depth = w4.depth;
+                if (3 * w4.depth + 2 > EZRT_ACCEL_STACK) { w4.nodes.clear(); have_accel = false; }  // too deep for the traversal stack
+                if (!have_accel) w4.q16.clear();
             }
         }
         if (!have_accel) {
             acc_order.resize(n_triangles);
             for (int i = 0; i < n_triangles; i++) acc_order[i] = (uint32_t)i;
         }
-        for (int i = 0; i < n_triangles; i++)
-            for (int k = 0; k < 4; k++) acc_geo[(size_t)i * 4 + k] = geo[(size_t)acc_order[i] * 4 + k];
+        raw.release();
     }
-    lap("acceleration tree: collapse, pack, reorder geometry");
-    // shading data and the reference-leaf map in the acceleration tree's order, and the inverse permutation
-    std::vector<float4> acc_shade((size_t)n_triangles * 3);
-    std::vector<int> acc_leaf(n_triangles);
-    std::vector<uint32_t> ref_to_acc(n_triangles);
-    for (int i = 0; i < n_triangles; i++) {
-        const uint32_t r = acc_order[i];
-        for (int k = 0; k < 3; k++) acc_shade[(size_t)i * 3 + k] = shade[(size_t)r * 3 + k];
-        acc_leaf[i] = tri_leaf[r];
-        ref_to_acc[r] = (uint32_t)i;
-    }
-
-    lap("shading records in the tree's order");
-    ezrt_scene* sc = new (std::nothrow) ezrt_scene();
-    if (!sc) return ezrt_set_error(EZRT_ERR_NOMEM, "scene_create: out of host memory");
-    sc->device = device;
+    lap("acceleration tree: collapse, pack");
+    // ---- the caller's tree is needed from here on ----
+    guard.worker.join();
+    if (verbose) fprintf(stderr, "[ezrt_scene_create] %-44s %8.1f ms (worker thread, overlapped)\n", "reference tree: decode, validate, repack", ref_ms);
+    if (ref_rc) return ezrt_set_error(ref_rc, "%s", ref_msg.c_str());
+    lap("wait for the reference-tree worker");
     cudaDeviceProp prop;
     memset(&prop, 0, sizeof(prop));
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
@@ -581,42 +499,49 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
             return ezrt_set_error(EZRT_ERR_CUDA, "scene_create: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return EZRT_OK;
     };
+    EzrtLap sub("ezrt_scene_create uploads");
     if (!rc) rc = upload(sc->nodes, gnodes.data(), gnodes.size() * sizeof(float4));
-    if (!rc) rc = upload(sc->tri_geo, geo.data(), geo.size() * sizeof(float4));
-    if (!rc) rc = upload(sc->tri_shade, shade.data(), shade.size() * sizeof(float4));
     if (!rc) rc = upload(sc->materials, mats.data(), mats.size() * sizeof(float4));
+    sub("reference-tree nodes, materials");
     // acceleration tree nodes | triangle geometry | shading records in ONE allocation: the window the
     // L2 persisting-access policy is set on while a render runs (the data every ray touches at random)
     const size_t acc_nodes_bytes = ((std::max<size_t>(w8_words.size(), 4) * sizeof(uint32_t) + 255) / 256) * 256;
-    const size_t acc_geo_bytes = ((acc_geo.size() * sizeof(float4) + 255) / 256) * 256;
-    const size_t acc_shade_bytes = ((acc_shade.size() * sizeof(float4) + 255) / 256) * 256;
+    const size_t acc_geo_bytes = (((size_t)n_triangles * 4 * sizeof(float4) + 255) / 256) * 256;
+    const size_t acc_shade_bytes = (((size_t)n_triangles * 3 * sizeof(float4) + 255) / 256) * 256;
     if (!rc) rc = sc->acc_hot.ensure(acc_nodes_bytes + acc_geo_bytes + acc_shade_bytes);
     if (!rc) {
         char* base = (char*)sc->acc_hot.p;
         cudaError_t e = w8_words.empty() ? cudaSuccess : cudaMemcpy(base, w8_words.data(), w8_words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(base + acc_nodes_bytes, acc_geo.data(), acc_geo.size() * sizeof(float4), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(base + acc_nodes_bytes + acc_geo_bytes, acc_shade.data(), acc_shade.size() * sizeof(float4), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) rc = ezrt_set_error(EZRT_ERR_CUDA, "scene_create: upload failed: %s", cudaGetErrorString(e));
         sc->hot_base = base;
         sc->hot_bytes = acc_nodes_bytes + acc_geo_bytes + acc_shade_bytes;
     }
+    sub("hot allocation");
     if (!rc) rc = upload(sc->acc_tri_ref, acc_order.data(), acc_order.size() * sizeof(uint32_t));
-    if (!rc && !acc_wide.empty()) rc = upload(sc->acc_wide, acc_wide.data(), acc_wide.size() * sizeof(float4));
+    if (!rc && !acc_wide.empty()) rc = upload(sc->acc_wide, acc_wide.data(), acc_wide.size() * sizeof(float));
     if (!rc && !acc_wide_q.empty()) rc = upload(sc->acc_wide_q16, acc_wide_q.data(), acc_wide_q.size() * sizeof(uint32_t));
     if (!rc) rc = upload(sc->tri_leaf, tri_leaf.data(), tri_leaf.size() * sizeof(int));
     if (!rc) rc = upload(sc->leaf_box, leaf_box.data(), leaf_box.size() * sizeof(float4));
-    if (!rc) rc = upload(sc->acc_tri_leaf, acc_leaf.data(), acc_leaf.size() * sizeof(int));
-    if (!rc) rc = upload(sc->ref_to_acc, ref_to_acc.data(), ref_to_acc.size() * sizeof(uint32_t));
+    sub("order, wide nodes, leaf map, leaf boxes");
+    // geometry, shading records and the reference-leaf map in the acceleration tree's order, and the inverse permutation:
+    // gathered on the device
+    if (!rc) rc = sc->acc_tri_leaf.ensure((size_t)n_triangles * sizeof(int));
+    if (!rc) rc = sc->ref_to_acc.ensure((size_t)n_triangles * sizeof(uint32_t));
+    if (!rc)
+        rc = ezrt_prep_gather(sc->tri_geo.p, sc->tri_shade.p, (const int*)sc->tri_leaf.p, (const uint32_t*)sc->acc_tri_ref.p, n_triangles,
+                              (char*)sc->acc_hot.p + acc_nodes_bytes, (char*)sc->acc_hot.p + acc_nodes_bytes + acc_geo_bytes,
+                              (int*)sc->acc_tri_leaf.p, (uint32_t*)sc->ref_to_acc.p);
+    sub("gather");
     if (!rc && hdr) rc = upload(sc->hdr, hdr, sizeof(float) * 3 * (size_t)hdr_w * hdr_h);
     if (!rc && hdr_cache) rc = upload(sc->hdr_cache, hdr_cache, sizeof(float) * 3 * (size_t)hdr_w * hdr_h);
+    sub("environment map, cache");
     if (!rc && cudaStreamCreateWithFlags(&sc->own_stream, cudaStreamNonBlocking) != cudaSuccess) rc = ezrt_set_error(EZRT_ERR_CUDA, "scene_create: stream");
     if (!rc && (cudaEventCreate(&sc->ev_start) != cudaSuccess || cudaEventCreate(&sc->ev_stop) != cudaSuccess)) rc = ezrt_set_error(EZRT_ERR_CUDA, "scene_create: events");
-    if (rc) {
-        ezrt_scene_destroy(sc);
-        return rc;
-    }
-    lap("uploads");
-    sc->n_materials = (int)mat_ids.size();
+    sub("stream, events");
+    if (rc) return rc;
+    lap("uploads, records in the tree's order (device)");
+    guard.sc = nullptr;   // from here on the scene is the caller's
+    sc->n_materials = prep.n_materials;
     sc->regular_tree = regular_tree;
     sc->have_accel = have_accel;
     sc->tree_depth = max_depth;
@@ -628,7 +553,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     d.hdr = hdr ? (const float*)sc->hdr.p : nullptr;
     d.hdr_cache = hdr_cache ? (const float*)sc->hdr_cache.p : nullptr;
     d.hdr_w = hdr_w; d.hdr_h = hdr_h; d.hdr_linear = hdr_filter_linear ? 1 : 0;
-    d.root_ref = child_ref(1);
+    d.root_ref = root_ref;
     d.w8_nodes = w8_words.empty() ? nullptr : (const uint4*)sc->acc_hot.p;
     for (int k = 0; k < 3; k++) d.w8_near_bit[k] = w8_near_bit[k];
     d.w8_stack_entries = std::max(1, std::min(w8_depth, EZRT_W8_SMEM_STACK));

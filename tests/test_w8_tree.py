@@ -66,3 +66,26 @@ def test_w8_traversal_large_grid_against_exact_boxes(tmp_path):
     tris, _, _, _ = scenes.s_grid(4, 3, 2, mesh="bunny")
     out = _run_model(str(tmp_path), tris, _rays(tris, 40000, 3), brute=False)
     print(out)
+
+
+def _run_w4_check(tmp_path, tris):
+    exe = build.build_w4_check()
+    tf = os.path.join(tmp_path, "tris_w4.f32")
+    np.ascontiguousarray(tris, np.float32).tofile(tf)
+    r = subprocess.run([exe, tf, str(tris.shape[0])], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout
+    return r.stdout
+
+
+def test_w4_builder_is_thread_count_independent_and_well_formed(tmp_path):
+    """ezrt_build_w4 (the default 4-wide form + its 96-byte Q16 twin): the same arrays for 1, 2, 5 and 16 threads and both collapse
+    rules; every triangle in exactly one leaf, child boxes (exact and quantised) contain their triangles."""
+    tris, _, _, _ = scenes.s_p3_bunny()
+    out = _run_w4_check(str(tmp_path), tris)
+    assert "violations 0" in out
+    rng = np.random.default_rng(11)
+    soup = np.zeros((70000, 36), np.float32)     # > 65536 binary nodes: the threaded path without the override, too
+    c = rng.uniform(-5, 5, (70000, 1, 3))
+    soup[:, :9] = (c + rng.uniform(-0.05, 0.05, (70000, 3, 3))).reshape(-1, 9).astype(np.float32)
+    soup[:300, :9] = soup[0, :9]                 # coincident triangles
+    _run_w4_check(str(tmp_path), soup)

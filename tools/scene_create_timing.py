@@ -1,6 +1,6 @@
 """Stage timing of ezrt_scene_create (env EZRT_VERBOSE=1) on the bench scenes.  Usage: python tools/scene_create_timing.py [c3 c2 ...]"""
 import os, sys, time
-os.environ["EZRT_VERBOSE"] = "1"
+os.environ.setdefault("EZRT_VERBOSE", "1")
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import bench
 from ezrt_b200 import api
