@@ -335,6 +335,7 @@ int ezrt_build_accel_device(const float* d_tris, int n, int leaf_n, std::vector<
     d.tri_box = tri_box;
 
     CUB_OK(cudaMemsetAsync(d.used, 0, (size_t)n_slots * sizeof(int)));
+    CUB_OK(cudaMemsetAsync(d.side, 0, (size_t)n));   // read by the partition scan for the triangles of finished leaves as well
     k_tri_boxes<<<blocks, threads>>>(d_tris, n, tri_box, keys[0], keys[1], keys[2], iota);
     for (int a = 0; a < 3; a++) {
         size_t b = temp_bytes;

@@ -99,6 +99,11 @@ struct ezrt_scene {
     size_t n_pixels = 0;       // pixels of the owned tiles
     size_t fmax = 0, fmax_key[2] = {0, 0};   // frames per batch that fit the free memory, for (slots per frame, bytes per slot)
     cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+    // the accel policy's deferred lane: exact traversal + shading of the few deferred rays beside the main k_shade
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    DeviceBuffer side_hit_buf;
+    int deferred_lane = 1;   // env EZRT_DEFERRED_LANE=0: the exact pass in line, as in round 1
     cudaEvent_t fb_event = nullptr, fb_wait = nullptr;   // ezrt_render: the H2D of lastFrame runs beside the tracing kernels
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool have_timing = false;
@@ -588,6 +593,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         d.cell_scale[k] = (ext > 0.0f) ? 32.0f / ext : 0.0f;
     }
     if (const char* e = getenv("EZRT_SORT_RAYS")) sc->sort_rays = atoi(e);
+    if (const char* e = getenv("EZRT_DEFERRED_LANE")) sc->deferred_lane = atoi(e) != 0;
     if (const char* e = getenv("EZRT_CAMERA_ORDER")) sc->camera_pixel_major = strcmp(e, "frame") != 0;
     {   // optional L2 persistence for the randomly-accessed tree data (env EZRT_L2_PERSIST=1)
         // measured on C3: -8 % (the set-aside shrinks the L2 left for the streaming queue traffic) -> off by default
@@ -625,6 +631,10 @@ int ezrt_scene_destroy(ezrt_scene* s) {
     s->lo_buf.release(); s->le_buf.release(); s->counters_buf.release(); s->totals_buf.release(); s->fb_buf.release(); s->sort_buf.release();
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    if (s->side_stream) cudaStreamDestroy(s->side_stream);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
+    s->side_hit_buf.release();
     if (s->fb_event) cudaEventDestroy(s->fb_event);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
     if (s->ev_stop) cudaEventDestroy(s->ev_stop);
@@ -739,6 +749,21 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     }
 
     unsigned long long* const count_ptr = (p->profile == 2) ? totals + 5 : nullptr;  // node visits, triangle tests of the W8 kernels
+    // the deferred lane needs a second stream (highest priority: its small blocks go first when an SM has room), two events and
+    // the hit records of up to EZRT_SIDE_CAP deferred rays
+    const bool lane = accel && s->deferred_lane;
+    float2* side_hit = nullptr;
+    if (lane) {
+        if (!s->side_stream) {
+            int lo_pri = 0, hi_pri = 0;
+            cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+            if (cudaStreamCreateWithPriority(&s->side_stream, cudaStreamNonBlocking, hi_pri) != cudaSuccess) return ezrt_set_error(EZRT_ERR_CUDA, "render: side stream");
+            if (cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess)
+                return ezrt_set_error(EZRT_ERR_CUDA, "render: events");
+        }
+        if ((rc = s->side_hit_buf.ensure(sizeof(float2) * (size_t)EZRT_SIDE_CAP))) return rc;
+        side_hit = (float2*)s->side_hit_buf.p;
+    }
     const bool l2_window = accel && s->l2_persist_bytes > 0 && s->hot_bytes > 0;
     if (l2_window) {
         cudaStreamAttrValue attr;
@@ -776,20 +801,31 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
                 perm = sort_perm;
             }
             sp = s->span_begin(0, st);
+            const int exact_gate = lane ? 2 : 0;   // lane: only an overflowing list of deferred rays is traced in line
             if (accel && fused_camera && b == 0) {
                 launch_extend_camera(s->dev, rd, d_tiles, batch_first, n_slots, s->camera_pixel_major ? (uint32_t)nf : 0u, qin, &w_ext[b], defer_list, &d_ext[b], &dw_ext[b],
-                                     s->n_sms, count_ptr, st);
+                                     s->n_sms, count_ptr, st, exact_gate);
                 s->launches++;
             } else if (accel) {
-                launch_extend_accel(s->dev, qin, &q_count[b], &w_ext[b], defer_list, &d_ext[b], &dw_ext[b], n_slots, s->n_sms, count_ptr, perm, st);
+                launch_extend_accel(s->dev, qin, &q_count[b], &w_ext[b], defer_list, &d_ext[b], &dw_ext[b], n_slots, s->n_sms, count_ptr, perm, st, exact_gate);
                 s->launches++;
             } else {
                 launch_extend(s->dev, prune, false, qin, &q_count[b], &w_ext[b], perm, 0, n_slots, s->n_sms, st);
             }
             s->span_end(sp, st);
+            const uint32_t n_fused = (fused_camera && b == 0) ? n_slots : 0u;
+            if (lane) {   // fork: the deferred rays of this bounce are traced exactly and shaded on the side stream ...
+                CU_CHECK(cudaEventRecord(s->ev_fork, st));
+                CU_CHECK(cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0));
+                launch_deferred_lane(s->dev, rd, d_tiles, b, batch_first, qin, defer_list, &d_ext[b], &dw_ext[b], side_hit, qout, &q_count[b + 1], sq, &s_count[b],
+                                     Lo, Le, n_fused, (uint32_t)nf, s->n_sms, s->side_stream);
+                CU_CHECK(cudaEventRecord(s->ev_join, s->side_stream));
+                s->launches += 2;
+            }
             sp = s->span_begin(1, st);
             launch_shade(s->dev, rd, d_tiles, b, batch_first, qin, &q_count[b], qout, &q_count[b + 1], sq, &s_count[b], Lo, Le,
-                         n_slots, (fused_camera && b == 0) ? n_slots : 0u, (uint32_t)nf, s->n_sms, st);
+                         n_slots, n_fused, (uint32_t)nf, s->n_sms, st);
+            if (lane) CU_CHECK(cudaStreamWaitEvent(st, s->ev_join, 0));   // ... while this k_shade shades all the others; join
             s->span_end(sp, st);
             s->launches += 2;
             if (is_mode && b < p->max_bounce) {

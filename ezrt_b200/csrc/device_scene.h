@@ -29,6 +29,8 @@
 #define EZRT_LEAF_FLAG 0x80000000u
 #define EZRT_LEAF_MAX_N 127
 #define EZRT_TOP_NODES_MAX 1023   // 10 full levels; 80 B each in shared memory (bank-conflict padding)
+#define EZRT_TRI_PENDING (-2)      // hit record of a ray the accel kernel deferred to the exact pass (a miss is -1)
+#define EZRT_SIDE_CAP 65536u       // deferred rays per pass handled on the side stream beside k_shade; more: in line, as before
 #define EZRT_ACCEL_STACK 64       // stack entries of the 4-wide accel kernel (<= 3 pushes per level): trees deeper than 20 levels are not built
 #define EZRT_W8_SMEM_STACK 16      // per-lane W8 stack entries held in shared memory (8 B each x 1024 threads = 128 KB at most)
 #define EZRT_TOP_STRIDE 5         // float4 per shared-memory record

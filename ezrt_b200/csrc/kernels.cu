@@ -206,6 +206,7 @@ struct ExtendIO {
     PathQueue q;
     const uint32_t* perm;      // null: trace in queue order
     const uint32_t* to_accel;  // non-null (fallback pass of the accel policy): hits are stored as accel-order indices
+    float2* side_hit;          // non-null (that pass on the side stream): hit i of the list goes to side_hit[i], not to the queue
     __device__ __forceinline__ bool load(uint32_t i, vec3& o, vec3& d) const {
         const uint32_t j = perm ? perm[i] : i;
         float4 o4 = __ldcs(q.ray_o + j), d4 = __ldcs(q.ray_d + j);  // queue data streams through the caches
@@ -217,22 +218,29 @@ struct ExtendIO {
         const uint32_t j = perm ? perm[i] : i;
         int tri = h.tri;
         if (to_accel && tri >= 0) tri = (int)__ldg(to_accel + tri);
-        __stcs(q.hit + j, make_float2(h.t, __int_as_float(tri)));
+        if (side_hit) side_hit[i] = make_float2(h.t, __int_as_float(tri));
+        else __stcs(q.hit + j, make_float2(h.t, __int_as_float(tri)));
     }
     __device__ __forceinline__ void defer(uint32_t, vec3, vec3) const {}
 };
 
+// gate (the accel policy's pass over the deferred rays, DESIGN.md "deferred lane"): 0 = always; 1 = only if the list holds at most
+// EZRT_SIDE_CAP rays (side stream, results to side_hit, no tree staging: a handful of rays, run beside k_shade); 2 = only if it holds
+// more (in line, results to the queue).  Exactly one of the passes 1 and 2 does the work.
 template <bool PRUNE, bool ANYHIT>
 __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS) k_extend(SceneDev sc, PathQueue q, const uint32_t* __restrict__ q_count,
-                                                                uint32_t* work, const uint32_t* __restrict__ perm, int to_accel) {
+                                                                uint32_t* work, const uint32_t* __restrict__ perm, int to_accel, float2* side_hit, int gate) {
     ExtendIO io;
     io.q = q;
     io.perm = perm;
     io.to_accel = to_accel ? sc.ref_to_acc : nullptr;
+    io.side_hit = side_hit;
     const uint32_t n = *q_count;
     if (blockIdx.x * blockDim.x >= n) return;   // nothing for this block (the pass over an accel kernel's deferred rays is usually empty):
                                                 // do not stage 80 KB of tree for it
-    const TreeView tree = reference_tree(sc);
+    if ((gate == 1 && n > EZRT_SIDE_CAP) || (gate == 2 && n <= EZRT_SIDE_CAP)) return;
+    TreeView tree = reference_tree(sc);
+    if (gate == 1) tree.top_nodes = 0;
     stage_top_nodes(tree);
     extend_persistent<PRUNE, ANYHIT, false, false, 8, false, false>(sc, tree, n, work, io, g_smem_top);
 }
@@ -316,7 +324,11 @@ struct AccelExtendIO {
         d = ez_v3(d4.x, d4.y, d4.z);
         return true;
     }
-    __device__ __forceinline__ void defer(uint32_t i, vec3, vec3) const { defer_list[atomicAdd(defer_count, 1u)] = perm ? perm[i] : i; }
+    __device__ __forceinline__ void defer(uint32_t i, vec3, vec3) const {
+        const uint32_t j = perm ? perm[i] : i;
+        __stcs(q.hit + j, make_float2(0.0f, __int_as_float(EZRT_TRI_PENDING)));   // k_shade leaves it to the pass over the deferred rays
+        defer_list[atomicAdd(defer_count, 1u)] = j;
+    }
     __device__ __forceinline__ void store(uint32_t i, HitRec h, bool tie, vec3 o, vec3 d, vec3 inv) const {
         if (h.tri >= 0 && (tie || !reference_reaches_leaf_inv(acc_tri_leaf, leaf_box, h.tri, o, inv))) {
             defer(i, o, d);
@@ -358,6 +370,7 @@ struct AccelCameraIO {
     __device__ __forceinline__ void defer_slot(uint32_t slot, vec3 o, vec3 d) const {
         q.ray_o[slot] = make_float4(o.x, o.y, o.z, 0.0f);
         q.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.0f);
+        __stcs(q.hit + slot, make_float2(0.0f, __int_as_float(EZRT_TRI_PENDING)));
         defer_list[atomicAdd(defer_count, 1u)] = slot;
     }
     __device__ __forceinline__ void defer(uint32_t i, vec3 o, vec3 d) const { defer_slot(slot_of(i), o, d); }
@@ -499,11 +512,15 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
 #ifndef EZRT_SHADE_MIN_BLOCKS
 #define EZRT_SHADE_MIN_BLOCKS 8   // 64 registers: k_shade is latency-bound, 32 resident warps beat 20 despite small spills
 #endif
-template <int MODE>
+// LIST (the pass over the accel policy's deferred rays, on the side stream beside the main k_shade): entry k is queue entry /
+// sample slot list[k], its hit is side_hit[k]; nothing to do when the list overflowed (then the in-line exact pass filled the
+// queue's hit records and the main k_shade found no pending ones).
+template <int MODE, bool LIST>
 __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev sc, RenderDev rd, const TileDev* __restrict__ tiles, int bounce,
                                                uint32_t batch_first_frame, PathQueue qin, const uint32_t* __restrict__ in_count,
                                                PathQueue qout, uint32_t* out_count, ShadowQueue sq, uint32_t* s_count,
-                                               float4* __restrict__ Lo, float4* __restrict__ Le, uint32_t n_fused, uint32_t n_frames) {
+                                               float4* __restrict__ Lo, float4* __restrict__ Le, uint32_t n_fused, uint32_t n_frames,
+                                               const uint32_t* __restrict__ list, const float2* __restrict__ side_hit) {
     // The Sobol pair of (bounce, frame) is the same for every pixel of a frame (P5/fsh:361-376: up to 2 x 32 table XORs per path): each
     // block computes the pairs of the batch's frames once into shared memory (batches of more than EZRT_SOBOL_TABLE frames compute per path).
     __shared__ float2 s_sobol[EZRT_SOBOL_TABLE];
@@ -515,7 +532,8 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
     // n_fused != 0 (bounce 0 of the W8 policy): entry i is sample slot i, its camera ray was generated inside
     // k_extend_w8_camera and is generated again here instead of being read from a queue; only q.hit[i] is read
     __shared__ uint32_t s_scan[34];
-    const uint32_t n = n_fused ? n_fused : *in_count;
+    const uint32_t n = (LIST || !n_fused) ? *in_count : n_fused;   // LIST: in_count = length of the list
+    if (LIST && n > EZRT_SIDE_CAP) return;
     const uint32_t n_round = ((n + blockDim.x - 1u) / blockDim.x) * blockDim.x;
     const uint32_t stride = gridDim.x * blockDim.x;
 #if EZRT_SHADE_REGROUP
@@ -564,9 +582,15 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
         uint32_t slot = 0;
         uint32_t px = 0, py = 0, fib = 0;
         bool present = i < n;
+        float2 hit = make_float2(0.0f, 0.0f);
+        if (LIST) {
+            if (present) { hit = side_hit[i]; i = list[i]; }
+        } else if (present) {
+            hit = __ldcs(qin.hit + i);
+            present = __float_as_int(hit.y) != EZRT_TRI_PENDING;   // deferred by the accel kernel: shaded by the LIST pass
+        }
         if (present && n_fused) present = slot_pixel(rd, tiles, i, px, py, fib);   // slots of clipped tiles outside the image
         if (present) {
-            const float2 hit = __ldcs(qin.hit + i);
             if (n_fused) {
                 slot = i;
                 primary_ray(rd, px, py, batch_first_frame + fib, p.seed, p.o, p.d);
@@ -841,7 +865,7 @@ static void set_dynamic_smem(const void* kernel, size_t bytes) {
     static std::map<const void*, size_t> done;
     std::lock_guard<std::mutex> lock(mu);
     auto it = done.find(kernel);
-    if (it != done.end() && it->second == bytes) return;
+    if (it != done.end() && it->second >= bytes) return;   // the attribute is a maximum
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     done[kernel] = bytes;
 }
@@ -859,12 +883,18 @@ static int persistent_blocks(uint32_t n_max, int n_sms) {
 // exact traversal of the reference tree (policies REFERENCE / PRUNED, and the accel policy's fallback pass
 // over the deferred indices in `perm`)
 void launch_extend(const SceneDev& sc, bool prune, bool anyhit, PathQueue q, const uint32_t* q_count, uint32_t* work,
-                   const uint32_t* perm, int to_accel, uint32_t n_max, int n_sms, cudaStream_t st) {
-    const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
-    if (prune && anyhit) k_extend<true, true><<<blocks, threads, smem_for(k_extend<true, true>, sc.top_nodes), st>>>(sc, q, q_count, work, perm, to_accel);
-    else if (prune) k_extend<true, false><<<blocks, threads, smem_for(k_extend<true, false>, sc.top_nodes), st>>>(sc, q, q_count, work, perm, to_accel);
-    else if (anyhit) k_extend<false, true><<<blocks, threads, smem_for(k_extend<false, true>, sc.top_nodes), st>>>(sc, q, q_count, work, perm, to_accel);
-    else k_extend<false, false><<<blocks, threads, smem_for(k_extend<false, false>, sc.top_nodes), st>>>(sc, q, q_count, work, perm, to_accel);
+                   const uint32_t* perm, int to_accel, uint32_t n_max, int n_sms, cudaStream_t st, float2* side_hit, int gate) {
+    int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
+    int top = sc.top_nodes;
+    if (gate == 1) {   // a few rays beside k_shade: small blocks find room on an SM as soon as one k_shade block retires
+        threads = 128;
+        blocks = std::max(1, std::min(div_up(n_max, threads), n_sms * 4));
+        top = 0;
+    }
+    if (prune && anyhit) k_extend<true, true><<<blocks, threads, smem_for(k_extend<true, true>, top), st>>>(sc, q, q_count, work, perm, to_accel, side_hit, gate);
+    else if (prune) k_extend<true, false><<<blocks, threads, smem_for(k_extend<true, false>, top), st>>>(sc, q, q_count, work, perm, to_accel, side_hit, gate);
+    else if (anyhit) k_extend<false, true><<<blocks, threads, smem_for(k_extend<false, true>, top), st>>>(sc, q, q_count, work, perm, to_accel, side_hit, gate);
+    else k_extend<false, false><<<blocks, threads, smem_for(k_extend<false, false>, top), st>>>(sc, q, q_count, work, perm, to_accel, side_hit, gate);
 }
 template <class K>
 static size_t w8_smem_for(K kernel, const SceneDev& sc) {
@@ -876,7 +906,7 @@ static size_t w8_smem_for(K kernel, const SceneDev& sc) {
 // exact pass over whatever it deferred.  counts != null selects the counting instantiation (params.profile = 2).
 void launch_extend_accel(const SceneDev& sc, PathQueue q, const uint32_t* q_count, uint32_t* work, uint32_t* defer_list,
                          uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, unsigned long long* counts, const uint32_t* perm,
-                         cudaStream_t st) {
+                         cudaStream_t st, int exact_gate) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_max, n_sms);
     if (sc.w8_nodes) {
         W8Counts c;
@@ -897,7 +927,7 @@ void launch_extend_accel(const SceneDev& sc, PathQueue q, const uint32_t* q_coun
             else k_extend_accel<false, false><<<blocks, threads, smem_for(k_extend_accel<false, false>, 0), st>>>(sc, q, q_count, work, defer_list, defer_count, c, perm);
         }
     }
-    launch_extend(sc, true, false, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_max, 65536u), n_sms, st);
+    launch_extend(sc, true, false, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_max, 65536u), n_sms, st, nullptr, exact_gate);
 }
 // counting sort of the queue's ray indices into `perm` (3 kernels; bins must hold EZRT_SORT_BINS counters)
 void launch_ray_sort(const SceneDev& sc, PathQueue q, const uint32_t* q_count, uint32_t* keys, uint32_t* bins, uint32_t* perm,
@@ -917,7 +947,7 @@ void launch_shadow(const SceneDev& sc, bool prune, ShadowQueue sq, const uint32_
 // camera pass of the W8 policy: rays generated in the kernel (slot i = ray i), then the exact pass over the deferred ones
 void launch_extend_camera(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, uint32_t batch_first_frame, uint32_t n_slots, uint32_t n_frames, PathQueue q,
                           uint32_t* work, uint32_t* defer_list, uint32_t* defer_count, uint32_t* defer_work, int n_sms, unsigned long long* counts,
-                          cudaStream_t st) {
+                          cudaStream_t st, int exact_gate) {
     const int threads = extend_threads(), blocks = persistent_blocks(n_slots, n_sms);
     W8Counts c;
     c.node_visits = counts ? (sc.w8_nodes ? counts + 2 : counts) : nullptr;   // the 4-wide camera pass reads the 128-byte exact nodes
@@ -929,7 +959,7 @@ void launch_extend_camera(const SceneDev& sc, const RenderDev& rd, const TileDev
         if (counts) k_extend_accel_camera<true><<<blocks, threads, smem_for(k_extend_accel_camera<true>, 0), st>>>(sc, rd, tiles, batch_first_frame, n_slots, n_frames, q, work, defer_list, defer_count, c);
         else k_extend_accel_camera<false><<<blocks, threads, smem_for(k_extend_accel_camera<false>, 0), st>>>(sc, rd, tiles, batch_first_frame, n_slots, n_frames, q, work, defer_list, defer_count, c);
     }
-    launch_extend(sc, true, false, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_slots, 65536u), n_sms, st);
+    launch_extend(sc, true, false, q, defer_count, defer_work, defer_list, 1, std::min<uint32_t>(n_slots, 65536u), n_sms, st, nullptr, exact_gate);
 }
 void launch_shadow_accel(const SceneDev& sc, ShadowQueue sq, const uint32_t* s_count, uint32_t* work, float4* Lo, uint32_t* defer_list,
                          uint32_t* defer_count, uint32_t* defer_work, uint32_t n_max, int n_sms, unsigned long long* counts, cudaStream_t st) {
@@ -959,7 +989,25 @@ void launch_shade(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles,
                   uint32_t* s_count, float4* Lo, float4* Le, uint32_t n_max, uint32_t n_fused, uint32_t n_frames, int n_sms, cudaStream_t st) {
     int blocks = std::min(div_up(n_max, 128), n_sms * 4 * EZRT_SHADE_MIN_BLOCKS);
     if (blocks < 1) blocks = 1;
-#define EZRT_LAUNCH_SHADE(M) k_shade<M><<<blocks, 128, 0, st>>>(sc, rd, tiles, bounce, batch_first_frame, qin, in_count, qout, out_count, sq, s_count, Lo, Le, n_fused, n_frames)
+#define EZRT_LAUNCH_SHADE(M) k_shade<M, false><<<blocks, 128, 0, st>>>(sc, rd, tiles, bounce, batch_first_frame, qin, in_count, qout, out_count, sq, s_count, Lo, Le, n_fused, n_frames, nullptr, nullptr)
+    switch (rd.mode) {
+        case EZRT_MODE_DIFFUSE_P3: EZRT_LAUNCH_SHADE(EZRT_MODE_DIFFUSE_P3); break;
+        case EZRT_MODE_DISNEY_ANISO_P4: EZRT_LAUNCH_SHADE(EZRT_MODE_DISNEY_ANISO_P4); break;
+        case EZRT_MODE_DISNEY_SOBOL_P5: EZRT_LAUNCH_SHADE(EZRT_MODE_DISNEY_SOBOL_P5); break;
+        default: EZRT_LAUNCH_SHADE(EZRT_MODE_DISNEY_IS_MIS_P5); break;
+    }
+#undef EZRT_LAUNCH_SHADE
+}
+// The accel policy's deferred lane (side stream, beside the main k_shade of the same bounce): exact traversal of the deferred
+// rays into side_hit, then their shading -- both do nothing if more than EZRT_SIDE_CAP rays were deferred (then
+// launch_extend_accel / launch_extend_camera with exact_gate = 2 traced them in line).
+void launch_deferred_lane(const SceneDev& sc, const RenderDev& rd, const TileDev* tiles, int bounce, uint32_t batch_first_frame, PathQueue qin,
+                          const uint32_t* defer_list, const uint32_t* defer_count, uint32_t* defer_work, float2* side_hit, PathQueue qout,
+                          uint32_t* out_count, ShadowQueue sq, uint32_t* s_count, float4* Lo, float4* Le, uint32_t n_fused, uint32_t n_frames,
+                          int n_sms, cudaStream_t st) {
+    launch_extend(sc, true, false, qin, defer_count, defer_work, defer_list, 1, EZRT_SIDE_CAP, n_sms, st, side_hit, 1);
+    const int blocks = 8;
+#define EZRT_LAUNCH_SHADE(M) k_shade<M, true><<<blocks, 128, 0, st>>>(sc, rd, tiles, bounce, batch_first_frame, qin, defer_count, qout, out_count, sq, s_count, Lo, Le, n_fused, n_frames, defer_list, side_hit)
     switch (rd.mode) {
         case EZRT_MODE_DIFFUSE_P3: EZRT_LAUNCH_SHADE(EZRT_MODE_DIFFUSE_P3); break;
         case EZRT_MODE_DISNEY_ANISO_P4: EZRT_LAUNCH_SHADE(EZRT_MODE_DISNEY_ANISO_P4); break;

@@ -153,6 +153,52 @@ def test_deep_caller_tree_and_degenerate_geometry(oracle):
         sc.close()
 
 
+@pytest.mark.parametrize("lane", ["1", "0"])
+def test_deferred_lane_few_and_many_deferred_rays(oracle, lane, monkeypatch):
+    """The accel policy's deferred rays are traced exactly and shaded on a side stream beside k_shade (capi.cu "deferred lane") when
+    there are at most EZRT_SIDE_CAP = 65536 of them in a pass, in line otherwise; EZRT_DEFERRED_LANE=0 is round 1's in-line pass.
+    A wall of 40 coincident triangles in front of the bunny defers every ray that hits it (ties): at 64x48 a few thousand rays per
+    pass, at 640x480x2 more than the cap in the camera pass and fewer in the others.  All bit-identical to the oracle,
+    with and without shadow rays (IS/MIS shades through the same lane), and equal ray counts."""
+    monkeypatch.setenv("EZRT_DEFERRED_LANE", lane)
+    tris, nodes, eye, cam = scenes.s_p3_bunny()
+    wall = np.zeros((40, 36), np.float32)
+    e = np.asarray(eye, np.float64)
+    n = e / np.linalg.norm(e)
+    u = np.cross([0.0, 1.0, 0.0], n)
+    u /= np.linalg.norm(u)
+    v = np.cross(n, u)
+    c, h = 0.55 * e, 0.6 * np.linalg.norm(e)      # between the camera and the bunny, facing the camera, wider than the view
+    wall[:, :9] = np.concatenate([c - 2 * h * u - h * v, c + 2 * h * u - h * v, c + 3 * h * v]).astype(np.float32)
+    wall[:, 9:18] = np.tile(n.astype(np.float32), 3)
+    wall[:, 18:21] = 0.0          # emissive 0
+    wall[:, 21:24] = (0.7, 0.6, 0.5)
+    wall[:, 28] = 0.4
+    tl = api.TriangleList()
+    tl.append_encoded(np.concatenate([tris, wall]))
+    tt, nn = tl.build_bvh(8, api.BVH_SAH_FAST)
+    hdr = scenes.synth_hdr(64, 32)
+    cache = api.hdr_cache(hdr)
+    sc = api.Scene(tt, nn, hdr, cache)
+    try:
+        for mode in (api.MODE_DISNEY_SOBOL_P5, api.MODE_DISNEY_IS_MIS_P5):
+            cfg = _cfg(eye, cam, width=64, height=48, spp=3, max_bounce=2, mode=mode)
+            ref, rc = oracle.render(tt, nn, cfg, hdr=hdr, hdr_cache=cache)
+            assert_same_bits(sc.render(cfg), ref, "few deferred rays, mode %d" % mode)
+            c = sc.counters()
+            assert c.rays == rc["rays"] and 0 < c.deferred_rays < 65536
+            cfg = _cfg(eye, cam, width=640, height=480, spp=2, max_bounce=2, mode=mode)
+            img = sc.render(cfg)
+            c = sc.counters()
+            assert c.deferred_rays > 5 * 65536, c.deferred_rays     # 3 extend + 2 shadow passes: at least one pass is over the cap
+            for win in _windows(640, 480, 48, 32):
+                ref, _ = oracle.render(tt, nn, cfg, hdr=hdr, hdr_cache=cache, window=win)
+                x0, y0, x1, y1 = win
+                assert_same_bits(img[y0:y1, x0:x1], ref, "many deferred rays, mode %d, window %s" % (mode, win))
+    finally:
+        sc.close()
+
+
 @pytest.mark.parametrize("env", [{}, {"EZRT_ACCEL_Q16": "0"}, {"EZRT_ACCEL": "8"}, {"EZRT_CAMERA_ORDER": "frame"}, {"EZRT_W4_COLLAPSE": "greedy"},
                                  {"EZRT_SORT_RAYS": "1"}])
 def test_every_form_of_the_accel_policy_gives_the_oracle_image(oracle, grid_scene, small_hdr, env, monkeypatch):

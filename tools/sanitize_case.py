@@ -42,6 +42,33 @@ def main():
         scene.trace_rays(o, d, traverse=traverse)
         scene.trace_rays(o, d, traverse=traverse, any_hit=True)
     scene.close()
+    # the accel policy's deferred lane (side stream): 30 coincident triangles facing the camera defer every ray that hits them
+    wall = np.zeros((30, 36), np.float32)
+    e = np.asarray(eye, np.float64)
+    nrm = e / np.linalg.norm(e)
+    u = np.cross([0.0, 1.0, 0.0], nrm)
+    u /= np.linalg.norm(u)
+    v = np.cross(nrm, u)
+    c, hh = 0.55 * e, 0.25 * np.linalg.norm(e)
+    wall[:, :9] = np.concatenate([c - 2 * hh * u - hh * v, c + 2 * hh * u - hh * v, c + 3 * hh * v]).astype(np.float32)
+    wall[:, 9:18] = np.tile(nrm.astype(np.float32), 3)
+    wall[:, 21:24] = 0.7
+    wall[:, 28] = 0.5
+    tl = api.TriangleList()
+    tl.append_encoded(np.concatenate([np.asarray(tris, np.float32).reshape(-1, 36), wall]))
+    t2, n2 = tl.build_bvh(8, api.BVH_SAH_FAST)
+    scene = api.Scene(t2, n2, hdr, cache, device=0)
+    for mode in (2, 3):
+        first = None
+        for traverse in (api.TRAVERSE_ACCEL, api.TRAVERSE_PRUNED):
+            cfg = api.RenderConfig(width=w, height=h, spp=2, max_bounce=2, mode=mode, eye=tuple(eye), camera_rotate=tuple(cam), traverse=traverse)
+            img = scene.render(cfg).copy()
+            if first is None:
+                first = img
+                assert scene.counters().deferred_rays > 0
+            assert img.tobytes() == first.tobytes(), "deferred lane: mode %d traverse %d differs" % (mode, traverse)
+            n += 1
+    scene.close()
     print("sanitize_case: %d renders + trace_rays done" % n)
 
 
