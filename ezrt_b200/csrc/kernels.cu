@@ -583,13 +583,12 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
         uint32_t px = 0, py = 0, fib = 0;
         bool present = i < n;
         float2 hit = make_float2(0.0f, 0.0f);
-        if (LIST) {
-            if (present) { hit = side_hit[i]; i = list[i]; }
-        } else if (present) {
+        if (LIST && present) { hit = side_hit[i]; i = list[i]; }
+        if (present && n_fused) present = slot_pixel(rd, tiles, i, px, py, fib);   // slots of clipped tiles outside the image
+        if (!LIST && present) {
             hit = __ldcs(qin.hit + i);
             present = __float_as_int(hit.y) != EZRT_TRI_PENDING;   // deferred by the accel kernel: shaded by the LIST pass
         }
-        if (present && n_fused) present = slot_pixel(rd, tiles, i, px, py, fib);   // slots of clipped tiles outside the image
         if (present) {
             if (n_fused) {
                 slot = i;

@@ -56,7 +56,7 @@ def kernel_class(name):
     if "k_extend" in name:
         return "extend"
     if "k_shade" in name:
-        return "shade"
+        return "shade_deferred_lane" if "(bool)1" in name else "shade"   # k_shade<MODE, LIST>: the handful of deferred rays, side stream
     return "other"
 
 

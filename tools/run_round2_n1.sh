@@ -6,6 +6,4 @@ import json; d=json.load(open('gpurun_out/bench_r2_n1.json'))
 print('value',d['value'],'e2e',d['e2e']['value'],'parity',d['parity'],'\nroofline',json.dumps(d['roofline'])[:1200],'\ncpu',d['cpu_baseline'],'\nkernel_ms',d['kernel_ms'])
 for k,v in d.get('workloads',{}).items(): print(k, v['value'], v['e2e']['value'], v['parity'], v['kernel_ms'])
 "
-EZRT_LIB_VARIANT=noregroup python bench.py --steps 6 --no-cpu-baseline --no-e2e --no-parity --extra-workloads c4 2>/dev/null | python -c "
-import sys,json; d=json.loads(sys.stdin.read()); print('noregroup c3', d['value'], d['kernel_ms'], 'c4', d['workloads']['c4']['value'], d['workloads']['c4']['kernel_ms'])"
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r2_ref.json 2>/dev/null; cat gpurun_out/bench_r2_ref.json | cut -c1-600
