@@ -585,11 +585,8 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
         float2 hit = make_float2(0.0f, 0.0f);
         if (LIST && present) { hit = side_hit[i]; i = list[i]; }
         if (present && n_fused) present = slot_pixel(rd, tiles, i, px, py, fib);   // slots of clipped tiles outside the image
-        if (!LIST && present) {
-            hit = __ldcs(qin.hit + i);
-            present = __float_as_int(hit.y) != EZRT_TRI_PENDING;   // deferred by the accel kernel: shaded by the LIST pass
-        }
         if (present) {
+            if (!LIST) hit = __ldcs(qin.hit + i);   // the other loads below do not wait for it
             if (n_fused) {
                 slot = i;
                 primary_ray(rd, px, py, batch_first_frame + fib, p.seed, p.o, p.d);
@@ -618,9 +615,11 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
                 p.pdf = 1.0f;
             }
             const float2 sob = sobol_table ? s_sobol[fib] : sobol_pair(bounce, batch_first_frame + fib);
-            alive = shade_step<MODE>(sc, rd, bounce, p, hit.x, __float_as_int(hit.y), px, py, sob, lo, le, pmiss, sh);
-            Lo[slot] = make_float4(lo.x, lo.y, lo.z, pmiss ? 1.0f : 0.0f);
-            if (bounce == 0) Le[slot] = make_float4(le.x, le.y, le.z, 0.0f);
+            if (LIST || __float_as_int(hit.y) != EZRT_TRI_PENDING) {   // pending: deferred by the accel kernel, shaded by the LIST pass
+                alive = shade_step<MODE>(sc, rd, bounce, p, hit.x, __float_as_int(hit.y), px, py, sob, lo, le, pmiss, sh);
+                Lo[slot] = make_float4(lo.x, lo.y, lo.z, pmiss ? 1.0f : 0.0f);
+                if (bounce == 0) Le[slot] = make_float4(le.x, le.y, le.z, 0.0f);
+            }
         }
         uint32_t pos = block_append(alive, out_count, s_scan);
         if (alive) {
@@ -887,7 +886,7 @@ void launch_extend(const SceneDev& sc, bool prune, bool anyhit, PathQueue q, con
     int top = sc.top_nodes;
     if (gate == 1) {   // a few rays beside k_shade: small blocks find room on an SM as soon as one k_shade block retires
         threads = 128;
-        blocks = std::max(1, std::min(div_up(n_max, threads), n_sms * 4));
+        blocks = std::max(1, std::min(div_up(n_max, threads), 64));
         top = 0;
     }
     if (prune && anyhit) k_extend<true, true><<<blocks, threads, smem_for(k_extend<true, true>, top), st>>>(sc, q, q_count, work, perm, to_accel, side_hit, gate);
