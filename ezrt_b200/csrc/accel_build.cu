@@ -134,13 +134,13 @@ struct LeftFlag {
 // then the lowest axis, then the lowest position (the host loop keeps the first strictly smaller candidate)
 __global__ void k_cost(BuildDev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.n) return;
-    const int s = d.seg[i];
-    const int l = d.nd_l[s], r = d.nd_r[s];
-    if (r - l + 1 <= d.leaf_n || i >= r) return;
+    const bool in = i < d.n;
+    const int s = in ? d.seg[i] : -1;
+    const int l = in ? d.nd_l[s] : 0, r = in ? d.nd_r[s] : 0;
+    const bool active = in && (r - l + 1 > d.leaf_n) && i < r;
     unsigned long long bestw = ~0ull;
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
+    for (int a = 0; a < 3 && active; a++) {
         const Box lb = d.L[a][i];
         const Box rb = d.Rrev[a][d.n - 1 - (i + 1)];
         float total = box_area2(lb) * (float)(i - l + 1) + box_area2(rb) * (float)(r - i);
@@ -150,7 +150,19 @@ __global__ void k_cost(BuildDev d) {
             if (w < bestw) bestw = w;
         }
     }
-    if (bestw != ~0ull) atomicMin(&d.best[s], bestw);
+    // one atomic per warp when the whole warp sits in one node (the big nodes of the top levels: n atomics on one word otherwise)
+    const unsigned full = 0xffffffffu;
+    const int s0 = __shfl_sync(full, s, 0);
+    if (__all_sync(full, s == s0)) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(full, bestw, off);
+            if (o < bestw) bestw = o;
+        }
+        if ((threadIdx.x & 31) == 0 && bestw != ~0ull) atomicMin(&d.best[s], bestw);
+    } else if (bestw != ~0ull) {
+        atomicMin(&d.best[s], bestw);
+    }
 }
 
 // per position: which side of its node's split it lies on; the node's first position also writes the two children
