@@ -490,9 +490,21 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     if (verbose) fprintf(stderr, "[ezrt_scene_create] %-44s %8.1f ms (worker thread, overlapped)\n", "reference tree: decode, validate, repack", ref_ms);
     if (ref_rc) return ezrt_set_error(ref_rc, "%s", ref_msg.c_str());
     lap("wait for the reference-tree worker");
-    cudaDeviceProp prop;
-    memset(&prop, 0, sizeof(prop));
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+    cudaDeviceProp prop;   // cudaGetDeviceProperties takes milliseconds: once per device and process
+    {
+        static std::mutex mu;
+        static std::map<int, cudaDeviceProp> cache;
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(device);
+        if (it == cache.end()) {
+            memset(&prop, 0, sizeof(prop));
+            if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) cudaGetLastError();
+            else cache[device] = prop;
+        } else {
+            prop = it->second;
+        }
+    }
+    if (prop.multiProcessorCount > 0) {
         sc->n_sms = prop.multiProcessorCount;
         sc->max_window_bytes = (size_t)prop.accessPolicyMaxWindowSize;
     }
