@@ -147,12 +147,15 @@ int carve_queue(DeviceBuffer& buf, size_t capacity, PathQueue& q) {
     return EZRT_OK;
 }
 int carve_shadow(DeviceBuffer& buf, size_t capacity, ShadowQueue& q) {
-    int rc = buf.ensure(sizeof(float4) * 3 * capacity + 256);
+    int rc = buf.ensure((size_t)EZRT_SHADOW_SLOT_BYTES * capacity + 256);
     if (rc) return rc;
     char* p = (char*)buf.p;
     q.ray_o = (float4*)p; p += sizeof(float4) * capacity;
     q.ray_d = (float4*)p; p += sizeof(float4) * capacity;
-    q.contrib = (float4*)p;
+    q.nrm = (float4*)p;   p += sizeof(float4) * capacity;
+    q.view = (float4*)p;  p += sizeof(float4) * capacity;
+    q.hist = (float4*)p;  p += sizeof(float4) * capacity;
+    q.lit = (unsigned char*)p;
     return EZRT_OK;
 }
 
@@ -715,7 +718,7 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
     {   // bound the batch by the memory that is actually there (scratch already held by this scene counts as available);
         // asked once per (slots per frame, integrator): cudaMemGetInfo is a driver round trip, the render path is launch-only
         const size_t per_slot = 2 * (sizeof(float4) * 4 + sizeof(float2)) + 2 * sizeof(float4) + sizeof(uint32_t) +
-                                (is_mode ? 3 * sizeof(float4) : 0) + (s->sort_rays ? 2 * sizeof(uint32_t) : 0);
+                                (is_mode ? (size_t)EZRT_SHADOW_SLOT_BYTES : 0) + (s->sort_rays ? 2 * sizeof(uint32_t) : 0);
         if (s->fmax_key[0] != per_frame || s->fmax_key[1] != per_slot) {
             size_t free_b = 0, total_b = 0;
             s->fmax = (size_t)1 << 30;
@@ -848,8 +851,9 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
                 } else {
                     launch_shadow(s->dev, prune, sq, &s_count[b], &w_sh[b], Lo, nullptr, n_slots, s->n_sms, st);
                 }
+                launch_nee(s->dev, rd, sq, &s_count[b], Lo, n_slots, s->n_sms, st);
                 s->span_end(sp, st);
-                s->launches++;
+                s->launches += 2;
             }
         }
         sp = s->span_begin(3, st);

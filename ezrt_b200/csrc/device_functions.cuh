@@ -1412,7 +1412,9 @@ struct PathRegs {
 };
 struct ShadowRay {
     bool valid;
-    vec3 o, d, contrib;
+    vec3 o, d, contrib;      // contrib: DEFER_NEE = false
+    vec3 N, V, history;      // DEFER_NEE = true: the inputs of nee_contrib, evaluated only if the shadow ray gets through (k_nee)
+    int matId;
 };
 
 // Lo += a*b*c*s/p evaluated left to right as GLSL does
@@ -1431,7 +1433,23 @@ __device__ __forceinline__ vec3 contrib3(vec3 a, vec3 b, vec3 c, float s, float 
 __device__ __forceinline__ float2 sobol_pair(int bounce, uint32_t frame) {
     return make_float2(sobol_gray((uint32_t)bounce * 2u, frame + 1u), sobol_gray((uint32_t)bounce * 2u + 1u, frame + 1u));
 }
-template <int MODE>
+// The environment sample's contribution if its shadow ray gets through (P5/fsh:829-841): history * mis * color * f_r * NdotL / pdf_light,
+// left to right.  One definition for the in-line evaluation (megakernel) and the deferred one (k_nee, after the shadow pass).
+__device__ __forceinline__ vec3 nee_contrib(const SceneDev& sc, const RenderDev& rd, int mode, vec3 V, vec3 N, vec3 Lh, const MaterialDev& mat,
+                                            vec3 history) {
+    const float NdotLh = ez_dot(N, Lh);
+    const vec3 fr_h = brdf_evaluate<false>(V, N, Lh, mat);
+    const float pdf_h = brdf_pdf(V, N, Lh, mat);
+    const vec3 color = hdr_color(sc, rd, Lh, mode);
+    const float pdf_light = hdr_pdf(sc, Lh);
+    const float mis_weight = mis_mix_weight(pdf_light, pdf_h);
+    return ez_divs(ez_scale(ez_mul(ez_mul(ez_scale(history, mis_weight), color), fr_h), NdotLh), pdf_light);
+}
+
+// DEFER_NEE (wavefront pipeline, IS/MIS mode): the shadow ray carries the inputs of nee_contrib instead of its value -- the
+// BRDF / environment evaluation of the light sample runs after the shadow pass, only for the rays that got through, and is
+// no longer part of k_shade (5104 instructions, instruction-fetch bound).
+template <int MODE, bool DEFER_NEE = false>
 __device__ __forceinline__ bool shade_step(const SceneDev& sc, const RenderDev& rd, int bounce, PathRegs& p, float hit_t,
                                            int hit_tri, uint32_t px, uint32_t py, float2 sob, vec3& Lo, vec3& Le,
                                            bool& primary_miss, ShadowRay& sh) {
@@ -1489,31 +1507,18 @@ __device__ __forceinline__ bool shade_step(const SceneDev& sc, const RenderDev& 
         const float NdotLh = ez_dot(N, Lh);
         L = sample_brdf(xi_1, xi_2, xi_3, V, N, mat);
         const float NdotL = ez_dot(N, L);
-        vec3 fr_h = splat3(0.0f), fr_l = splat3(0.0f);
-        float pdf_h = 0.0f, pdf_l = 0.0f;
-#if EZRT_IS_DEDUPE   // one copy of the BRDF code for both directions (a two-trip loop that is not unrolled): smaller kernel
-#pragma unroll 1
-        for (int k = 0; k < 2; k++) {
-            const bool want = (k == 0) ? (NdotLh > 0.0f) : (NdotL > 0.0f);
-            if (want) {
-                const vec3 dir = (k == 0) ? Lh : L;
-                const vec3 f = brdf_evaluate<false>(V, N, dir, mat);
-                const float q = brdf_pdf(V, N, dir, mat);
-                if (k == 0) { fr_h = f; pdf_h = q; } else { fr_l = f; pdf_l = q; }
-            }
-        }
-#else
-        if (NdotLh > 0.0f) { fr_h = brdf_evaluate<false>(V, N, Lh, mat); pdf_h = brdf_pdf(V, N, Lh, mat); }
+        vec3 fr_l = splat3(0.0f);
+        float pdf_l = 0.0f;
         if (NdotL > 0.0f) { fr_l = brdf_evaluate<false>(V, N, L, mat); pdf_l = brdf_pdf(V, N, L, mat); }
-#endif
         if (NdotLh > 0.0f) {
-            vec3 color = hdr_color(sc, rd, Lh, mode);
-            float pdf_light = hdr_pdf(sc, Lh);
-            float mis_weight = mis_mix_weight(pdf_light, pdf_h);
             sh.valid = true;
             sh.o = hit.P;
             sh.d = Lh;
-            sh.contrib = ez_divs(ez_scale(ez_mul(ez_mul(ez_scale(p.history, mis_weight), color), fr_h), NdotLh), pdf_light);
+            if (DEFER_NEE) {
+                sh.N = N; sh.V = V; sh.history = p.history; sh.matId = hit.matId;
+            } else {
+                sh.contrib = nee_contrib(sc, rd, mode, V, N, Lh, mat, p.history);
+            }
         }
         if (NdotL <= 0.0f) return false;  // :854
         p.f_r = fr_l;

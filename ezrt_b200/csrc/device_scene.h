@@ -112,10 +112,16 @@ struct PathQueue {
     float4* fr;       // (f_r.xyz, pdf)   pdf <= 0 marks "break after trace" (P5/fsh:865)
 };
 
+// A shadow ray and what k_nee needs to evaluate the light sample's contribution once the ray got through (nee_contrib):
+// the BRDF / environment evaluation of the light sample is done after the shadow pass, for unoccluded rays only.
+#define EZRT_SHADOW_SLOT_BYTES (5 * 16 + 1)
 struct ShadowQueue {
-    float4* ray_o;    // (origin.xyz, sample slot as bits)
-    float4* ray_d;    // (direction.xyz, -)
-    float4* contrib;  // (contribution.xyz, -)
+    float4* ray_o;       // (origin.xyz, sample slot as bits)
+    float4* ray_d;       // (direction to the light.xyz, material id as bits)
+    float4* nrm;         // (shading normal N.xyz, -)
+    float4* view;        // (V = -incoming direction.xyz, -)
+    float4* hist;        // (path history.xyz, -)
+    unsigned char* lit;  // written by the shadow pass: 1 = nothing between the surface and the environment
 };
 
 #endif

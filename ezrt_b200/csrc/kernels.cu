@@ -252,8 +252,7 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
 // (the IO structs of the accel kernels -- queue rays, fused camera rays, shadow rays -- are shared by the 4-wide and the W8
 // kernel: AccelExtendIO, AccelCameraIO, AccelShadowIO below)
 
-// ---- shadow rays: any hit; an unoccluded ray adds its precomputed contribution (P5/fsh:829-841).
-// One path per sample slot -> no two lanes touch the same Lo entry.
+// ---- shadow rays: any hit; the pass marks each ray lit / occluded, k_nee then adds the contribution of the lit ones (P5/fsh:829-841).
 struct ShadowIO {
     ShadowQueue sq;
     float4* Lo;
@@ -265,16 +264,9 @@ struct ShadowIO {
         d = ez_v3(d4.x, d4.y, d4.z);
         return true;
     }
-    __device__ __forceinline__ void add(uint32_t j) const {
-        uint32_t slot = __float_as_uint(sq.ray_o[j].w);
-        float4 c = sq.contrib[j];
-        float4 lo = Lo[slot];
-        lo.x += c.x; lo.y += c.y; lo.z += c.z;
-        Lo[slot] = lo;
-    }
-    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3, vec3, vec3) const {
-        if (h.tri < 0) add(perm ? perm[i] : i);
-    }
+    // every shadow ray's flag is written exactly once per pass (here, or by the exact pass over the rays an accel kernel deferred)
+    __device__ __forceinline__ void mark(uint32_t j, bool lit) const { sq.lit[j] = lit ? 1 : 0; }
+    __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3, vec3, vec3) const { mark(perm ? perm[i] : i, h.tri < 0); }
     __device__ __forceinline__ void defer(uint32_t, vec3, vec3) const {}
 };
 
@@ -431,11 +423,12 @@ struct AccelShadowIO {
     __device__ __forceinline__ void defer(uint32_t i, vec3, vec3) const { defer_list[atomicAdd(defer_count, 1u)] = i; }
     __device__ __forceinline__ void store(uint32_t i, HitRec h, bool, vec3 o, vec3 d, vec3 inv) const {
         if (h.tri < 0) {  // nothing accepted anywhere: the shader finds nothing either
-            base.add(i);
+            base.mark(i, true);
             return;
         }
         // occluded if the shader reaches the occluder's leaf; otherwise the exact kernel decides
         if (!reference_reaches_leaf_inv(acc_tri_leaf, leaf_box, h.tri, o, inv)) defer(i, o, d);
+        else base.mark(i, false);
     }
 };
 
@@ -616,7 +609,7 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
             }
             const float2 sob = sobol_table ? s_sobol[fib] : sobol_pair(bounce, batch_first_frame + fib);
             if (LIST || __float_as_int(hit.y) != EZRT_TRI_PENDING) {   // pending: deferred by the accel kernel, shaded by the LIST pass
-                alive = shade_step<MODE>(sc, rd, bounce, p, hit.x, __float_as_int(hit.y), px, py, sob, lo, le, pmiss, sh);
+                alive = shade_step<MODE, MODE == EZRT_MODE_DISNEY_IS_MIS_P5>(sc, rd, bounce, p, hit.x, __float_as_int(hit.y), px, py, sob, lo, le, pmiss, sh);
                 Lo[slot] = make_float4(lo.x, lo.y, lo.z, pmiss ? 1.0f : 0.0f);
                 if (bounce == 0) Le[slot] = make_float4(le.x, le.y, le.z, 0.0f);
             }
@@ -632,10 +625,50 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
             uint32_t spos = block_append(sh.valid, s_count, s_scan);
             if (sh.valid) {
                 __stcs(sq.ray_o + spos, make_float4(sh.o.x, sh.o.y, sh.o.z, __uint_as_float(slot)));
-                __stcs(sq.ray_d + spos, make_float4(sh.d.x, sh.d.y, sh.d.z, 0.0f));
-                __stcs(sq.contrib + spos, make_float4(sh.contrib.x, sh.contrib.y, sh.contrib.z, 0.0f));
+                __stcs(sq.ray_d + spos, make_float4(sh.d.x, sh.d.y, sh.d.z, __int_as_float(sh.matId)));
+                __stcs(sq.nrm + spos, make_float4(sh.N.x, sh.N.y, sh.N.z, 0.0f));
+                __stcs(sq.view + spos, make_float4(sh.V.x, sh.V.y, sh.V.z, 0.0f));
+                __stcs(sq.hist + spos, make_float4(sh.history.x, sh.history.y, sh.history.z, 0.0f));
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_nee: the light samples whose shadow ray got through (sq.lit) add their contribution to Lo -- the BRDF value and pdf of the
+// light direction, the environment colour and pdf and the MIS weight (nee_contrib, P5/fsh:829-841) are evaluated here, after
+// the shadow pass, instead of for every light sample in k_shade.  Each block compacts the lit rays of 512 queue entries in
+// shared memory so that full warps evaluate.  One shadow ray per sample slot and bounce: no two threads touch one Lo entry.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 8) k_nee(SceneDev sc, RenderDev rd, ShadowQueue sq, const uint32_t* __restrict__ s_count, float4* __restrict__ Lo) {
+    __shared__ uint32_t s_scan[34];
+    __shared__ uint32_t s_total;
+    __shared__ uint32_t s_list[512];
+    const uint32_t n = *s_count;
+    for (uint32_t base = blockIdx.x * 512u; base < n; base += gridDim.x * 512u) {
+        if (threadIdx.x == 0) s_total = 0u;
+        __syncthreads();
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) {
+            const uint32_t j = base + (uint32_t)k * 128u + threadIdx.x;
+            const bool lit = j < n && sq.lit[j] != 0;
+            const uint32_t pos = block_append(lit, &s_total, s_scan);
+            if (lit) s_list[pos] = j;
+        }
+        __syncthreads();
+        const uint32_t total = s_total;
+        for (uint32_t q = threadIdx.x; q < total; q += blockDim.x) {
+            const uint32_t j = s_list[q];
+            const float4 o4 = __ldcs(sq.ray_o + j), d4 = __ldcs(sq.ray_d + j), n4 = __ldcs(sq.nrm + j), v4 = __ldcs(sq.view + j), h4 = __ldcs(sq.hist + j);
+            const uint32_t slot = __float_as_uint(o4.w);
+            const MaterialDev mat = load_material(sc, __float_as_int(d4.w));
+            const vec3 c = nee_contrib(sc, rd, EZRT_MODE_DISNEY_IS_MIS_P5, ez_v3(v4.x, v4.y, v4.z), ez_v3(n4.x, n4.y, n4.z), ez_v3(d4.x, d4.y, d4.z), mat,
+                                       ez_v3(h4.x, h4.y, h4.z));
+            float4 lo = Lo[slot];
+            lo.x += c.x; lo.y += c.y; lo.z += c.z;
+            Lo[slot] = lo;
+        }
+        __syncthreads();
     }
 }
 
@@ -1013,6 +1046,10 @@ void launch_deferred_lane(const SceneDev& sc, const RenderDev& rd, const TileDev
         default: EZRT_LAUNCH_SHADE(EZRT_MODE_DISNEY_IS_MIS_P5); break;
     }
 #undef EZRT_LAUNCH_SHADE
+}
+void launch_nee(const SceneDev& sc, const RenderDev& rd, ShadowQueue sq, const uint32_t* s_count, float4* Lo, uint32_t n_max, int n_sms, cudaStream_t st) {
+    const int blocks = std::max(1, std::min(div_up(n_max, 512), n_sms * 8));
+    k_nee<<<blocks, 128, 0, st>>>(sc, rd, sq, s_count, Lo);
 }
 void launch_blend(const RenderDev& rd, const TileDev* tiles, int nf, uint32_t batch_first_frame, const float4* Lo,
                   const float4* Le, float* fb, cudaStream_t st) {
