@@ -851,6 +851,8 @@ int ezrt_render_device(ezrt_scene* s, const ezrt_render_params* p, float* d_fb, 
                 } else {
                     launch_shadow(s->dev, prune, sq, &s_count[b], &w_sh[b], Lo, nullptr, n_slots, s->n_sms, st);
                 }
+                s->span_end(sp, st);
+                sp = s->span_begin(1, st);   // shading work: counted with k_shade
                 launch_nee(s->dev, rd, sq, &s_count[b], Lo, n_slots, s->n_sms, st);
                 s->span_end(sp, st);
                 s->launches += 2;

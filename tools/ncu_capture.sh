@@ -6,9 +6,9 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 export EZRT_AUTO_BUILD=0
 for WL in ${@:-c3 c4}; do
-    SKIP=9; [ "$WL" = c4 ] && SKIP=11         # accel / shade / deferred-lane shade (/ shadow) launches of the warm-up step
+    SKIP=9; [ "$WL" = c4 ] && SKIP=13         # accel / shade / deferred-lane shade (/ shadow / nee) launches of the warm-up step
     CMD="python bench.py --workload $WL --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-parity --extra-workloads ''"
-    ncu --set full --clock-control none --import-source on -k regex:"k_extend_accel|k_extend_w8|k_shade|k_shadow_accel|k_shadow_w8" -s $SKIP -c $SKIP \
+    ncu --set full --clock-control none --import-source on -k regex:"k_extend_accel|k_extend_w8|k_shade|k_shadow_accel|k_shadow_w8|k_nee" -s $SKIP -c $SKIP \
         -f -o gpurun_out/prof_${WL}_r2 python bench.py --workload $WL --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-parity --extra-workloads "" > gpurun_out/ncu_${WL}_r2.log 2>&1
     ncu -i gpurun_out/prof_${WL}_r2.ncu-rep --page raw --csv > gpurun_out/prof_${WL}_r2_raw.csv 2>/dev/null
     echo "$WL: $(grep -c . gpurun_out/prof_${WL}_r2_raw.csv) csv lines; $CMD"

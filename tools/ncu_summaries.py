@@ -51,6 +51,8 @@ def raw(src):
 
 
 def kernel_class(name):
+    if "k_nee" in name:
+        return "nee"
     if "k_shadow" in name:
         return "shadow"
     if "k_extend" in name:
