@@ -9,6 +9,7 @@ import json
 import os
 import collections
 import csv
+import re
 import sys
 
 METRICS = [
@@ -58,7 +59,8 @@ def kernel_class(name):
     if "k_extend" in name:
         return "extend"
     if "k_shade" in name:
-        return "shade_deferred_lane" if "(bool)1" in name else "shade"   # k_shade<MODE, LIST>: the handful of deferred rays, side stream
+        lane = "(bool)1" in name or re.search(r"k_shade<[^>]*,\s*(1|true)>", name)   # k_shade<MODE, LIST>: the handful of deferred rays, side stream
+        return "shade_deferred_lane" if lane else "shade"
     return "other"
 
 
