@@ -495,10 +495,8 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
 
 // ------------------------------------------------------------------------------------------
 #ifndef EZRT_SHADE_REGROUP
-#define EZRT_SHADE_REGROUP 0      // k_shade: reorder each 128-path chunk -- 1: surface hits before paths that left the scene; 2: hits also
-                                  // by material id; 0: queue order.  Measured on B200 (profiles/sweep_shade_r2.txt): shade ms per step
-                                  // C3 2.73 / 2.86 / 3.03, C4 9.45 / 9.95 / 10.10 for 0 / 1 / 2 -- the warps get fuller (ncu) but the
-                                  // kernel waits on its scattered record reads, not on issue slots, and the sort adds three barriers: off.
+#define EZRT_SHADE_REGROUP 0      // k_shade, bounces > 0: 1 = each block shades its 128 paths in the order hits | misses (exchange through shared
+                                  // memory after the loads); 0 = queue order.  profiles/sweep_shade_r2.txt.
 #endif
 #define EZRT_SOBOL_TABLE 256      // frames per batch whose Sobol pairs a k_shade block keeps in shared memory
 #define EZRT_SHADE_KEYS 18        // material id mod 16, "left the scene", "beyond the queue end"
@@ -530,44 +528,17 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
     const uint32_t n_round = ((n + blockDim.x - 1u) / blockDim.x) * blockDim.x;
     const uint32_t stride = gridDim.x * blockDim.x;
 #if EZRT_SHADE_REGROUP
-    // Regrouping between bounces (north_star: "compact active rays and sort by material-id"): the 128 paths a block takes per
-    // iteration are reordered in shared memory by key = miss | material id, so that a warp shades paths that run the same code
-    // on the same material record: bounce paths that left the scene (one environment lookup) no longer idle through the BRDF of
-    // their neighbours (ncu: 16 of 32 lanes active on bounce 1 before, profiles/).  The result does not depend on the order.
-    __shared__ unsigned short s_cnt[4][EZRT_SHADE_KEYS];
-    __shared__ unsigned char s_order[128];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // Regrouping between bounces (north_star: "compact active rays and sort by material-id"), second version: every thread loads ITS queue
+    // entry (all loads in flight at once, coalesced), the 128 entries of the block are then exchanged through shared memory into the order
+    // surface hits | paths that left the scene | nothing to do, and thread t shades the t-th entry of that order: warps run one branch of the
+    // integrator instead of both.  (First version, profiles/sweep_shade_r2.txt: the block sorted on the hit record BEFORE loading the rest,
+    // which serialised two memory latencies per path and lost 5 %.)  The result does not depend on the order.
+    __shared__ float4 s_rg[4][128];
+    __shared__ float2 s_rg_hit[128];
+    __shared__ unsigned short s_rg_cnt[4][2];
 #endif
     for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n_round; i0 += stride) {
         uint32_t i = i0;
-#if EZRT_SHADE_REGROUP
-        if (bounce > 0) {   // camera paths are coherent as they are
-            uint32_t key = EZRT_SHADE_KEYS - 1;                      // beyond the queue end: last
-            if (i0 < n) {
-                const int tri = __float_as_int(__ldcs(qin.hit + i0).y);
-                key = EZRT_SHADE_KEYS - 2;                           // left the scene
-                if (tri >= 0) {
-                    key = 0;
-#if EZRT_SHADE_REGROUP >= 2   // ... and by material id (one more dependent load before the sort)
-                    const float4* sh4 = (rd.accel_space ? sc.acc_tri_shade : sc.tri_shade) + (size_t)tri * 3;
-                    key = (uint32_t)__float_as_int(ldg4(sh4).w) % (EZRT_SHADE_KEYS - 2);
-#endif
-                }
-            }
-            const unsigned same = __match_any_sync(0xffffffffu, key);
-            const uint32_t rank = (uint32_t)__popc(same & ((1u << lane) - 1u));
-            if (threadIdx.x < 4 * EZRT_SHADE_KEYS) (&s_cnt[0][0])[threadIdx.x] = 0;
-            __syncthreads();
-            if (rank == 0) s_cnt[wid][key] = (unsigned short)__popc(same);
-            __syncthreads();
-            uint32_t before = 0;                                      // paths with a smaller key, or the same key in an earlier warp
-            for (uint32_t k = 0; k < key; k++) before += s_cnt[0][k] + s_cnt[1][k] + s_cnt[2][k] + s_cnt[3][k];
-            for (int w = 0; w < wid; w++) before += s_cnt[w][key];
-            s_order[before + rank] = (unsigned char)threadIdx.x;
-            __syncthreads();
-            i = i0 - threadIdx.x + s_order[threadIdx.x];
-        }
-#endif
         bool alive = false;
         PathRegs p;
         ShadowRay sh;
@@ -576,15 +547,51 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
         uint32_t px = 0, py = 0, fib = 0;
         bool present = i < n;
         float2 hit = make_float2(0.0f, 0.0f);
+        float4 o4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d4 = o4, h4 = o4, f4 = o4;
+        bool staged = false;
+#if EZRT_SHADE_REGROUP
+        if (!LIST && bounce > 0) {   // camera paths are coherent as they are
+            staged = true;
+            hit = make_float2(0.0f, __int_as_float(EZRT_TRI_PENDING));
+            if (present) {
+                hit = __ldcs(qin.hit + i);
+                o4 = __ldcs(qin.ray_o + i); d4 = __ldcs(qin.ray_d + i); h4 = __ldcs(qin.hist + i); f4 = __ldcs(qin.fr + i);
+            }
+            const int tri0 = __float_as_int(hit.y);
+            const int key = (tri0 == EZRT_TRI_PENDING) ? 2 : (tri0 >= 0 ? 0 : 1);
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            const unsigned lt = (1u << lane) - 1u;
+            const unsigned m0 = __ballot_sync(0xffffffffu, key == 0), m1 = __ballot_sync(0xffffffffu, key == 1);
+            if (lane == 0) { s_rg_cnt[wid][0] = (unsigned short)__popc(m0); s_rg_cnt[wid][1] = (unsigned short)__popc(m1); }
+            __syncthreads();
+            uint32_t n0 = 0, n1 = 0, b0 = 0, b1 = 0;
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const uint32_t c0 = s_rg_cnt[w][0], c1 = s_rg_cnt[w][1];
+                n0 += c0; n1 += c1;
+                if (w < wid) { b0 += c0; b1 += c1; }
+            }
+            uint32_t dest;
+            if (key == 0) dest = b0 + (uint32_t)__popc(m0 & lt);
+            else if (key == 1) dest = n0 + b1 + (uint32_t)__popc(m1 & lt);
+            else dest = n0 + n1 + ((uint32_t)wid * 32u - b0 - b1) + (uint32_t)__popc(~(m0 | m1) & lt);
+            s_rg_hit[dest] = hit;
+            s_rg[0][dest] = o4; s_rg[1][dest] = d4; s_rg[2][dest] = h4; s_rg[3][dest] = f4;
+            __syncthreads();
+            hit = s_rg_hit[threadIdx.x];
+            o4 = s_rg[0][threadIdx.x]; d4 = s_rg[1][threadIdx.x]; h4 = s_rg[2][threadIdx.x]; f4 = s_rg[3][threadIdx.x];
+            present = threadIdx.x < n0 + n1;   // the block_append barriers below separate these reads from the next round's writes
+        }
+#endif
         if (LIST && present) { hit = side_hit[i]; i = list[i]; }
         if (present && n_fused) present = slot_pixel(rd, tiles, i, px, py, fib);   // slots of clipped tiles outside the image
         if (present) {
-            if (!LIST) hit = __ldcs(qin.hit + i);   // the other loads below do not wait for it
+            if (!LIST && !staged) hit = __ldcs(qin.hit + i);   // the other loads below do not wait for it
             if (n_fused) {
                 slot = i;
                 primary_ray(rd, px, py, batch_first_frame + fib, p.seed, p.o, p.d);
             } else {
-                float4 o4 = __ldcs(qin.ray_o + i), d4 = __ldcs(qin.ray_d + i);   // .w: rng seed / sample slot
+                if (!staged) { o4 = __ldcs(qin.ray_o + i); d4 = __ldcs(qin.ray_d + i); }   // .w: rng seed / sample slot
                 slot = __float_as_uint(d4.w);
                 p.o = ez_v3(o4.x, o4.y, o4.z);
                 p.d = ez_v3(d4.x, d4.y, d4.z);
@@ -594,7 +601,7 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
             vec3 lo = splat3(0.0f), le = splat3(0.0f);
             bool pmiss = false;
             if (bounce > 0) {
-                float4 h4 = __ldcs(qin.hist + i), f4 = __ldcs(qin.fr + i);
+                if (!staged) { h4 = __ldcs(qin.hist + i); f4 = __ldcs(qin.fr + i); }
                 p.history = ez_v3(h4.x, h4.y, h4.z);
                 p.cosine_i = h4.w;
                 p.f_r = ez_v3(f4.x, f4.y, f4.z);

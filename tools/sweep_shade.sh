@@ -5,6 +5,6 @@ run() { echo "== $*"; env "$@" EZRT_AUTO_BUILD=0 python bench.py --steps 8 --war
 import sys,json; d=json.loads(sys.stdin.read()); w=d['workloads']['c4']
 print('  c3 %.0f Mrays/s shade %.2f ms/step | c4 %.0f Mrays/s shade %.2f ms/step' % (d['value'], d['kernel_ms']['shade']/d['steps'], w['value'], w['kernel_ms']['shade']/w['steps']))"; }
 run X=0
-run EZRT_LIB_VARIANT=ni
-run EZRT_LIB_VARIANT=mb6
+run EZRT_LIB_VARIANT=rg
 run X=0
+run EZRT_LIB_VARIANT=rg
