@@ -500,6 +500,9 @@ __global__ void __launch_bounds__(EZRT_EXTEND_MAX_THREADS, EZRT_EXTEND_LB_BLOCKS
 #endif
 #define EZRT_SOBOL_TABLE 256      // frames per batch whose Sobol pairs a k_shade block keeps in shared memory
 #define EZRT_SHADE_KEYS 18        // material id mod 16, "left the scene", "beyond the queue end"
+#ifndef EZRT_SHADE_PREFETCH
+#define EZRT_SHADE_PREFETCH 0     // k_shade: prefetch (L2) the triangle records of the path this thread shades in its next round
+#endif
 #ifndef EZRT_SHADE_MIN_BLOCKS
 #define EZRT_SHADE_MIN_BLOCKS 8   // 64 registers: k_shade is latency-bound, 32 resident warps beat 20 despite small spills
 #endif
@@ -539,6 +542,10 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
 #endif
     for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n_round; i0 += stride) {
         uint32_t i = i0;
+#if EZRT_SHADE_PREFETCH
+        int next_tri = -1;
+        if (!LIST && i0 + stride < n) next_tri = __float_as_int(__ldcs(qin.hit + i0 + stride).y);
+#endif
         bool alive = false;
         PathRegs p;
         ShadowRay sh;
@@ -615,6 +622,18 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
                 p.pdf = 1.0f;
             }
             const float2 sob = sobol_table ? s_sobol[fib] : sobol_pair(bounce, batch_first_frame + fib);
+#if EZRT_SHADE_PREFETCH
+            // the geometry and shading records of the triangle this thread's NEXT path hit (its hit record was requested at the top of
+            // this round): into L2 while this path is shaded -- the two random 48-byte gathers of surface_hit miss L2 three times in four
+            if (!LIST && next_tri >= 0) {
+                const float4* g = (rd.accel_space ? sc.acc_tri_geo : sc.tri_geo) + (size_t)next_tri * 4;
+                const float4* sr = (rd.accel_space ? sc.acc_tri_shade : sc.tri_shade) + (size_t)next_tri * 3;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(g + 2));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(sr));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(sr + 2));
+            }
+#endif
             if (LIST || __float_as_int(hit.y) != EZRT_TRI_PENDING) {   // pending: deferred by the accel kernel, shaded by the LIST pass
                 alive = shade_step<MODE, MODE == EZRT_MODE_DISNEY_IS_MIS_P5>(sc, rd, bounce, p, hit.x, __float_as_int(hit.y), px, py, sob, lo, le, pmiss, sh);
                 Lo[slot] = make_float4(lo.x, lo.y, lo.z, pmiss ? 1.0f : 0.0f);
