@@ -11,6 +11,7 @@ for WL in ${@:-c3 c4}; do
     ncu --set full --clock-control none --import-source on -k regex:"k_extend_accel|k_extend_w8|k_shade|k_shadow_accel|k_shadow_w8|k_nee" -s $SKIP -c $SKIP \
         -f -o gpurun_out/prof_${WL}_r2 python bench.py --workload $WL --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-parity --extra-workloads "" > gpurun_out/ncu_${WL}_r2.log 2>&1
     ncu -i gpurun_out/prof_${WL}_r2.ncu-rep --page raw --csv > gpurun_out/prof_${WL}_r2_raw.csv 2>/dev/null
+    [ "${KEEP_REP:-0}" = 1 ] || rm -f gpurun_out/prof_${WL}_r2.ncu-rep    # gpurun copies at most 64 MiB back: the csv export is what the summaries read
     echo "$WL: $(grep -c . gpurun_out/prof_${WL}_r2_raw.csv) csv lines; $CMD"
     # every launch of one warm-up + one timed step with its device time (shares of a step)
     ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_${WL}_r2.csv \
