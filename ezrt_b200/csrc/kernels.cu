@@ -1,14 +1,17 @@
 // kernels.cu -- sm_100a kernels of the wavefront path tracer and their launchers.
 //
 // Pipeline per batch of `nf` frames (= display() calls, P5/main.cpp:697-748) x owned pixels:
-//   k_generate : camera rays (main(), P5/fsh:920-925)                     -> queue 0
+//   k_generate : camera rays (main(), P5/fsh:920-925) -> queue 0   (exact policies; the accel policy generates them inside
+//                the first extend kernel, k_extend_accel_camera, and again in k_shade(0))
 //   per bounce b = 0..maxBounce:
 //     k_extend_accel : hitBVH for every queued ray on the device's 4-wide acceleration tree (persistent warps,
 //                      per-lane refill, vote-driven inner / leaf phases); rays it cannot decide exactly are
 //                      deferred to  k_extend  = the exact reference-order traversal (also the whole extend
-//                      stage under the REFERENCE / PRUNED policies)
-//     k_shade        : account the hit/miss, NEE + BRDF sampling, block-aggregated compaction -> queue b+1
-//     k_shadow_accel / k_shadow : any-hit trace of the environment shadow rays (IS mode only)
+//                      stage under the REFERENCE / PRUNED policies) -- on a side stream, followed by
+//                      k_shade<MODE, LIST> over the deferred rays, beside the main k_shade ("deferred lane")
+//     k_shade        : account the hit/miss, light sample + BRDF sampling, block-aggregated compaction -> queue b+1
+//     k_shadow_accel / k_shadow : any-hit trace of the environment shadow rays (IS mode only): marks each ray lit / occluded
+//     k_nee          : the lit light samples' contributions (BRDF, environment, MIS) -> Lo
 //   k_blend    : running mean into the framebuffer in frame order (P5/fsh:942-947)
 // No host synchronisation inside a render: queue sizes live in device counters.
 #include "kernels.h"
