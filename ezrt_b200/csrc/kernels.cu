@@ -610,6 +610,7 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
             }
             vec3 lo = splat3(0.0f), le = splat3(0.0f);
             bool pmiss = false;
+            float lo_w = 0.0f;   // Lo.w: 0 = Le absent (zero), 1 = the primary ray left the scene, 2 = Le[slot] holds the first hit's emission
             if (bounce > 0) {
                 if (!staged) { h4 = __ldcs(qin.hist + i); f4 = __ldcs(qin.fr + i); }
                 p.history = ez_v3(h4.x, h4.y, h4.z);
@@ -618,6 +619,7 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
                 p.pdf = f4.w;
                 float4 l4 = Lo[slot];
                 lo = ez_v3(l4.x, l4.y, l4.z);
+                lo_w = l4.w;
             } else {
                 p.history = splat3(1.0f);
                 p.f_r = splat3(0.0f);
@@ -639,8 +641,16 @@ __global__ void __launch_bounds__(128, EZRT_SHADE_MIN_BLOCKS) k_shade(SceneDev s
 #endif
             if (LIST || __float_as_int(hit.y) != EZRT_TRI_PENDING) {   // pending: deferred by the accel kernel, shaded by the LIST pass
                 alive = shade_step<MODE, MODE == EZRT_MODE_DISNEY_IS_MIS_P5>(sc, rd, bounce, p, hit.x, __float_as_int(hit.y), px, py, sob, lo, le, pmiss, sh);
-                Lo[slot] = make_float4(lo.x, lo.y, lo.z, pmiss ? 1.0f : 0.0f);
-                if (bounce == 0) Le[slot] = make_float4(le.x, le.y, le.z, 0.0f);
+                if (bounce == 0) {
+                    // Le is zero for every surface that does not emit: it is stored (and read back by k_blend) only otherwise.
+                    // color = Le + Lo with Le = +-0 is Lo bit for bit, because Lo is never -0.0 (it starts at +0.0 and only grows by additions)
+                    lo_w = pmiss ? 1.0f : 0.0f;
+                    if (le.x != 0.0f || le.y != 0.0f || le.z != 0.0f) {
+                        Le[slot] = make_float4(le.x, le.y, le.z, 0.0f);
+                        lo_w = 2.0f;
+                    }
+                }
+                Lo[slot] = make_float4(lo.x, lo.y, lo.z, lo_w);
             }
         }
         uint32_t pos = block_append(alive, out_count, s_scan);
@@ -722,8 +732,11 @@ __global__ void __launch_bounds__(256) k_blend(RenderDev rd, const TileDev* __re
     vec3 acc = (batch_first_frame == 0u) ? splat3(0.0f) : ez_v3(fb[idx], fb[idx + 1], fb[idx + 2]);
     for (int f = 0; f < nf; f++) {
         float4 lo = Lo[(size_t)f * per_frame + r];
-        float4 le = Le[(size_t)f * per_frame + r];
-        vec3 color = (lo.w != 0.0f) ? ez_v3(lo.x, lo.y, lo.z) : ez_add(ez_v3(le.x, le.y, le.z), ez_v3(lo.x, lo.y, lo.z));
+        vec3 color = ez_v3(lo.x, lo.y, lo.z);   // primary miss: the sky; no emission at the first hit: 0 + Lo = Lo
+        if (lo.w == 2.0f) {
+            float4 le = Le[(size_t)f * per_frame + r];
+            color = ez_add(ez_v3(le.x, le.y, le.z), color);
+        }
         float a = EZ_DIV(1.0f, __uint2float_rn(batch_first_frame + (uint32_t)f + 1u));
         acc = ez_vmix(acc, color, a);
     }
