@@ -131,7 +131,9 @@ int EzrtCollapse::build(const std::vector<EzrtAccelNode>& an_, int width_, int m
     {
         std::vector<std::thread> pool;
         const int nt = std::max(1, std::min(threads, (int)ranges.size()));
-        for (int t = 1; t < nt; t++) pool.emplace_back(worker);
+        for (int t = 1; t < nt; t++) {
+            try { pool.emplace_back(worker); } catch (...) { break; }   // no more threads: the ones we have take all the ranges
+        }
         worker();
         for (auto& t : pool) t.join();
     }
@@ -496,7 +498,9 @@ int ezrt_build_w4(const std::vector<EzrtAccelNode>& an, float pad, float max_abs
         };
         std::vector<std::thread> pool;
         const int nt = std::max(1, std::min(threads, (int)tasks.size()));
-        for (int t = 1; t < nt; t++) pool.emplace_back(worker);
+        for (int t = 1; t < nt; t++) {
+            try { pool.emplace_back(worker); } catch (...) { break; }   // no more threads: the ones we have take all the ranges
+        }
         worker();
         for (auto& t : pool) t.join();
     }
@@ -570,7 +574,9 @@ int ezrt_build_w4(const std::vector<EzrtAccelNode>& an, float pad, float max_abs
         };
         std::vector<std::thread> pool;
         const int nt = std::max(1, std::min(threads, (int)tasks.size()));
-        for (int t = 1; t < nt; t++) pool.emplace_back(copier);
+        for (int t = 1; t < nt; t++) {
+            try { pool.emplace_back(copier); } catch (...) { break; }
+        }
         copier();
         for (auto& t : pool) t.join();
     }

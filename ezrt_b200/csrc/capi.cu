@@ -382,11 +382,16 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
         }
     } guard;
     guard.sc = sc;
-    guard.worker = std::thread([&]() {
+    auto ref_timed = [&]() {
         const auto t0 = std::chrono::steady_clock::now();
         ref_rc = ref_stage();
         ref_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    });
+    };
+    try {
+        guard.worker = std::thread(ref_timed);
+    } catch (...) {
+        ref_timed();   // no thread to be had: in line
+    }
     // ---- triangles: upload the caller's array once; geometry records, shading records, material runs and the scene
     // bounds are made from it on the device (scene_prep.cu) ----
     DeviceBuffer& raw = guard.raw;
@@ -489,7 +494,7 @@ int ezrt_scene_create(int device, const float* tris, int n_triangles, const floa
     }
     lap("acceleration tree: collapse, pack");
     // ---- the caller's tree is needed from here on ----
-    guard.worker.join();
+    if (guard.worker.joinable()) guard.worker.join();
     if (verbose) fprintf(stderr, "[ezrt_scene_create] %-44s %8.1f ms (worker thread, overlapped)\n", "reference tree: decode, validate, repack", ref_ms);
     if (ref_rc) return ezrt_set_error(ref_rc, "%s", ref_msg.c_str());
     lap("wait for the reference-tree worker");

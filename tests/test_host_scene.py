@@ -364,3 +364,29 @@ hdr env.hdr
     (tmp_path / "bad.txt").write_text("mesh nothere.obj smooth")
     with pytest.raises(api.EzrtError):
         api.load_scene_file(tmp_path / "bad.txt")
+
+
+def test_accel_build_host_tree_is_well_formed(bunny_scene):
+    """ezrt_accel_build(where = host): the binary SAH tree behind the device's acceleration structure (the GPU builder must
+    reproduce it node for node, tests/test_gpu_accel_build.py): pre-order numbering, every triangle in exactly one leaf of
+    <= leaf_n triangles, every node's box = the union of its triangles' boxes, children inside their parent."""
+    tris = np.asarray(bunny_scene[0], np.float32).reshape(-1, 36)
+    for leaf_n in (1, 4):
+        links, boxes, order, ms = api.accel_build(tris, leaf_n, "host")
+        n = len(tris)
+        assert sorted(order.tolist()) == list(range(n))
+        v = tris[order, :9].reshape(n, 3, 3)
+        lo, hi = v.min(1), v.max(1)
+        covered = np.zeros(n, np.int32)
+        for i, (left, right, cnt, index) in enumerate(links):
+            if cnt > 0:
+                assert left == 0 and right == 0 and cnt <= leaf_n
+                covered[index:index + cnt] += 1
+                assert np.array_equal(boxes[i, :3], lo[index:index + cnt].min(0)) and np.array_equal(boxes[i, 3:], hi[index:index + cnt].max(0))
+            else:
+                assert left == i + 1 and right > left          # pre-order: the left sub-tree follows its parent
+                for c in (left, right):
+                    assert (boxes[c, :3] >= boxes[i, :3]).all() and (boxes[c, 3:] <= boxes[i, 3:]).all()
+                assert np.array_equal(boxes[i, :3], np.minimum(boxes[left, :3], boxes[right, :3]))
+                assert np.array_equal(boxes[i, 3:], np.maximum(boxes[left, 3:], boxes[right, 3:]))
+        assert (covered == 1).all()
